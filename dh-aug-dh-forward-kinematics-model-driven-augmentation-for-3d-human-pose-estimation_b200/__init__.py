@@ -1,0 +1,25 @@
+"""dhfk -- B200-native DH forward kinematics + camera projection (forward & backward) for DH-AUG.
+
+Public surface:
+  fk_project, fk_world16, world_to_camera, project_to_2d, fk_project_host   (functional.py)
+  Forward_Kinematics_DH_Model                                               (reference-shaped class)
+  camera.GAN_torch_world_to_camera / camera.project_to_2d                   (reference-shaped functions)
+  dropin.install()                                                          (patch the imported reference)
+  tables, synthetic, parallel
+
+Importing this package does not touch the GPU and does not load libdhfk.so; the first call does,
+and raises if the library is missing (no CPU fallback).
+"""
+from . import _cabi, tables  # noqa: F401
+
+
+def __getattr__(name):
+    # torch-dependent modules are imported lazily so that `import dhfk` stays cheap
+    import importlib
+    if name in ("functional", "camera", "dropin", "parallel", "synthetic", "forward_kinematics_DH_model"):
+        return importlib.import_module("." + name, __name__)
+    if name in ("fk_project", "fk_world16", "world_to_camera", "project_to_2d", "fk_project_host"):
+        return getattr(importlib.import_module(".functional", __name__), name)
+    if name == "Forward_Kinematics_DH_Model":
+        return importlib.import_module(".forward_kinematics_DH_model", __name__).Forward_Kinematics_DH_Model
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -1,0 +1,82 @@
+"""ctypes binding of libdhfk.so (C ABI declared in include/dhfk.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C <pkg>/csrc -j``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdhfk.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+ABI_VERSION = 1
+FLAG_FAST_TRIG = 0x1
+E_INVAL, E_ALIGN, E_UNSUPPORTED = -1, -2, -3
+
+_c_f32p = ctypes.c_void_p  # raw device/host addresses are passed as integers
+_i64 = ctypes.c_int64
+_u32 = ctypes.c_uint32
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/dhfk.h declares
+SIGNATURES = {
+    "dhfk_abi_version": (ctypes.c_int, []),
+    "dhfk_last_error": (ctypes.c_char_p, []),
+    "dhfk_tile_rows": (ctypes.c_int, []),
+    "dhfk_topology": (ctypes.c_int, [_vp] * 8),
+    "dhfk_forward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64,
+                                    _vp, _vp, _vp, _i64, _u32, _vp]),
+    "dhfk_backward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64,
+                                     _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                                     _i64, _u32, _vp]),
+    "dhfk_world_to_camera_forward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, _vp, _i64, _vp]),
+    "dhfk_world_to_camera_backward": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _i64, _vp]),
+    "dhfk_project_forward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp]),
+    "dhfk_project_backward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
+    "dhfk_host_workspace_bytes": (_i64, [_i64, ctypes.c_int32]),
+    "dhfk_forward_backward_host": (ctypes.c_int, [_vp] * 12 + [_i64, _i64, ctypes.c_int32, _vp, _i64, _u32]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libdhfk.so (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libdhfk.so not found at %s -- the CUDA extension has not been built and there is no CPU "
+            "fallback.  Run `make -C %s -j` (needs nvcc, sm_100a) or __graft_entry__.build()." % (LIB_PATH, CSRC_DIR))
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.dhfk_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError("libdhfk.so ABI version %d, binding expects %d" % (got, ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().dhfk_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == E_INVAL:
+        raise ValueError("%s: invalid argument: %s" % (what, msg))
+    if rc == E_ALIGN:
+        raise ValueError("%s: alignment: %s" % (what, msg))
+    if rc == E_UNSUPPORTED:
+        raise NotImplementedError("%s: %s" % (what, msg))
+    raise RuntimeError("%s: CUDA error %d: %s" % (what, rc, msg))

@@ -1,0 +1,16 @@
+// dhfk_bwd.cu -- instantiates the fused backward kernels for one (trig policy, bone-grad) pair
+// (-DDHFK_TRIG=0|1 -DDHFK_GBONE=0|1).
+#include "dhfk_launch.h"
+#if !defined(DHFK_TRIG) || !defined(DHFK_GBONE)
+#error "compile with -DDHFK_TRIG=0|1 -DDHFK_GBONE=0|1"
+#endif
+#define DHFK_CAT_(a, b, c, d) a##b##c##d
+#define DHFK_CAT(a, b, c, d) DHFK_CAT_(a, b, c, d)
+namespace dhfk {
+int DHFK_CAT(launch_bwd_trig, DHFK_TRIG, _bone, DHFK_GBONE)(const BwdParams& p, bool guv, cudaStream_t st,
+                                                            const char** where) {
+    const size_t smem = bwd_smem_bytes(p.g_world != nullptr, p.g_cam != nullptr, guv);
+    if (guv) return launch_tiles(dhfk_bwd_kernel<true, (DHFK_GBONE != 0), DHFK_TRIG>, smem, p, st, where);
+    return launch_tiles(dhfk_bwd_kernel<false, (DHFK_GBONE != 0), DHFK_TRIG>, smem, p, st, where);
+}
+}  // namespace dhfk

@@ -1,0 +1,424 @@
+// dhfk_cabi.cu -- extern "C" boundary of libdhfk.so (include/dhfk.h): argument validation,
+// camera constants, kernel dispatch, the standalone camera kernels and the host-buffer pipeline.
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dhfk.h"
+#include "dhfk_launch.h"
+
+namespace dhfk {
+
+// ---- standalone camera ops (common/camera.py used on its own) ---------------------------------
+struct RotConst { float M[9]; float t[3]; };
+
+// out = M (x - t): one thread per point, 3 floats; consecutive threads touch consecutive 12-byte
+// records so every 128-byte line is fully consumed across the three loads.
+__global__ void __launch_bounds__(256) w2c_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                     long long npts, const __grid_constant__ RotConst rc) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    V3 v = v3(x[3 * i] - rc.t[0], x[3 * i + 1] - rc.t[1], x[3 * i + 2] - rc.t[2]);
+    V3 o = mat_vec(rc.M, v);
+    out[3 * i] = o.x; out[3 * i + 1] = o.y; out[3 * i + 2] = o.z;
+}
+__global__ void __launch_bounds__(256) w2c_bwd_kernel(const float* __restrict__ g, float* __restrict__ gx,
+                                                     long long npts, const __grid_constant__ RotConst rc) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    V3 o = matT_vec(rc.M, v3(g[3 * i], g[3 * i + 1], g[3 * i + 2]));
+    gx[3 * i] = o.x; gx[3 * i + 1] = o.y; gx[3 * i + 2] = o.z;
+}
+
+// same map with q / t read from device memory (fp32 matrix build per thread; 7 broadcast loads)
+DHFK_DI void rot_from_quat_dev(const float* __restrict__ q, float* M) {
+    const float w = q[0], ux = -q[1], uy = -q[2], uz = -q[3];
+    // M = I + 2 w [u]x + 2 [u]x^2
+    const float xx = ux * ux, yy = uy * uy, zz = uz * uz, xy = ux * uy, xz = ux * uz, yz = uy * uz;
+    M[0] = 1.f - 2.f * (yy + zz); M[1] = 2.f * (xy - w * uz);   M[2] = 2.f * (xz + w * uy);
+    M[3] = 2.f * (xy + w * uz);   M[4] = 1.f - 2.f * (xx + zz); M[5] = 2.f * (yz - w * ux);
+    M[6] = 2.f * (xz - w * uy);   M[7] = 2.f * (yz + w * ux);   M[8] = 1.f - 2.f * (xx + yy);
+}
+__global__ void __launch_bounds__(256) w2c_fwd_dev_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                         long long npts, const float* __restrict__ q,
+                                                         const float* __restrict__ t) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    float M[9];
+    rot_from_quat_dev(q, M);
+    V3 v = v3(x[3 * i] - t[0], x[3 * i + 1] - t[1], x[3 * i + 2] - t[2]);
+    V3 o = mat_vec(M, v);
+    out[3 * i] = o.x; out[3 * i + 1] = o.y; out[3 * i + 2] = o.z;
+}
+__global__ void __launch_bounds__(256) w2c_bwd_dev_kernel(const float* __restrict__ g, float* __restrict__ gx,
+                                                         long long npts, const float* __restrict__ q) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    float M[9];
+    rot_from_quat_dev(q, M);
+    V3 o = matT_vec(M, v3(g[3 * i], g[3 * i + 1], g[3 * i + 2]));
+    gx[3 * i] = o.x; gx[3 * i + 1] = o.y; gx[3 * i + 2] = o.z;
+}
+
+DHFK_DI CamConst load_cam_row(const float* row) {
+    CamConst cc;
+    cc.f[0] = row[0]; cc.f[1] = row[1]; cc.c[0] = row[2]; cc.c[1] = row[3];
+    cc.k[0] = row[4]; cc.k[1] = row[5]; cc.k[2] = row[6]; cc.p[0] = row[7]; cc.p[1] = row[8];
+    cc.k1x2 = 2.f * cc.k[1]; cc.k2x3 = 3.f * cc.k[2];
+    return cc;
+}
+// project_to_2d with per-row intrinsics; one thread per (row, joint) point
+__global__ void __launch_bounds__(256) project_fwd_kernel(const float* __restrict__ x, const float* __restrict__ cam,
+                                                         long long cam_stride, float* __restrict__ uv,
+                                                         long long npts, int joints) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    CamConst cc = load_cam_row(cam + (i / joints) * cam_stride);
+    ProjAux a;
+    float u, v;
+    project_point(cc, v3(x[3 * i], x[3 * i + 1], x[3 * i + 2]), u, v, a);
+    reinterpret_cast<float2*>(uv)[i] = make_float2(u, v);
+}
+__global__ void __launch_bounds__(256) project_bwd_kernel(const float* __restrict__ x, const float* __restrict__ cam,
+                                                         long long cam_stride, const float* __restrict__ g_uv,
+                                                         float* __restrict__ gx, long long npts, int joints) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    CamConst cc = load_cam_row(cam + (i / joints) * cam_stride);
+    ProjAux a;
+    float u, v;
+    project_point(cc, v3(x[3 * i], x[3 * i + 1], x[3 * i + 2]), u, v, a);
+    float2 g = reinterpret_cast<const float2*>(g_uv)[i];
+    V3 o = project_point_bwd(cc, a, g.x, g.y);
+    gx[3 * i] = o.x; gx[3 * i + 1] = o.y; gx[3 * i + 2] = o.z;
+}
+
+}  // namespace dhfk
+
+// =================================================================================================
+// Host side: C ABI
+// =================================================================================================
+
+namespace {
+
+using namespace dhfk;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof g_err, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+RowSrc row_src(const float* p, int64_t stride, int ncols) {
+    RowSrc r;
+    r.p = p;
+    r.stride = stride;
+    r.vec = (stride == ncols && aligned16(p)) ? 1 : 0;
+    return r;
+}
+RowDst row_dst(float* p, int64_t stride, int ncols) {
+    RowDst r;
+    r.p = p;
+    r.stride = stride;
+    r.vec = (p != nullptr && stride == ncols && aligned16(p)) ? 1 : 0;
+    return r;
+}
+
+// v -> qrot(conj(q), v) as a 3x3 matrix (double arithmetic on the host), common/quaternion.py:6-35
+void camera_matrix(const float* q, float* M) {
+    double w = q[0], u[3] = {-(double)q[1], -(double)q[2], -(double)q[3]};
+    for (int col = 0; col < 3; ++col) {
+        double v[3] = {0, 0, 0};
+        v[col] = 1;
+        double uv[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+        double uuv[3] = {u[1] * uv[2] - u[2] * uv[1], u[2] * uv[0] - u[0] * uv[2], u[0] * uv[1] - u[1] * uv[0]};
+        for (int r = 0; r < 3; ++r) M[r * 3 + col] = (float)(v[r] + 2 * (w * uv[r] + uuv[r]));
+    }
+}
+CamConst make_cam(const float* cam) {
+    CamConst cc;
+    memset(&cc, 0, sizeof cc);
+    if (cam) {
+        camera_matrix(cam, cc.M);
+        for (int i = 0; i < 3; ++i) cc.t[i] = cam[4 + i];
+        cc.f[0] = cam[7]; cc.f[1] = cam[8]; cc.c[0] = cam[9]; cc.c[1] = cam[10];
+        cc.k[0] = cam[11]; cc.k[1] = cam[12]; cc.k[2] = cam[13]; cc.p[0] = cam[14]; cc.p[1] = cam[15];
+        cc.k1x2 = 2.f * cc.k[1];
+        cc.k2x3 = 3.f * cc.k[2];
+    }
+    return cc;
+}
+
+int check_inputs(const float* ang, int64_t as, const float* grot, int64_t gs, const float* bone, int64_t bs,
+                 const float* root, int64_t rs, int64_t n) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
+    if (n == 0) return DHFK_OK;
+    if (!ang || !grot || !bone || !root) return fail(DHFK_E_INVAL, "ang/grot/bone/root must be non-null");
+    if (as < 33 || gs < 3 || bs < 15 || rs < 3)
+        return fail(DHFK_E_INVAL, "row strides must be >= 33 (ang), 3 (grot), 15 (bone), 3 (root)");
+    return DHFK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dhfk_abi_version(void) { return DHFK_ABI_VERSION; }
+const char* dhfk_last_error(void) { return g_err; }
+int dhfk_tile_rows(void) { return dhfk::kTile; }
+
+int dhfk_topology(int32_t* parent33, int32_t* out16, float* alpha33, float* theta0_33, int32_t* len_kind33,
+                  int32_t* len_bone33, int32_t* len_sign33, int32_t* h36m_32_to_16) {
+    for (int j = 0; j < dhfk::NJ; ++j) {
+        if (parent33) parent33[j] = dhfk::PARENT[j];
+        if (alpha33) alpha33[j] = 90.0f * (float)dhfk::ALPHA_Q[j];
+        if (theta0_33) theta0_33[j] = 90.0f * (float)dhfk::THETA0_Q[j];
+        if (len_kind33) len_kind33[j] = dhfk::LEN_KIND[j];
+        if (len_bone33) len_bone33[j] = dhfk::LEN_BONE[j];
+        if (len_sign33) len_sign33[j] = dhfk::LEN_SIGN[j];
+    }
+    for (int k = 0; k < dhfk::NOUT; ++k) {
+        if (out16) out16[k] = dhfk::OUT16[k];
+        if (h36m_32_to_16) h36m_32_to_16[k] = dhfk::H36M_32_TO_16[k];
+    }
+    return DHFK_OK;
+}
+
+int dhfk_forward(const float* ang, int64_t ang_stride, const float* grot, int64_t grot_stride, const float* bone,
+                 int64_t bone_stride, const float* root, int64_t root_stride, const float* cam,
+                 const float* cam_rows, int64_t cam_rows_stride, float* out_world, float* out_cam, float* out_uv,
+                 int64_t n, uint32_t flags, void* stream) {
+    (void)cam_rows_stride;
+    int rc = check_inputs(ang, ang_stride, grot, grot_stride, bone, bone_stride, root, root_stride, n);
+    if (rc != DHFK_OK) return rc;
+    if (n == 0) return DHFK_OK;
+    if (cam_rows) return fail(DHFK_E_UNSUPPORTED, "per-row intrinsics are not supported in the fused path; use dhfk_project_*");
+    if (!out_world) return fail(DHFK_E_INVAL, "out_world is required");
+    if ((out_cam || out_uv) && !cam) return fail(DHFK_E_INVAL, "cam block required for out_cam / out_uv");
+    if (!aligned16(out_world) || !aligned16(out_cam) || !aligned16(out_uv))
+        return fail(DHFK_E_ALIGN, "outputs must be 16-byte aligned");
+    FwdParams p;
+    p.ang = row_src(ang, ang_stride, 33);
+    p.grot = row_src(grot, grot_stride, 3);
+    p.bone = row_src(bone, bone_stride, 15);
+    p.root = row_src(root, root_stride, 3);
+    p.out_world = out_world;
+    p.out_cam = out_cam;
+    p.out_uv = out_uv;
+    p.n = n;
+    p.cam = make_cam(cam);
+    if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* where = "";
+    const bool oc = out_cam != nullptr, ou = out_uv != nullptr;
+    int e = (flags & DHFK_FLAG_FAST_TRIG) ? dhfk::launch_fwd_trig1(p, oc, ou, st, &where)
+                                          : dhfk::launch_fwd_trig0(p, oc, ou, st, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+
+int dhfk_backward(const float* ang, int64_t ang_stride, const float* grot, int64_t grot_stride, const float* bone,
+                  int64_t bone_stride, const float* root, int64_t root_stride, const float* cam,
+                  const float* cam_rows, int64_t cam_rows_stride, const float* g_world, const float* g_cam,
+                  const float* g_uv, float* g_ang, int64_t g_ang_stride, float* g_grot, int64_t g_grot_stride,
+                  float* g_root, int64_t g_root_stride, float* g_bone, int64_t g_bone_stride, int64_t n,
+                  uint32_t flags, void* stream) {
+    (void)cam_rows_stride;
+    int rc = check_inputs(ang, ang_stride, grot, grot_stride, bone, bone_stride, root, root_stride, n);
+    if (rc != DHFK_OK) return rc;
+    if (n == 0) return DHFK_OK;
+    if (cam_rows) return fail(DHFK_E_UNSUPPORTED, "per-row intrinsics are not supported in the fused path; use dhfk_project_*");
+    if (!g_world && !g_cam && !g_uv) return fail(DHFK_E_INVAL, "at least one upstream gradient is required");
+    if ((g_cam || g_uv) && !cam) return fail(DHFK_E_INVAL, "cam block required for g_cam / g_uv");
+    if (!g_ang || !g_grot || !g_root) return fail(DHFK_E_INVAL, "g_ang, g_grot and g_root are required");
+    if (g_ang_stride < 33 || g_grot_stride < 3 || g_root_stride < 3 || (g_bone && g_bone_stride < 15))
+        return fail(DHFK_E_INVAL, "gradient row strides too small");
+    if (!aligned16(g_world) || !aligned16(g_cam) || !aligned16(g_uv))
+        return fail(DHFK_E_ALIGN, "upstream gradients must be 16-byte aligned");
+    BwdParams p;
+    p.ang = row_src(ang, ang_stride, 33);
+    p.grot = row_src(grot, grot_stride, 3);
+    p.bone = row_src(bone, bone_stride, 15);
+    p.root = row_src(root, root_stride, 3);
+    p.g_world = g_world;
+    p.g_cam = g_cam;
+    p.g_uv = g_uv;
+    p.g_ang = row_dst(g_ang, g_ang_stride, 33);
+    p.g_grot = row_dst(g_grot, g_grot_stride, 3);
+    p.g_root = row_dst(g_root, g_root_stride, 3);
+    p.g_bone = row_dst(g_bone, g_bone_stride, 15);
+    p.n = n;
+    p.cam = make_cam(cam);
+    if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool gu = g_uv != nullptr;
+    const bool fast = (flags & DHFK_FLAG_FAST_TRIG) != 0;
+    const char* where = "";
+    int e;
+    if (g_bone) e = fast ? dhfk::launch_bwd_trig1_bone1(p, gu, st, &where) : dhfk::launch_bwd_trig0_bone1(p, gu, st, &where);
+    else e = fast ? dhfk::launch_bwd_trig1_bone0(p, gu, st, &where) : dhfk::launch_bwd_trig0_bone0(p, gu, st, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+
+int dhfk_world_to_camera_forward(const float* x, const float* cam_q, const float* cam_t, int32_t cam_on_device,
+                                 float* out, int64_t num_points, void* stream) {
+    if (num_points < 0) return fail(DHFK_E_INVAL, "num_points must be >= 0");
+    if (num_points == 0) return DHFK_OK;
+    if (!x || !cam_q || !cam_t || !out) return fail(DHFK_E_INVAL, "null argument");
+    if (cam_on_device) {
+        long long nb = (num_points + 255) / 256;
+        dhfk::w2c_fwd_dev_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(x, out, num_points, cam_q, cam_t);
+        cudaError_t e2 = cudaGetLastError();
+        return e2 == cudaSuccess ? DHFK_OK : cuda_fail(e2, "w2c_fwd_dev_kernel");
+    }
+    dhfk::RotConst rc;
+    camera_matrix(cam_q, rc.M);
+    for (int i = 0; i < 3; ++i) rc.t[i] = cam_t[i];
+    long long blocks = (num_points + 255) / 256;
+    dhfk::w2c_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, out, num_points, rc);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DHFK_OK : cuda_fail(e, "w2c_fwd_kernel");
+}
+int dhfk_world_to_camera_backward(const float* g_out, const float* cam_q, int32_t cam_on_device, float* g_x,
+                                  int64_t num_points, void* stream) {
+    if (num_points < 0) return fail(DHFK_E_INVAL, "num_points must be >= 0");
+    if (num_points == 0) return DHFK_OK;
+    if (!g_out || !cam_q || !g_x) return fail(DHFK_E_INVAL, "null argument");
+    if (cam_on_device) {
+        long long nb = (num_points + 255) / 256;
+        dhfk::w2c_bwd_dev_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(g_out, g_x, num_points, cam_q);
+        cudaError_t e2 = cudaGetLastError();
+        return e2 == cudaSuccess ? DHFK_OK : cuda_fail(e2, "w2c_bwd_dev_kernel");
+    }
+    dhfk::RotConst rc;
+    camera_matrix(cam_q, rc.M);
+    rc.t[0] = rc.t[1] = rc.t[2] = 0.f;
+    long long blocks = (num_points + 255) / 256;
+    dhfk::w2c_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g_out, g_x, num_points, rc);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DHFK_OK : cuda_fail(e, "w2c_bwd_kernel");
+}
+
+int dhfk_project_forward(const float* x, const float* cam_rows, int64_t cam_rows_stride, float* uv, int64_t n,
+                         int64_t joints, void* stream) {
+    if (n < 0 || joints < 0) return fail(DHFK_E_INVAL, "n and joints must be >= 0");
+    if (n == 0 || joints == 0) return DHFK_OK;
+    if (!x || !cam_rows || !uv) return fail(DHFK_E_INVAL, "null argument");
+    if (cam_rows_stride < 9) return fail(DHFK_E_INVAL, "camera rows need >= 9 columns");
+    if ((reinterpret_cast<uintptr_t>(uv) & 7u) != 0) return fail(DHFK_E_ALIGN, "uv must be 8-byte aligned");
+    long long npts = n * joints, blocks = (npts + 255) / 256;
+    dhfk::project_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, cam_rows, cam_rows_stride, uv,
+                                                                                npts, (int)joints);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DHFK_OK : cuda_fail(e, "project_fwd_kernel");
+}
+int dhfk_project_backward(const float* x, const float* cam_rows, int64_t cam_rows_stride, const float* g_uv,
+                          float* g_x, int64_t n, int64_t joints, void* stream) {
+    if (n < 0 || joints < 0) return fail(DHFK_E_INVAL, "n and joints must be >= 0");
+    if (n == 0 || joints == 0) return DHFK_OK;
+    if (!x || !cam_rows || !g_uv || !g_x) return fail(DHFK_E_INVAL, "null argument");
+    if (cam_rows_stride < 9) return fail(DHFK_E_INVAL, "camera rows need >= 9 columns");
+    if ((reinterpret_cast<uintptr_t>(g_uv) & 7u) != 0) return fail(DHFK_E_ALIGN, "g_uv must be 8-byte aligned");
+    long long npts = n * joints, blocks = (npts + 255) / 256;
+    dhfk::project_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, cam_rows, cam_rows_stride, g_uv,
+                                                                                g_x, npts, (int)joints);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DHFK_OK : cuda_fail(e, "project_bwd_kernel");
+}
+
+// ---- host-buffer end-to-end entry --------------------------------------------------------------
+// per-row device scratch: inputs 54, world 48, uv 32, g_world 48, g_uv 32, g_ang 33, g_grot 3, g_root 3
+static const int64_t kHostRowFloats = 54 + 48 + 32 + 48 + 32 + 33 + 3 + 3;
+
+int64_t dhfk_host_workspace_bytes(int64_t chunk_rows, int32_t num_streams) {
+    if (chunk_rows <= 0 || num_streams <= 0) return 0;
+    int64_t rows = (chunk_rows + 3) / 4 * 4;  // keep every sub-buffer 16-byte aligned
+    return rows * kHostRowFloats * (int64_t)sizeof(float) * num_streams;
+}
+
+int dhfk_forward_backward_host(const float* ang_h, const float* grot_h, const float* bone_h, const float* root_h,
+                               const float* cam, const float* g_world_h, const float* g_uv_h, float* out_world_h,
+                               float* out_uv_h, float* g_ang_h, float* g_grot_h, float* g_root_h, int64_t n,
+                               int64_t chunk_rows, int32_t num_streams, void* workspace, int64_t workspace_bytes,
+                               uint32_t flags) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
+    if (n == 0) return DHFK_OK;
+    if (!ang_h || !grot_h || !bone_h || !root_h || !cam || !out_world_h || !out_uv_h)
+        return fail(DHFK_E_INVAL, "null host argument");
+    const bool do_bwd = g_world_h != nullptr || g_uv_h != nullptr;
+    if (do_bwd && (!g_world_h || !g_uv_h || !g_ang_h || !g_grot_h || !g_root_h))
+        return fail(DHFK_E_INVAL, "backward needs g_world, g_uv and the three gradient outputs");
+    if (chunk_rows <= 0 || chunk_rows % 4 != 0) return fail(DHFK_E_INVAL, "chunk_rows must be a positive multiple of 4");
+    if (num_streams <= 0 || num_streams > 8) return fail(DHFK_E_INVAL, "num_streams must be in 1..8");
+    if (!workspace || workspace_bytes < dhfk_host_workspace_bytes(chunk_rows, num_streams))
+        return fail(DHFK_E_INVAL, "workspace too small (see dhfk_host_workspace_bytes)");
+    if (!aligned16(workspace)) return fail(DHFK_E_ALIGN, "workspace must be 16-byte aligned");
+
+    cudaStream_t streams[8];
+    cudaError_t e = cudaSuccess;
+    int made = 0;
+    for (; made < num_streams; ++made) {
+        e = cudaStreamCreateWithFlags(&streams[made], cudaStreamNonBlocking);
+        if (e != cudaSuccess) break;
+    }
+    int rc = DHFK_OK;
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamCreate");
+
+    const size_t F = sizeof(float);
+    const int64_t slot_floats = chunk_rows * kHostRowFloats;
+    int64_t chunk_idx = 0;
+    for (int64_t r0 = 0; r0 < n && rc == DHFK_OK; r0 += chunk_rows, ++chunk_idx) {
+        const int64_t rows = (n - r0 < chunk_rows) ? (n - r0) : chunk_rows;
+        cudaStream_t st = streams[chunk_idx % num_streams];
+        float* base = reinterpret_cast<float*>(workspace) + (chunk_idx % num_streams) * slot_floats;
+        float* d_ang = base;
+        float* d_grot = d_ang + chunk_rows * 33;
+        float* d_bone = d_grot + chunk_rows * 3;
+        float* d_root = d_bone + chunk_rows * 15;
+        float* d_world = d_root + chunk_rows * 3;
+        float* d_uv = d_world + chunk_rows * 48;
+        float* d_gw = d_uv + chunk_rows * 32;
+        float* d_gu = d_gw + chunk_rows * 48;
+        float* d_gang = d_gu + chunk_rows * 32;
+        float* d_ggrot = d_gang + chunk_rows * 33;
+        float* d_groot = d_ggrot + chunk_rows * 3;
+#define DHFK_CP(dst, src, cnt, kind)                                                      \
+    if (rc == DHFK_OK) {                                                                  \
+        e = cudaMemcpyAsync(dst, src, (size_t)(cnt)*F, kind, st);                         \
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync");                       \
+    }
+        DHFK_CP(d_ang, ang_h + r0 * 33, rows * 33, cudaMemcpyHostToDevice)
+        DHFK_CP(d_grot, grot_h + r0 * 3, rows * 3, cudaMemcpyHostToDevice)
+        DHFK_CP(d_bone, bone_h + r0 * 15, rows * 15, cudaMemcpyHostToDevice)
+        DHFK_CP(d_root, root_h + r0 * 3, rows * 3, cudaMemcpyHostToDevice)
+        if (rc == DHFK_OK)
+            rc = dhfk_forward(d_ang, 33, d_grot, 3, d_bone, 15, d_root, 3, cam, nullptr, 0, d_world, nullptr, d_uv,
+                              rows, flags, st);
+        DHFK_CP(out_world_h + r0 * 48, d_world, rows * 48, cudaMemcpyDeviceToHost)
+        DHFK_CP(out_uv_h + r0 * 32, d_uv, rows * 32, cudaMemcpyDeviceToHost)
+        if (do_bwd) {
+            DHFK_CP(d_gw, g_world_h + r0 * 48, rows * 48, cudaMemcpyHostToDevice)
+            DHFK_CP(d_gu, g_uv_h + r0 * 32, rows * 32, cudaMemcpyHostToDevice)
+            if (rc == DHFK_OK)
+                rc = dhfk_backward(d_ang, 33, d_grot, 3, d_bone, 15, d_root, 3, cam, nullptr, 0, d_gw, nullptr, d_gu,
+                                   d_gang, 33, d_ggrot, 3, d_groot, 3, nullptr, 0, rows, flags, st);
+            DHFK_CP(g_ang_h + r0 * 33, d_gang, rows * 33, cudaMemcpyDeviceToHost)
+            DHFK_CP(g_grot_h + r0 * 3, d_ggrot, rows * 3, cudaMemcpyDeviceToHost)
+            DHFK_CP(g_root_h + r0 * 3, d_groot, rows * 3, cudaMemcpyDeviceToHost)
+        }
+#undef DHFK_CP
+    }
+    for (int i = 0; i < made; ++i) {
+        e = cudaStreamSynchronize(streams[i]);
+        if (e != cudaSuccess && rc == DHFK_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+        cudaStreamDestroy(streams[i]);
+    }
+    return rc;
+}
+
+}  // extern "C"

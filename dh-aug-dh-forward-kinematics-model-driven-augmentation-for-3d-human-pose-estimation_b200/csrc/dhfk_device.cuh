@@ -1,0 +1,306 @@
+// dhfk_device.cuh -- per-pose device math: degree-argument sincos, DH joint steps as signed
+// axis permutation + planar rotation, pinhole projection forward/backward, and the
+// compile-time tree walkers (forward: emit origins; backward: wrench accumulation).
+//
+// One thread owns one pose; everything here is straight-line register code after inlining.
+#pragma once
+#include "dhfk_topology.h"
+
+namespace dhfk {
+
+struct V3 { float x, y, z; };
+struct Frame { V3 X, Y, Z, O; };   // columns of the 3x4 world transform of a joint frame
+struct Wrench { V3 F, M; };        // sum of forces / moments about the chain origin
+
+#define DHFK_DI __device__ __forceinline__
+
+DHFK_DI V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+DHFK_DI V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+DHFK_DI V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+DHFK_DI V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+DHFK_DI V3 axpy(float s, V3 a, V3 b) { return v3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
+DHFK_DI V3 scale(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+DHFK_DI float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+DHFK_DI V3 cross(V3 a, V3 b) {
+    return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+// a - o x f
+DHFK_DI V3 sub_cross(V3 a, V3 o, V3 f) {
+    return v3(fmaf(o.z, f.y, fmaf(-o.y, f.z, a.x)), fmaf(o.x, f.z, fmaf(-o.z, f.x, a.y)),
+              fmaf(o.y, f.x, fmaf(-o.x, f.y, a.z)));
+}
+// a + o x f
+DHFK_DI V3 add_cross(V3 a, V3 o, V3 f) {
+    return v3(fmaf(o.y, f.z, fmaf(-o.z, f.y, a.x)), fmaf(o.z, f.x, fmaf(-o.x, f.z, a.y)),
+              fmaf(o.x, f.y, fmaf(-o.y, f.x, a.z)));
+}
+// 3x3 row-major matrix (array of 9) times vector, and transpose times vector
+DHFK_DI V3 mat_vec(const float* m, V3 v) {
+    return v3(fmaf(m[0], v.x, fmaf(m[1], v.y, m[2] * v.z)), fmaf(m[3], v.x, fmaf(m[4], v.y, m[5] * v.z)),
+              fmaf(m[6], v.x, fmaf(m[7], v.y, m[8] * v.z)));
+}
+DHFK_DI V3 mat_vec_add(const float* m, V3 v, V3 b) {
+    return v3(fmaf(m[0], v.x, fmaf(m[1], v.y, fmaf(m[2], v.z, b.x))),
+              fmaf(m[3], v.x, fmaf(m[4], v.y, fmaf(m[5], v.z, b.y))),
+              fmaf(m[6], v.x, fmaf(m[7], v.y, fmaf(m[8], v.z, b.z))));
+}
+DHFK_DI V3 matT_vec(const float* m, V3 v) {
+    return v3(fmaf(m[0], v.x, fmaf(m[3], v.y, m[6] * v.z)), fmaf(m[1], v.x, fmaf(m[4], v.y, m[7] * v.z)),
+              fmaf(m[2], v.x, fmaf(m[5], v.y, m[8] * v.z)));
+}
+DHFK_DI V3 matT_vec_add(const float* m, V3 v, V3 b) {
+    return v3(fmaf(m[0], v.x, fmaf(m[3], v.y, fmaf(m[6], v.z, b.x))),
+              fmaf(m[1], v.x, fmaf(m[4], v.y, fmaf(m[7], v.z, b.y))),
+              fmaf(m[2], v.x, fmaf(m[5], v.y, fmaf(m[8], v.z, b.z))));
+}
+
+constexpr float kDegToRad = 0.017453292519943295f;
+
+// ---------------------------------------------------------------------------------------
+// sin/cos of (deg + 90*Q0) degrees.  Q0 is the compile-time theta0 quadrant of the joint.
+//
+// TRIG_ACCURATE: exact range reduction in degrees (r = deg - 90*rint(deg/90) is exact in
+// fp32), degree-scaled minimax polynomials on |r| <= 45 (cephes sinf/cosf coefficients),
+// quadrant fix-up by swap + sign-bit xor.  ~1 ulp; independent of |deg| up to ~3e8.
+// TRIG_MUFU: exact reduction to |r| <= 180, then MUFU.SIN / MUFU.COS (abs err ~4e-7).
+// The reference computes fl(fl(deg/180)*pi_f32) and then libm sinf: its own argument error
+// is ~1e-7 relative, so either variant is at least as close to the true value as it is.
+// ---------------------------------------------------------------------------------------
+enum { TRIG_ACCURATE = 0, TRIG_MUFU = 1 };
+
+template <int TRIG, int Q0>
+DHFK_DI void sincos_deg(float deg, float& s, float& c) {
+    const float kMagic = 12582912.0f;  // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x) for |x| < 2^22
+    if (TRIG == TRIG_ACCURATE) {
+        float t = fmaf(deg, 1.0f / 90.0f, kMagic);
+        int n = __float_as_int(t) + Q0;           // low 2 bits: quadrant
+        float q = t - kMagic;
+        float r = fmaf(q, -90.0f, deg);           // exact, |r| <= 45 (+ 1 ulp of slack)
+        float r2 = r * r;
+        constexpr double D = 3.14159265358979323846 / 180.0;
+        constexpr float S0 = (float)D;
+        constexpr float S1 = (float)(-1.6666654611e-1 * D * D * D);
+        constexpr float S2 = (float)(8.3321608736e-3 * D * D * D * D * D);
+        constexpr float S3 = (float)(-1.9515295891e-4 * D * D * D * D * D * D * D);
+        constexpr float C1 = (float)(-0.5 * D * D);
+        constexpr float C2 = (float)(4.166664568298827e-2 * D * D * D * D);
+        constexpr float C3 = (float)(-1.388731625493765e-3 * D * D * D * D * D * D);
+        constexpr float C4 = (float)(2.443315711809948e-5 * D * D * D * D * D * D * D * D);
+        float ps = fmaf(r2, S3, S2);
+        ps = fmaf(r2, ps, S1);
+        ps = fmaf(r2, ps, S0);
+        float sv = r * ps;
+        float pc = fmaf(r2, C4, C3);
+        pc = fmaf(r2, pc, C2);
+        pc = fmaf(r2, pc, C1);
+        float cv = fmaf(r2, pc, 1.0f);
+        bool odd = (n & 1) != 0;
+        float so = odd ? cv : sv;
+        float co = odd ? sv : cv;
+        s = __int_as_float(__float_as_int(so) ^ ((n << 30) & 0x80000000));
+        c = __int_as_float(__float_as_int(co) ^ (((n + 1) << 30) & 0x80000000));
+    } else {
+        float t = fmaf(deg, 1.0f / 360.0f, kMagic);
+        float q = t - kMagic;
+        float r = fmaf(q, -360.0f, deg);          // exact, |r| <= 180
+        float x = r * kDegToRad;
+        float sv = __sinf(x), cv = __cosf(x);
+        constexpr int Q = ((Q0 % 4) + 4) % 4;
+        if (Q == 0) { s = sv; c = cv; }
+        else if (Q == 1) { s = cv; c = -sv; }
+        else if (Q == 2) { s = -sv; c = -cv; }
+        else { s = -cv; c = sv; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// DH joint step.  T_j = Rot_x(alpha) Trans_x(a) Rot_z(theta) Trans_z(d) (modified DH,
+// forward_kinematics_DH_model.py:99-114):  W_j = W_parent * T_j, i.e.
+//   o_j = o_p + a x_p - sin(alpha) d y_p + cos(alpha) d z_p
+//   [x y z]_j = [x_p, ca y_p + sa z_p, -sa y_p + ca z_p] * Rz(theta)
+// With alpha in {0,+-90} the twist is a signed axis permutation.
+// ---------------------------------------------------------------------------------------
+template <int J>
+DHFK_DI void twist(const Frame& F, V3& y1, V3& z1) {
+    constexpr int A = ALPHA_Q[J];
+    if constexpr (A == 0) { y1 = F.Y; z1 = F.Z; }
+    else if constexpr (A == -1) { y1 = -F.Z; z1 = F.Y; }
+    else { y1 = F.Z; z1 = -F.Y; }
+}
+// direction (in the parent frame axes) along which this joint's bone length moves the origin
+template <int J>
+DHFK_DI V3 length_axis(const Frame& F) {
+    constexpr int A = ALPHA_Q[J], KIND = LEN_KIND[J], SIGN = LEN_SIGN[J];
+    V3 a;
+    if constexpr (KIND == 1) a = F.X;
+    else if constexpr (A == 0) a = F.Z;   // 'd': -sin(alpha) y_p + cos(alpha) z_p
+    else if constexpr (A == -1) a = F.Y;
+    else a = -F.Y;
+    if constexpr (SIGN > 0) return a;
+    else return -a;
+}
+template <int J>
+DHFK_DI void advance_origin(Frame& F, const float* bone) {
+    constexpr int KIND = LEN_KIND[J], BONE = LEN_BONE[J];
+    if constexpr (KIND != 0) F.O = axpy(bone[BONE], length_axis<J>(F), F.O);
+}
+template <int J>
+DHFK_DI void rotate_joint(Frame& F, float s, float c) {
+    V3 y1, z1;
+    twist<J>(F, y1, z1);
+    V3 x = axpy(s, y1, scale(c, F.X));
+    V3 y = axpy(c, y1, scale(-s, F.X));
+    F.X = x; F.Y = y; F.Z = z1;
+}
+DHFK_DI Frame identity_frame() {
+    Frame F;
+    F.X = v3(1.f, 0.f, 0.f); F.Y = v3(0.f, 1.f, 0.f); F.Z = v3(0.f, 0.f, 1.f); F.O = v3(0.f, 0.f, 0.f);
+    return F;
+}
+
+// ---------------------------------------------------------------------------------------
+// Camera constants: passed by value as a kernel parameter (constant bank operands).
+// M maps v = X_world - t to camera space exactly as qrot(conj(q), v) does
+// (common/quaternion.py:6-24, common/camera.py:36-38), valid for non-unit q too.
+// ---------------------------------------------------------------------------------------
+struct CamConst {
+    float M[9];
+    float t[3];
+    float f[2], c[2], k[3], p[2];
+    float k1x2, k2x3;  // 2*k[1], 3*k[2]
+};
+
+struct ProjAux { float rx, ry, x, y, r2, S, iz; };
+
+// project_to_2d (common/camera.py:85-94) for one camera-space point
+DHFK_DI float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.RCP, <= 1 ulp; 1/0 = inf like the reference's x / 0
+    return r;
+}
+DHFK_DI void project_point(const CamConst& cc, V3 X, float& u, float& v, ProjAux& a) {
+    float iz = rcp_approx(X.z);
+    a.iz = iz;
+    a.rx = X.x * iz;
+    a.ry = X.y * iz;
+    a.x = fminf(fmaxf(a.rx, -1.f), 1.f);
+    a.y = fminf(fmaxf(a.ry, -1.f), 1.f);
+    a.r2 = fmaf(a.x, a.x, a.y * a.y);
+    float radial = fmaf(a.r2, fmaf(a.r2, fmaf(a.r2, cc.k[2], cc.k[1]), cc.k[0]), 1.f);
+    float tan = fmaf(cc.p[0], a.x, cc.p[1] * a.y);
+    a.S = radial + tan;
+    float sx = fmaf(a.x, a.S, cc.p[0] * a.r2);
+    float sy = fmaf(a.y, a.S, cc.p[1] * a.r2);
+    u = fmaf(cc.f[0], sx, cc.c[0]);
+    v = fmaf(cc.f[1], sy, cc.c[1]);
+}
+// gradient wrt the camera-space point; torch.clamp passes gradient where -1 <= x/z <= 1
+DHFK_DI V3 project_point_bwd(const CamConst& cc, const ProjAux& a, float gu, float gv) {
+    float a0 = cc.f[0] * gu, a1 = cc.f[1] * gv;
+    float drad = fmaf(a.r2, fmaf(a.r2, cc.k2x3, cc.k1x2), cc.k[0]);
+    float ax = fmaf(a0, a.x, a1 * a.y);
+    float ap = fmaf(a0, cc.p[0], a1 * cc.p[1]);
+    float t2 = 2.f * fmaf(ax, drad, ap);
+    float gx = fmaf(a0, a.S, fmaf(a.x, t2, ax * cc.p[0]));
+    float gy = fmaf(a1, a.S, fmaf(a.y, t2, ax * cc.p[1]));
+    gx = (a.x == a.rx) ? gx : 0.f;
+    gy = (a.y == a.ry) ? gy : 0.f;
+    return v3(gx * a.iz, gy * a.iz, -fmaf(gx, a.rx, gy * a.ry) * a.iz);
+}
+
+// ---------------------------------------------------------------------------------------
+// Forward walker: depth-first over the compile-time tree.  Ctx provides
+//   const float* ang (33 joint angles, degrees), const float* bone (15 lengths)
+//   template<int K> void emit(V3 origin_in_chain_frame)
+// ---------------------------------------------------------------------------------------
+template <int TRIG, int J, class Ctx> DHFK_DI void fwd_walk(Frame F, Ctx& ctx);
+
+template <int TRIG, int J, int I, class Ctx>
+DHFK_DI void fwd_children(const Frame& F, Ctx& ctx) {
+    constexpr int C = nth_child(J, I);
+    if constexpr (C >= 0) {
+        fwd_walk<TRIG, C>(F, ctx);
+        fwd_children<TRIG, J, I + 1>(F, ctx);
+    }
+}
+template <int TRIG, int J, class Ctx>
+DHFK_DI void fwd_walk(Frame F, Ctx& ctx) {
+    advance_origin<J>(F, ctx.bone);
+    constexpr int K = out_index_of_joint(J);
+    if constexpr (K >= 0) ctx.template emit<K>(F.O);
+    if constexpr (!is_leaf(J)) {
+        float s, c;
+        constexpr int Q0 = THETA0_Q[J];
+        sincos_deg<TRIG, Q0>(ctx.ang[J], s, c);
+        rotate_joint<J>(F, s, c);
+        fwd_children<TRIG, J, 0>(F, ctx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Backward walker.  Returns the wrench (F, M about the chain origin, chain-frame
+// coordinates) of every output at or below joint J.  For a rotating joint
+//   dL/dtheta_j = (pi/180) * z_j . (M_j - o_j x F_j)
+// where (F_j, M_j) sums the outputs strictly below j (the joint's own origin does not
+// depend on its own theta), z_j is the joint axis after the alpha twist, o_j its origin.
+// Ctx provides ang, bone and
+//   template<int K> V3 upstream(V3 origin)   -- total dL/d(origin) in the chain frame
+//   void grad_angle(int j, float g)          -- j is a compile-time constant after inlining
+//   void grad_bone(int b, float g)           -- only called when Ctx::kBoneGrad
+// ---------------------------------------------------------------------------------------
+template <int TRIG, int J, class Ctx> DHFK_DI Wrench bwd_walk(Frame F, Ctx& ctx);
+
+template <int TRIG, int J, int I, class Ctx>
+DHFK_DI Wrench bwd_children(const Frame& F, Ctx& ctx) {
+    constexpr int C = nth_child(J, I);
+    static_assert(C >= 0, "bwd_children called past the last child");
+    Wrench w = bwd_walk<TRIG, C>(F, ctx);
+    if constexpr (nth_child(J, I + 1) >= 0) {
+        Wrench r = bwd_children<TRIG, J, I + 1>(F, ctx);
+        w.F = w.F + r.F;
+        w.M = w.M + r.M;
+    }
+    return w;
+}
+template <int TRIG, int J, class Ctx>
+DHFK_DI Wrench bwd_walk(Frame F, Ctx& ctx) {
+    V3 laxis = v3(0.f, 0.f, 0.f);
+    constexpr bool kLen = Ctx::kBoneGrad && LEN_KIND[J] != 0;
+    if constexpr (kLen) laxis = length_axis<J>(F);
+    advance_origin<J>(F, ctx.bone);
+    const V3 o = F.O;
+    constexpr int K = out_index_of_joint(J);
+    V3 gh = v3(0.f, 0.f, 0.f);
+    if constexpr (K >= 0) gh = ctx.template upstream<K>(o);
+    Wrench w;
+    if constexpr (!is_leaf(J)) {
+        V3 y1, zj;
+        twist<J>(F, y1, zj);
+        float s, c;
+        constexpr int Q0 = THETA0_Q[J];
+        sincos_deg<TRIG, Q0>(ctx.ang[J], s, c);
+        rotate_joint<J>(F, s, c);
+        w = bwd_children<TRIG, J, 0>(F, ctx);
+        constexpr bool kZero = origin_is_zero(J);
+        V3 tau;
+        if constexpr (kZero) tau = w.M;
+        else tau = sub_cross(w.M, o, w.F);
+        ctx.grad_angle(J, kDegToRad * dot(zj, tau));
+        if constexpr (K >= 0) {
+            w.F = w.F + gh;
+            if constexpr (!kZero) w.M = add_cross(w.M, o, gh);
+        }
+    } else {
+        static_assert(K >= 0, "every chain end is an output joint");
+        ctx.grad_angle(J, 0.f);
+        w.F = gh;
+        w.M = cross(o, gh);
+    }
+    if constexpr (kLen) {
+        constexpr int BONE = LEN_BONE[J];
+        ctx.grad_bone(BONE, dot(laxis, w.F));
+    }
+    return w;
+}
+
+}  // namespace dhfk

@@ -1,0 +1,370 @@
+// dhfk_kernels.cuh -- fused DH-FK + global rotation + world->camera + pinhole projection,
+// forward and analytic backward, for sm_100a.  One thread per pose, 96 poses per CTA.
+//
+// Data movement (see DESIGN.md "HBM layout"):
+//   inputs  [N,33] [N,3] [N,15] [N,3] are AoS rows with odd lengths.  A tile of 96 rows of each
+//           is one contiguous, 16-byte aligned slab; the CTA copies it to shared memory with
+//           coalesced 128-bit loads (exact image, odd row stride => conflict-free per-thread
+//           scalar reads).
+//   outputs [N,16,3] / [N,16,2] (and upstream gradients in the backward) have 48 / 32 float
+//           rows; they are staged in shared memory with the row stride padded to 13 / 9
+//           16-byte chunks so that both the per-thread 128-bit accesses and the cooperative
+//           coalesced 128-bit global accesses are bank-conflict free.  With 96 threads the
+//           cooperative copy needs no index arithmetic (96 = 8*12 = 12*8).
+//   backward results d(ang), d(grot), d(root), d(bone) overwrite the input slabs in place and
+//           leave through the same coalesced path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dhfk_device.cuh"
+
+namespace dhfk {
+
+constexpr int kTile = 96;        // poses (threads) per CTA
+constexpr int kWorldChunks = 12; // 48 floats
+constexpr int kUvChunks = 8;     // 32 floats
+constexpr int kWorldRow4 = kWorldChunks + 1;  // padded row stride in float4
+constexpr int kUvRow4 = kUvChunks + 1;
+
+static_assert(kTile % kWorldChunks == 0 && kTile % kUvChunks == 0, "tile must tile both row shapes");
+static_assert(kTile % 4 == 0, "tile slabs must stay 16-byte aligned");
+static_assert(nth_child(-1, 0) == 0 && nth_child(-1, 1) == 5 && nth_child(-1, 2) == 10 &&
+              nth_child(-1, 3) == -1, "chain roots are joints 0, 5, 10");
+
+struct RowSrc {
+    const float* p;
+    long long stride;  // floats
+    int vec;           // 1: packed + 16-byte aligned => slab path
+};
+struct RowDst {
+    float* p;
+    long long stride;
+    int vec;
+};
+
+struct FwdParams {
+    RowSrc ang, grot, bone, root;
+    float* out_world;
+    float* out_cam;
+    float* out_uv;
+    long long n;
+    CamConst cam;
+};
+struct BwdParams {
+    RowSrc ang, grot, bone, root;
+    const float* g_world;
+    const float* g_cam;
+    const float* g_uv;
+    RowDst g_ang, g_grot, g_root, g_bone;
+    long long n;
+    CamConst cam;
+};
+
+// ---- shared <-> global staging -----------------------------------------------------------------
+// exact-image rows (row stride NCOLS in shared)
+template <int NCOLS>
+DHFK_DI void stage_rows_in(float* s, const RowSrc& src, long long row0, int rows) {
+    const int tid = threadIdx.x;
+    const float* g = src.p + row0 * src.stride;
+    if (src.vec) {
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        float4* s4 = reinterpret_cast<float4*>(s);
+        if (rows == kTile) {
+            constexpr int NV = kTile * NCOLS / 4;
+#pragma unroll
+            for (int k = 0; k < (NV + kTile - 1) / kTile; ++k) {
+                int i = tid + k * kTile;
+                if (i < NV) s4[i] = __ldcs(g4 + i);
+            }
+        } else {
+            const int nfl = rows * NCOLS, nv = nfl >> 2;
+            for (int i = tid; i < nv; i += kTile) s4[i] = __ldcs(g4 + i);
+            for (int i = (nv << 2) + tid; i < nfl; i += kTile) s[i] = __ldcs(g + i);
+        }
+    } else {
+        const int nfl = rows * NCOLS;
+        for (int i = tid; i < nfl; i += kTile) {
+            int r = i / NCOLS, c = i - r * NCOLS;
+            s[i] = __ldg(g + (long long)r * src.stride + c);
+        }
+    }
+}
+template <int NCOLS>
+DHFK_DI void stage_rows_out(const float* s, const RowDst& dst, long long row0, int rows) {
+    const int tid = threadIdx.x;
+    float* g = dst.p + row0 * dst.stride;
+    if (dst.vec) {
+        float4* g4 = reinterpret_cast<float4*>(g);
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        if (rows == kTile) {
+            constexpr int NV = kTile * NCOLS / 4;
+#pragma unroll
+            for (int k = 0; k < (NV + kTile - 1) / kTile; ++k) {
+                int i = tid + k * kTile;
+                if (i < NV) __stcs(g4 + i, s4[i]);
+            }
+        } else {
+            const int nfl = rows * NCOLS, nv = nfl >> 2;
+            for (int i = tid; i < nv; i += kTile) __stcs(g4 + i, s4[i]);
+            for (int i = (nv << 2) + tid; i < nfl; i += kTile) __stcs(g + i, s[i]);
+        }
+    } else {
+        const int nfl = rows * NCOLS;
+        for (int i = tid; i < nfl; i += kTile) {
+            int r = i / NCOLS, c = i - r * NCOLS;
+            g[(long long)r * dst.stride + c] = s[i];
+        }
+    }
+}
+// padded rows: CH 16-byte chunks per row in global (packed, aligned), CH+1 in shared
+template <int CH>
+DHFK_DI void stage_padded_in(float4* s4, const float* gbase, long long row0, int rows) {
+    constexpr int RPI = kTile / CH;
+    const int tid = threadIdx.x;
+    const int r0 = tid / CH, c0 = tid - r0 * CH;
+    const float4* g4 = reinterpret_cast<const float4*>(gbase) + row0 * CH;
+#pragma unroll
+    for (int m = 0; m < CH; ++m) {
+        int r = r0 + m * RPI;
+        if (r < rows) s4[r * (CH + 1) + c0] = __ldcs(g4 + r * CH + c0);
+    }
+}
+template <int CH>
+DHFK_DI void stage_padded_out(const float4* s4, float* gbase, long long row0, int rows) {
+    constexpr int RPI = kTile / CH;
+    const int tid = threadIdx.x;
+    const int r0 = tid / CH, c0 = tid - r0 * CH;
+    float4* g4 = reinterpret_cast<float4*>(gbase) + row0 * CH;
+#pragma unroll
+    for (int m = 0; m < CH; ++m) {
+        int r = r0 + m * RPI;
+        if (r < rows) __stcs(g4 + r * CH + c0, s4[r * (CH + 1) + c0]);
+    }
+}
+
+// global rotation R = Rx(gx) Ry(gy) Rz(gz), forward_kinematics_DH_model.py:141-191 (row-major)
+template <int TRIG>
+DHFK_DI void global_rotation(const float* g, float* R, float& sx, float& cx, float& sy, float& cy) {
+    float sz, cz;
+    sincos_deg<TRIG, 0>(g[0], sx, cx);
+    sincos_deg<TRIG, 0>(g[1], sy, cy);
+    sincos_deg<TRIG, 0>(g[2], sz, cz);
+    R[0] = cy * cz;                      R[1] = -cy * sz;                     R[2] = sy;
+    R[3] = fmaf(sx * sy, cz, cx * sz);   R[4] = fmaf(-sx * sy, sz, cx * cz);  R[5] = -sx * cy;
+    R[6] = fmaf(-cx * sy, cz, sx * sz);  R[7] = fmaf(cx * sy, sz, sx * cz);   R[8] = cx * cy;
+}
+
+// ---- forward -------------------------------------------------------------------------------------
+template <bool CAM, bool UV>
+struct FwdCtx {
+    const float* ang;
+    const float* bone;
+    const CamConst* cc;
+    float R[9];
+    V3 root;
+    float w[48];
+    float cm[CAM ? 48 : 1];
+    float uv[UV ? 32 : 1];
+
+    template <int K>
+    DHFK_DI void emit(V3 o) {
+        constexpr bool kZero = origin_is_zero(OUT16[K]);
+        V3 W;
+        if constexpr (kZero) W = root;
+        else W = mat_vec_add(R, o, root);
+        w[3 * K] = W.x; w[3 * K + 1] = W.y; w[3 * K + 2] = W.z;
+        if (CAM || UV) {
+            V3 X = mat_vec(cc->M, v3(W.x - cc->t[0], W.y - cc->t[1], W.z - cc->t[2]));
+            if (CAM) { cm[3 * K] = X.x; cm[3 * K + 1] = X.y; cm[3 * K + 2] = X.z; }
+            if (UV) {
+                ProjAux a;
+                project_point(*cc, X, uv[2 * K], uv[2 * K + 1], a);
+            }
+        }
+    }
+};
+
+template <int LO, int HI>
+DHFK_DI void flush_chunks(float4* row4, const float* v) {
+#pragma unroll
+    for (int c = LO; c < HI; ++c) row4[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
+template <bool CAM, bool UV, int TRIG>
+__global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__ FwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* s_ang = smem;
+    float* s_grot = s_ang + kTile * 33;
+    float* s_bone = s_grot + kTile * 3;
+    float* s_root = s_bone + kTile * 15;
+    float4* s_world = reinterpret_cast<float4*>(s_root + kTile * 3);
+    float4* s_cam = s_world + kTile * kWorldRow4;
+    float4* s_uv = s_cam + (CAM ? kTile * kWorldRow4 : 0);
+
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * kTile;
+    const long long left = p.n - row0;
+    const int rows = left < kTile ? (int)left : kTile;
+
+    stage_rows_in<33>(s_ang, p.ang, row0, rows);
+    stage_rows_in<3>(s_grot, p.grot, row0, rows);
+    stage_rows_in<15>(s_bone, p.bone, row0, rows);
+    stage_rows_in<3>(s_root, p.root, row0, rows);
+    __syncthreads();
+
+    if (tid < rows) {
+        FwdCtx<CAM, UV> ctx;
+        ctx.ang = s_ang + tid * 33;
+        ctx.bone = s_bone + tid * 15;
+        ctx.cc = &p.cam;
+        float sx, cx, sy, cy;
+        global_rotation<TRIG>(s_grot + tid * 3, ctx.R, sx, cx, sy, cy);
+        ctx.root = v3(s_root[tid * 3], s_root[tid * 3 + 1], s_root[tid * 3 + 2]);
+        float4* wrow = s_world + tid * kWorldRow4;
+        float4* crow = s_cam + tid * kWorldRow4;
+        float4* urow = s_uv + tid * kUvRow4;
+        const Frame I = identity_frame();
+        // body, head, arms: outputs 0,7,8,9,13,14,15,10,11,12 -> joints 8..15 complete
+        fwd_walk<TRIG, 10>(I, ctx);
+        flush_chunks<6, 12>(wrow, ctx.w);
+        if (CAM) flush_chunks<6, 12>(crow, ctx.cm);
+        if (UV) flush_chunks<4, 8>(urow, ctx.uv);
+        // right leg: outputs 1,2,3 -> joints 0..3 complete
+        fwd_walk<TRIG, 0>(I, ctx);
+        flush_chunks<0, 3>(wrow, ctx.w);
+        if (CAM) flush_chunks<0, 3>(crow, ctx.cm);
+        if (UV) flush_chunks<0, 2>(urow, ctx.uv);
+        // left leg: outputs 4,5,6 -> joints 4..7 complete
+        fwd_walk<TRIG, 5>(I, ctx);
+        flush_chunks<3, 6>(wrow, ctx.w);
+        if (CAM) flush_chunks<3, 6>(crow, ctx.cm);
+        if (UV) flush_chunks<2, 4>(urow, ctx.uv);
+    }
+    __syncthreads();
+
+    stage_padded_out<kWorldChunks>(s_world, p.out_world, row0, rows);
+    if (CAM) stage_padded_out<kWorldChunks>(s_cam, p.out_cam, row0, rows);
+    if (UV) stage_padded_out<kUvChunks>(s_uv, p.out_uv, row0, rows);
+}
+
+// ---- backward ------------------------------------------------------------------------------------
+template <bool GUV, bool GBONE>
+struct BwdCtx {
+    static constexpr bool kBoneGrad = GBONE;
+    const float* ang;
+    const float* bone;
+    float* g_ang;   // same shared row as ang (in place)
+    float* g_bone;  // same shared row as bone (in place)
+    const CamConst* cc;
+    const float4* gw4;   // padded shared rows of the upstream gradients (may be null)
+    const float4* gc4;
+    const float4* gu4;
+    float R[9];
+    V3 root;
+
+    // 3 consecutive floats starting at float index 3K of a padded row, via 128-bit loads only
+    template <int K>
+    DHFK_DI V3 load3(const float4* row) const {
+        constexpr int F0 = 3 * K, C0 = F0 / 4, OFF = F0 % 4;
+        float4 a = row[C0];
+        if (OFF == 0) return v3(a.x, a.y, a.z);
+        if (OFF == 1) return v3(a.y, a.z, a.w);
+        float4 b = row[C0 + 1];
+        if (OFF == 2) return v3(a.z, a.w, b.x);
+        return v3(a.w, b.x, b.y);
+    }
+
+    // total dL/d(origin of output K) rotated back into the chain frame
+    template <int K>
+    DHFK_DI V3 upstream(V3 o) const {
+        V3 g = v3(0.f, 0.f, 0.f);
+        if (gw4) g = load3<K>(gw4);            // block-uniform branch
+        if (GUV || gc4) {
+            V3 gc = v3(0.f, 0.f, 0.f);
+            if (gc4) gc = load3<K>(gc4);       // block-uniform branch
+            if (GUV) {
+                constexpr bool kZero = origin_is_zero(OUT16[K]);
+                V3 W;
+                if constexpr (kZero) W = root;
+                else W = mat_vec_add(R, o, root);
+                V3 X = mat_vec(cc->M, v3(W.x - cc->t[0], W.y - cc->t[1], W.z - cc->t[2]));
+                float u, v;
+                ProjAux a;
+                project_point(*cc, X, u, v, a);
+                float4 q = gu4[K / 2];
+                V3 gp = project_point_bwd(*cc, a, (K & 1) ? q.z : q.x, (K & 1) ? q.w : q.y);
+                gc = gc + gp;
+            }
+            g = matT_vec_add(cc->M, gc, g);
+        }
+        return matT_vec(R, g);
+    }
+    DHFK_DI void grad_angle(int j, float g) { g_ang[j] = g; }
+    DHFK_DI void grad_bone(int b, float g) { g_bone[b] = g; }
+};
+
+template <bool GUV, bool GBONE, int TRIG>
+__global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__ BwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* s_ang = smem;
+    float* s_grot = s_ang + kTile * 33;
+    float* s_bone = s_grot + kTile * 3;
+    float* s_root = s_bone + kTile * 15;
+    float4* s_gw = reinterpret_cast<float4*>(s_root + kTile * 3);
+    const bool GW = p.g_world != nullptr, GCAM = p.g_cam != nullptr;
+    float4* s_gc = s_gw + (GW ? kTile * kWorldRow4 : 0);
+    float4* s_gu = s_gc + (GCAM ? kTile * kWorldRow4 : 0);
+
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * kTile;
+    const long long left = p.n - row0;
+    const int rows = left < kTile ? (int)left : kTile;
+
+    stage_rows_in<33>(s_ang, p.ang, row0, rows);
+    stage_rows_in<3>(s_grot, p.grot, row0, rows);
+    stage_rows_in<15>(s_bone, p.bone, row0, rows);
+    stage_rows_in<3>(s_root, p.root, row0, rows);
+    if (GW) stage_padded_in<kWorldChunks>(s_gw, p.g_world, row0, rows);
+    if (GCAM) stage_padded_in<kWorldChunks>(s_gc, p.g_cam, row0, rows);
+    if (GUV) stage_padded_in<kUvChunks>(s_gu, p.g_uv, row0, rows);
+    __syncthreads();
+
+    if (tid < rows) {
+        BwdCtx<GUV, GBONE> ctx;
+        ctx.ang = s_ang + tid * 33;
+        ctx.g_ang = s_ang + tid * 33;
+        ctx.bone = s_bone + tid * 15;
+        ctx.g_bone = s_bone + tid * 15;
+        ctx.cc = &p.cam;
+        ctx.gw4 = GW ? s_gw + tid * kWorldRow4 : nullptr;
+        ctx.gc4 = GCAM ? s_gc + tid * kWorldRow4 : nullptr;
+        ctx.gu4 = GUV ? s_gu + tid * kUvRow4 : nullptr;
+        float sx, cx, sy, cy;
+        global_rotation<TRIG>(s_grot + tid * 3, ctx.R, sx, cx, sy, cy);
+        ctx.root = v3(s_root[tid * 3], s_root[tid * 3 + 1], s_root[tid * 3 + 2]);
+        const Frame I = identity_frame();
+        Wrench wb = bwd_walk<TRIG, 10>(I, ctx);
+        Wrench wr = bwd_walk<TRIG, 0>(I, ctx);
+        Wrench wl = bwd_walk<TRIG, 5>(I, ctx);
+        V3 Ft = wb.F + wr.F + wl.F;
+        V3 Mt = wb.M + wr.M + wl.M;
+        // d/d root = sum_k g_k = R * sum_k (R^T g_k)
+        V3 gr = mat_vec(ctx.R, Ft);
+        s_root[tid * 3] = gr.x; s_root[tid * 3 + 1] = gr.y; s_root[tid * 3 + 2] = gr.z;
+        // d/d global angles: torque about the world axes e_x, Rx e_y, Rx Ry e_z
+        V3 tw = mat_vec(ctx.R, Mt);
+        s_grot[tid * 3] = kDegToRad * tw.x;
+        s_grot[tid * 3 + 1] = kDegToRad * fmaf(cx, tw.y, sx * tw.z);
+        s_grot[tid * 3 + 2] = kDegToRad * fmaf(sy, tw.x, fmaf(-sx * cy, tw.y, cx * cy * tw.z));
+    }
+    __syncthreads();
+
+    stage_rows_out<33>(s_ang, p.g_ang, row0, rows);
+    stage_rows_out<3>(s_grot, p.g_grot, row0, rows);
+    stage_rows_out<3>(s_root, p.g_root, row0, rows);
+    if (GBONE) stage_rows_out<15>(s_bone, p.g_bone, row0, rows);
+}
+
+}  // namespace dhfk
+

@@ -1,0 +1,36 @@
+// dhfk_launch.h -- internal launch entry points, one translation unit per kernel family so the
+// (long, fully unrolled) kernels compile in parallel.
+#pragma once
+#include "dhfk_kernels.cuh"
+
+namespace dhfk {
+// return 0 or a cudaError_t; `where` receives a static string naming the failing call
+int launch_fwd_trig0(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
+int launch_fwd_trig1(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
+int launch_bwd_trig0_bone0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+int launch_bwd_trig0_bone1(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+int launch_bwd_trig1_bone0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+int launch_bwd_trig1_bone1(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+
+inline size_t fwd_smem_bytes(bool cam, bool uv) {
+    return sizeof(float) * kTile * 54 +
+           sizeof(float4) * kTile * (kWorldRow4 * (1 + (cam ? 1 : 0)) + (uv ? kUvRow4 : 0));
+}
+inline size_t bwd_smem_bytes(bool gw, bool gcam, bool guv) {
+    return sizeof(float) * kTile * 54 +
+           sizeof(float4) * kTile * (kWorldRow4 * ((gw ? 1 : 0) + (gcam ? 1 : 0)) + (guv ? kUvRow4 : 0));
+}
+
+template <typename K, typename P>
+int launch_tiles(K kernel, size_t smem, const P& p, cudaStream_t st, const char** where) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *where = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"; return (int)e; }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { *where = "cudaFuncSetAttribute(PreferredSharedMemoryCarveout)"; return (int)e; }
+    long long blocks = (p.n + kTile - 1) / kTile;
+    void* args[] = {const_cast<P*>(&p)};
+    e = cudaLaunchKernel((const void*)kernel, dim3((unsigned)blocks), dim3(kTile), args, smem, st);
+    if (e != cudaSuccess) { *where = "cudaLaunchKernel"; return (int)e; }
+    return 0;
+}
+}  // namespace dhfk

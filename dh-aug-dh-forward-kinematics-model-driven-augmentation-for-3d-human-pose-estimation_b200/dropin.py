@@ -1,0 +1,48 @@
+"""Make the unmodified reference (run_Fk_GAN.py and friends) use the native kernels.
+
+The reference has no plugin mechanism -- its modules import each other by name.  ``install()``
+therefore (1) replaces ``models_Fk_GAN.forward_kinematics_DH_model.Forward_Kinematics_DH_Model``
+with the native class in the already-imported reference module (and in every module that did
+``from ... import`` it), and (2) rebinds ``GAN_torch_world_to_camera`` / ``project_to_2d`` in
+``common.camera`` and in the caller modules that imported them by name.  Nothing else is touched.
+See INTEGRATION.md for the three-line patch on the reference side.
+"""
+from __future__ import annotations
+
+import sys
+
+from . import camera as _camera
+from . import forward_kinematics_DH_model as _fk
+
+_CALLERS = (
+    "models_Fk_GAN.model_fk_gan_train", "models_Fk_GAN.video_GAN_fun", "models_Fk_GAN.video_mode_operate",
+    "models_Fk_GAN.special_operate", "function_aug.dataloader_update", "run_Fk_GAN", "__main__",
+)
+
+
+def install(verbose: bool = False):
+    """Patch the reference modules that are currently imported.  Idempotent.  Returns the names patched."""
+    patched = []
+    fkmod = sys.modules.get("models_Fk_GAN.forward_kinematics_DH_model")
+    if fkmod is not None:
+        fkmod.Forward_Kinematics_DH_Model = _fk.Forward_Kinematics_DH_Model
+        patched.append("models_Fk_GAN.forward_kinematics_DH_model.Forward_Kinematics_DH_Model")
+    cammod = sys.modules.get("common.camera")
+    if cammod is not None:
+        cammod.GAN_torch_world_to_camera = _camera.GAN_torch_world_to_camera
+        cammod.project_to_2d = _camera.project_to_2d
+        patched.append("common.camera.{GAN_torch_world_to_camera,project_to_2d}")
+    for name in _CALLERS:
+        mod = sys.modules.get(name)
+        if mod is None:
+            continue
+        for sym, repl in (("Forward_Kinematics_DH_Model", _fk.Forward_Kinematics_DH_Model),
+                          ("GAN_torch_world_to_camera", _camera.GAN_torch_world_to_camera),
+                          ("project_to_2d", _camera.project_to_2d)):
+            if hasattr(mod, sym):
+                setattr(mod, sym, repl)
+                patched.append("%s.%s" % (name, sym))
+    if verbose:
+        for p in patched:
+            print("[dhfk] patched", p)
+    return patched

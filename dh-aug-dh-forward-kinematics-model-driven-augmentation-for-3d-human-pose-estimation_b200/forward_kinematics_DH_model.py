@@ -1,0 +1,188 @@
+"""Drop-in for ``models_Fk_GAN/forward_kinematics_DH_model.py`` (the hot part).
+
+``Forward_Kinematics_DH_Model`` keeps the reference's constructor, attributes and the 22-kwarg
+``change_3d_joint_angle`` (forward_kinematics_DH_model.py:354-364), but the torch branch
+(:562-822: 33 dh_matrix builds, 46 bmm, 51 column scatters, ~6.9k ATen calls) is one fused
+sm_100a kernel launch plus a 32-slot scatter, and its backward is one more launch.
+
+Differences from the reference, all deliberate:
+  * N is taken from the inputs, not from ``args.batch_size * F`` baked in at construction.
+  * No O(N) Python table replication at construction, no persistent [N,n] tables, no in-place
+    bone-length writes -> bone lengths may require grad and calls are stateless.
+  * Non-tensor inputs (the reference's numpy branch, :366-560, used by ``init_Fk_DH_angle`` and the
+    GUI) also run on the GPU kernel with N=1 and return float32 numpy (32,3) like the reference.
+  * There is no CPU path: without a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import tables
+from .functional import fk_world16
+from .tables import used_16key_15bone_len_table  # noqa: F401  (re-exported like the reference module)
+
+H36M_POINTS_LEFT = [6, 7, 8, 17, 18, 19]
+H36M_POINTS_RIGHT = [1, 2, 3, 25, 26, 27]
+
+_BONE_KWARGS = tables.BONE_NAMES
+_IDX16 = None
+
+
+def _index16(device):
+    global _IDX16
+    if _IDX16 is None or _IDX16.device != device:
+        _IDX16 = torch.as_tensor(tables.H36M_32_To_16_Table, dtype=torch.long, device=device)
+    return _IDX16
+
+
+def scatter_16_to_32(world16: torch.Tensor, root: torch.Tensor) -> torch.Tensor:
+    """[N,16,3] -> the reference's [N,32,3] layout (:745-820): gathered slots hold the joints, slot 14
+    duplicates the head joint (slot 15), every other slot equals root (0 + root)."""
+    n = world16.shape[0]
+    out = root.reshape(n, 1, 3).expand(n, 32, 3).clone()
+    out = out.index_copy(1, _index16(world16.device), world16)
+    out[:, 14] = world16[:, tables.H36M_EXTRA_SLOT_14_OUT]
+    return out
+
+
+class Forward_Kinematics_DH_Model:
+    def __init__(self, args, train_subjects, dataset):
+        self.args = args
+        self.train_subjects = train_subjects
+        self.GAN_BATCH_SIZE = getattr(args, "batch_size", None)
+        self.dataset = dataset
+        self.random = np.random.RandomState(getattr(args, "random_seed", 0))  # Fk_generator.py:201,383 use it
+
+        self.generator_3d_pos_angle = []
+        self.generator_global_rot_3d_pos_angle = []
+        self.generator_bone_len = []
+        self.generator_root = []
+        self.show_3d_pos_num = 0
+        self.record_bone_len = []
+        self.camera_parameters = {}
+        self.root_3d_pos = np.array([0, 0, 0])
+        self.dataSet_world_3d_pos = {}
+        self.dataSet_2d_pos = {}
+        self.choice_subject = []
+        self.choice_action = []
+        self.choice_cam = []
+
+        self.right_leg_joint_num = 5
+        self.left_leg_joint_num = 5
+        self.body_joint_num = 13
+        self.right_hand_joint_num = 5 + self.body_joint_num - 4
+        self.left_hand_joint_num = 5 + self.body_joint_num - 4
+        # the constant DH tables as plain lists, for callers that read them (GUI); degrees / metres
+        a = tables.ALPHA_DEG.tolist()
+        t0 = tables.THETA0_DEG.tolist()
+        self.right_leg_joints_alpha, self.right_leg_joints_theta = a[0:5], t0[0:5]
+        self.left_leg_joints_alpha, self.left_leg_joints_theta = a[5:10], t0[5:10]
+        self.body_joints_alpha, self.body_joints_theta = a[10:23], t0[10:23]
+        self.right_hand_joints_alpha, self.right_hand_joints_theta = a[23:28], t0[23:28]
+        self.left_hand_joints_alpha, self.left_hand_joints_theta = a[28:33], t0[28:33]
+
+        self.real_used_num = 1
+        if getattr(args, "single_or_multi_train_mode", "single") == "multi":
+            frames = 1
+            for f in [int(x) for x in args.architecture.split(",")]:
+                frames *= f  # video_receptive_field = product (video_mode_operate.py:411-415)
+            self.real_used_num = frames
+
+    # ------------------------------------------------------------------------------------------
+    def change_3d_joint_angle(self, left_leg_joints_angle, right_leg_joints_angle, body_joints_angle,
+                              left_hand_joints_angle, right_hand_joints_angle, generator_global_rot_3d_pos_angle,
+                              left_small_leg_len, right_small_leg_len, left_big_leg_len, right_big_leg_len,
+                              left_hip_len, right_hip_len, waist_len, thorax_len, left_shoulder_len,
+                              right_shoulder_len, left_big_arm_len, right_big_arm_len, left_small_arm_len,
+                              right_small_arm_len, neck_len, root_3d_pos):
+        lens = (left_small_leg_len, right_small_leg_len, left_big_leg_len, right_big_leg_len, left_hip_len,
+                right_hip_len, waist_len, thorax_len, left_shoulder_len, right_shoulder_len, left_big_arm_len,
+                right_big_arm_len, left_small_arm_len, right_small_arm_len, neck_len)
+        if not torch.is_tensor(left_leg_joints_angle):
+            return self._single_pose_numpy(left_leg_joints_angle, right_leg_joints_angle, body_joints_angle,
+                                           left_hand_joints_angle, right_hand_joints_angle,
+                                           generator_global_rot_3d_pos_angle, lens, root_3d_pos)
+        if not torch.cuda.is_available():
+            raise RuntimeError("dhfk needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = right_leg_joints_angle.device
+        if dev.type != "cuda":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        to = lambda t: t if t.device == dev else t.to(dev)
+        ang = torch.cat([to(right_leg_joints_angle), to(left_leg_joints_angle), to(body_joints_angle),
+                         to(right_hand_joints_angle), to(left_hand_joints_angle)], dim=1)
+        n = ang.shape[0]
+        grot = to(generator_global_rot_3d_pos_angle)
+        cols = []
+        for v in lens:
+            if not torch.is_tensor(v):
+                v = torch.full((n,), float(v), dtype=torch.float32, device=dev)
+            cols.append(to(v).reshape(-1))
+        bone = torch.stack(cols, dim=1)
+        root = to(root_3d_pos).reshape(-1, 3)
+        self.global_rot_angle = generator_global_rot_3d_pos_angle
+        world16 = fk_world16(ang, grot, bone, root)
+        self.single_generator_3d_world_32keyPoint = scatter_16_to_32(world16, root)
+        return self.single_generator_3d_world_32keyPoint
+
+    def _single_pose_numpy(self, ll, rl, body, lh, rh, grot, lens, root):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dhfk needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ang = np.concatenate([np.asarray(rl, np.float64), np.asarray(ll, np.float64), np.asarray(body, np.float64),
+                              np.asarray(rh, np.float64), np.asarray(lh, np.float64)]).astype(np.float32)
+        f = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(1, -1), device=dev)
+        with torch.no_grad():
+            world16 = fk_world16(f(ang), f(grot), f(lens), f(root))
+            out = scatter_16_to_32(world16, f(root))
+        self.single_generator_3d_world_32keyPoint = out[0].cpu().numpy().astype(np.float32)
+        return self.single_generator_3d_world_32keyPoint
+
+    def init_Fk_DH_angle(self):
+        """T-pose known answer of the reference (:824-858)."""
+        return self.change_3d_joint_angle(
+            left_leg_joints_angle=[0] * 5, right_leg_joints_angle=[0] * 5, body_joints_angle=[0] * 13,
+            left_hand_joints_angle=[0] * 5, right_hand_joints_angle=[0] * 5,
+            generator_global_rot_3d_pos_angle=(0.0, 0.0, 0.0),
+            left_small_leg_len=0.5, right_small_leg_len=0.5, left_big_leg_len=0.6, right_big_leg_len=0.6,
+            left_hip_len=0.25, right_hip_len=0.25, waist_len=0.25, thorax_len=0.2, left_shoulder_len=0.4,
+            right_shoulder_len=0.4, left_big_arm_len=0.4, right_big_arm_len=0.4, left_small_arm_len=0.35,
+            right_small_arm_len=0.35, neck_len=0.15, root_3d_pos=(0.0, 0.0, 0.0))
+
+    # ---- host-side bookkeeping kept for interface compatibility (:861-929) ---------------------
+    def random_state(self):
+        return self.random
+
+    def set_random_state(self, random):
+        self.random = random
+
+    def get_dataSet_3d_and_2d_pose(self, dataset, pix_2d):
+        world_3d = {}
+        for subject in dataset.subjects():
+            world_3d[subject] = {}
+            for action in dataset[subject].keys():
+                anim = dataset[subject][action]
+                world_3d[subject][action] = {cam_idx: anim["positions"]
+                                             for cam_idx, _ in enumerate(pix_2d[subject][action])}
+        self.dataSet_world_3d_pos = world_3d
+        self.dataSet_2d_pos = pix_2d
+
+    def my_random_get_sigle_frame_data(self):
+        # RNG draw order must match the reference (:883-898) so seeded runs pick the same frames
+        subject = self.train_subjects[self.random.randint(0, len(self.train_subjects))]
+        actions = list(self.dataSet_world_3d_pos[subject].keys())
+        action = actions[self.random.randint(0, len(actions))]
+        cams = list(self.dataSet_world_3d_pos[subject][action].keys())
+        cam = cams[self.random.randint(0, len(cams))]
+        frame = self.random.randint(0, self.dataSet_world_3d_pos[subject][action][cam].shape[0])
+        return subject, action, cam, frame
+
+    def get_bone_len_from_dataSet(self):
+        subject, action, cam, frame = self.my_random_get_sigle_frame_data()
+        pose = np.array(self.dataSet_world_3d_pos[subject][action][cam][frame], copy=True)
+        self.record_bone_len = [float(np.linalg.norm(pose[i] - pose[j])) for (i, j) in used_16key_15bone_len_table]
+
+    def get_root_3d_pos_from_dataSet(self):
+        subject, action, cam, frame = self.my_random_get_sigle_frame_data()
+        pose = np.array(self.dataSet_world_3d_pos[subject][action][cam][frame], copy=True)
+        self.root_3d_pos = pose[0].copy()

@@ -1,0 +1,317 @@
+"""torch.autograd entry points over the C ABI (libdhfk.so).
+
+PyTorch is plumbing here: it owns device memory and streams; every number is produced by the
+hand-written sm_100a kernels.  There is no CPU or eager fallback -- CPU tensors are moved to the
+CUDA device (as the reference's ``.cuda()`` calls do) and a missing GPU / library raises.
+
+Backward contract: forward saves only its *inputs*; backward recomputes the chain in
+registers and is once-differentiable (nothing in the reference differentiates twice through FK:
+``calc_gradient_penalty`` works on ``.data``, models_Fk_GAN/model_fk_gan_train.py:213-214).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _cabi
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("dhfk needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _rows(t: torch.Tensor, ncols: int, device) -> torch.Tensor:
+    """2-D float32 CUDA view [N, >=ncols] with unit column stride (row stride may exceed ncols)."""
+    if t.dim() != 2:
+        t = t.reshape(-1, t.shape[-1])
+    if t.shape[1] < ncols:
+        raise ValueError("expected at least %d columns, got %d" % (ncols, t.shape[1]))
+    if t.device != device or t.dtype != torch.float32:
+        t = t.to(device=device, dtype=torch.float32)
+    ok = t.stride(1) == 1 and (t.shape[0] <= 1 or t.stride(0) >= ncols) and t.data_ptr() % 4 == 0
+    if not ok:
+        t = t.contiguous()
+    return t
+
+
+def _row_stride(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+
+
+def _packed(t, shape, device):
+    """Contiguous, 16-byte aligned float32 CUDA tensor of `shape`, or None."""
+    if t is None:
+        return None
+    t = t.to(device=device, dtype=torch.float32).reshape(shape)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def cam_block_array(cam) -> np.ndarray:
+    """Host float32[16] camera block [q4 (w,x,y,z), t3 (m), f2, c2, k3, p2]."""
+    if isinstance(cam, torch.Tensor):
+        cam = cam.detach().cpu().numpy()
+    a = np.ascontiguousarray(np.asarray(cam, dtype=np.float32).reshape(-1))
+    if a.shape[0] != 16:
+        raise ValueError("camera block must have 16 floats (q4,t3,f2,c2,k3,p2), got %d" % a.shape[0])
+    return a
+
+
+class _FKProject(torch.autograd.Function):
+    """Fused FK (+ camera + projection).  Outputs: world16 [N,16,3] [, cam16 [N,16,3]] [, uv16 [N,16,2]]."""
+
+    @staticmethod
+    def forward(ctx, ang, grot, bone, root, cam, want_cam, want_uv, flags):
+        _require_cuda()
+        lib = _cabi.load()
+        device = ang.device if ang.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        ang2 = _rows(ang, 33, device)
+        n = ang2.shape[0]
+        grot2 = _rows(grot, 3, device)
+        bone2 = _rows(bone, 15, device)
+        root2 = _rows(root, 3, device)
+        if not (grot2.shape[0] == n and bone2.shape[0] == n and root2.shape[0] == n):
+            raise ValueError("row counts differ: ang %d, grot %d, bone %d, root %d"
+                             % (n, grot2.shape[0], bone2.shape[0], root2.shape[0]))
+        cam_arr = cam_block_array(cam) if (want_cam or want_uv) else None
+        world = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
+        camo = torch.empty((n, 16, 3), dtype=torch.float32, device=device) if want_cam else None
+        uv = torch.empty((n, 16, 2), dtype=torch.float32, device=device) if want_uv else None
+        with torch.cuda.device(device):
+            rc = lib.dhfk_forward(
+                ang2.data_ptr(), _row_stride(ang2), grot2.data_ptr(), _row_stride(grot2),
+                bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
+                cam_arr.ctypes.data if cam_arr is not None else None, None, 0,
+                world.data_ptr(), camo.data_ptr() if want_cam else None, uv.data_ptr() if want_uv else None,
+                n, flags, _stream_ptr(device))
+        _cabi.check(rc, "dhfk_forward")
+        ctx.save_for_backward(ang2, grot2, bone2, root2)
+        ctx.cam_arr = cam_arr
+        ctx.flags = flags
+        ctx.layout = (want_cam, want_uv)
+        ctx.in_shapes = (ang.shape, grot.shape, bone.shape, root.shape)
+        ctx.in_meta = tuple((t.device, t.dtype) for t in (ang, grot, bone, root))
+        outs = (world,) + ((camo,) if want_cam else ()) + ((uv,) if want_uv else ())
+        return outs
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        lib = _cabi.load()
+        ang2, grot2, bone2, root2 = ctx.saved_tensors
+        device = ang2.device
+        n = ang2.shape[0]
+        want_cam, want_uv = ctx.layout
+        it = iter(grads)
+        g_world = _packed(next(it), (n, 16, 3), device)
+        g_cam = _packed(next(it), (n, 16, 3), device) if want_cam else None
+        g_uv = _packed(next(it), (n, 16, 2), device) if want_uv else None
+        need_bone = ctx.needs_input_grad[2]
+        g_ang = torch.empty((n, 33), dtype=torch.float32, device=device)
+        g_grot = torch.empty((n, 3), dtype=torch.float32, device=device)
+        g_root = torch.empty((n, 3), dtype=torch.float32, device=device)
+        g_bone = torch.empty((n, 15), dtype=torch.float32, device=device) if need_bone else None
+        if g_world is None and g_cam is None and g_uv is None:
+            g_ang.zero_(); g_grot.zero_(); g_root.zero_()
+            if g_bone is not None:
+                g_bone.zero_()
+        elif n > 0:
+            with torch.cuda.device(device):
+                rc = lib.dhfk_backward(
+                    ang2.data_ptr(), _row_stride(ang2), grot2.data_ptr(), _row_stride(grot2),
+                    bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
+                    ctx.cam_arr.ctypes.data if ctx.cam_arr is not None else None, None, 0,
+                    g_world.data_ptr() if g_world is not None else None,
+                    g_cam.data_ptr() if g_cam is not None else None,
+                    g_uv.data_ptr() if g_uv is not None else None,
+                    g_ang.data_ptr(), 33, g_grot.data_ptr(), 3, g_root.data_ptr(), 3,
+                    g_bone.data_ptr() if g_bone is not None else None, 15,
+                    n, ctx.flags, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_backward")
+
+        def back(g, shape, meta, ncols):
+            if g is None:
+                return None
+            if shape[-1] != ncols:  # wider input rows (e.g. a [N,37] angle tensor): pad with zeros
+                full = torch.zeros(tuple(shape[:-1]) + (shape[-1],), dtype=torch.float32, device=device)
+                full.reshape(-1, shape[-1])[:, :ncols] = g
+                g = full
+            g = g.reshape(shape)
+            if (g.device, g.dtype) != meta:
+                g = g.to(device=meta[0], dtype=meta[1])
+            return g
+
+        shapes, metas = ctx.in_shapes, ctx.in_meta
+        return (back(g_ang if ctx.needs_input_grad[0] else None, shapes[0], metas[0], 33),
+                back(g_grot if ctx.needs_input_grad[1] else None, shapes[1], metas[1], 3),
+                back(g_bone, shapes[2], metas[2], 15),
+                back(g_root if ctx.needs_input_grad[3] else None, shapes[3], metas[3], 3),
+                None, None, None, None)
+
+
+def fk_project(angles, global_rot, bone_len, root, cam, *, return_cam=True, fast_trig=False):
+    """Fused DH-FK -> global rotation/translation -> world->camera -> pinhole projection.
+
+    angles [N,>=33] deg, global_rot [N,3] deg, bone_len [N,15] m, root [N,3] (or [B,F,3]) m,
+    cam: 16 floats (see tables.camera_block).  Returns (world16 [N,16,3], cam16 [N,16,3] or None,
+    uv16 [N,16,2]).  Replaces Fk_generator.py:232-259 + model_fk_gan_train.py:374-376 in one launch.
+    """
+    flags = _cabi.FLAG_FAST_TRIG if fast_trig else 0
+    outs = _FKProject.apply(angles, global_rot, bone_len, root, cam, bool(return_cam), True, flags)
+    if return_cam:
+        return outs[0], outs[1], outs[2]
+    return outs[0], None, outs[1]
+
+
+def fk_world16(angles, global_rot, bone_len, root, *, fast_trig=False):
+    """DH-FK only: world-space 16 joints [N,16,3] (forward_kinematics_DH_model.py:562-822 followed by
+    the [:, H36M_32_To_16_Table] gather of Fk_generator.py:259)."""
+    flags = _cabi.FLAG_FAST_TRIG if fast_trig else 0
+    return _FKProject.apply(angles, global_rot, bone_len, root, None, False, False, flags)[0]
+
+
+class _WorldToCamera(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, q, t):
+        _require_cuda()
+        lib = _cabi.load()
+        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        xs = x.to(device=device, dtype=torch.float32).contiguous()
+        q = q.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+        t = t.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+        out = torch.empty_like(xs)
+        npts = xs.numel() // 3
+        with torch.cuda.device(device):
+            rc = lib.dhfk_world_to_camera_forward(xs.data_ptr(), q.data_ptr(), t.data_ptr(), 1, out.data_ptr(),
+                                                  npts, _stream_ptr(device))
+        _cabi.check(rc, "dhfk_world_to_camera_forward")
+        ctx.save_for_backward(q)
+        ctx.meta = (x.device, x.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _cabi.load()
+        (q,) = ctx.saved_tensors
+        device = q.device
+        g = g.to(device=device, dtype=torch.float32).contiguous()
+        gx = torch.empty_like(g)
+        with torch.cuda.device(device):
+            rc = lib.dhfk_world_to_camera_backward(g.data_ptr(), q.data_ptr(), 1, gx.data_ptr(), g.numel() // 3,
+                                                   _stream_ptr(device))
+        _cabi.check(rc, "dhfk_world_to_camera_backward")
+        if (gx.device, gx.dtype) != ctx.meta:
+            gx = gx.to(device=ctx.meta[0], dtype=ctx.meta[1])
+        return gx, None, None
+
+
+def world_to_camera(x, q, t):
+    """out = qrot(conj(q), x - t) for one camera (q [1,4] or [4], t [1,3] or [3]); x [..., 3].
+    Mirrors common/camera.py:36-38 incl. its shape assertions (quaternion.py:17-19)."""
+    assert q.shape[-1] == 4
+    assert x.shape[-1] == 3
+    if q.numel() != 4 or t.numel() != 3:
+        raise AssertionError("GAN_torch_world_to_camera expects one camera: R [1,4], t [1,3] "
+                             "(the reference's repeat() asserts otherwise, quaternion.py:19)")
+    return _WorldToCamera.apply(x, q, t)
+
+
+class _Project(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cam_rows):
+        _require_cuda()
+        lib = _cabi.load()
+        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        xs = x.to(device=device, dtype=torch.float32).contiguous()
+        cams = _rows(cam_rows, 9, device)
+        n = xs.shape[0]
+        joints = xs.numel() // (3 * n) if n > 0 else 0
+        uv = torch.empty(tuple(xs.shape[:-1]) + (2,), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            rc = lib.dhfk_project_forward(xs.data_ptr(), cams.data_ptr(), _row_stride(cams), uv.data_ptr(), n, joints,
+                                          _stream_ptr(device))
+        _cabi.check(rc, "dhfk_project_forward")
+        ctx.save_for_backward(xs, cams)
+        ctx.meta = (x.device, x.dtype)
+        return uv
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _cabi.load()
+        xs, cams = ctx.saved_tensors
+        device = xs.device
+        n = xs.shape[0]
+        joints = xs.numel() // (3 * n) if n > 0 else 0
+        g = g.to(device=device, dtype=torch.float32).contiguous()
+        gx = torch.empty_like(xs)
+        with torch.cuda.device(device):
+            rc = lib.dhfk_project_backward(xs.data_ptr(), cams.data_ptr(), _row_stride(cams), g.data_ptr(),
+                                           gx.data_ptr(), n, joints, _stream_ptr(device))
+        _cabi.check(rc, "dhfk_project_backward")
+        if (gx.device, gx.dtype) != ctx.meta:
+            gx = gx.to(device=ctx.meta[0], dtype=ctx.meta[1])
+        return gx, None
+
+
+def project_to_2d(x, camera_params):
+    """H36M pinhole projection with radial+tangential distortion and the +-1 clamp, per-row
+    intrinsics.  Same assertions as common/camera.py:71-74."""
+    assert x.shape[-1] == 3
+    assert len(camera_params.shape) == 2
+    assert camera_params.shape[-1] == 9 or camera_params.shape[-1] == 16
+    assert x.shape[0] == camera_params.shape[0]
+    return _Project.apply(x, camera_params)
+
+
+def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chunk_rows=65536, num_streams=3,
+                    workspace=None, out=None, fast_trig=False):
+    """End-to-end over HOST (ideally pinned) float32 tensors through dhfk_forward_backward_host:
+    chunk-pipelined H2D -> fused forward -> D2H and H2D(grads) -> fused backward -> D2H.
+    Returns dict(world, uv[, g_ang, g_grot, g_root]) of host tensors (pinned if allocated here)."""
+    _require_cuda()
+    lib = _cabi.load()
+    n = ang.shape[0]
+    for name, t, c in (("ang", ang, 33), ("grot", grot, 3), ("bone", bone, 15), ("root", root, 3)):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != (n, c):
+            raise ValueError("%s must be a contiguous float32 host tensor of shape [%d,%d]" % (name, n, c))
+    do_bwd = g_world is not None or g_uv is not None
+    if do_bwd and (g_world is None or g_uv is None):
+        raise ValueError("backward needs both g_world and g_uv")
+    cam_arr = cam_block_array(cam)
+    device = torch.device("cuda", torch.cuda.current_device())
+    need = lib.dhfk_host_workspace_bytes(chunk_rows, num_streams)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need // 4, dtype=torch.float32, device=device)
+    if out is None:
+        out = {}
+    def host(name, shape):
+        t = out.get(name)
+        if t is None or tuple(t.shape) != shape:
+            t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+            out[name] = t
+        return t
+    world = host("world", (n, 16, 3))
+    uv = host("uv", (n, 16, 2))
+    g_ang = host("g_ang", (n, 33)) if do_bwd else None
+    g_grot = host("g_grot", (n, 3)) if do_bwd else None
+    g_root = host("g_root", (n, 3)) if do_bwd else None
+    p = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(device):
+        rc = lib.dhfk_forward_backward_host(
+            p(ang), p(grot), p(bone), p(root), cam_arr.ctypes.data, p(g_world), p(g_uv), p(world), p(uv),
+            p(g_ang), p(g_grot), p(g_root), n, chunk_rows, num_streams, workspace.data_ptr(),
+            workspace.numel() * workspace.element_size(), _cabi.FLAG_FAST_TRIG if fast_trig else 0)
+    _cabi.check(rc, "dhfk_forward_backward_host")
+    out["_workspace"] = workspace
+    return out

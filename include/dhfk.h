@@ -1,0 +1,147 @@
+/*
+ * dhfk.h -- C ABI of the B200-native DH-AUG hot path (libdhfk.so).
+ *
+ * The reference (hlz0606/DH-AUG, Python + torch) has no FFI of its own; the path it runs in
+ * torch eager is listed below next to the entry point that replaces it.  Citations are
+ * relative to DH-AUG_master/ in the reference tree.  INTEGRATION.md shows the ctypes binding
+ * a maintainer adds on the reference side.
+ *
+ *   dhfk_forward / dhfk_backward
+ *       Forward_Kinematics_DH_Model.change_3d_joint_angle, torch branch
+ *         models_Fk_GAN/forward_kinematics_DH_model.py:562-822   (FK: 33 dh_matrix, 46 bmm)
+ *       dh_matrix / rotationMatrix               ...:80-116, :141-191
+ *       [:, H36M_32_To_16_Table] gather           models_Fk_GAN/Fk_generator.py:259,453
+ *       GAN_torch_world_to_camera                 common/camera.py:36-38 (+ quaternion.py:6-35)
+ *       project_to_2d                             common/camera.py:62-94
+ *       autograd through all of the above         model_fk_gan_train.py:480 (gen_loss.backward)
+ *   dhfk_world_to_camera_*      common/camera.py:36-38 called on its own
+ *       (model_fk_gan_train.py:374,434; video_GAN_fun.py:321,440)
+ *   dhfk_project_*              common/camera.py:62-94 called on its own, per-row intrinsics
+ *       (function_aug/dataloader_update.py:69; model_fk_gan_train.py:376,436)
+ *   dhfk_topology               the constant tables the reference keeps as Python lists
+ *       (forward_kinematics_DH_model.py:234-261,:571-589,:751-817; common/h36m_dataset.py:37-38)
+ *
+ * Conventions
+ *   - All tensors fp32, row-major.  Pointers named *_dev are device pointers owned by the
+ *     caller (e.g. the PyTorch caching allocator); the library never allocates, frees or
+ *     retains device memory.  `cam` blocks are small HOST arrays read during the call.
+ *   - Angles in degrees, lengths / positions in metres.
+ *   - Joint order of the 33 angles: right leg 0-4, left leg 5-9, body 10-22, right hand 23-27,
+ *     left hand 28-32 (Fk_generator.py:179-184).  Bone order: used_16key_15bone_len_table
+ *     (forward_kinematics_DH_model.py:46-49).  Output joints: the 16-joint H36M layout.
+ *   - Row strides are in floats and must be >= the logical row length.  Packed, 16-byte
+ *     aligned rows take the 128-bit slab path; anything else takes a gather path.
+ *     Outputs and upstream gradients ([N,16,3] / [N,16,2]) must be packed and 16-byte aligned.
+ *   - Launches are asynchronous on `stream` (a cudaStream_t, e.g.
+ *     torch.cuda.current_stream().cuda_stream); no host synchronisation inside.
+ *     The caller selects the device (cudaSetDevice / torch.cuda.device).
+ *   - Return value: 0 on success, negative DHFK_E_* on argument errors, positive cudaError_t
+ *     on CUDA errors.  dhfk_last_error() returns a thread-local message for the last failure.
+ *   - Entry points are re-entrant; the library holds no mutable global state.
+ */
+#ifndef DHFK_H_
+#define DHFK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DHFK_ABI_VERSION 1
+
+#define DHFK_OK 0
+#define DHFK_E_INVAL (-1)       /* null / negative / inconsistent argument                     */
+#define DHFK_E_ALIGN (-2)       /* a packed output or gradient pointer is not 16-byte aligned  */
+#define DHFK_E_UNSUPPORTED (-3) /* combination not implemented                                 */
+
+/* flags */
+#define DHFK_FLAG_FAST_TRIG 0x1u /* MUFU.SIN/COS after exact degree range reduction (abs err ~4e-7)
+                                    instead of the ~1 ulp polynomial path                        */
+
+#define DHFK_NUM_JOINTS 33
+#define DHFK_NUM_OUT 16
+#define DHFK_NUM_BONES 15
+#define DHFK_CAM_BLOCK 16 /* host camera block: q(4: w,x,y,z) t(3, metres) f(2) c(2) k(3) p(2)   */
+
+int dhfk_abi_version(void);
+const char* dhfk_last_error(void);
+
+/* Constant tables, in joint order 0..32 (any pointer may be NULL).  alpha33 / theta0_33 in degrees. */
+int dhfk_topology(int32_t* parent33, int32_t* out16, float* alpha33, float* theta0_33, int32_t* len_kind33,
+                  int32_t* len_bone33, int32_t* len_sign33, int32_t* h36m_32_to_16);
+
+/* Poses per CTA of the fused kernels (rows are processed in tiles of this many). */
+int dhfk_tile_rows(void);
+
+/*
+ * Fused forward:  angles, global rotation, bone lengths, root  ->  world-space 16 joints,
+ * optionally camera-space joints and 2D keypoints.
+ *   ang_dev   [N, >=33] joint angles (deg), row stride ang_stride
+ *   grot_dev  [N, >=3]  global rotation angles x,y,z (deg), row stride grot_stride
+ *   bone_dev  [N, >=15] bone lengths (m), row stride bone_stride
+ *   root_dev  [N, >=3]  root translation (m), row stride root_stride
+ *   cam       host, 16 floats (DHFK_CAM_BLOCK); required iff out_cam_dev or out_uv_dev
+ *   cam_rows_dev  reserved for per-row intrinsics in the fused path; must be NULL (use
+ *                 dhfk_project_* for per-row cameras)
+ *   out_world_dev [N,16,3] required; out_cam_dev [N,16,3] / out_uv_dev [N,16,2] optional
+ */
+int dhfk_forward(const float* ang_dev, int64_t ang_stride, const float* grot_dev, int64_t grot_stride,
+                 const float* bone_dev, int64_t bone_stride, const float* root_dev, int64_t root_stride,
+                 const float* cam, const float* cam_rows_dev, int64_t cam_rows_stride,
+                 float* out_world_dev, float* out_cam_dev, float* out_uv_dev, int64_t n, uint32_t flags,
+                 void* stream);
+
+/*
+ * Fused backward (recomputes the forward in registers):
+ *   d/d(ang, grot, root[, bone]) of  <g_world, world> + <g_cam, cam> + <g_uv, uv>.
+ *   g_world_dev [N,16,3], g_cam_dev [N,16,3], g_uv_dev [N,16,2]: any may be NULL (= zero), at
+ *   least one must be given.  g_ang_dev [N, >=33] (columns 0..32 written), g_grot_dev [N,>=3],
+ *   g_root_dev [N,>=3] required; g_bone_dev [N,>=15] optional (the reference never
+ *   differentiates bone lengths).
+ */
+int dhfk_backward(const float* ang_dev, int64_t ang_stride, const float* grot_dev, int64_t grot_stride,
+                  const float* bone_dev, int64_t bone_stride, const float* root_dev, int64_t root_stride,
+                  const float* cam, const float* cam_rows_dev, int64_t cam_rows_stride,
+                  const float* g_world_dev, const float* g_cam_dev, const float* g_uv_dev,
+                  float* g_ang_dev, int64_t g_ang_stride, float* g_grot_dev, int64_t g_grot_stride,
+                  float* g_root_dev, int64_t g_root_stride, float* g_bone_dev, int64_t g_bone_stride,
+                  int64_t n, uint32_t flags, void* stream);
+
+/* world -> camera for P = prod(X.shape[:-1]) points with one camera q[4] (w,x,y,z), t[3]:
+ * out = qrot(conj(q), X - t).  Backward: g_x = R(q) g_out.
+ * cam_on_device = 0: cam_q / cam_t are host arrays read during the call;
+ * cam_on_device = 1: they are device pointers read by the kernel (no host sync; this is what the
+ * reference call sites have: cam_R / cam_t already live on the GPU, model_fk_gan_train.py:365-366). */
+int dhfk_world_to_camera_forward(const float* x_dev, const float* cam_q, const float* cam_t, int32_t cam_on_device,
+                                 float* out_dev, int64_t num_points, void* stream);
+int dhfk_world_to_camera_backward(const float* g_out_dev, const float* cam_q, int32_t cam_on_device,
+                                  float* g_x_dev, int64_t num_points, void* stream);
+
+/* project_to_2d with per-row intrinsics: x_dev [N, J, 3], cam_rows_dev [N, >=9] = f2 c2 k3 p2
+ * (row stride cam_rows_stride: 9 or 16 in the reference), uv_dev [N, J, 2]. */
+int dhfk_project_forward(const float* x_dev, const float* cam_rows_dev, int64_t cam_rows_stride, float* uv_dev,
+                         int64_t n, int64_t joints, void* stream);
+int dhfk_project_backward(const float* x_dev, const float* cam_rows_dev, int64_t cam_rows_stride,
+                          const float* g_uv_dev, float* g_x_dev, int64_t n, int64_t joints, void* stream);
+
+/*
+ * Host-buffer end-to-end entry: forward + backward over N poses whose inputs, upstream gradients
+ * and results all live in HOST memory (pinned for full speed).  The rows are cut into chunks that
+ * are pipelined H2D -> fused forward -> D2H(world, uv) and H2D(grads) -> fused backward ->
+ * D2H(grads) on `num_streams` internal streams.  `workspace_dev` is caller-owned device scratch
+ * of at least dhfk_host_workspace_bytes(chunk_rows, num_streams) bytes.  Synchronous: returns when
+ * all results are in host memory.  g_world_host / g_uv_host may be NULL to run forward only.
+ */
+int64_t dhfk_host_workspace_bytes(int64_t chunk_rows, int32_t num_streams);
+int dhfk_forward_backward_host(const float* ang_host, const float* grot_host, const float* bone_host,
+                               const float* root_host, const float* cam, const float* g_world_host,
+                               const float* g_uv_host, float* out_world_host, float* out_uv_host,
+                               float* g_ang_host, float* g_grot_host, float* g_root_host, int64_t n,
+                               int64_t chunk_rows, int32_t num_streams, void* workspace_dev,
+                               int64_t workspace_bytes, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DHFK_H_ */

@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/dhfk_oracle.c (float64 CPU restatement).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libdhfk_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle (gcc) if needed; returns the .so path."""
+    src = os.path.join(_HERE, "dhfk_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B" if force else "all"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.dhfk_oracle_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def _f32(a, cols=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if cols is not None:
+        assert a.ndim == 2 and a.shape[1] == cols, (a.shape, cols)
+    return a
+
+
+def _ptr(a, ty=ctypes.c_float):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ty))
+
+
+def num_threads() -> int:
+    return int(lib().dhfk_oracle_num_threads())
+
+
+def forward(ang, grot, bone, root, cam16=None, cam_rows=None, want_world32=False):
+    """-> dict(world16 [N,16,3], cam [N,16,3], uv [N,16,2], world32 [N,32,3]) float64 numpy."""
+    ang = _f32(ang); grot = _f32(grot, 3); bone = _f32(bone, 15); root = _f32(root, 3)
+    n = ang.shape[0]
+    assert ang.shape[1] >= 33
+    cam16 = None if cam16 is None else _f32(np.asarray(cam16).reshape(16))
+    cam_rows = None if cam_rows is None else _f32(cam_rows)
+    out = {"world16": np.empty((n, 16, 3), np.float64)}
+    if want_world32:
+        out["world32"] = np.empty((n, 32, 3), np.float64)
+    if cam16 is not None:
+        out["cam"] = np.empty((n, 16, 3), np.float64)
+        out["uv"] = np.empty((n, 16, 2), np.float64)
+    d = ctypes.c_double
+    rc = lib().dhfk_oracle_forward(
+        ctypes.c_int64(n), _ptr(ang), ctypes.c_int64(ang.shape[1]), _ptr(grot), ctypes.c_int64(3),
+        _ptr(bone), ctypes.c_int64(15), _ptr(root), ctypes.c_int64(3), _ptr(cam16), _ptr(cam_rows),
+        ctypes.c_int64(0 if cam_rows is None else cam_rows.shape[1]),
+        _ptr(out.get("world32"), d), _ptr(out["world16"], d), _ptr(out.get("cam"), d), _ptr(out.get("uv"), d))
+    assert rc == 0, rc
+    return out
+
+
+def backward(ang, grot, bone, root, cam16=None, cam_rows=None, g_world=None, g_cam=None, g_uv=None,
+             want_bone=True):
+    """-> dict(g_ang [N,33], g_grot [N,3], g_root [N,3], g_bone [N,15]) float64 numpy."""
+    ang = _f32(ang); grot = _f32(grot, 3); bone = _f32(bone, 15); root = _f32(root, 3)
+    n = ang.shape[0]
+    cam16 = None if cam16 is None else _f32(np.asarray(cam16).reshape(16))
+    cam_rows = None if cam_rows is None else _f32(cam_rows)
+    g_world = None if g_world is None else _f32(np.asarray(g_world).reshape(n, 48))
+    g_cam = None if g_cam is None else _f32(np.asarray(g_cam).reshape(n, 48))
+    g_uv = None if g_uv is None else _f32(np.asarray(g_uv).reshape(n, 32))
+    out = {"g_ang": np.empty((n, 33), np.float64), "g_grot": np.empty((n, 3), np.float64),
+           "g_root": np.empty((n, 3), np.float64)}
+    if want_bone:
+        out["g_bone"] = np.empty((n, 15), np.float64)
+    d = ctypes.c_double
+    rc = lib().dhfk_oracle_backward(
+        ctypes.c_int64(n), _ptr(ang), ctypes.c_int64(ang.shape[1]), _ptr(grot), ctypes.c_int64(3),
+        _ptr(bone), ctypes.c_int64(15), _ptr(root), ctypes.c_int64(3), _ptr(cam16), _ptr(cam_rows),
+        ctypes.c_int64(0 if cam_rows is None else cam_rows.shape[1]),
+        _ptr(g_world), _ptr(g_cam), _ptr(g_uv),
+        _ptr(out["g_ang"], d), _ptr(out["g_grot"], d), _ptr(out["g_root"], d), _ptr(out.get("g_bone"), d))
+    assert rc == 0, rc
+    return out
+
+
+def tables():
+    """Restated topology tables in generator joint order (see dhfk_oracle_tables)."""
+    alpha = np.empty(33, np.float64); theta0 = np.empty(33, np.float64)
+    parent = np.empty(33, np.int32); kind = np.empty(33, np.int32)
+    bone = np.empty(33, np.int32); sign = np.empty(33, np.int32)
+    out16 = np.empty(16, np.int32); h = np.empty(16, np.int32)
+    i32 = ctypes.c_int32
+    lib().dhfk_oracle_tables(_ptr(alpha, ctypes.c_double), _ptr(theta0, ctypes.c_double), _ptr(parent, i32),
+                             _ptr(kind, i32), _ptr(bone, i32), _ptr(sign, i32), _ptr(out16, i32), _ptr(h, i32))
+    return dict(alpha=alpha, theta0=theta0, parent=parent, len_kind=kind, len_bone=bone, len_sign=sign,
+                out16=out16, h36m_32_to_16=h)

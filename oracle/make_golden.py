@@ -1,0 +1,196 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (torch fp32, CPU branch).
+
+Run in the build container only (needs /root/reference):
+    python oracle/make_golden.py
+The fixtures are committed; nothing that runs on the GPU box reads /root/reference.
+
+Fixtures
+  tables.npz       constant tables read off the reference modules/objects + the structural
+                   dependency matrix of its autograd Jacobian (which angle moves which output)
+  kat.npz          KAT-1 T-pose (init_Fk_DH_angle, numpy float64 branch) and KAT-2 bent pose
+  gan133.npz       133 generator-like poses (ragged vs the 96-row kernel tile), S1/cam0, in-volume root
+  stress200.npz    200 poses, U(-180,180) on every slot, root 10*tanh(randn) (clamp active), S7/cam2
+  video36.npz      multi-frame mode: B=4 clips x F=9 frames, root given as [B,F,3]
+  camera_ops.npz   GAN_torch_world_to_camera / project_to_2d on their own, per-row intrinsics (9 and 16 cols)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def t(x, grad=False):
+    return torch.tensor(np.asarray(x, dtype=np.float32), requires_grad=grad)
+
+
+def run_case(inp, cam_blk, grads, mode="single", architecture="3,3,3", root_shape=None):
+    ref = rh.import_reference()
+    ang, grot, root = t(inp["ang"], True), t(inp["grot"], True), t(inp["root"], True)
+    bone = t(inp["bone"])
+    n = ang.shape[0]
+    frames = 1
+    if mode == "multi":
+        for f in architecture.split(","):
+            frames *= int(f)
+    model = ref.fk.Forward_Kinematics_DH_Model(rh.make_args(n // frames, mode, architecture), ["S1"], None)
+    root_in = root if root_shape is None else root.view(*root_shape)
+    kw = dict(right_leg_joints_angle=ang[:, 0:5], left_leg_joints_angle=ang[:, 5:10],
+              body_joints_angle=ang[:, 10:23], right_hand_joints_angle=ang[:, 23:28],
+              left_hand_joints_angle=ang[:, 28:33], generator_global_rot_3d_pos_angle=grot, root_3d_pos=root_in)
+    for i, name in enumerate(rh.BONE_KWARGS):
+        kw[name] = bone[:, i]
+    w32 = model.change_3d_joint_angle(**kw)
+    w16 = w32[:, ref.h36m.H36M_32_To_16_Table]
+    q, tt = t(cam_blk[0:4]).view(1, 4), t(cam_blk[4:7]).view(1, 3)
+    cp = t(cam_blk[7:16]).view(1, 9).repeat(n, 1)
+    cam = ref.camera.GAN_torch_world_to_camera(w16, R=q, t=tt)
+    uv = ref.camera.project_to_2d(cam, cp)
+    out = dict(inp)
+    out.update(cam_block=cam_blk, world32=w32.detach().numpy(), world16=w16.detach().numpy(),
+               cam=cam.detach().numpy(), uv=uv.detach().numpy())
+    # gradient sets: (world only) and (world + cam + uv) and (world + uv)
+    gw, gc, gu = t(grads["g_world"]), t(grads["g_cam"]), t(grads["g_uv"])
+    out.update(g_world=grads["g_world"], g_cam=grads["g_cam"], g_uv=grads["g_uv"])
+    for tag, loss in (("w", (w16 * gw).sum()),
+                      ("wu", (w16 * gw).sum() + (uv * gu).sum()),
+                      ("wcu", (w16 * gw).sum() + (cam * gc).sum() + (uv * gu).sum())):
+        ga, gg, gr = torch.autograd.grad(loss, (ang, grot, root), retain_graph=True)
+        out["g_ang_" + tag] = ga.numpy()
+        out["g_grot_" + tag] = gg.numpy()
+        out["g_root_" + tag] = gr.numpy()
+    return out
+
+
+def tables_fixture():
+    ref = rh.import_reference()
+    m = ref.fk.Forward_Kinematics_DH_Model(rh.make_args(1), ["S1"], None)
+    alpha = np.array(m.right_leg_joints_alpha + m.left_leg_joints_alpha + m.body_joints_alpha +
+                     m.right_hand_joints_alpha + m.left_hand_joints_alpha, dtype=np.float32)
+    theta0 = np.array(m.right_leg_joints_theta + m.left_leg_joints_theta + m.body_joints_theta +
+                      m.right_hand_joints_theta + m.left_hand_joints_theta, dtype=np.float32)
+    # bone-length slots: call the reference with distinct lengths and read its a/d tables back
+    lens = np.array([0.5 + 0.01 * i for i in range(15)], dtype=np.float32)
+    kw = dict(right_leg_joints_angle=torch.zeros(1, 5), left_leg_joints_angle=torch.zeros(1, 5),
+              body_joints_angle=torch.zeros(1, 13), right_hand_joints_angle=torch.zeros(1, 5),
+              left_hand_joints_angle=torch.zeros(1, 5), generator_global_rot_3d_pos_angle=torch.zeros(1, 3),
+              root_3d_pos=torch.zeros(1, 3))
+    for i, name in enumerate(rh.BONE_KWARGS):
+        kw[name] = torch.tensor([lens[i]])
+    m.change_3d_joint_angle(**kw)
+    a = torch.cat([m.GAN_right_leg_joints_a, m.GAN_left_leg_joints_a, m.GAN_body_joints_a,
+                   m.GAN_right_hand_joints_a, m.GAN_left_hand_joints_a], 1)[0].numpy()
+    d = torch.cat([m.GAN_right_leg_joints_d, m.GAN_left_leg_joints_d, m.GAN_body_joints_d,
+                   m.GAN_right_hand_joints_d, m.GAN_left_hand_joints_d], 1)[0].numpy()
+    kind = np.zeros(33, np.int32); bone = -np.ones(33, np.int32); sign = np.zeros(33, np.int32)
+    for j in range(33):
+        for arr, k in ((a, 1), (d, 2)):
+            hit = [i for i in range(15) if abs(abs(arr[j]) - lens[i]) < 1e-6]
+            if hit:
+                kind[j], bone[j], sign[j] = k, hit[0], int(np.sign(arr[j]))
+    assert (kind > 0).sum() == 15, kind
+    # structural dependency of the 16 outputs on the 33 angles, from the reference's own autograd
+    rng = np.random.RandomState(7)
+    dep = np.zeros((16, 33), dtype=bool)
+    for _ in range(3):
+        ang = t(rng.uniform(-170, 170, (1, 33)), True)
+        mm = ref.fk.Forward_Kinematics_DH_Model(rh.make_args(1), ["S1"], None)
+        kw2 = dict(kw)
+        kw2.update(right_leg_joints_angle=ang[:, 0:5], left_leg_joints_angle=ang[:, 5:10],
+                   body_joints_angle=ang[:, 10:23], right_hand_joints_angle=ang[:, 23:28],
+                   left_hand_joints_angle=ang[:, 28:33])
+        w16 = mm.change_3d_joint_angle(**kw2)[:, ref.h36m.H36M_32_To_16_Table]
+        for k in range(16):
+            for ax in range(3):
+                (g,) = torch.autograd.grad(w16[0, k, ax], ang, retain_graph=True)
+                dep[k] |= (g[0].abs() > 1e-9).numpy()
+    gtab = ref.generator.GAN_angle_range_table
+    ranges = np.array([gtab["joint%d" % (i + 1)]["range"] for i in range(34)], dtype=np.float32)
+    grtab = ref.generator.GAN_global_rotation_table
+    granges = np.array([grtab["angle_" + c]["range"] for c in "xyz"], dtype=np.float32)
+    subjects = ["S1", "S5", "S6", "S7", "S8", "S9", "S11"]
+    cams = np.stack([np.stack([rh.camera_block(s, c) for c in range(4)]) for s in subjects])
+    tmpl = np.load(os.path.join(rh.REF_ROOT, "data_extra", "bone_length_npy", "hm36s15678_bl_templates.npy"))
+    return dict(alpha=alpha, theta0=theta0, len_kind=kind, len_bone=bone, len_sign=sign, dep=dep,
+                h36m_32_to_16=np.array(ref.h36m.H36M_32_To_16_Table, np.int32),
+                used_16key_15bone_len_table=np.array(ref.fk.used_16key_15bone_len_table, np.int32),
+                gan_angle_range=ranges, gan_global_rot_range=granges, camera_blocks=cams,
+                camera_subjects=np.array(subjects), bone_templates=tmpl)
+
+
+def kat_fixture():
+    ref = rh.import_reference()
+    m = ref.fk.Forward_Kinematics_DH_Model(rh.make_args(1), ["S1"], None)
+    tpose = m.init_Fk_DH_angle()
+    inp = dict(ang=np.full((1, 33), 10.0, np.float32), grot=np.array([[10.0, 20.0, 30.0]], np.float32),
+               bone=np.array([[.45, .45, .44, .44, .13, .13, .23, .26, .15, .15, .28, .28, .25, .25, .18]], np.float32),
+               root=np.array([[1.0, 2.0, 3.0]], np.float32))
+    blk = rh.camera_block("S1", 0)
+    z = dict(g_world=np.ones((1, 16, 3), np.float32), g_cam=np.ones((1, 16, 3), np.float32),
+             g_uv=np.ones((1, 16, 2), np.float32))
+    bent = run_case(inp, blk, z)
+    inp2 = dict(inp); inp2["root"] = np.array([[0.0, 0.0, 1.0]], np.float32)
+    bent2 = run_case(inp2, blk, z)
+    out = {"tpose32": tpose}
+    out.update({"bent_" + k: v for k, v in bent.items()})
+    out.update({"bent2_" + k: v for k, v in bent2.items()})
+    return out
+
+
+def camera_ops_fixture():
+    ref = rh.import_reference()
+    rng = np.random.RandomState(11)
+    n = 77
+    x = rng.uniform(-2, 2, (n, 16, 3)).astype(np.float32)
+    x[..., 2] = rng.uniform(1.5, 6.0, (n, 16)).astype(np.float32)  # some |x/z| > 1 -> clamp active
+    subjects = ["S1", "S5", "S6", "S7", "S8"]
+    rows = np.stack([rh.camera_block(subjects[rng.randint(5)], rng.randint(4))[7:16] for _ in range(n)])
+    rows16 = np.concatenate([rows, rng.randn(n, 7).astype(np.float32)], 1)  # 16-col variant: only 9 used
+    g_uv = rng.randn(n, 16, 2).astype(np.float32)
+    xt = t(x, True)
+    uv = ref.camera.project_to_2d(xt, t(rows))
+    (gx,) = torch.autograd.grad((uv * t(g_uv)).sum(), xt)
+    uv16 = ref.camera.project_to_2d(t(x), t(rows16))
+    blk = rh.camera_block("S6", 3)
+    xw = t(rng.uniform(-3, 3, (n, 16, 3)), True)
+    cam = ref.camera.GAN_torch_world_to_camera(xw, R=t(blk[0:4]).view(1, 4), t=t(blk[4:7]).view(1, 3))
+    g_cam = rng.randn(n, 16, 3).astype(np.float32)
+    (gxw,) = torch.autograd.grad((cam * t(g_cam)).sum(), xw)
+    return dict(x=x, cam_rows9=rows, cam_rows16=rows16, uv=uv.detach().numpy(), uv16=uv16.detach().numpy(),
+                g_uv=g_uv, g_x=gx.numpy(), clamped=(np.abs(x[..., :2] / x[..., 2:]) > 1),
+                w_x=xw.detach().numpy(), w_q=blk[0:4], w_t=blk[4:7], w_cam=cam.detach().numpy(), w_g_cam=g_cam,
+                w_g_x=gxw.numpy())
+
+
+def main():
+    from dhfk import synthetic
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    np.savez(os.path.join(OUT, "tables.npz"), **tables_fixture())
+    np.savez(os.path.join(OUT, "kat.npz"), **kat_fixture())
+    np.savez(os.path.join(OUT, "gan133.npz"),
+             **run_case(synthetic.gan_like(133, seed=1234), rh.camera_block("S1", 0), synthetic.upstream_grads(133)))
+    np.savez(os.path.join(OUT, "stress200.npz"),
+             **run_case(synthetic.gan_like(200, seed=99, root_mode="generator", angle_mode="stress"),
+                        rh.camera_block("S7", 2), synthetic.upstream_grads(200, seed=5)))
+    np.savez(os.path.join(OUT, "video36.npz"),
+             **run_case(synthetic.gan_like(36, seed=3), rh.camera_block("S8", 1), synthetic.upstream_grads(36, seed=8),
+                        mode="multi", architecture="3,3", root_shape=(4, 9, 3)))
+    np.savez(os.path.join(OUT, "camera_ops.npz"), **camera_ops_fixture())
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,67 @@
+"""The C-ABI library must load without a GPU and export every symbol include/dhfk.h declares.
+No compute is launched here; only argument validation paths (which run before any CUDA call)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dhfk import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "dhfk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dhfk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    names = _declared_functions()
+    assert len(names) >= 12
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libdhfk.so does not export %s" % n
+        assert n in _cabi.SIGNATURES, "python binding lacks %s" % n
+    assert sorted(_cabi.SIGNATURES) == names
+
+
+def test_abi_version_and_tile():
+    lib = _cabi.load()
+    assert lib.dhfk_abi_version() == _cabi.ABI_VERSION == 1
+    assert lib.dhfk_tile_rows() == 96
+
+
+def test_argument_validation_without_gpu():
+    lib = _cabi.load()
+    z = None
+    # n == 0 is a no-op success for every entry point
+    assert lib.dhfk_forward(z, 33, z, 3, z, 15, z, 3, z, z, 0, z, z, z, 0, 0, z) == 0
+    assert lib.dhfk_backward(z, 33, z, 3, z, 15, z, 3, z, z, 0, z, z, z, z, 33, z, 3, z, 3, z, 15, 0, 0, z) == 0
+    assert lib.dhfk_world_to_camera_forward(z, z, z, 0, z, 0, z) == 0
+    assert lib.dhfk_project_forward(z, z, 9, z, 0, 16, z) == 0
+    # negative n, null pointers, short strides -> DHFK_E_INVAL with a message
+    assert lib.dhfk_forward(z, 33, z, 3, z, 15, z, 3, z, z, 0, z, z, z, -1, 0, z) == _cabi.E_INVAL
+    assert "n must be" in _cabi.last_error()
+    assert lib.dhfk_forward(z, 33, z, 3, z, 15, z, 3, z, z, 0, z, z, z, 5, 0, z) == _cabi.E_INVAL
+    buf = np.zeros(64 * 48, np.float32)
+    p = buf.ctypes.data
+    assert lib.dhfk_forward(p, 32, p, 3, p, 15, p, 3, z, z, 0, p, z, z, 4, 0, z) == _cabi.E_INVAL   # ang stride < 33
+    assert "stride" in _cabi.last_error()
+    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, z, z, z, 4, 0, z) == _cabi.E_INVAL   # out_world missing
+    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, p, z, p, 4, 0, z) == _cabi.E_INVAL   # uv without cam
+    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, p, p, 9, p, z, p, 4, 0, z) == _cabi.E_UNSUPPORTED  # cam_rows
+    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, p + 4, z, z, 4, 0, z) == _cabi.E_ALIGN
+    assert lib.dhfk_backward(p, 33, p, 3, p, 15, p, 3, z, z, 0, z, z, z, p, 33, p, 3, p, 3, z, 15, 4, 0, z) == _cabi.E_INVAL
+    assert "upstream" in _cabi.last_error()
+    assert lib.dhfk_project_forward(p, p, 8, p, 4, 16, z) == _cabi.E_INVAL
+    assert lib.dhfk_host_workspace_bytes(0, 2) == 0
+    assert lib.dhfk_host_workspace_bytes(1024, 2) == 1024 * 253 * 4 * 2
+    with pytest.raises(ValueError):
+        _cabi.check(_cabi.E_INVAL, "x")
+    with pytest.raises(NotImplementedError):
+        _cabi.check(_cabi.E_UNSUPPORTED, "x")
+    with pytest.raises(RuntimeError):
+        _cabi.check(700, "x")

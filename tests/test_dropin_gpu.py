@@ -1,0 +1,102 @@
+"""The reference-shaped surface (class + camera functions) on the GPU: same call signatures as
+run_Fk_GAN.py / Fk_generator.py / model_fk_gan_train.py use, checked against the reference's goldens."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_parity, projection_conditioning
+
+pytestmark = pytest.mark.gpu
+
+BONES = ("left_small_leg_len", "right_small_leg_len", "left_big_leg_len", "right_big_leg_len", "left_hip_len",
+         "right_hip_len", "waist_len", "thorax_len", "left_shoulder_len", "right_shoulder_len", "left_big_arm_len",
+         "right_big_arm_len", "left_small_arm_len", "right_small_arm_len", "neck_len")
+
+
+def T(x, grad=False):
+    return torch.tensor(np.asarray(x, dtype=np.float32), device="cuda", requires_grad=grad)
+
+
+def _model(batch=16, mode="single", arch="3,3,3"):
+    from dhfk import Forward_Kinematics_DH_Model
+    args = argparse.Namespace(batch_size=batch, random_seed=0, single_or_multi_train_mode=mode, architecture=arch)
+    return Forward_Kinematics_DH_Model(args, ["S1"], None)
+
+
+def _kwargs(gen, bone, root):
+    kw = dict(right_leg_joints_angle=gen[:, 0:5], left_leg_joints_angle=gen[:, 5:10], body_joints_angle=gen[:, 10:23],
+              right_hand_joints_angle=gen[:, 23:28], left_hand_joints_angle=gen[:, 28:33],
+              generator_global_rot_3d_pos_angle=gen[:, -3:], root_3d_pos=root)
+    for i, name in enumerate(BONES):
+        kw[name] = bone[:, i]
+    return kw
+
+
+@pytest.mark.parametrize("case,root_shape", [("gan133", None), ("video36", (4, 9, 3))])
+def test_change_3d_joint_angle_like_the_generator_calls_it(golden, case, root_shape):
+    from dhfk import camera
+    g = golden(case)
+    n = g["ang"].shape[0]
+    gen = torch.zeros(n, 37, device="cuda")
+    gen[:, :33] = T(g["ang"]); gen[:, 34:] = T(g["grot"])
+    gen.requires_grad_(True)
+    root = T(g["root"], True)
+    root_in = root if root_shape is None else root.view(*root_shape)
+    m = _model(batch=n)                                   # N is NOT pinned to args.batch_size any more
+    w32 = m.change_3d_joint_angle(**_kwargs(gen, T(g["bone"]), root_in))
+    assert w32.shape == (n, 32, 3) and w32.is_cuda
+    assert_parity(w32.detach().cpu().numpy(), g["world32"], "world32")
+    idx = [0, 1, 2, 3, 6, 7, 8, 12, 13, 15, 17, 18, 19, 25, 26, 27]
+    fake = w32[:, idx].view(-1, 16, 3)                    # Fk_generator.py:259
+    blk = g["cam_block"]
+    cam = camera.GAN_torch_world_to_camera(fake, R=T(blk[0:4]).view(1, 4), t=T(blk[4:7]).view(1, 3))
+    uv = camera.project_to_2d(cam, T(blk[7:16]).view(1, 9).repeat(n, 1))
+    assert_parity(cam.detach().cpu().numpy(), g["cam"], "cam")
+    assert_parity(uv.detach().cpu().numpy(), g["uv"], "uv")
+    ((fake * T(g["g_world"])).sum() + (cam * T(g["g_cam"])).sum() + (uv * T(g["g_uv"])).sum()).backward()
+    cond = projection_conditioning(g["cam"])
+    gg = gen.grad.cpu().numpy()
+    assert_parity(gg[:, :33], g["g_ang_wcu"], "g_ang", row_scale=cond)
+    assert_parity(gg[:, 34:], g["g_grot_wcu"], "g_grot", row_scale=cond)
+    assert_parity(root.grad.cpu().numpy(), g["g_root_wcu"], "g_root", row_scale=cond)
+    # stateless: a second call with other lengths does not see the first one's (the reference mutates tables)
+    w32b = m.change_3d_joint_angle(**_kwargs(gen.detach(), 2 * T(g["bone"]), root_in.detach()))
+    assert not torch.allclose(w32b, w32.detach())
+
+
+def test_init_fk_dh_angle_numpy_branch(golden):
+    g = golden("kat")
+    m = _model()
+    out = m.init_Fk_DH_angle()
+    assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == (32, 3)
+    assert np.abs(out - g["tpose32"]).max() < 1e-6
+
+
+def test_cpu_inputs_are_moved_like_the_reference_cuda_calls(golden):
+    g = golden("gan133")
+    n = 133
+    gen = torch.zeros(n, 37); gen[:, :33] = torch.tensor(g["ang"])   # CPU tensors
+    kw = _kwargs(gen, torch.tensor(g["bone"]), torch.tensor(g["root"]))
+    kw["generator_global_rot_3d_pos_angle"] = torch.zeros(n, 3)      # whether_use_RT=False passes CPU zeros
+    w32 = _model().change_3d_joint_angle(**kw)
+    assert w32.is_cuda and w32.shape == (n, 32, 3)
+
+
+def test_camera_functions_standalone(golden):
+    from dhfk import camera
+    g = golden("camera_ops")
+    x = T(g["x"], True)
+    uv = camera.project_to_2d(x, T(g["cam_rows9"]))
+    assert_parity(uv.detach().cpu().numpy(), g["uv"], "uv")
+    (uv * T(g["g_uv"])).sum().backward()
+    cond = projection_conditioning(g["x"], z_ok=1.0)
+    assert_parity(x.grad.cpu().numpy(), g["g_x"], "g_x", row_scale=cond)
+    uv16 = camera.project_to_2d(T(g["x"]), T(g["cam_rows16"]))       # 16-column rows: only 9 are read
+    assert torch.equal(uv16, uv.detach())
+    xw = T(g["w_x"], True)
+    cam = camera.GAN_torch_world_to_camera(xw, T(g["w_q"]).view(1, 4), T(g["w_t"]).view(1, 3))
+    assert_parity(cam.detach().cpu().numpy(), g["w_cam"], "w_cam")
+    (cam * T(g["w_g_cam"])).sum().backward()
+    assert_parity(xw.grad.cpu().numpy(), g["w_g_x"], "w_g_x")

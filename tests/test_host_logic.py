@@ -1,0 +1,111 @@
+"""Host-side logic that needs no GPU: sharding, synthetic inputs, the reference-shaped class's
+bookkeeping, the 16->32 scatter, drop-in patching, and the loud failure without CUDA."""
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from dhfk import parallel, synthetic, tables
+from dhfk.forward_kinematics_DH_model import Forward_Kinematics_DH_Model, scatter_16_to_32
+
+
+def test_shard_rows_partition():
+    for n in (0, 1, 7, 96, 1000, 16777216):
+        for r in (1, 2, 3, 4, 8):
+            spans = [parallel.shard_rows(n, k, r) for k in range(r)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(r - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_rows(10, 2, 2)
+
+
+def test_synthetic_inputs_follow_generator_ranges():
+    d = synthetic.gan_like(4096, seed=1)
+    assert d["ang"].dtype == np.float32 and d["ang"].shape == (4096, 33)
+    lo, hi = tables.GAN_ANGLE_RANGE[:33, 0], tables.GAN_ANGLE_RANGE[:33, 1]
+    assert (d["ang"] >= lo - 1e-3).all() and (d["ang"] <= hi + 1e-3).all()
+    assert (d["ang"][:, [4, 9, 22, 23, 28]] == 0).all()
+    assert np.abs(d["grot"]).max() <= 180 and d["grot"].std() > 90
+    ratio = d["bone"][:, 7:8] / tables.BONE_TEMPLATES[:, 7][None, :]
+    assert (np.abs(ratio - 1).min(1) < 1e-6).all()          # thorax is never scaled
+    assert (d["bone"] > 0.08).all() and (d["bone"] < 0.6).all()
+    assert np.array_equal(d["bone"][:, 0] / d["bone"][:, 1] > 0.99, np.ones(4096, bool))  # symmetric groups
+    d2 = synthetic.gan_like(4096, seed=1)
+    assert all(np.array_equal(d[k], d2[k]) for k in d)       # deterministic
+    s = synthetic.gan_like(512, seed=2, root_mode="generator", angle_mode="stress")
+    assert np.abs(s["root"]).max() <= 10 and np.abs(s["ang"]).max() <= 180
+
+
+def test_scatter_16_to_32_matches_reference_layout(golden):
+    g = golden("gan133")
+    out = scatter_16_to_32(torch.tensor(g["world16"]), torch.tensor(g["root"]))
+    assert np.array_equal(out.numpy(), g["world32"])          # pure data movement: bit-exact
+    gv = golden("video36")
+    out = scatter_16_to_32(torch.tensor(gv["world16"]), torch.tensor(gv["root"]).view(4, 9, 3))
+    assert np.array_equal(out.numpy(), gv["world32"])
+
+
+def test_reference_shaped_class_without_gpu():
+    import argparse
+    args = argparse.Namespace(batch_size=8, random_seed=3, single_or_multi_train_mode="multi", architecture="3,3")
+    m = Forward_Kinematics_DH_Model(args, ["S1", "S5"], None)
+    assert m.real_used_num == 9 and m.GAN_BATCH_SIZE == 8
+    assert m.random.randint(0, 1000) == np.random.RandomState(3).randint(0, 1000)
+    assert m.record_bone_len == [] and list(m.root_3d_pos) == [0, 0, 0]
+    assert m.body_joints_alpha == tables.ALPHA_DEG[10:23].tolist()
+    r = np.random.RandomState(5)
+    m.set_random_state(r)
+    assert m.random_state() is r
+    # dataset bookkeeping draws follow the reference order (subject, action, camera, frame)
+    m.dataSet_world_3d_pos = {"S1": {"a": {0: np.arange(48 * 3, dtype=np.float64).reshape(3, 16, 3)}},
+                              "S5": {"b": {0: np.ones((2, 16, 3))}}}
+    m.dataSet_2d_pos = m.dataSet_world_3d_pos
+    m.set_random_state(np.random.RandomState(0))
+    m.get_bone_len_from_dataSet()
+    assert len(m.record_bone_len) == 15
+    m.get_root_3d_pos_from_dataSet()
+    assert m.root_3d_pos.shape == (3,)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m.init_Fk_DH_angle()
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            from dhfk import fk_world16
+            fk_world16(torch.zeros(2, 33), torch.zeros(2, 3), torch.ones(2, 15), torch.zeros(2, 3))
+
+
+def test_dropin_install_patches_imported_reference_modules(monkeypatch):
+    from dhfk import camera, dropin
+    fk = types.ModuleType("models_Fk_GAN.forward_kinematics_DH_model")
+    fk.Forward_Kinematics_DH_Model = object
+    cam = types.ModuleType("common.camera")
+    cam.GAN_torch_world_to_camera = cam.project_to_2d = cam.normalize_screen_coordinates = (lambda *a: None)
+    keep = cam.normalize_screen_coordinates
+    train = types.ModuleType("models_Fk_GAN.model_fk_gan_train")
+    train.project_to_2d = train.GAN_torch_world_to_camera = train.Forward_Kinematics_DH_Model = None
+    monkeypatch.setitem(sys.modules, "models_Fk_GAN.forward_kinematics_DH_model", fk)
+    monkeypatch.setitem(sys.modules, "common.camera", cam)
+    monkeypatch.setitem(sys.modules, "models_Fk_GAN.model_fk_gan_train", train)
+    patched = dropin.install()
+    assert fk.Forward_Kinematics_DH_Model is Forward_Kinematics_DH_Model
+    assert cam.project_to_2d is camera.project_to_2d and cam.GAN_torch_world_to_camera is camera.GAN_torch_world_to_camera
+    assert cam.normalize_screen_coordinates is keep
+    assert train.project_to_2d is camera.project_to_2d and train.Forward_Kinematics_DH_Model is Forward_Kinematics_DH_Model
+    assert len(patched) >= 5
+
+
+def test_camera_dropin_assertions_match_reference():
+    from dhfk import camera
+    with pytest.raises(AssertionError):
+        camera.project_to_2d(torch.zeros(4, 16, 2), torch.zeros(4, 9))       # last dim must be 3
+    with pytest.raises(AssertionError):
+        camera.project_to_2d(torch.zeros(4, 16, 3), torch.zeros(9))          # camera_params.ndim == 2
+    with pytest.raises(AssertionError):
+        camera.project_to_2d(torch.zeros(4, 16, 3), torch.zeros(4, 10))      # 9 or 16 columns
+    with pytest.raises(AssertionError):
+        camera.project_to_2d(torch.zeros(4, 16, 3), torch.zeros(5, 9))       # batch mismatch
+    with pytest.raises(AssertionError):
+        camera.GAN_torch_world_to_camera(torch.zeros(4, 16, 3), torch.zeros(1, 3), torch.zeros(1, 3))

@@ -1,0 +1,224 @@
+"""Parity of the sm_100a kernels against (a) the golden vectors produced by the unmodified reference
+and (b) the float64 C oracle on seeded inputs, through the public API (-> ctypes -> C ABI).
+
+Tolerance (BASELINE.json north_star): |x - ref| <= 1e-5 * max(|ref|, 1), fp32.
+Gradients that pass through x/z use the conditioning multiplier of conftest.projection_conditioning
+for poses with a joint closer than 0.5 m to the camera plane (multiplier 1 everywhere else)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import RTOL, assert_parity, projection_conditioning, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["gan133", "stress200", "video36"]
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def T(x, grad=False):
+    return torch.tensor(np.asarray(x, dtype=np.float32), device=dev(), requires_grad=grad)
+
+
+def run_fused(g, fast, grads):
+    """grads: subset string of 'wcu' -> returns outputs and input gradients as numpy."""
+    import dhfk
+    ang, grot, root = T(g["ang"], True), T(g["grot"], True), T(g["root"], True)
+    bone = T(g["bone"])
+    world, cam, uv = dhfk.fk_project(ang, grot, bone, root, g["cam_block"], return_cam=True, fast_trig=fast)
+    loss = (world * T(g["g_world"])).sum()
+    if "c" in grads:
+        loss = loss + (cam * T(g["g_cam"])).sum()
+    if "u" in grads:
+        loss = loss + (uv * T(g["g_uv"])).sum()
+    loss.backward()
+    return (world.detach().cpu().numpy(), cam.detach().cpu().numpy(), uv.detach().cpu().numpy(),
+            ang.grad.cpu().numpy(), grot.grad.cpu().numpy(), root.grad.cpu().numpy())
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["poly", "mufu"])
+@pytest.mark.parametrize("case", CASES)
+def test_forward_matches_reference_golden(golden, case, fast):
+    g = golden(case)
+    world, cam, uv, *_ = run_fused(g, fast, "w")
+    assert_parity(world, g["world16"], "world16")
+    assert_parity(cam, g["cam"], "cam")
+    assert_parity(uv, g["uv"], "uv")
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["poly", "mufu"])
+@pytest.mark.parametrize("tag", ["w", "wu", "wcu"])
+@pytest.mark.parametrize("case", CASES)
+def test_backward_matches_reference_autograd(golden, case, tag, fast):
+    g = golden(case)
+    *_, g_ang, g_grot, g_root = run_fused(g, fast, tag)
+    cond = projection_conditioning(g["cam"]) if "u" in tag else None
+    assert_parity(g_ang, g["g_ang_" + tag], "g_ang", row_scale=cond)
+    assert_parity(g_grot, g["g_grot_" + tag], "g_grot", row_scale=cond)
+    assert_parity(g_root, g["g_root_" + tag], "g_root", row_scale=cond)
+    assert np.all(g_ang[:, [4, 9, 22, 27, 32]] == 0)
+
+
+def test_kat_tpose_and_bent(golden):
+    import dhfk
+    g = golden("kat")
+    bone = np.array([[.5, .5, .6, .6, .25, .25, .25, .2, .4, .4, .4, .4, .35, .35, .15]], np.float32)
+    w = dhfk.fk_world16(T(np.zeros((1, 33))), T(np.zeros((1, 3))), T(bone), T(np.zeros((1, 3))))
+    idx = [0, 1, 2, 3, 6, 7, 8, 12, 13, 15, 17, 18, 19, 25, 26, 27]
+    assert np.abs(w.cpu().numpy()[0] - g["tpose32"][idx]).max() < 1e-6
+    for pre in ("bent_", "bent2_"):
+        gg = {k[len(pre):]: v for k, v in g.items() if k.startswith(pre)}
+        world, cam, uv, *_ = run_fused(gg, False, "w")
+        assert_parity(world, gg["world16"], pre + "world16")
+        assert_parity(uv, gg["uv"], pre + "uv")
+
+
+@pytest.mark.parametrize("n", [1, 5, 95, 96, 97, 191, 193, 1000, 4608])
+def test_ragged_sizes_vs_c_oracle(c_oracle, n):
+    """Tile edges (96 rows per CTA), single pose, BASELINE cfg-4 size 512*9."""
+    import dhfk
+    from dhfk import synthetic, tables
+    inp = synthetic.gan_like(n, seed=100 + n)
+    up = synthetic.upstream_grads(n, seed=7 + n)
+    blk = tables.camera_block("S5", 1)
+    g = dict(inp, cam_block=blk, **up)
+    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, False, "wcu")
+    o = c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
+    b = c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"],
+                          g_cam=up["g_cam"], g_uv=up["g_uv"])
+    assert_parity(world, o["world16"], "world16"); assert_parity(cam, o["cam"], "cam"); assert_parity(uv, o["uv"], "uv")
+    assert_parity(g_ang, b["g_ang"], "g_ang"); assert_parity(g_grot, b["g_grot"], "g_grot")
+    assert_parity(g_root, b["g_root"], "g_root")
+
+
+def test_empty_batch():
+    import dhfk
+    w, c, u = dhfk.fk_project(T(np.zeros((0, 33))), T(np.zeros((0, 3))), T(np.zeros((0, 15))), T(np.zeros((0, 3))),
+                              np.zeros(16, np.float32))
+    assert w.shape == (0, 16, 3) and c.shape == (0, 16, 3) and u.shape == (0, 16, 2)
+
+
+def test_strided_views_and_bone_gradient(c_oracle):
+    """The generator hands FK column slices of one [N,37] tensor and root as a slice of [N,35]
+    (Fk_generator.py:126,179-186): non-packed rows take the gather path.  Also checks d/d(bone)."""
+    import dhfk
+    from dhfk import synthetic, tables
+    n = 333
+    inp = synthetic.gan_like(n, seed=21)
+    up = synthetic.upstream_grads(n, seed=22)
+    blk = tables.camera_block("S6", 2)
+    gen = torch.zeros(n, 37, device=dev())
+    gen[:, :33] = T(inp["ang"]); gen[:, 34:] = T(inp["grot"])
+    gen.requires_grad_(True)
+    netout = torch.zeros(n, 35, device=dev()); netout[:, -3:] = T(inp["root"]); netout.requires_grad_(True)
+    bone = T(inp["bone"], True)
+    world, cam, uv = dhfk.fk_project(gen[:, 0:33], gen[:, -3:], bone, netout[:, -3:], blk)
+    ((world * T(up["g_world"])).sum() + (uv * T(up["g_uv"])).sum()).backward()
+    o = c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
+    b = c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"], g_uv=up["g_uv"])
+    assert_parity(world.detach().cpu().numpy(), o["world16"], "world16")
+    assert_parity(uv.detach().cpu().numpy(), o["uv"], "uv")
+    gg = gen.grad.cpu().numpy()
+    assert_parity(gg[:, :33], b["g_ang"], "g_ang"); assert_parity(gg[:, 34:], b["g_grot"], "g_grot")
+    assert np.all(gg[:, 33] == 0)
+    assert_parity(netout.grad.cpu().numpy()[:, -3:], b["g_root"], "g_root")
+    assert_parity(bone.grad.cpu().numpy(), b["g_bone"], "g_bone")
+    # full [N,37] tensor passed directly (stride 37, 33 columns used)
+    w2 = dhfk.fk_world16(gen.detach(), gen.detach()[:, -3:], bone.detach(), netout.detach()[:, -3:])
+    assert torch.equal(w2, world.detach())
+
+
+def test_fk_only_and_no_cam_variants_agree():
+    import dhfk
+    from dhfk import synthetic, tables
+    inp = synthetic.gan_like(500, seed=5)
+    a, g, b, r = (T(inp[k]) for k in ("ang", "grot", "bone", "root"))
+    blk = tables.camera_block("S1", 0)
+    w0 = dhfk.fk_world16(a, g, b, r)
+    w1, c1, u1 = dhfk.fk_project(a, g, b, r, blk, return_cam=True)
+    w2, c2, u2 = dhfk.fk_project(a, g, b, r, blk, return_cam=False)
+    assert c2 is None and torch.equal(w0, w1) and torch.equal(w0, w2) and torch.equal(u1, u2)
+    # skeleton invariant: every bone keeps its length whatever the angles are
+    from dhfk.tables import used_16key_15bone_len_table
+    w = w0.cpu().numpy().astype(np.float64)
+    for bi, (i, j) in enumerate(used_16key_15bone_len_table):
+        L = np.linalg.norm(w[:, i] - w[:, j], axis=1)
+        assert np.abs(L - inp["bone"][:, bi]).max() < 2e-6, bi
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["poly", "mufu"])
+def test_full_size_1m_vs_c_oracle(c_oracle, fast):
+    """BASELINE config 2 size (1,048,576 poses): forward and backward against the float64 oracle on
+    every pose, plus size-independent properties (linearity of the backward in the upstream gradient,
+    root-translation equivariance)."""
+    import dhfk
+    from dhfk import synthetic, tables
+    n = 1 << 20
+    inp = synthetic.gan_like(n, seed=1234)
+    up = synthetic.upstream_grads(n, seed=4321)
+    blk = tables.camera_block("S1", 0)
+    g = dict(inp, cam_block=blk, **up)
+    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, fast, "wu")
+    o = c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
+    assert (np.abs(o["cam"][..., :2] / o["cam"][..., 2:]) < 1).all()     # in-volume roots: clamp inactive
+    e = [assert_parity(world, o["world16"], "world16"), assert_parity(cam, o["cam"], "cam"),
+         assert_parity(uv, o["uv"], "uv")]
+    b = c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"],
+                          g_uv=up["g_uv"], want_bone=False)
+    e += [assert_parity(g_ang, b["g_ang"], "g_ang"), assert_parity(g_grot, b["g_grot"], "g_grot"),
+          assert_parity(g_root, b["g_root"], "g_root")]
+    print("\n[1M %s] max rel err world/cam/uv/g_ang/g_grot/g_root = %s" % ("mufu" if fast else "poly",
+                                                                          " ".join("%.2e" % x for x in e)))
+    # linearity: backward(2*g) == 2*backward(g) bit-exactly (power-of-two scaling commutes with fp32 rounding)
+    g2 = dict(g, g_world=2 * up["g_world"], g_uv=2 * up["g_uv"])
+    *_, a2, r2, t2 = run_fused(g2, fast, "wu")
+    assert np.array_equal(a2, 2 * g_ang) and np.array_equal(r2, 2 * g_grot) and np.array_equal(t2, 2 * g_root)
+
+
+def test_stress_1m_clamp_active(c_oracle):
+    """1M poses with roots 10*tanh(randn): most poses leave the image (clamp active) or sit behind the
+    camera.  Forward must match everywhere; gradients are compared with the conditioning multiplier,
+    excluding points whose |x/z| is within 1e-5 of the clamp edge (the mask is discontinuous there)."""
+    import dhfk
+    from dhfk import synthetic, tables
+    n = 1 << 20
+    inp = synthetic.gan_like(n, seed=77, root_mode="generator", angle_mode="stress")
+    up = synthetic.upstream_grads(n, seed=78)
+    blk = tables.camera_block("S8", 3)
+    g = dict(inp, cam_block=blk, **up)
+    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, False, "wu")
+    o = c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
+    assert_parity(world, o["world16"], "world16"); assert_parity(cam, o["cam"], "cam")
+    ratio = np.abs(o["cam"][..., :2] / o["cam"][..., 2:])
+    assert (ratio > 1).mean() > 0.2
+    edge = (np.abs(ratio - 1) < 1e-5).any(axis=(1, 2))
+    cond = projection_conditioning(o["cam"])
+    ok = ~edge
+    assert ok.mean() > 0.999
+    assert_parity(uv[ok], o["uv"][ok], "uv", row_scale=np.sqrt(cond[ok]))
+    b = c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"],
+                          g_uv=up["g_uv"], want_bone=False)
+    assert_parity(g_ang[ok], b["g_ang"][ok], "g_ang", row_scale=cond[ok])
+    assert_parity(g_grot[ok], b["g_grot"][ok], "g_grot", row_scale=cond[ok])
+    assert_parity(g_root[ok], b["g_root"][ok], "g_root", row_scale=cond[ok])
+
+
+def test_host_pipeline_matches_device_path():
+    """dhfk_forward_backward_host (pinned host buffers, chunked copies) == device-resident path, bit-exact."""
+    import dhfk
+    from dhfk import synthetic, tables
+    n = 50000
+    inp = synthetic.gan_like(n, seed=9)
+    up = synthetic.upstream_grads(n, seed=10)
+    blk = tables.camera_block("S7", 0)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    res = dhfk.fk_project_host(pin(inp["ang"]), pin(inp["grot"]), pin(inp["bone"]), pin(inp["root"]), blk,
+                               pin(up["g_world"]), pin(up["g_uv"]), chunk_rows=8192, num_streams=3)
+    g = dict(inp, cam_block=blk, **up)
+    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, False, "wu")
+    assert np.array_equal(res["world"].numpy(), world) and np.array_equal(res["uv"].numpy(), uv)
+    assert np.array_equal(res["g_ang"].numpy(), g_ang) and np.array_equal(res["g_grot"].numpy(), g_grot)
+    assert np.array_equal(res["g_root"].numpy(), g_root)
