@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- augmented poses/sec of the fused DH-FK + projection forward+backward path.
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the hot path over one batch of synthetic poses: dhfk_forward
+(world16 + uv16) followed by dhfk_backward (d angles, d global rotation, d root from upstream
+gradients on world16 and uv16).  Workload = BASELINE.json configs[1]: 1,048,576 poses per GPU,
+S1/cam0, generator-range angles, template bone lengths x (1 +- 0.2), in-volume roots.
+Rows shard across ranks with no data-path collective (weak scaling: per-GPU batch fixed).
+
+Rank 0 prints ONE JSON line (keys: see the task contract).  `value` is device-resident
+throughput; `e2e` goes through the host-buffer C-ABI entry (pinned host memory in and out, copies
+inside the timed region); `roofline` is for the dominant kernel (backward); `cpu_baseline` is the
+torch port of the reference's own CPU path timed on this host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "augmented poses/sec (FK+proj fwd+bwd)"
+UNIT = "poses/s"
+FWD_BYTES = 536    # per pose: 54 floats in, 48 + 32 floats out           (SURVEY 8d / BASELINE.md 4)
+BWD_BYTES = 692    # per pose: 54 + 48 + 32 floats in, 33 + 3 + 3 floats out
+HBM_FALLBACK_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--poses", type=int, default=1 << 20, help="poses per GPU per step")
+    ap.add_argument("--fast-trig", action="store_true", help="MUFU sin/cos variant (DHFK_FLAG_FAST_TRIG)")
+    ap.add_argument("--buffers", type=int, default=4, help="rotating input buffer sets (L2 hygiene)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-chunk", type=int, default=1024, help="reference arm: poses per torch call")
+    ap.add_argument("--ref-chunks", type=int, default=4, help="reference arm: chunks per step")
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    cfg = {
+        "workload": "BASELINE configs[1]: fused DH-FK + projection forward+backward, 1M poses per B200, "
+                    "16-joint H36M skeleton, synthetic generator-range angles + template bone lengths, S1/cam0",
+        "poses_per_gpu": args.poses,
+        "outputs": "world16[N,16,3]+uv16[N,16,2]; grads d_ang[N,33]+d_grot[N,3]+d_root[N,3]",
+        "bytes_per_pose": {"forward": FWD_BYTES, "backward": BWD_BYTES},
+        "parallelism": "dp%d (rows sharded, no data-path collective)" % args.gpus,
+        "trig": "mufu" if args.fast_trig else "poly(~1ulp)",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock / throttle reasons while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz, self.err = [], set(), None, None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {
+                "nvmlClocksEventReasonSwPowerCap": "sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap": "sw_power_cap",
+                "nvmlClocksEventReasonHwSlowdown": "hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown": "hw_slowdown",
+                "nvmlClocksEventReasonSwThermalSlowdown": "sw_thermal_slowdown",
+                "nvmlClocksThrottleReasonSwThermalSlowdown": "sw_thermal_slowdown",
+                "nvmlClocksEventReasonHwThermalSlowdown": "hw_thermal_slowdown",
+                "nvmlClocksThrottleReasonHwThermalSlowdown": "hw_thermal_slowdown",
+                "nvmlClocksEventReasonHwPowerBrakeSlowdown": "hw_power_brake",
+                "nvmlClocksThrottleReasonHwPowerBrakeSlowdown": "hw_power_brake",
+            }
+            masks = {}
+            for attr, nm in names.items():
+                if hasattr(pynvml, attr):
+                    masks[int(getattr(pynvml, attr))] = nm
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop_evt.is_set():
+                self.samples.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for m, nm in masks.items():
+                    if r & m:
+                        self.reasons.add(nm)
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: report it rather than fail the bench
+            self.err = repr(e)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(2.0)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s), **({"error": self.err} if self.err else {})}
+
+
+def physical_gpu_index(local_index):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except Exception:
+            return local_index
+    return local_index
+
+
+# ---------------------------------------------------------------------------------------------------
+def time_torch_port(chunk, chunks, steps, warmup, threads=None):
+    """Reference arm / cpu_baseline: the torch port of the reference's own CPU path (oracle/torch_port.py,
+    bit-identical to the reference on the build host), forward + backward, `chunks` calls of `chunk` poses
+    per step.  Returns (poses_per_s, seconds_per_step, threads)."""
+    import numpy as np
+    import torch
+    import torch_port
+    from dhfk import synthetic, tables
+    if threads:
+        torch.set_num_threads(threads)
+    threads = torch.get_num_threads()
+    blk = tables.camera_block("S1", 0)
+    inp = synthetic.gan_like(chunk, seed=1234)
+    up = synthetic.upstream_grads(chunk, seed=4321)
+    ang, grot, bone, root = (torch.tensor(inp[k]) for k in ("ang", "grot", "bone", "root"))
+    gw, gu = torch.tensor(up["g_world"]), torch.tensor(up["g_uv"])
+
+    def one_step():
+        for _ in range(chunks):
+            a = ang.clone().requires_grad_(True); g = grot.clone().requires_grad_(True)
+            r = root.clone().requires_grad_(True)
+            _, w16, _, uv = torch_port.pipeline(a, g, bone, r, blk)
+            ((w16 * gw).sum() + (uv * gu).sum()).backward()
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return chunk * chunks / dt, dt, threads
+
+
+def time_c_oracle(n=131072):
+    """Extra context: the float64 C oracle (OpenMP, all cores) forward+backward."""
+    import c_oracle
+    from dhfk import synthetic, tables
+    inp = synthetic.gan_like(n, seed=1)
+    up = synthetic.upstream_grads(n, seed=2)
+    blk = tables.camera_block("S1", 0)
+    c_oracle.forward(inp["ang"][:1024], inp["grot"][:1024], inp["bone"][:1024], inp["root"][:1024], blk)
+    t0 = time.perf_counter()
+    c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
+    c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"], g_uv=up["g_uv"],
+                      want_bone=False)
+    dt = time.perf_counter() - t0
+    return n / dt, c_oracle.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    # bound the run: a step is ref_chunks x ref_chunk poses (~0.1 s per 1024-pose call on 8 cores)
+    pps, dt, threads = time_torch_port(args.ref_chunk, args.ref_chunks, steps, warmup)
+    sample = "%d x %d-pose torch calls per step (reference batch size), fwd+bwd, CPU" % (args.ref_chunks, args.ref_chunk)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, {"reference_arm": "oracle/torch_port.py: the reference's own torch op sequence "
+                                                           "(bit-identical to /root/reference on the build host), host cores only"}),
+        "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import dhfk
+    from dhfk import _cabi, synthetic, tables
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world_size > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = _cabi.load()
+    n = args.poses
+    flags = _cabi.FLAG_FAST_TRIG if args.fast_trig else 0
+    blk = tables.camera_block("S1", 0)
+    cam_ptr = blk.ctypes.data
+    nbuf = max(1, args.buffers)
+    sets = []
+    for b in range(nbuf):
+        d = synthetic.gan_like_torch(n, dev, seed=1234 + 97 * rank + b)
+        g = torch.Generator(device=dev).manual_seed(4321 + 97 * rank + b)
+        d["g_world"] = torch.randn((n, 16, 3), generator=g, device=dev)
+        d["g_uv"] = torch.randn((n, 16, 2), generator=g, device=dev)
+        sets.append(d)
+    world = torch.empty((n, 16, 3), device=dev); uv = torch.empty((n, 16, 2), device=dev)
+    g_ang = torch.empty((n, 33), device=dev); g_grot = torch.empty((n, 3), device=dev)
+    g_root = torch.empty((n, 3), device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    def fwd(d):
+        rc = lib.dhfk_forward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
+                              d["root"].data_ptr(), 3, cam_ptr, None, 0, world.data_ptr(), None, uv.data_ptr(),
+                              n, flags, sp)
+        _cabi.check(rc, "dhfk_forward")
+
+    def bwd(d):
+        rc = lib.dhfk_backward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
+                               d["root"].data_ptr(), 3, cam_ptr, None, 0, d["g_world"].data_ptr(), None,
+                               d["g_uv"].data_ptr(), g_ang.data_ptr(), 33, g_grot.data_ptr(), 3, g_root.data_ptr(), 3,
+                               None, 15, n, flags, sp)
+        _cabi.check(rc, "dhfk_backward")
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
+    for i in range(warmup):
+        fwd(sets[i % nbuf]); bwd(sets[i % nbuf])
+    barrier()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    barrier()
+    for i in range(steps):
+        d = sets[i % nbuf]
+        ev[i][0].record(stream); fwd(d)
+        ev[i][1].record(stream); bwd(d)
+        ev[i][2].record(stream)
+    torch.cuda.synchronize(dev)
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    barrier()
+    # keep the sampler fed if the timed region was shorter than a few polling periods
+    extension = False
+    if sampler and len(sampler.samples) < 10:
+        extension = True
+        t_end = time.time() + 1.0
+        i = 0
+        while time.time() < t_end:
+            fwd(sets[i % nbuf]); bwd(sets[i % nbuf]); i += 1
+            if i % 32 == 0:
+                torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.stop()
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+
+    t = torch.tensor([total_ms, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, fwd_ms, bwd_ms = (float(x) for x in t.tolist())
+    ms_per_step = total_ms / steps
+    value = n * world_size / (ms_per_step * 1e-3)
+
+    # ---- e2e through the host-buffer C-ABI entry (pinned host in/out, copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        hin = synthetic.gan_like(min(n, 1 << 16), seed=5 + rank)      # tile a 64k-pose draw to N (host RNG is slow)
+        rep = (n + hin["ang"].shape[0] - 1) // hin["ang"].shape[0]
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:n])).pin_memory()
+        h_ang, h_grot, h_bone, h_root = (pin(hin[k]) for k in ("ang", "grot", "bone", "root"))
+        up = synthetic.upstream_grads(min(n, 1 << 16), seed=6 + rank)
+        h_gw, h_gu = pin(up["g_world"]), pin(up["g_uv"])
+        out = {}
+        e2e_steps = max(3, min(steps, 10))
+        chunk = 1 << 16
+        for _ in range(2):
+            out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=4,
+                                       workspace=out.get("_workspace"), out=out, fast_trig=args.fast_trig)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=4,
+                                       workspace=out["_workspace"], out=out, fast_trig=args.fast_trig)
+        torch.cuda.synchronize(dev)
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if distributed:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        e2e = {"value": n * world_size / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * (FWD_BYTES - 320 + 320),
+               "d2h_bytes_per_step": n * (320 + 156), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "api": "dhfk.fk_project_host -> dhfk_forward_backward_host (pinned host buffers, %d-row chunks, 4 streams)" % chunk}
+
+    if distributed:
+        dist.barrier()
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = HBM_FALLBACK_GBS; peak_src = "fallback (B200_PROFILING.md)"
+    bwd_gbs = BWD_BYTES * n / (bwd_ms * 1e-3) / 1e9
+    fwd_gbs = FWD_BYTES * n / (fwd_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")     # written from an `ncu --set full` capture (per launch)
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dhfk_bwd_kernel_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, {"l2": "inputs rotate over %d buffer sets (%.1f GB per set) > 126 MB L2"
+                                                % (nbuf, n * (216 + 320) / 1e9)}),
+        "roofline": {"bound": "hbm", "kernel": "dhfk_bwd_kernel<GUV=1,GBONE=0>", "achieved": bwd_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                     "ms_per_launch": bwd_ms, "algorithmic_bytes_per_launch": BWD_BYTES * n},
+        "roofline_fwd": {"bound": "hbm", "kernel": "dhfk_fwd_kernel<CAM=0,UV=1>", "achieved": fwd_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
+                         "algorithmic_bytes_per_launch": FWD_BYTES * n},
+        "roofline_step": {"achieved": (FWD_BYTES + BWD_BYTES) * n / (ms_per_step * 1e-3) / 1e9, "peak": peak,
+                          "frac": (FWD_BYTES + BWD_BYTES) * n / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"},
+        "clocks": dict(sampler.summary(), window="timed region" + (" + 1 s extension of the same loop" if extension else "")),
+        "gpu_launches": 2 * steps,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        pps, dt, threads = time_torch_port(args.ref_chunk, 1, steps=10, warmup=2)
+        line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "10 x %d-pose torch calls (reference batch size), fwd+bwd, oracle/torch_port.py" % args.ref_chunk}
+        try:
+            cps, cthreads = time_c_oracle()
+            line["cpu_baseline_c"] = {"value": cps, "unit": UNIT, "cores": cthreads, "kind": "port",
+                                      "sample": "131072 poses fwd+bwd, oracle/dhfk_oracle.c (float64, OpenMP)"}
+        except Exception as e:
+            line["cpu_baseline_c"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,42 @@ struct BwdParams {
     CamConst cam;
 };
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier -------------------------------------
+// A full tile's inputs are fetched with ONE round trip: four slab copies issued by thread 0 and
+// (backward) one row copy per thread and gradient tensor, all completing on a single mbarrier.
+// Outputs leave the same way: each thread bulk-stores its own padded row(s); slabs by thread 0.
+DHFK_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DHFK_DI void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DHFK_DI void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DHFK_DI void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DHFK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DHFK_DONE;\n"
+        "bra DHFK_WAIT;\n"
+        "DHFK_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+DHFK_DI void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+DHFK_DI void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+                 "r"(bytes) : "memory");
+}
+DHFK_DI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DHFK_DI void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA)
+DHFK_DI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- shared <-> global staging -----------------------------------------------------------------
 // exact-image rows (row stride NCOLS in shared)
 template <int NCOLS>
@@ -201,17 +237,33 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
     float4* s_world = reinterpret_cast<float4*>(s_root + kTile * 3);
     float4* s_cam = s_world + kTile * kWorldRow4;
     float4* s_uv = s_cam + (CAM ? kTile * kWorldRow4 : 0);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_uv + (UV ? kTile * kUvRow4 : 0));
 
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kTile;
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
+    // full tile of packed, aligned rows: TMA bulk path; ragged last tile / strided views: gather path
+    const bool bulk = rows == kTile && p.ang.vec && p.grot.vec && p.bone.vec && p.root.vec;
 
-    stage_rows_in<33>(s_ang, p.ang, row0, rows);
-    stage_rows_in<3>(s_grot, p.grot, row0, rows);
-    stage_rows_in<15>(s_bone, p.bone, row0, rows);
-    stage_rows_in<3>(s_root, p.root, row0, rows);
-    __syncthreads();
+    if (bulk) {
+        if (tid == 0) mbar_init(s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(s_bar, kTile * 54 * 4);
+            bulk_g2s(s_ang, p.ang.p + row0 * 33, kTile * 33 * 4, s_bar);
+            bulk_g2s(s_bone, p.bone.p + row0 * 15, kTile * 15 * 4, s_bar);
+            bulk_g2s(s_grot, p.grot.p + row0 * 3, kTile * 3 * 4, s_bar);
+            bulk_g2s(s_root, p.root.p + row0 * 3, kTile * 3 * 4, s_bar);
+        }
+        mbar_wait(s_bar, 0);
+    } else {
+        stage_rows_in<33>(s_ang, p.ang, row0, rows);
+        stage_rows_in<3>(s_grot, p.grot, row0, rows);
+        stage_rows_in<15>(s_bone, p.bone, row0, rows);
+        stage_rows_in<3>(s_root, p.root, row0, rows);
+        __syncthreads();
+    }
 
     if (tid < rows) {
         FwdCtx<CAM, UV> ctx;
@@ -240,7 +292,17 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
         flush_chunks<3, 6>(wrow, ctx.w);
         if (CAM) flush_chunks<3, 6>(crow, ctx.cm);
         if (UV) flush_chunks<2, 4>(urow, ctx.uv);
+        if (bulk) {
+            // every thread ships its own rows: no CTA barrier, no cooperative copy loop
+            fence_proxy_async();
+            bulk_s2g(p.out_world + (row0 + tid) * 48, wrow, 48 * 4);
+            if (CAM) bulk_s2g(p.out_cam + (row0 + tid) * 48, crow, 48 * 4);
+            if (UV) bulk_s2g(p.out_uv + (row0 + tid) * 32, urow, 32 * 4);
+            bulk_commit();
+            bulk_wait_read_all();
+        }
     }
+    if (bulk) return;
     __syncthreads();
 
     stage_padded_out<kWorldChunks>(s_world, p.out_world, row0, rows);
@@ -315,20 +377,39 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
     const bool GW = p.g_world != nullptr, GCAM = p.g_cam != nullptr;
     float4* s_gc = s_gw + (GW ? kTile * kWorldRow4 : 0);
     float4* s_gu = s_gc + (GCAM ? kTile * kWorldRow4 : 0);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_gu + (GUV ? kTile * kUvRow4 : 0));
 
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kTile;
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
+    const bool bulk = rows == kTile && p.ang.vec && p.grot.vec && p.bone.vec && p.root.vec;
 
-    stage_rows_in<33>(s_ang, p.ang, row0, rows);
-    stage_rows_in<3>(s_grot, p.grot, row0, rows);
-    stage_rows_in<15>(s_bone, p.bone, row0, rows);
-    stage_rows_in<3>(s_root, p.root, row0, rows);
-    if (GW) stage_padded_in<kWorldChunks>(s_gw, p.g_world, row0, rows);
-    if (GCAM) stage_padded_in<kWorldChunks>(s_gc, p.g_cam, row0, rows);
-    if (GUV) stage_padded_in<kUvChunks>(s_gu, p.g_uv, row0, rows);
-    __syncthreads();
+    if (bulk) {
+        if (tid == 0) mbar_init(s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(s_bar, kTile * 4 * (54 + (GW ? 48 : 0) + (GCAM ? 48 : 0) + (GUV ? 32 : 0)));
+            bulk_g2s(s_ang, p.ang.p + row0 * 33, kTile * 33 * 4, s_bar);
+            bulk_g2s(s_bone, p.bone.p + row0 * 15, kTile * 15 * 4, s_bar);
+            bulk_g2s(s_grot, p.grot.p + row0 * 3, kTile * 3 * 4, s_bar);
+            bulk_g2s(s_root, p.root.p + row0 * 3, kTile * 3 * 4, s_bar);
+        }
+        // one row copy per thread into the padded rows (192 B / 128 B, 16-byte aligned both sides)
+        if (GW) bulk_g2s(s_gw + tid * kWorldRow4, p.g_world + (row0 + tid) * 48, 48 * 4, s_bar);
+        if (GCAM) bulk_g2s(s_gc + tid * kWorldRow4, p.g_cam + (row0 + tid) * 48, 48 * 4, s_bar);
+        if (GUV) bulk_g2s(s_gu + tid * kUvRow4, p.g_uv + (row0 + tid) * 32, 32 * 4, s_bar);
+        mbar_wait(s_bar, 0);
+    } else {
+        stage_rows_in<33>(s_ang, p.ang, row0, rows);
+        stage_rows_in<3>(s_grot, p.grot, row0, rows);
+        stage_rows_in<15>(s_bone, p.bone, row0, rows);
+        stage_rows_in<3>(s_root, p.root, row0, rows);
+        if (GW) stage_padded_in<kWorldChunks>(s_gw, p.g_world, row0, rows);
+        if (GCAM) stage_padded_in<kWorldChunks>(s_gc, p.g_cam, row0, rows);
+        if (GUV) stage_padded_in<kUvChunks>(s_gu, p.g_uv, row0, rows);
+        __syncthreads();
+    }
 
     if (tid < rows) {
         BwdCtx<GUV, GBONE> ctx;
@@ -357,6 +438,21 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         s_grot[tid * 3] = kDegToRad * tw.x;
         s_grot[tid * 3 + 1] = kDegToRad * fmaf(cx, tw.y, sx * tw.z);
         s_grot[tid * 3 + 2] = kDegToRad * fmaf(sy, tw.x, fmaf(-sx * cy, tw.y, cx * cy * tw.z));
+    }
+    const bool bulk_out = rows == kTile && p.g_ang.vec && p.g_grot.vec && p.g_root.vec && (!GBONE || p.g_bone.vec);
+    if (bulk_out) {
+        // results overwrote the input slabs in place; ship the four slabs with one thread
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(p.g_ang.p + row0 * 33, s_ang, kTile * 33 * 4);
+            bulk_s2g(p.g_grot.p + row0 * 3, s_grot, kTile * 3 * 4);
+            bulk_s2g(p.g_root.p + row0 * 3, s_root, kTile * 3 * 4);
+            if (GBONE) bulk_s2g(p.g_bone.p + row0 * 15, s_bone, kTile * 15 * 4);
+            bulk_commit();
+            bulk_wait_read_all();
+        }
+        return;
     }
     __syncthreads();
 

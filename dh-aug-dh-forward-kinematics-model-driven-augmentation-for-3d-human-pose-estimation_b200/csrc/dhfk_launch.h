@@ -14,11 +14,11 @@ int launch_bwd_trig1_bone1(const BwdParams& p, bool guv, cudaStream_t st, const 
 
 inline size_t fwd_smem_bytes(bool cam, bool uv) {
     return sizeof(float) * kTile * 54 +
-           sizeof(float4) * kTile * (kWorldRow4 * (1 + (cam ? 1 : 0)) + (uv ? kUvRow4 : 0));
+           sizeof(float4) * kTile * (kWorldRow4 * (1 + (cam ? 1 : 0)) + (uv ? kUvRow4 : 0)) + 16 /* mbarrier */;
 }
 inline size_t bwd_smem_bytes(bool gw, bool gcam, bool guv) {
     return sizeof(float) * kTile * 54 +
-           sizeof(float4) * kTile * (kWorldRow4 * ((gw ? 1 : 0) + (gcam ? 1 : 0)) + (guv ? kUvRow4 : 0));
+           sizeof(float4) * kTile * (kWorldRow4 * ((gw ? 1 : 0) + (gcam ? 1 : 0)) + (guv ? kUvRow4 : 0)) + 16 /* mbarrier */;
 }
 
 template <typename K, typename P>

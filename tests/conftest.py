@@ -38,16 +38,27 @@ def assert_parity(x, ref, what="", rtol=RTOL, row_scale=None):
     return e
 
 
-def projection_conditioning(cam_xyz, z_ok=0.5):
-    """Per-pose tolerance multiplier for gradients that pass through x/z.
+def projection_conditioning(cam_xyz, kind="grad"):
+    """Per-pose tolerance multiplier for quantities that pass through x/z (>= 1; exactly 1 for every
+    pose that is in front of the camera at a normal distance).
 
-    d(x/z)/dz = -x/z^2: when a joint is within `z_ok` metres of the camera plane (z -> 0, i.e. a pose
-    the generator placed *inside* the camera; only the 10*tanh(randn) root mode does that) fp32
-    rounding of z is amplified by (1/z)^2 and the REFERENCE's own fp32 gradient is only accurate to
-    ~1e-7*(|X|/z)^2 relative.  Those poses are held to 1e-5 * (z_ok/min|z|)^2; every pose with all
-    joints at least z_ok from the camera plane is held to the plain 1e-5 bound (multiplier 1)."""
-    z = np.abs(np.asarray(cam_xyz, dtype=np.float64)[..., 2]).min(axis=-1)
-    return np.maximum(1.0, (z_ok / np.maximum(z, 1e-12)) ** 2)
+    Camera-space coordinates carry an absolute fp32 rounding error of about eps*|X| (eps = 2^-23,
+    |X| = largest coordinate).  First-order propagation:
+        uv   = f(x/z):            error ~ eps * |X| / |z|          (per unclamped point)
+        grad ~ g/z, g*x/z^2:      error ~ eps * |X| / z^2          (relative to an O(1) gradient)
+    so a pose with a joint close to the camera plane (only the 10*tanh(randn) root mode produces
+    these: the generator places the skeleton *inside* the camera) is ill-conditioned for ANY fp32
+    implementation -- the reference's own torch result misses the float64 value by >1e-5 there
+    (e.g. stress pose 32104: |X| = 10.9 m, z = -0.44 m, reference error 1.7e-5).  Such poses are held
+    to 1e-5 * multiplier with
+        grad: max(1, 0.5 * |X|max / zmin^2)        uv: max(1, 0.2 * |X|max / zmin)
+    For the H36M set-up (|X| ~ 5 m, z ~ 5 m) both are 1 and the plain 1e-5 bound applies."""
+    c = np.abs(np.asarray(cam_xyz, dtype=np.float64))
+    zmin = np.maximum(c[..., 2].min(axis=-1), 1e-12)
+    xmax = c.max(axis=(-1, -2))
+    if kind == "uv":
+        return np.maximum(1.0, 0.2 * xmax / zmin)
+    return np.maximum(1.0, 0.5 * xmax / zmin ** 2)
 
 
 @pytest.fixture(scope="session")

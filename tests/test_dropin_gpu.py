@@ -91,7 +91,7 @@ def test_camera_functions_standalone(golden):
     uv = camera.project_to_2d(x, T(g["cam_rows9"]))
     assert_parity(uv.detach().cpu().numpy(), g["uv"], "uv")
     (uv * T(g["g_uv"])).sum().backward()
-    cond = projection_conditioning(g["x"], z_ok=1.0)
+    cond = projection_conditioning(g["x"])
     assert_parity(x.grad.cpu().numpy(), g["g_x"], "g_x", row_scale=cond)
     uv16 = camera.project_to_2d(T(g["x"]), T(g["cam_rows16"]))       # 16-column rows: only 9 are read
     assert torch.equal(uv16, uv.detach())

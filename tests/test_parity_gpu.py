@@ -180,8 +180,10 @@ def test_full_size_1m_vs_c_oracle(c_oracle, fast):
 
 def test_stress_1m_clamp_active(c_oracle):
     """1M poses with roots 10*tanh(randn): most poses leave the image (clamp active) or sit behind the
-    camera.  Forward must match everywhere; gradients are compared with the conditioning multiplier,
-    excluding points whose |x/z| is within 1e-5 of the clamp edge (the mask is discontinuous there)."""
+    camera.  Forward must match everywhere.  Gradients are compared with the conditioning multiplier;
+    poses with a point whose x/z sits on the clamp edge within fp32 resolution are excluded, because
+    torch.clamp's gradient mask is discontinuous there (an fp32 reference and a float64 oracle can
+    legitimately disagree about which side the point is on)."""
     import dhfk
     from dhfk import synthetic, tables
     n = 1 << 20
@@ -194,16 +196,23 @@ def test_stress_1m_clamp_active(c_oracle):
     assert_parity(world, o["world16"], "world16"); assert_parity(cam, o["cam"], "cam")
     ratio = np.abs(o["cam"][..., :2] / o["cam"][..., 2:])
     assert (ratio > 1).mean() > 0.2
-    edge = (np.abs(ratio - 1) < 1e-5).any(axis=(1, 2))
+    # fp32 resolution of x/z: camera coordinates (|X| <= ~25 m) carry ~2e-6 m absolute rounding error
+    band = 4e-6 * (1.0 + ratio) / np.abs(o["cam"][..., 2:])
+    edge = (np.abs(ratio - 1) < band).any(axis=(1, 2))
     cond = projection_conditioning(o["cam"])
     ok = ~edge
     assert ok.mean() > 0.999
-    assert_parity(uv[ok], o["uv"][ok], "uv", row_scale=np.sqrt(cond[ok]))
+    assert_parity(uv[ok], o["uv"][ok], "uv", row_scale=projection_conditioning(o["cam"], "uv")[ok])
     b = c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"],
                           g_uv=up["g_uv"], want_bone=False)
-    assert_parity(g_ang[ok], b["g_ang"][ok], "g_ang", row_scale=cond[ok])
-    assert_parity(g_grot[ok], b["g_grot"][ok], "g_grot", row_scale=cond[ok])
-    assert_parity(g_root[ok], b["g_root"][ok], "g_root", row_scale=cond[ok])
+    for name, x, ref in (("g_ang", g_ang, b["g_ang"]), ("g_grot", g_grot, b["g_grot"]), ("g_root", g_root, b["g_root"])):
+        err = (np.abs(x.astype(np.float64) - ref) / np.maximum(np.abs(ref), 1.0)).max(axis=1) / cond
+        err[~ok] = 0
+        worst = int(np.argmax(err))
+        assert np.isfinite(err).all() and err[worst] <= RTOL, (
+            "%s: worst pose %d scaled err %.3e (cond %.1f, min|z| %.4g, ratios %s)" % (
+                name, worst, err[worst], cond[worst], np.abs(o["cam"][worst, :, 2]).min(),
+                np.round(ratio[worst].ravel(), 6).tolist()))
 
 
 def test_host_pipeline_matches_device_path():
