@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdhfk.so")
+# DHFK_LIB_PATH selects an alternative build (A/B measurements of compile-time tunables)
+LIB_PATH = os.environ.get("DHFK_LIB_PATH") or os.path.join(_HERE, "lib", "libdhfk.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 ABI_VERSION = 1

@@ -61,6 +61,18 @@ struct BwdParams {
     CamConst cam;
 };
 
+// Tunables for A/B measurement (see profiles/): how padded rows enter / leave shared memory on the
+// bulk path and who waits on the mbarrier.
+#ifndef DHFK_ROWS_IN
+#define DHFK_ROWS_IN 1    // 0: one cp.async.bulk per row and thread, 1: 16-byte LDGSTS by all threads
+#endif
+#ifndef DHFK_ROWS_OUT
+#define DHFK_ROWS_OUT 1   // 0: one cp.async.bulk per row and thread, 1: cooperative LDS.128 -> STG.128
+#endif
+#ifndef DHFK_WAIT_ONE
+#define DHFK_WAIT_ONE 1   // 1: thread 0 waits on the mbarrier, the CTA waits on bar.sync (no spinning)
+#endif
+
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier -------------------------------------
 // A full tile's inputs are fetched with ONE round trip: four slab copies issued by thread 0 and
 // (backward) one row copy per thread and gradient tensor, all completing on a single mbarrier.
@@ -91,6 +103,23 @@ DHFK_DI void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* ba
 DHFK_DI void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
                  "r"(bytes) : "memory");
+}
+// Ampere-style 16-byte async copy (SASS LDGSTS) whose completion is tracked by an mbarrier
+DHFK_DI void ldgsts16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+DHFK_DI void ldgsts_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int CH>
+DHFK_DI void ldgsts_padded_rows(float4* s4, const float* gbase, long long row0) {
+    constexpr int RPI = kTile / CH;
+    const int tid = threadIdx.x;
+    const int r0 = tid / CH, c0 = tid - r0 * CH;
+    const float4* g4 = reinterpret_cast<const float4*>(gbase) + row0 * CH + r0 * CH + c0;
+    float4* d4 = s4 + r0 * (CH + 1) + c0;
+#pragma unroll
+    for (int m = 0; m < CH; ++m) ldgsts16(d4 + m * RPI * (CH + 1), g4 + m * RPI * CH);
 }
 DHFK_DI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DHFK_DI void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -256,7 +285,12 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
             bulk_g2s(s_grot, p.grot.p + row0 * 3, kTile * 3 * 4, s_bar);
             bulk_g2s(s_root, p.root.p + row0 * 3, kTile * 3 * 4, s_bar);
         }
+#if DHFK_WAIT_ONE
+        if (tid == 0) mbar_wait(s_bar, 0);
+        __syncthreads();
+#else
         mbar_wait(s_bar, 0);
+#endif
     } else {
         stage_rows_in<33>(s_ang, p.ang, row0, rows);
         stage_rows_in<3>(s_grot, p.grot, row0, rows);
@@ -292,7 +326,7 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
         flush_chunks<3, 6>(wrow, ctx.w);
         if (CAM) flush_chunks<3, 6>(crow, ctx.cm);
         if (UV) flush_chunks<2, 4>(urow, ctx.uv);
-        if (bulk) {
+        if (bulk && DHFK_ROWS_OUT == 0) {
             // every thread ships its own rows: no CTA barrier, no cooperative copy loop
             fence_proxy_async();
             bulk_s2g(p.out_world + (row0 + tid) * 48, wrow, 48 * 4);
@@ -302,7 +336,7 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
             bulk_wait_read_all();
         }
     }
-    if (bulk) return;
+    if (bulk && DHFK_ROWS_OUT == 0) return;
     __syncthreads();
 
     stage_padded_out<kWorldChunks>(s_world, p.out_world, row0, rows);
@@ -386,20 +420,40 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
     const bool bulk = rows == kTile && p.ang.vec && p.grot.vec && p.bone.vec && p.root.vec;
 
     if (bulk) {
+#if DHFK_ROWS_IN == 1
+        if (tid == 0) mbar_init(s_bar, 1 + kTile);   // thread 0's expect_tx arrive + one LDGSTS arrive per thread
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(s_bar, kTile * 4 * 54);
+#else
         if (tid == 0) mbar_init(s_bar, 1);
         __syncthreads();
         if (tid == 0) {
             mbar_arrive_expect_tx(s_bar, kTile * 4 * (54 + (GW ? 48 : 0) + (GCAM ? 48 : 0) + (GUV ? 32 : 0)));
+#endif
             bulk_g2s(s_ang, p.ang.p + row0 * 33, kTile * 33 * 4, s_bar);
             bulk_g2s(s_bone, p.bone.p + row0 * 15, kTile * 15 * 4, s_bar);
             bulk_g2s(s_grot, p.grot.p + row0 * 3, kTile * 3 * 4, s_bar);
             bulk_g2s(s_root, p.root.p + row0 * 3, kTile * 3 * 4, s_bar);
         }
+#if DHFK_ROWS_IN == 1
+        // padded gradient rows: coalesced 16-byte LDGSTS, completion counted on the same mbarrier
+        if (GW) ldgsts_padded_rows<kWorldChunks>(s_gw, p.g_world, row0);
+        if (GCAM) ldgsts_padded_rows<kWorldChunks>(s_gc, p.g_cam, row0);
+        if (GUV) ldgsts_padded_rows<kUvChunks>(s_gu, p.g_uv, row0);
+        ldgsts_arrive_noinc(s_bar);
+#else
         // one row copy per thread into the padded rows (192 B / 128 B, 16-byte aligned both sides)
         if (GW) bulk_g2s(s_gw + tid * kWorldRow4, p.g_world + (row0 + tid) * 48, 48 * 4, s_bar);
         if (GCAM) bulk_g2s(s_gc + tid * kWorldRow4, p.g_cam + (row0 + tid) * 48, 48 * 4, s_bar);
         if (GUV) bulk_g2s(s_gu + tid * kUvRow4, p.g_uv + (row0 + tid) * 32, 32 * 4, s_bar);
+#endif
+#if DHFK_WAIT_ONE
+        if (tid == 0) mbar_wait(s_bar, 0);
+        __syncthreads();
+#else
         mbar_wait(s_bar, 0);
+#endif
     } else {
         stage_rows_in<33>(s_ang, p.ang, row0, rows);
         stage_rows_in<3>(s_grot, p.grot, row0, rows);

@@ -56,7 +56,7 @@ def test_change_3d_joint_angle_like_the_generator_calls_it(golden, case, root_sh
     assert_parity(cam.detach().cpu().numpy(), g["cam"], "cam")
     assert_parity(uv.detach().cpu().numpy(), g["uv"], "uv")
     ((fake * T(g["g_world"])).sum() + (cam * T(g["g_cam"])).sum() + (uv * T(g["g_uv"])).sum()).backward()
-    cond = projection_conditioning(g["cam"])
+    cond = projection_conditioning(g["cam"], g["world16"], g["cam_block"], g["g_uv"])
     gg = gen.grad.cpu().numpy()
     assert_parity(gg[:, :33], g["g_ang_wcu"], "g_ang", row_scale=cond)
     assert_parity(gg[:, 34:], g["g_grot_wcu"], "g_grot", row_scale=cond)
@@ -91,7 +91,7 @@ def test_camera_functions_standalone(golden):
     uv = camera.project_to_2d(x, T(g["cam_rows9"]))
     assert_parity(uv.detach().cpu().numpy(), g["uv"], "uv")
     (uv * T(g["g_uv"])).sum().backward()
-    cond = projection_conditioning(g["x"])
+    cond = projection_conditioning(g["x"], g_uv=g["g_uv"])
     assert_parity(x.grad.cpu().numpy(), g["g_x"], "g_x", row_scale=cond)
     uv16 = camera.project_to_2d(T(g["x"]), T(g["cam_rows16"]))       # 16-column rows: only 9 are read
     assert torch.equal(uv16, uv.detach())

@@ -25,7 +25,7 @@ def test_c_oracle_backward_matches_reference_autograd(golden, c_oracle, case, ta
     g = golden(case)
     b = c_oracle.backward(g["ang"], g["grot"], g["bone"], g["root"], g["cam_block"], g_world=g["g_world"],
                           g_cam=g["g_cam"] if "c" in tag else None, g_uv=g["g_uv"] if "u" in tag else None)
-    cond = projection_conditioning(g["cam"]) if "u" in tag else None
+    cond = projection_conditioning(g["cam"], g["world16"], g["cam_block"], g["g_uv"]) if "u" in tag else None
     assert_parity(b["g_ang"], g["g_ang_" + tag], "g_ang", row_scale=cond)
     assert_parity(b["g_grot"], g["g_grot_" + tag], "g_grot", row_scale=cond)
     assert_parity(b["g_root"], g["g_root_" + tag], "g_root", row_scale=cond)
@@ -107,7 +107,7 @@ def test_torch_port_matches_reference(golden, case):
         assert_parity(x.detach().numpy(), g[name], name, rtol=2e-6)
     loss = (w16 * torch.tensor(g["g_world"])).sum() + (cam * torch.tensor(g["g_cam"])).sum() + (uv * torch.tensor(g["g_uv"])).sum()
     loss.backward()
-    cond = projection_conditioning(g["cam"])
+    cond = projection_conditioning(g["cam"], g["world16"], g["cam_block"], g["g_uv"])
     assert_parity(ang.grad.numpy(), g["g_ang_wcu"], "g_ang", rtol=2e-6, row_scale=cond)
     assert_parity(grot.grad.numpy(), g["g_grot_wcu"], "g_grot", rtol=2e-6, row_scale=cond)
     assert_parity(root.grad.numpy(), g["g_root_wcu"], "g_root", rtol=2e-6, row_scale=cond)

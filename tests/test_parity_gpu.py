@@ -55,7 +55,7 @@ def test_forward_matches_reference_golden(golden, case, fast):
 def test_backward_matches_reference_autograd(golden, case, tag, fast):
     g = golden(case)
     *_, g_ang, g_grot, g_root = run_fused(g, fast, tag)
-    cond = projection_conditioning(g["cam"]) if "u" in tag else None
+    cond = projection_conditioning(g["cam"], g["world16"], g["cam_block"], g["g_uv"]) if "u" in tag else None
     assert_parity(g_ang, g["g_ang_" + tag], "g_ang", row_scale=cond)
     assert_parity(g_grot, g["g_grot_" + tag], "g_grot", row_scale=cond)
     assert_parity(g_root, g["g_root_" + tag], "g_root", row_scale=cond)
@@ -199,10 +199,10 @@ def test_stress_1m_clamp_active(c_oracle):
     # fp32 resolution of x/z: camera coordinates (|X| <= ~25 m) carry ~2e-6 m absolute rounding error
     band = 4e-6 * (1.0 + ratio) / np.abs(o["cam"][..., 2:])
     edge = (np.abs(ratio - 1) < band).any(axis=(1, 2))
-    cond = projection_conditioning(o["cam"])
+    cond = projection_conditioning(o["cam"], o["world16"], blk, up["g_uv"])
     ok = ~edge
     assert ok.mean() > 0.999
-    assert_parity(uv[ok], o["uv"][ok], "uv", row_scale=projection_conditioning(o["cam"], "uv")[ok])
+    assert_parity(uv[ok], o["uv"][ok], "uv", row_scale=projection_conditioning(o["cam"], o["world16"], blk, kind="uv")[ok])
     b = c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"],
                           g_uv=up["g_uv"], want_bone=False)
     for name, x, ref in (("g_ang", g_ang, b["g_ang"]), ("g_grot", g_grot, b["g_grot"]), ("g_root", g_root, b["g_root"])):
