@@ -69,6 +69,15 @@ struct BwdParams {
 #ifndef DHFK_ROWS_OUT
 #define DHFK_ROWS_OUT 1   // 0: one cp.async.bulk per row and thread, 1: cooperative LDS.128 -> STG.128
 #endif
+// L2 prefetch distance in tiles (148 SMs x 4 resident CTAs = one resident wave); 0 = off.
+// Measured (profiles/r1_ab_staging.md): forward 0.110 -> 0.098 ms; backward unchanged/slightly worse
+// (it is issue / i-cache bound, not load-latency bound), so it stays off there.
+#ifndef DHFK_PREFETCH_TILES_FWD
+#define DHFK_PREFETCH_TILES_FWD 592
+#endif
+#ifndef DHFK_PREFETCH_TILES_BWD
+#define DHFK_PREFETCH_TILES_BWD 0
+#endif
 #ifndef DHFK_WAIT_ONE
 #define DHFK_WAIT_ONE 1   // 1: thread 0 waits on the mbarrier, the CTA waits on bar.sync (no spinning)
 #endif
@@ -120,6 +129,10 @@ DHFK_DI void ldgsts_padded_rows(float4* s4, const float* gbase, long long row0) 
     float4* d4 = s4 + r0 * (CH + 1) + c0;
 #pragma unroll
     for (int m = 0; m < CH; ++m) ldgsts16(d4 + m * RPI * (CH + 1), g4 + m * RPI * CH);
+}
+// L2 prefetch of a contiguous global range (multiple of 16 bytes, 16-byte aligned)
+DHFK_DI void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 DHFK_DI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DHFK_DI void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -284,6 +297,15 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
             bulk_g2s(s_bone, p.bone.p + row0 * 15, kTile * 15 * 4, s_bar);
             bulk_g2s(s_grot, p.grot.p + row0 * 3, kTile * 3 * 4, s_bar);
             bulk_g2s(s_root, p.root.p + row0 * 3, kTile * 3 * 4, s_bar);
+#if DHFK_PREFETCH_TILES_FWD > 0
+            const long long rowp = row0 + (long long)DHFK_PREFETCH_TILES_FWD * kTile;
+            if (rowp + kTile <= p.n) {   // the CTA one resident wave later finds its slabs in L2
+                bulk_prefetch_l2(p.ang.p + rowp * 33, kTile * 33 * 4);
+                bulk_prefetch_l2(p.bone.p + rowp * 15, kTile * 15 * 4);
+                bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
+                bulk_prefetch_l2(p.root.p + rowp * 3, kTile * 3 * 4);
+            }
+#endif
         }
 #if DHFK_WAIT_ONE
         if (tid == 0) mbar_wait(s_bar, 0);
@@ -435,6 +457,18 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
             bulk_g2s(s_bone, p.bone.p + row0 * 15, kTile * 15 * 4, s_bar);
             bulk_g2s(s_grot, p.grot.p + row0 * 3, kTile * 3 * 4, s_bar);
             bulk_g2s(s_root, p.root.p + row0 * 3, kTile * 3 * 4, s_bar);
+#if DHFK_PREFETCH_TILES_BWD > 0
+            const long long rowp = row0 + (long long)DHFK_PREFETCH_TILES_BWD * kTile;
+            if (rowp + kTile <= p.n) {
+                bulk_prefetch_l2(p.ang.p + rowp * 33, kTile * 33 * 4);
+                bulk_prefetch_l2(p.bone.p + rowp * 15, kTile * 15 * 4);
+                bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
+                bulk_prefetch_l2(p.root.p + rowp * 3, kTile * 3 * 4);
+                if (GW) bulk_prefetch_l2(p.g_world + rowp * 48, kTile * 48 * 4);
+                if (GCAM) bulk_prefetch_l2(p.g_cam + rowp * 48, kTile * 48 * 4);
+                if (GUV) bulk_prefetch_l2(p.g_uv + rowp * 32, kTile * 32 * 4);
+            }
+#endif
         }
 #if DHFK_ROWS_IN == 1
         // padded gradient rows: coalesced 16-byte LDGSTS, completion counted on the same mbarrier
