@@ -113,6 +113,50 @@ DHFK_DI void sincos_deg(float deg, float& s, float& c) {
     }
 }
 
+// Same with a runtime quadrant offset (used by the shared limb routine).
+template <int TRIG>
+DHFK_DI void sincos_deg_rt(float deg, int q0, float& s, float& c) {
+    const float kMagic = 12582912.0f;
+    if (TRIG == TRIG_ACCURATE) {
+        float t = fmaf(deg, 1.0f / 90.0f, kMagic);
+        int n = __float_as_int(t) + q0;
+        float q = t - kMagic;
+        float r = fmaf(q, -90.0f, deg);
+        float r2 = r * r;
+        constexpr double D = 3.14159265358979323846 / 180.0;
+        constexpr float S0 = (float)D;
+        constexpr float S1 = (float)(-1.6666654611e-1 * D * D * D);
+        constexpr float S2 = (float)(8.3321608736e-3 * D * D * D * D * D);
+        constexpr float S3 = (float)(-1.9515295891e-4 * D * D * D * D * D * D * D);
+        constexpr float C1 = (float)(-0.5 * D * D);
+        constexpr float C2 = (float)(4.166664568298827e-2 * D * D * D * D);
+        constexpr float C3 = (float)(-1.388731625493765e-3 * D * D * D * D * D * D);
+        constexpr float C4 = (float)(2.443315711809948e-5 * D * D * D * D * D * D * D * D);
+        float ps = fmaf(r2, S3, S2);
+        ps = fmaf(r2, ps, S1);
+        ps = fmaf(r2, ps, S0);
+        float sv = r * ps;
+        float pc = fmaf(r2, C4, C3);
+        pc = fmaf(r2, pc, C2);
+        pc = fmaf(r2, pc, C1);
+        float cv = fmaf(r2, pc, 1.0f);
+        bool odd = (n & 1) != 0;
+        float so = odd ? cv : sv;
+        float co = odd ? sv : cv;
+        s = __int_as_float(__float_as_int(so) ^ ((n << 30) & 0x80000000));
+        c = __int_as_float(__float_as_int(co) ^ (((n + 1) << 30) & 0x80000000));
+    } else {
+        // the reference itself forms fl(theta0 + angle) in fp32 before sin/cos (:601 etc.)
+        float d2 = fmaf(90.0f, (float)q0, deg);
+        float t = fmaf(d2, 1.0f / 360.0f, kMagic);
+        float q = t - kMagic;
+        float r = fmaf(q, -360.0f, d2);
+        float x = r * kDegToRad;
+        s = __sinf(x);
+        c = __cosf(x);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // DH joint step.  T_j = Rot_x(alpha) Trans_x(a) Rot_z(theta) Trans_z(d) (modified DH,
 // forward_kinematics_DH_model.py:99-114):  W_j = W_parent * T_j, i.e.
@@ -250,17 +294,110 @@ DHFK_DI void fwd_walk(Frame F, Ctx& ctx) {
 // ---------------------------------------------------------------------------------------
 template <int TRIG, int J, class Ctx> DHFK_DI Wrench bwd_walk(Frame F, Ctx& ctx);
 
+// Limb descriptors live in constant memory: the limb loop index is warp-uniform, so they are read
+// through the uniform datapath.
+static __constant__ LimbDesc c_limbs[NLIMB] = {make_limb(0), make_limb(1), make_limb(2), make_limb(3)};
+
+// One 5-joint limb, forward then reverse.  B = parent frame with the limb's alpha0 twist folded in.
+// Extra Ctx members used:  V3 upstream_rt(int k, V3 origin)
+template <int TRIG, class Ctx>
+DHFK_DI Wrench bwd_limb(const Frame& B, const LimbDesc& L, Ctx& ctx) {
+    const float* ang = ctx.ang + L.ang0;
+    const float sg = L.sigma;
+    float s, c;
+    // joint 0: hip / shoulder offset along parent x, rotation about B.Z
+    const V3 o0 = axpy(L.sgn0 * ctx.bone[L.b0], B.X, B.O);
+    const V3 g0 = ctx.upstream_rt(L.k0, o0);
+    sincos_deg_rt<TRIG>(ang[0], L.q0, s, c);
+    const V3 X1 = axpy(s, B.Y, scale(c, B.X));
+    const V3 Y1 = axpy(c, B.Y, scale(-s, B.X));
+    // joint 1: alpha = sigma*90  =>  y' = sigma z_p, z' = -sigma y_p
+    const V3 zj1 = scale(-sg, Y1);
+    sincos_deg_rt<TRIG>(ang[1], -1, s, c);
+    const V3 X2 = axpy(s * sg, B.Z, scale(c, X1));
+    const V3 Y2 = axpy(c * sg, B.Z, scale(-s, X1));
+    // joint 2: same twist
+    const V3 zj2 = scale(-sg, Y2);
+    sincos_deg_rt<TRIG>(ang[2], L.q2, s, c);
+    const V3 X3 = axpy(s * sg, zj1, scale(c, X2));
+    const V3 Y3 = axpy(c * sg, zj1, scale(-s, X2));
+    // joint 3: knee / elbow, alpha 0, axis zj2
+    const V3 o3 = axpy(ctx.bone[L.b3], X3, o0);
+    const V3 g3 = ctx.upstream_rt(L.k0 + 1, o3);
+    sincos_deg_rt<TRIG>(ang[3], 0, s, c);
+    const V3 X4 = axpy(s, Y3, scale(c, X3));
+    // joint 4: foot / wrist, leaf
+    const V3 o4 = axpy(ctx.bone[L.b4], X4, o3);
+    const V3 g4 = ctx.upstream_rt(L.k0 + 2, o4);
+    // reverse sweep
+    Wrench w;
+    w.F = g4;
+    w.M = cross(o4, g4);
+    ctx.grad_angle(L.ang0 + 4, 0.f);
+    ctx.grad_angle(L.ang0 + 3, kDegToRad * dot(zj2, sub_cross(w.M, o3, w.F)));
+    if (Ctx::kBoneGrad) ctx.grad_bone(L.b4, dot(X4, w.F));
+    w.F = w.F + g3;
+    w.M = add_cross(w.M, o3, g3);
+    if (Ctx::kBoneGrad) ctx.grad_bone(L.b3, dot(X3, w.F));
+    const V3 tau = sub_cross(w.M, o0, w.F);
+    ctx.grad_angle(L.ang0 + 2, kDegToRad * dot(zj2, tau));
+    ctx.grad_angle(L.ang0 + 1, kDegToRad * dot(zj1, tau));
+    ctx.grad_angle(L.ang0, kDegToRad * dot(B.Z, tau));
+    w.F = w.F + g0;
+    w.M = add_cross(w.M, o0, g0);
+    if (Ctx::kBoneGrad) ctx.grad_bone(L.b0, L.sgn0 * dot(B.X, w.F));
+    return w;
+}
+
+// All four limbs in ONE non-unrolled loop (called where the arms branch off the body; the legs, which
+// hang off the chain origin, ride along so that the limb code exists exactly once).  Returns the
+// arms' wrench; the legs' wrench is left in ctx.legs.
+template <int TRIG, class Ctx>
+DHFK_DI Wrench bwd_all_limbs(const Frame& P /*frame of the arms' parent joint*/, Ctx& ctx) {
+    Frame A = P;            // arms: alpha0 = -90 folded into the base frame (y' = -z, z' = y)
+    A.Y = -P.Z;
+    A.Z = P.Y;
+    const Frame I = identity_frame();
+    Wrench arms, legs;
+    arms.F = arms.M = legs.F = legs.M = v3(0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int l = 0; l < NLIMB; ++l) {
+        const bool arm = l >= 2;
+        Frame B;
+        B.X = arm ? A.X : I.X; B.Y = arm ? A.Y : I.Y; B.Z = arm ? A.Z : I.Z; B.O = arm ? A.O : I.O;
+        const Wrench w = bwd_limb<TRIG>(B, c_limbs[l], ctx);
+        if (arm) { arms.F = arms.F + w.F; arms.M = arms.M + w.M; }
+        else { legs.F = legs.F + w.F; legs.M = legs.M + w.M; }
+    }
+    ctx.legs = legs;
+    return arms;
+}
+
+// children of joint J from index I on; limb roots are routed to the shared limb loop
+template <int TRIG, int J, int I, bool HAVE, class Ctx>
+DHFK_DI Wrench bwd_children_acc(const Frame& F, Ctx& ctx, Wrench acc) {
+    constexpr int C = nth_child(J, I);
+    if constexpr (C < 0) {
+        static_assert(HAVE, "joint without children reached bwd_children_acc");
+        return acc;
+    } else {
+        constexpr int LIMB = limb_of_root(C);
+        if constexpr (LIMB == 3) {   // second arm: handled together with the first
+            return bwd_children_acc<TRIG, J, I + 1, HAVE>(F, ctx, acc);
+        } else {
+            Wrench w;
+            if constexpr (LIMB == 2) w = bwd_all_limbs<TRIG>(F, ctx);
+            else w = bwd_walk<TRIG, C>(F, ctx);
+            if constexpr (HAVE) { w.F = acc.F + w.F; w.M = acc.M + w.M; }
+            return bwd_children_acc<TRIG, J, I + 1, true>(F, ctx, w);
+        }
+    }
+}
 template <int TRIG, int J, int I, class Ctx>
 DHFK_DI Wrench bwd_children(const Frame& F, Ctx& ctx) {
-    constexpr int C = nth_child(J, I);
-    static_assert(C >= 0, "bwd_children called past the last child");
-    Wrench w = bwd_walk<TRIG, C>(F, ctx);
-    if constexpr (nth_child(J, I + 1) >= 0) {
-        Wrench r = bwd_children<TRIG, J, I + 1>(F, ctx);
-        w.F = w.F + r.F;
-        w.M = w.M + r.M;
-    }
-    return w;
+    Wrench zero;
+    zero.F = zero.M = v3(0.f, 0.f, 0.f);
+    return bwd_children_acc<TRIG, J, I, false>(F, ctx, zero);
 }
 template <int TRIG, int J, class Ctx>
 DHFK_DI Wrench bwd_walk(Frame F, Ctx& ctx) {

@@ -1,16 +1,15 @@
 // dhfk_kernels.cuh -- fused DH-FK + global rotation + world->camera + pinhole projection,
-// forward and analytic backward, for sm_100a.  One thread per pose, 96 poses per CTA.
+// forward and analytic backward, for sm_100a.  One thread per pose, one warp (32 poses) per CTA.
 //
 // Data movement (see DESIGN.md "HBM layout"):
-//   inputs  [N,33] [N,3] [N,15] [N,3] are AoS rows with odd lengths.  A tile of 96 rows of each
-//           is one contiguous, 16-byte aligned slab; the CTA copies it to shared memory with
-//           coalesced 128-bit loads (exact image, odd row stride => conflict-free per-thread
+//   inputs  [N,33] [N,3] [N,15] [N,3] are AoS rows with odd lengths.  A tile of 32 rows of each
+//           is one contiguous, 16-byte aligned slab; lane 0 fetches the four slabs with TMA bulk
+//           copies (exact image in shared memory, odd row stride => conflict-free per-thread
 //           scalar reads).
 //   outputs [N,16,3] / [N,16,2] (and upstream gradients in the backward) have 48 / 32 float
 //           rows; they are staged in shared memory with the row stride padded to 13 / 9
 //           16-byte chunks so that both the per-thread 128-bit accesses and the cooperative
-//           coalesced 128-bit global accesses are bank-conflict free.  With 96 threads the
-//           cooperative copy needs no index arithmetic (96 = 8*12 = 12*8).
+//           coalesced 128-bit global accesses (LDGSTS in, STG out) are bank-conflict free.
 //   backward results d(ang), d(grot), d(root), d(bone) overwrite the input slabs in place and
 //           leave through the same coalesced path.
 #pragma once
@@ -21,16 +20,24 @@
 
 namespace dhfk {
 
-constexpr int kTile = 96;        // poses (threads) per CTA
+constexpr int kTile = 32;        // poses per CTA: exactly one warp, so every barrier is a __syncwarp
 constexpr int kWorldChunks = 12; // 48 floats
 constexpr int kUvChunks = 8;     // 32 floats
-constexpr int kWorldRow4 = kWorldChunks + 1;  // padded row stride in float4
+constexpr int kWorldRow4 = kWorldChunks + 1;  // padded row stride in float4 (odd => conflict-free 128-bit access)
 constexpr int kUvRow4 = kUvChunks + 1;
 
-static_assert(kTile % kWorldChunks == 0 && kTile % kUvChunks == 0, "tile must tile both row shapes");
-static_assert(kTile % 4 == 0, "tile slabs must stay 16-byte aligned");
+static_assert(kTile == 32, "the kernels assume one warp per tile");
 static_assert(nth_child(-1, 0) == 0 && nth_child(-1, 1) == 5 && nth_child(-1, 2) == 10 &&
               nth_child(-1, 3) == -1, "chain roots are joints 0, 5, 10");
+
+// Tunables for A/B measurement (profiles/r1_ab_staging.md).
+// L2 prefetch distance in tiles (148 SMs x 12 resident warps = one resident wave); 0 = off.
+#ifndef DHFK_PREFETCH_TILES_FWD
+#define DHFK_PREFETCH_TILES_FWD 1776
+#endif
+#ifndef DHFK_PREFETCH_TILES_BWD
+#define DHFK_PREFETCH_TILES_BWD 0
+#endif
 
 struct RowSrc {
     const float* p;
@@ -61,31 +68,14 @@ struct BwdParams {
     CamConst cam;
 };
 
-// Tunables for A/B measurement (see profiles/): how padded rows enter / leave shared memory on the
-// bulk path and who waits on the mbarrier.
-#ifndef DHFK_ROWS_IN
-#define DHFK_ROWS_IN 1    // 0: one cp.async.bulk per row and thread, 1: 16-byte LDGSTS by all threads
-#endif
-#ifndef DHFK_ROWS_OUT
-#define DHFK_ROWS_OUT 1   // 0: one cp.async.bulk per row and thread, 1: cooperative LDS.128 -> STG.128
-#endif
-// L2 prefetch distance in tiles (148 SMs x 4 resident CTAs = one resident wave); 0 = off.
-// Measured (profiles/r1_ab_staging.md): forward 0.110 -> 0.098 ms; backward unchanged/slightly worse
-// (it is issue / i-cache bound, not load-latency bound), so it stays off there.
-#ifndef DHFK_PREFETCH_TILES_FWD
-#define DHFK_PREFETCH_TILES_FWD 592
-#endif
-#ifndef DHFK_PREFETCH_TILES_BWD
-#define DHFK_PREFETCH_TILES_BWD 0
-#endif
-#ifndef DHFK_WAIT_ONE
-#define DHFK_WAIT_ONE 1   // 1: thread 0 waits on the mbarrier, the CTA waits on bar.sync (no spinning)
-#endif
-
-// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier -------------------------------------
-// A full tile's inputs are fetched with ONE round trip: four slab copies issued by thread 0 and
-// (backward) one row copy per thread and gradient tensor, all completing on a single mbarrier.
-// Outputs leave the same way: each thread bulk-stores its own padded row(s); slabs by thread 0.
+// ---- asynchronous staging: LDGSTS in, TMA bulk (UBLKCP) out, TMA L2 prefetch ---------------------
+// A full tile's inputs are fetched with ONE round trip: every lane issues its share of coalesced
+// 16-byte LDGSTS (cp.async) for the four input slabs and the padded gradient rows, then blocks on
+// cp.async.wait_all -- a scoreboard wait that costs no issue slots.  Measured alternatives
+// (profiles/r1_ab_staging.md): TMA bulk loads completing on an mbarrier need a try_wait loop, which
+// with one waiter per warp doubled the executed instructions; one cp.async.bulk per row was 25 %
+// slower (the TMA unit serialises small requests).  TMA is kept where no wait loop is needed:
+// bulk stores of the result slabs and L2 prefetch of the next wave's inputs.
 DHFK_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 DHFK_DI void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -94,16 +84,25 @@ DHFK_DI void mbar_init(uint64_t* bar, uint32_t count) {
 DHFK_DI void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Wait without burning issue slots: try_wait with a suspend-time hint lets the hardware park the
+// thread; if it still returns early, back off with nanosleep instead of polling (a bare try_wait
+// loop was measured to DOUBLE the kernel's executed instructions -- profiles/r1_prof_v4).
 DHFK_DI void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "DHFK_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DHFK_DONE;\n"
-        "bra DHFK_WAIT;\n"
-        "DHFK_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(4000u)
+            : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
 }
 DHFK_DI void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -113,24 +112,6 @@ DHFK_DI void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
                  "r"(bytes) : "memory");
 }
-// Ampere-style 16-byte async copy (SASS LDGSTS) whose completion is tracked by an mbarrier
-DHFK_DI void ldgsts16(void* sdst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
-}
-DHFK_DI void ldgsts_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-template <int CH>
-DHFK_DI void ldgsts_padded_rows(float4* s4, const float* gbase, long long row0) {
-    constexpr int RPI = kTile / CH;
-    const int tid = threadIdx.x;
-    const int r0 = tid / CH, c0 = tid - r0 * CH;
-    const float4* g4 = reinterpret_cast<const float4*>(gbase) + row0 * CH + r0 * CH + c0;
-    float4* d4 = s4 + r0 * (CH + 1) + c0;
-#pragma unroll
-    for (int m = 0; m < CH; ++m) ldgsts16(d4 + m * RPI * (CH + 1), g4 + m * RPI * CH);
-}
-// L2 prefetch of a contiguous global range (multiple of 16 bytes, 16-byte aligned)
 DHFK_DI void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
@@ -138,31 +119,70 @@ DHFK_DI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "mem
 DHFK_DI void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA)
 DHFK_DI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+DHFK_DI void ldgsts16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+DHFK_DI void ldgsts_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-// ---- shared <-> global staging -----------------------------------------------------------------
-// exact-image rows (row stride NCOLS in shared)
+// ---- shared <-> global staging (all warp-wide; lane = threadIdx.x) -------------------------------
+// Full-tile padded rows: the warp walks the tile's 32*CH 16-byte chunks in global order (512 B per
+// instruction, fully coalesced); chunk i lives in shared at row i/CH, column i%CH of a (CH+1)-chunk
+// padded row.  (row, col) advance incrementally: no division in the loop.
+template <int CH, class F>
+DHFK_DI void for_each_tile_chunk(F&& f) {
+    const int lane = threadIdx.x;
+    int r = lane / CH, c = lane - r * CH;
+#pragma unroll
+    for (int m = 0; m < CH; ++m) {
+        f(m * 32 + lane, r * (CH + 1) + c);
+        c += 32 % CH;
+        r += 32 / CH;
+        if (c >= CH) { c -= CH; r += 1; }
+    }
+}
+template <int CH>
+DHFK_DI void ldgsts_padded_tile(float4* s4, const float* gbase, long long row0) {
+    const float4* g4 = reinterpret_cast<const float4*>(gbase) + row0 * CH;
+    for_each_tile_chunk<CH>([&](int gi, int si) { ldgsts16(s4 + si, g4 + gi); });
+}
+// exact-image slab of kTile rows x NCOLS floats (contiguous, 16-byte aligned): coalesced LDGSTS
+template <int NCOLS>
+DHFK_DI void ldgsts_slab(float* s, const float* g) {
+    constexpr int NV = kTile * NCOLS / 4;
+    static_assert(kTile * NCOLS % 4 == 0, "slab must be a whole number of 16-byte chunks");
+    const int lane = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < (NV + 31) / 32; ++k) {
+        const int i = lane + 32 * k;
+        if (NV % 32 == 0 || i < NV)
+            ldgsts16(reinterpret_cast<float4*>(s) + i, reinterpret_cast<const float4*>(g) + i);
+    }
+}
+// block until every cp.async (LDGSTS) this thread issued has landed: a scoreboard wait, no polling
+DHFK_DI void ldgsts_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int CH>
+DHFK_DI void store_padded_tile(const float4* s4, float* gbase, long long row0) {
+    float4* g4 = reinterpret_cast<float4*>(gbase) + row0 * CH;
+    for_each_tile_chunk<CH>([&](int gi, int si) { __stcs(g4 + gi, s4[si]); });
+}
+
+// Generic (ragged last tile, strided / unaligned views) paths: plain loads and stores.
 template <int NCOLS>
 DHFK_DI void stage_rows_in(float* s, const RowSrc& src, long long row0, int rows) {
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x;
     const float* g = src.p + row0 * src.stride;
+    const int nfl = rows * NCOLS;
     if (src.vec) {
+        const int nv = nfl >> 2;
         const float4* g4 = reinterpret_cast<const float4*>(g);
         float4* s4 = reinterpret_cast<float4*>(s);
-        if (rows == kTile) {
-            constexpr int NV = kTile * NCOLS / 4;
-#pragma unroll
-            for (int k = 0; k < (NV + kTile - 1) / kTile; ++k) {
-                int i = tid + k * kTile;
-                if (i < NV) s4[i] = __ldcs(g4 + i);
-            }
-        } else {
-            const int nfl = rows * NCOLS, nv = nfl >> 2;
-            for (int i = tid; i < nv; i += kTile) s4[i] = __ldcs(g4 + i);
-            for (int i = (nv << 2) + tid; i < nfl; i += kTile) s[i] = __ldcs(g + i);
-        }
+        for (int i = lane; i < nv; i += kTile) s4[i] = __ldcs(g4 + i);
+        for (int i = (nv << 2) + lane; i < nfl; i += kTile) s[i] = __ldcs(g + i);
     } else {
-        const int nfl = rows * NCOLS;
-        for (int i = tid; i < nfl; i += kTile) {
+        for (int i = lane; i < nfl; i += kTile) {
             int r = i / NCOLS, c = i - r * NCOLS;
             s[i] = __ldg(g + (long long)r * src.stride + c);
         }
@@ -170,54 +190,36 @@ DHFK_DI void stage_rows_in(float* s, const RowSrc& src, long long row0, int rows
 }
 template <int NCOLS>
 DHFK_DI void stage_rows_out(const float* s, const RowDst& dst, long long row0, int rows) {
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x;
     float* g = dst.p + row0 * dst.stride;
+    const int nfl = rows * NCOLS;
     if (dst.vec) {
+        const int nv = nfl >> 2;
         float4* g4 = reinterpret_cast<float4*>(g);
         const float4* s4 = reinterpret_cast<const float4*>(s);
-        if (rows == kTile) {
-            constexpr int NV = kTile * NCOLS / 4;
-#pragma unroll
-            for (int k = 0; k < (NV + kTile - 1) / kTile; ++k) {
-                int i = tid + k * kTile;
-                if (i < NV) __stcs(g4 + i, s4[i]);
-            }
-        } else {
-            const int nfl = rows * NCOLS, nv = nfl >> 2;
-            for (int i = tid; i < nv; i += kTile) __stcs(g4 + i, s4[i]);
-            for (int i = (nv << 2) + tid; i < nfl; i += kTile) __stcs(g + i, s[i]);
-        }
+        for (int i = lane; i < nv; i += kTile) __stcs(g4 + i, s4[i]);
+        for (int i = (nv << 2) + lane; i < nfl; i += kTile) __stcs(g + i, s[i]);
     } else {
-        const int nfl = rows * NCOLS;
-        for (int i = tid; i < nfl; i += kTile) {
+        for (int i = lane; i < nfl; i += kTile) {
             int r = i / NCOLS, c = i - r * NCOLS;
             g[(long long)r * dst.stride + c] = s[i];
         }
     }
 }
-// padded rows: CH 16-byte chunks per row in global (packed, aligned), CH+1 in shared
 template <int CH>
 DHFK_DI void stage_padded_in(float4* s4, const float* gbase, long long row0, int rows) {
-    constexpr int RPI = kTile / CH;
-    const int tid = threadIdx.x;
-    const int r0 = tid / CH, c0 = tid - r0 * CH;
     const float4* g4 = reinterpret_cast<const float4*>(gbase) + row0 * CH;
-#pragma unroll
-    for (int m = 0; m < CH; ++m) {
-        int r = r0 + m * RPI;
-        if (r < rows) s4[r * (CH + 1) + c0] = __ldcs(g4 + r * CH + c0);
+    for (int i = threadIdx.x; i < rows * CH; i += kTile) {
+        int r = i / CH, c = i - r * CH;
+        s4[r * (CH + 1) + c] = __ldcs(g4 + i);
     }
 }
 template <int CH>
 DHFK_DI void stage_padded_out(const float4* s4, float* gbase, long long row0, int rows) {
-    constexpr int RPI = kTile / CH;
-    const int tid = threadIdx.x;
-    const int r0 = tid / CH, c0 = tid - r0 * CH;
     float4* g4 = reinterpret_cast<float4*>(gbase) + row0 * CH;
-#pragma unroll
-    for (int m = 0; m < CH; ++m) {
-        int r = r0 + m * RPI;
-        if (r < rows) __stcs(g4 + r * CH + c0, s4[r * (CH + 1) + c0]);
+    for (int i = threadIdx.x; i < rows * CH; i += kTile) {
+        int r = i / CH, c = i - r * CH;
+        __stcs(g4 + i, s4[r * (CH + 1) + c]);
     }
 }
 
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
     float4* s_uv = s_cam + (CAM ? kTile * kWorldRow4 : 0);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_uv + (UV ? kTile * kUvRow4 : 0));
 
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kTile;
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
@@ -289,49 +291,41 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
     const bool bulk = rows == kTile && p.ang.vec && p.grot.vec && p.bone.vec && p.root.vec;
 
     if (bulk) {
-        if (tid == 0) mbar_init(s_bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            mbar_arrive_expect_tx(s_bar, kTile * 54 * 4);
-            bulk_g2s(s_ang, p.ang.p + row0 * 33, kTile * 33 * 4, s_bar);
-            bulk_g2s(s_bone, p.bone.p + row0 * 15, kTile * 15 * 4, s_bar);
-            bulk_g2s(s_grot, p.grot.p + row0 * 3, kTile * 3 * 4, s_bar);
-            bulk_g2s(s_root, p.root.p + row0 * 3, kTile * 3 * 4, s_bar);
+        ldgsts_slab<33>(s_ang, p.ang.p + row0 * 33);
+        ldgsts_slab<15>(s_bone, p.bone.p + row0 * 15);
+        ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
+        ldgsts_slab<3>(s_root, p.root.p + row0 * 3);
 #if DHFK_PREFETCH_TILES_FWD > 0
+        if (lane == 0) {
             const long long rowp = row0 + (long long)DHFK_PREFETCH_TILES_FWD * kTile;
-            if (rowp + kTile <= p.n) {   // the CTA one resident wave later finds its slabs in L2
+            if (rowp + kTile <= p.n) {   // the warp one resident wave later finds its slabs in L2
                 bulk_prefetch_l2(p.ang.p + rowp * 33, kTile * 33 * 4);
                 bulk_prefetch_l2(p.bone.p + rowp * 15, kTile * 15 * 4);
                 bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
                 bulk_prefetch_l2(p.root.p + rowp * 3, kTile * 3 * 4);
             }
-#endif
         }
-#if DHFK_WAIT_ONE
-        if (tid == 0) mbar_wait(s_bar, 0);
-        __syncthreads();
-#else
-        mbar_wait(s_bar, 0);
 #endif
+        ldgsts_wait_all();
     } else {
         stage_rows_in<33>(s_ang, p.ang, row0, rows);
         stage_rows_in<3>(s_grot, p.grot, row0, rows);
         stage_rows_in<15>(s_bone, p.bone, row0, rows);
         stage_rows_in<3>(s_root, p.root, row0, rows);
-        __syncthreads();
     }
+    __syncwarp();
 
-    if (tid < rows) {
+    if (lane < rows) {
         FwdCtx<CAM, UV> ctx;
-        ctx.ang = s_ang + tid * 33;
-        ctx.bone = s_bone + tid * 15;
+        ctx.ang = s_ang + lane * 33;
+        ctx.bone = s_bone + lane * 15;
         ctx.cc = &p.cam;
         float sx, cx, sy, cy;
-        global_rotation<TRIG>(s_grot + tid * 3, ctx.R, sx, cx, sy, cy);
-        ctx.root = v3(s_root[tid * 3], s_root[tid * 3 + 1], s_root[tid * 3 + 2]);
-        float4* wrow = s_world + tid * kWorldRow4;
-        float4* crow = s_cam + tid * kWorldRow4;
-        float4* urow = s_uv + tid * kUvRow4;
+        global_rotation<TRIG>(s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
+        ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
+        float4* wrow = s_world + lane * kWorldRow4;
+        float4* crow = s_cam + lane * kWorldRow4;
+        float4* urow = s_uv + lane * kUvRow4;
         const Frame I = identity_frame();
         // body, head, arms: outputs 0,7,8,9,13,14,15,10,11,12 -> joints 8..15 complete
         fwd_walk<TRIG, 10>(I, ctx);
@@ -348,22 +342,18 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
         flush_chunks<3, 6>(wrow, ctx.w);
         if (CAM) flush_chunks<3, 6>(crow, ctx.cm);
         if (UV) flush_chunks<2, 4>(urow, ctx.uv);
-        if (bulk && DHFK_ROWS_OUT == 0) {
-            // every thread ships its own rows: no CTA barrier, no cooperative copy loop
-            fence_proxy_async();
-            bulk_s2g(p.out_world + (row0 + tid) * 48, wrow, 48 * 4);
-            if (CAM) bulk_s2g(p.out_cam + (row0 + tid) * 48, crow, 48 * 4);
-            if (UV) bulk_s2g(p.out_uv + (row0 + tid) * 32, urow, 32 * 4);
-            bulk_commit();
-            bulk_wait_read_all();
-        }
     }
-    if (bulk && DHFK_ROWS_OUT == 0) return;
-    __syncthreads();
+    __syncwarp();
 
-    stage_padded_out<kWorldChunks>(s_world, p.out_world, row0, rows);
-    if (CAM) stage_padded_out<kWorldChunks>(s_cam, p.out_cam, row0, rows);
-    if (UV) stage_padded_out<kUvChunks>(s_uv, p.out_uv, row0, rows);
+    if (rows == kTile) {
+        store_padded_tile<kWorldChunks>(s_world, p.out_world, row0);
+        if (CAM) store_padded_tile<kWorldChunks>(s_cam, p.out_cam, row0);
+        if (UV) store_padded_tile<kUvChunks>(s_uv, p.out_uv, row0);
+    } else {
+        stage_padded_out<kWorldChunks>(s_world, p.out_world, row0, rows);
+        if (CAM) stage_padded_out<kWorldChunks>(s_cam, p.out_cam, row0, rows);
+        if (UV) stage_padded_out<kUvChunks>(s_uv, p.out_uv, row0, rows);
+    }
 }
 
 // ---- backward ------------------------------------------------------------------------------------
@@ -380,6 +370,7 @@ struct BwdCtx {
     const float4* gu4;
     float R[9];
     V3 root;
+    Wrench legs;   // filled by bwd_all_limbs
 
     // 3 consecutive floats starting at float index 3K of a padded row, via 128-bit loads only
     template <int K>
@@ -418,6 +409,32 @@ struct BwdCtx {
         }
         return matT_vec(R, g);
     }
+    // same for a runtime output index (shared limb routine): scalar shared loads at runtime offsets
+    DHFK_DI V3 upstream_rt(int k, V3 o) const {
+        V3 g = v3(0.f, 0.f, 0.f);
+        if (gw4) {
+            const float* r = reinterpret_cast<const float*>(gw4) + 3 * k;
+            g = v3(r[0], r[1], r[2]);
+        }
+        if (GUV || gc4) {
+            V3 gc = v3(0.f, 0.f, 0.f);
+            if (gc4) {
+                const float* r = reinterpret_cast<const float*>(gc4) + 3 * k;
+                gc = v3(r[0], r[1], r[2]);
+            }
+            if (GUV) {
+                V3 W = mat_vec_add(R, o, root);
+                V3 X = mat_vec(cc->M, v3(W.x - cc->t[0], W.y - cc->t[1], W.z - cc->t[2]));
+                float u, v;
+                ProjAux a;
+                project_point(*cc, X, u, v, a);
+                const float2 q = reinterpret_cast<const float2*>(gu4)[k];
+                gc = gc + project_point_bwd(*cc, a, q.x, q.y);
+            }
+            g = matT_vec_add(cc->M, gc, g);
+        }
+        return matT_vec(R, g);
+    }
     DHFK_DI void grad_angle(int j, float g) { g_ang[j] = g; }
     DHFK_DI void grad_bone(int b, float g) { g_bone[b] = g; }
 };
@@ -435,29 +452,23 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
     float4* s_gu = s_gc + (GCAM ? kTile * kWorldRow4 : 0);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_gu + (GUV ? kTile * kUvRow4 : 0));
 
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kTile;
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
     const bool bulk = rows == kTile && p.ang.vec && p.grot.vec && p.bone.vec && p.root.vec;
 
     if (bulk) {
-#if DHFK_ROWS_IN == 1
-        if (tid == 0) mbar_init(s_bar, 1 + kTile);   // thread 0's expect_tx arrive + one LDGSTS arrive per thread
-        __syncthreads();
-        if (tid == 0) {
-            mbar_arrive_expect_tx(s_bar, kTile * 4 * 54);
-#else
-        if (tid == 0) mbar_init(s_bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            mbar_arrive_expect_tx(s_bar, kTile * 4 * (54 + (GW ? 48 : 0) + (GCAM ? 48 : 0) + (GUV ? 32 : 0)));
-#endif
-            bulk_g2s(s_ang, p.ang.p + row0 * 33, kTile * 33 * 4, s_bar);
-            bulk_g2s(s_bone, p.bone.p + row0 * 15, kTile * 15 * 4, s_bar);
-            bulk_g2s(s_grot, p.grot.p + row0 * 3, kTile * 3 * 4, s_bar);
-            bulk_g2s(s_root, p.root.p + row0 * 3, kTile * 3 * 4, s_bar);
+        // one round trip: every byte of the tile is requested before anything is waited for
+        ldgsts_slab<33>(s_ang, p.ang.p + row0 * 33);
+        ldgsts_slab<15>(s_bone, p.bone.p + row0 * 15);
+        ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
+        ldgsts_slab<3>(s_root, p.root.p + row0 * 3);
+        if (GW) ldgsts_padded_tile<kWorldChunks>(s_gw, p.g_world, row0);
+        if (GCAM) ldgsts_padded_tile<kWorldChunks>(s_gc, p.g_cam, row0);
+        if (GUV) ldgsts_padded_tile<kUvChunks>(s_gu, p.g_uv, row0);
 #if DHFK_PREFETCH_TILES_BWD > 0
+        if (lane == 0) {
             const long long rowp = row0 + (long long)DHFK_PREFETCH_TILES_BWD * kTile;
             if (rowp + kTile <= p.n) {
                 bulk_prefetch_l2(p.ang.p + rowp * 33, kTile * 33 * 4);
@@ -468,26 +479,9 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
                 if (GCAM) bulk_prefetch_l2(p.g_cam + rowp * 48, kTile * 48 * 4);
                 if (GUV) bulk_prefetch_l2(p.g_uv + rowp * 32, kTile * 32 * 4);
             }
-#endif
         }
-#if DHFK_ROWS_IN == 1
-        // padded gradient rows: coalesced 16-byte LDGSTS, completion counted on the same mbarrier
-        if (GW) ldgsts_padded_rows<kWorldChunks>(s_gw, p.g_world, row0);
-        if (GCAM) ldgsts_padded_rows<kWorldChunks>(s_gc, p.g_cam, row0);
-        if (GUV) ldgsts_padded_rows<kUvChunks>(s_gu, p.g_uv, row0);
-        ldgsts_arrive_noinc(s_bar);
-#else
-        // one row copy per thread into the padded rows (192 B / 128 B, 16-byte aligned both sides)
-        if (GW) bulk_g2s(s_gw + tid * kWorldRow4, p.g_world + (row0 + tid) * 48, 48 * 4, s_bar);
-        if (GCAM) bulk_g2s(s_gc + tid * kWorldRow4, p.g_cam + (row0 + tid) * 48, 48 * 4, s_bar);
-        if (GUV) bulk_g2s(s_gu + tid * kUvRow4, p.g_uv + (row0 + tid) * 32, 32 * 4, s_bar);
 #endif
-#if DHFK_WAIT_ONE
-        if (tid == 0) mbar_wait(s_bar, 0);
-        __syncthreads();
-#else
-        mbar_wait(s_bar, 0);
-#endif
+        ldgsts_wait_all();
     } else {
         stage_rows_in<33>(s_ang, p.ang, row0, rows);
         stage_rows_in<3>(s_grot, p.grot, row0, rows);
@@ -496,43 +490,42 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         if (GW) stage_padded_in<kWorldChunks>(s_gw, p.g_world, row0, rows);
         if (GCAM) stage_padded_in<kWorldChunks>(s_gc, p.g_cam, row0, rows);
         if (GUV) stage_padded_in<kUvChunks>(s_gu, p.g_uv, row0, rows);
-        __syncthreads();
     }
+    __syncwarp();
 
-    if (tid < rows) {
+    if (lane < rows) {
         BwdCtx<GUV, GBONE> ctx;
-        ctx.ang = s_ang + tid * 33;
-        ctx.g_ang = s_ang + tid * 33;
-        ctx.bone = s_bone + tid * 15;
-        ctx.g_bone = s_bone + tid * 15;
+        ctx.ang = s_ang + lane * 33;
+        ctx.g_ang = s_ang + lane * 33;
+        ctx.bone = s_bone + lane * 15;
+        ctx.g_bone = s_bone + lane * 15;
         ctx.cc = &p.cam;
-        ctx.gw4 = GW ? s_gw + tid * kWorldRow4 : nullptr;
-        ctx.gc4 = GCAM ? s_gc + tid * kWorldRow4 : nullptr;
-        ctx.gu4 = GUV ? s_gu + tid * kUvRow4 : nullptr;
+        ctx.gw4 = GW ? s_gw + lane * kWorldRow4 : nullptr;
+        ctx.gc4 = GCAM ? s_gc + lane * kWorldRow4 : nullptr;
+        ctx.gu4 = GUV ? s_gu + lane * kUvRow4 : nullptr;
         float sx, cx, sy, cy;
-        global_rotation<TRIG>(s_grot + tid * 3, ctx.R, sx, cx, sy, cy);
-        ctx.root = v3(s_root[tid * 3], s_root[tid * 3 + 1], s_root[tid * 3 + 2]);
+        global_rotation<TRIG>(s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
+        ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
         const Frame I = identity_frame();
+        // body + head chain unrolled; at joint 18 the walker runs the shared limb loop (arms AND legs)
         Wrench wb = bwd_walk<TRIG, 10>(I, ctx);
-        Wrench wr = bwd_walk<TRIG, 0>(I, ctx);
-        Wrench wl = bwd_walk<TRIG, 5>(I, ctx);
-        V3 Ft = wb.F + wr.F + wl.F;
-        V3 Mt = wb.M + wr.M + wl.M;
+        V3 Ft = wb.F + ctx.legs.F;
+        V3 Mt = wb.M + ctx.legs.M;
         // d/d root = sum_k g_k = R * sum_k (R^T g_k)
         V3 gr = mat_vec(ctx.R, Ft);
-        s_root[tid * 3] = gr.x; s_root[tid * 3 + 1] = gr.y; s_root[tid * 3 + 2] = gr.z;
+        s_root[lane * 3] = gr.x; s_root[lane * 3 + 1] = gr.y; s_root[lane * 3 + 2] = gr.z;
         // d/d global angles: torque about the world axes e_x, Rx e_y, Rx Ry e_z
         V3 tw = mat_vec(ctx.R, Mt);
-        s_grot[tid * 3] = kDegToRad * tw.x;
-        s_grot[tid * 3 + 1] = kDegToRad * fmaf(cx, tw.y, sx * tw.z);
-        s_grot[tid * 3 + 2] = kDegToRad * fmaf(sy, tw.x, fmaf(-sx * cy, tw.y, cx * cy * tw.z));
+        s_grot[lane * 3] = kDegToRad * tw.x;
+        s_grot[lane * 3 + 1] = kDegToRad * fmaf(cx, tw.y, sx * tw.z);
+        s_grot[lane * 3 + 2] = kDegToRad * fmaf(sy, tw.x, fmaf(-sx * cy, tw.y, cx * cy * tw.z));
     }
     const bool bulk_out = rows == kTile && p.g_ang.vec && p.g_grot.vec && p.g_root.vec && (!GBONE || p.g_bone.vec);
     if (bulk_out) {
-        // results overwrote the input slabs in place; ship the four slabs with one thread
+        // results overwrote the input slabs in place; lane 0 ships the slabs
         fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
+        __syncwarp();
+        if (lane == 0) {
             bulk_s2g(p.g_ang.p + row0 * 33, s_ang, kTile * 33 * 4);
             bulk_s2g(p.g_grot.p + row0 * 3, s_grot, kTile * 3 * 4);
             bulk_s2g(p.g_root.p + row0 * 3, s_root, kTile * 3 * 4);
@@ -542,8 +535,7 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         }
         return;
     }
-    __syncthreads();
-
+    __syncwarp();
     stage_rows_out<33>(s_ang, p.g_ang, row0, rows);
     stage_rows_out<3>(s_grot, p.g_grot, row0, rows);
     stage_rows_out<3>(s_root, p.g_root, row0, rows);
@@ -551,4 +543,3 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
 }
 
 }  // namespace dhfk
-

@@ -75,4 +75,56 @@ constexpr bool origin_is_zero(int j) {
     return true;
 }
 
+// ---------------------------------------------------------------------------------------
+// Limbs.  The four 5-joint chains (right leg, left leg, right arm, left arm) have ONE structure:
+//   joint 0: length along parent x (sign sgn0), output k0, alpha0 in {0,-90}, theta0 quadrant q0
+//   joint 1: alpha = sigma*90, theta0 = -90          joint 2: alpha = sigma*90, theta0 quadrant q2
+//   joint 3: length (+) along x, output k0+1, alpha 0, theta0 0
+//   joint 4: length (+) along x, output k0+2, leaf
+// so the backward kernel runs them through one runtime-parametrised routine (4x smaller hot code,
+// which is what keeps the kernel resident in the instruction cache).  The descriptors below are
+// DERIVED from the tables above and the pattern is checked at compile time.
+// ---------------------------------------------------------------------------------------
+constexpr int NLIMB = 4;
+constexpr int LIMB_ROOT[NLIMB] = {0, 5, 23, 28};
+constexpr int limb_of_root(int j) {
+    for (int l = 0; l < NLIMB; ++l)
+        if (LIMB_ROOT[l] == j) return l;
+    return -1;
+}
+struct LimbDesc {
+    int ang0;          // first joint / angle index
+    int k0;            // output index of joint 0 (joints 3 and 4 are k0+1, k0+2)
+    int b0, b3, b4;    // bone indices of the three lengths
+    int q0, q2;        // theta0 quadrants of joints 0 and 2
+    float sgn0;        // sign of the first length
+    float sigma;       // alpha of joints 1 and 2 is sigma * 90 deg
+};
+constexpr LimbDesc make_limb(int l) {
+    const int j = LIMB_ROOT[l];
+    return LimbDesc{j, out_index_of_joint(j), LEN_BONE[j], LEN_BONE[j + 3], LEN_BONE[j + 4],
+                    THETA0_Q[j], THETA0_Q[j + 2], (float)LEN_SIGN[j], (float)ALPHA_Q[j + 1]};
+}
+constexpr bool limb_pattern_ok(int l) {
+    const int j = LIMB_ROOT[l];
+    const int k = out_index_of_joint(j);
+    return PARENT[j + 1] == j && PARENT[j + 2] == j + 1 && PARENT[j + 3] == j + 2 && PARENT[j + 4] == j + 3 &&
+           num_children(j) == 1 && num_children(j + 1) == 1 && num_children(j + 2) == 1 &&
+           num_children(j + 3) == 1 && is_leaf(j + 4) &&
+           LEN_KIND[j] == 1 && LEN_KIND[j + 1] == 0 && LEN_KIND[j + 2] == 0 && LEN_KIND[j + 3] == 1 &&
+           LEN_KIND[j + 4] == 1 && LEN_SIGN[j + 3] == 1 && LEN_SIGN[j + 4] == 1 &&
+           (ALPHA_Q[j] == 0 || ALPHA_Q[j] == -1) && (ALPHA_Q[j + 1] == 1 || ALPHA_Q[j + 1] == -1) &&
+           ALPHA_Q[j + 2] == ALPHA_Q[j + 1] && ALPHA_Q[j + 3] == 0 && ALPHA_Q[j + 4] == 0 &&
+           THETA0_Q[j + 1] == -1 && THETA0_Q[j + 3] == 0 &&
+           k >= 0 && out_index_of_joint(j + 1) < 0 && out_index_of_joint(j + 2) < 0 &&
+           out_index_of_joint(j + 3) == k + 1 && out_index_of_joint(j + 4) == k + 2;
+}
+static_assert(limb_pattern_ok(0) && limb_pattern_ok(1) && limb_pattern_ok(2) && limb_pattern_ok(3),
+              "a limb does not follow the generic 5-joint pattern");
+// legs hang off the chain origin with alpha0 = 0; both arms hang off the same body joint with alpha0 = -90
+static_assert(PARENT[LIMB_ROOT[0]] == -1 && PARENT[LIMB_ROOT[1]] == -1 && ALPHA_Q[LIMB_ROOT[0]] == 0 &&
+              ALPHA_Q[LIMB_ROOT[1]] == 0, "legs");
+static_assert(PARENT[LIMB_ROOT[2]] == PARENT[LIMB_ROOT[3]] && PARENT[LIMB_ROOT[2]] >= 0 &&
+              ALPHA_Q[LIMB_ROOT[2]] == -1 && ALPHA_Q[LIMB_ROOT[3]] == -1, "arms");
+
 }  // namespace dhfk

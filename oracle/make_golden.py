@@ -8,7 +8,7 @@ Fixtures
   tables.npz       constant tables read off the reference modules/objects + the structural
                    dependency matrix of its autograd Jacobian (which angle moves which output)
   kat.npz          KAT-1 T-pose (init_Fk_DH_angle, numpy float64 branch) and KAT-2 bent pose
-  gan133.npz       133 generator-like poses (ragged vs the 96-row kernel tile), S1/cam0, in-volume root
+  gan133.npz       133 generator-like poses (ragged vs the 32-row kernel tile), S1/cam0, in-volume root
   stress200.npz    200 poses, U(-180,180) on every slot, root 10*tanh(randn) (clamp active), S7/cam2
   video36.npz      multi-frame mode: B=4 clips x F=9 frames, root given as [B,F,3]
   camera_ops.npz   GAN_torch_world_to_camera / project_to_2d on their own, per-row intrinsics (9 and 16 cols)

@@ -31,7 +31,7 @@ def test_header_symbols_exported_and_bound():
 def test_abi_version_and_tile():
     lib = _cabi.load()
     assert lib.dhfk_abi_version() == _cabi.ABI_VERSION == 1
-    assert lib.dhfk_tile_rows() == 96
+    assert lib.dhfk_tile_rows() == 32
 
 
 def test_argument_validation_without_gpu():
