@@ -29,6 +29,25 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# stdout must carry exactly ONE JSON line.  Libraries (NCCL prints its version banner, torchrun children
+# inherit the pipe) write to fd 1 as well, so fd 1 is pointed at stderr for the whole run and the JSON
+# line goes to a private duplicate of the original stdout.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(obj):
+    os.write(_JSON_FD, (json.dumps(obj) + "\n").encode())
+
+
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 METRIC = "augmented poses/sec (FK+proj fwd+bwd)"
 UNIT = "poses/s"
 FWD_BYTES = 536    # per pose: 54 floats in, 48 + 32 floats out           (SURVEY 8d / BASELINE.md 4)
@@ -138,8 +157,7 @@ def time_torch_port(chunk, chunks, steps, warmup, threads=None):
     import torch
     import torch_port
     from dhfk import synthetic, tables
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())
     threads = torch.get_num_threads()
     blk = tables.camera_block("S1", 0)
     inp = synthetic.gan_like(chunk, seed=1234)
@@ -167,6 +185,7 @@ def time_c_oracle(n=131072):
     """Extra context: the float64 C oracle (OpenMP, all cores) forward+backward."""
     import c_oracle
     from dhfk import synthetic, tables
+    c_oracle.set_num_threads(host_threads())
     inp = synthetic.gan_like(n, seed=1)
     up = synthetic.upstream_grads(n, seed=2)
     blk = tables.camera_block("S1", 0)
@@ -197,7 +216,7 @@ def run_reference(args):
         "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -379,7 +398,7 @@ def run_native(args):
                                       "sample": "131072 poses fwd+bwd, oracle/dhfk_oracle.c (float64, OpenMP)"}
         except Exception as e:
             line["cpu_baseline_c"] = {"error": repr(e)}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     if distributed:
         dist.destroy_process_group()
 

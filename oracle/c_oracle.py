@@ -44,6 +44,10 @@ def _ptr(a, ty=ctypes.c_float):
     return None if a is None else a.ctypes.data_as(ctypes.POINTER(ty))
 
 
+def set_num_threads(n: int) -> None:
+    lib().dhfk_oracle_set_num_threads(ctypes.c_int(int(n)))
+
+
 def num_threads() -> int:
     return int(lib().dhfk_oracle_num_threads())
 
