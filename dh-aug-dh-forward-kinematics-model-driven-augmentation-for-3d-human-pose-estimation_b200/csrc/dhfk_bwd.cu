@@ -1,5 +1,10 @@
 // dhfk_bwd.cu -- instantiates the fused backward kernels for one (trig policy, bone-grad) pair
 // (-DDHFK_TRIG=0|1 -DDHFK_GBONE=0|1).
+// Backward is issue-bound: the table sincos (15 instead of 23 instructions) is worth its 31 L1-hit loads
+// per pose (0.151 -> 0.143 ms -- profiles/r1_ab_staging.md).
+#ifndef DHFK_ACCURATE_TABLE
+#define DHFK_ACCURATE_TABLE 1
+#endif
 #include "dhfk_launch.h"
 #if !defined(DHFK_TRIG) || !defined(DHFK_GBONE)
 #error "compile with -DDHFK_TRIG=0|1 -DDHFK_GBONE=0|1"

@@ -5,6 +5,7 @@
 // One thread owns one pose; everything here is straight-line register code after inlining.
 #pragma once
 #include "dhfk_topology.h"
+#include "dhfk_sincos_table.h"
 
 namespace dhfk {
 
@@ -68,10 +69,39 @@ constexpr float kDegToRad = 0.017453292519943295f;
 // ---------------------------------------------------------------------------------------
 enum { TRIG_ACCURATE = 0, TRIG_MUFU = 1 };
 
+// TRIG_ACCURATE implementation: 1 = table + remainder (default), 0 = polynomial on |r| <= 45 deg.
+//   table: deg = k*2.8125 + d exactly (k = rint(deg*128/360), |d| <= 1.40625); {sin,cos}(k*2.8125) come from
+//   a 128-entry fp32 table (1 KB, L1-resident, LDG.64), sin d = d*(D + S1 d^2), cos d = 1 - D^2 d^2/2, then
+//   the angle-sum formulas.  Max abs error 1.0e-7 (fp32 emulation over [-720,720] deg; polynomial path
+//   7.7e-8; the reference's own fl(fl(deg/180)*pi) argument rounding costs it 1.1e-6) at ~15 instead of ~23
+//   instructions per sincos.  theta0 quadrants fold into the table index.
+#ifndef DHFK_ACCURATE_TABLE
+#define DHFK_ACCURATE_TABLE 1
+#endif
+static __device__ const float2 c_sincos_table[DHFK_SINCOS_TABLE_SIZE] = {DHFK_SINCOS_TABLE_VALUES};
+static_assert(DHFK_SINCOS_TABLE_SIZE == 128, "index arithmetic below assumes 128 entries");
+
+DHFK_DI void sincos_table_core(float deg, int q0, float& s, float& c) {
+    const float kMagic = 12582912.0f;
+    float t = fmaf(deg, 128.0f / 360.0f, kMagic);
+    int idx = (__float_as_int(t) + 32 * q0) & 127;
+    float kf = t - kMagic;
+    float d = fmaf(kf, -2.8125f, deg);            // exact remainder in degrees
+    float2 sc = __ldg(&c_sincos_table[idx]);
+    constexpr double D = 3.14159265358979323846 / 180.0;
+    float d2 = d * d;
+    float sd = d * fmaf(d2, (float)(-D * D * D / 6.0), (float)D);
+    float cd = fmaf(d2, (float)(-0.5 * D * D), 1.0f);
+    s = fmaf(sc.x, cd, sc.y * sd);
+    c = fmaf(sc.y, cd, -(sc.x * sd));
+}
+
 template <int TRIG, int Q0>
 DHFK_DI void sincos_deg(float deg, float& s, float& c) {
     const float kMagic = 12582912.0f;  // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x) for |x| < 2^22
-    if (TRIG == TRIG_ACCURATE) {
+    if (TRIG == TRIG_ACCURATE && DHFK_ACCURATE_TABLE) {
+        sincos_table_core(deg, Q0, s, c);
+    } else if (TRIG == TRIG_ACCURATE) {
         float t = fmaf(deg, 1.0f / 90.0f, kMagic);
         int n = __float_as_int(t) + Q0;           // low 2 bits: quadrant
         float q = t - kMagic;
@@ -117,7 +147,9 @@ DHFK_DI void sincos_deg(float deg, float& s, float& c) {
 template <int TRIG>
 DHFK_DI void sincos_deg_rt(float deg, int q0, float& s, float& c) {
     const float kMagic = 12582912.0f;
-    if (TRIG == TRIG_ACCURATE) {
+    if (TRIG == TRIG_ACCURATE && DHFK_ACCURATE_TABLE) {
+        sincos_table_core(deg, q0, s, c);
+    } else if (TRIG == TRIG_ACCURATE) {
         float t = fmaf(deg, 1.0f / 90.0f, kMagic);
         int n = __float_as_int(t) + q0;
         float q = t - kMagic;

@@ -1,4 +1,9 @@
 // dhfk_fwd.cu -- instantiates the fused forward kernels for one trig policy (-DDHFK_TRIG=0|1).
+// Forward is HBM-bound (96 % of the copy roofline): the polynomial sincos keeps the LSU free for the
+// tile traffic.  (The table variant measured 0.099 ms vs 0.090 ms here -- profiles/r1_ab_staging.md.)
+#ifndef DHFK_ACCURATE_TABLE
+#define DHFK_ACCURATE_TABLE 0
+#endif
 #include "dhfk_launch.h"
 #ifndef DHFK_TRIG
 #error "compile with -DDHFK_TRIG=0 (polynomial) or 1 (MUFU)"

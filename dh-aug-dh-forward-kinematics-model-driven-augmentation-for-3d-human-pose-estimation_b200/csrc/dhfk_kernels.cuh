@@ -370,7 +370,27 @@ struct BwdCtx {
     const float4* gu4;
     float R[9];
     V3 root;
+    float MR[9];   // M * R: chain frame -> camera frame in one 3x3 (only when GUV)
+    V3 v0;         // M * (root - t)
     Wrench legs;   // filled by bwd_all_limbs
+
+    DHFK_DI void setup_camera() {
+        if (GUV) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    MR[3 * i + j] = fmaf(cc->M[3 * i], R[j], fmaf(cc->M[3 * i + 1], R[3 + j], cc->M[3 * i + 2] * R[6 + j]));
+            v0 = mat_vec(cc->M, v3(root.x - cc->t[0], root.y - cc->t[1], root.z - cc->t[2]));
+        }
+    }
+    // dL/d(origin) in the chain frame from the world-space gradient g and the camera-space gradient gc
+    DHFK_DI V3 to_chain(V3 g, V3 gc, bool have_gc) const {
+        V3 r = matT_vec(R, g);
+        if (GUV) return matT_vec_add(MR, gc, r);                 // R^T g + (M R)^T gc
+        if (have_gc) return matT_vec_add(R, matT_vec(cc->M, gc), r);
+        return r;
+    }
 
     // 3 consecutive floats starting at float index 3K of a padded row, via 128-bit loads only
     template <int K>
@@ -389,25 +409,20 @@ struct BwdCtx {
     DHFK_DI V3 upstream(V3 o) const {
         V3 g = v3(0.f, 0.f, 0.f);
         if (gw4) g = load3<K>(gw4);            // block-uniform branch
-        if (GUV || gc4) {
-            V3 gc = v3(0.f, 0.f, 0.f);
-            if (gc4) gc = load3<K>(gc4);       // block-uniform branch
-            if (GUV) {
-                constexpr bool kZero = origin_is_zero(OUT16[K]);
-                V3 W;
-                if constexpr (kZero) W = root;
-                else W = mat_vec_add(R, o, root);
-                V3 X = mat_vec(cc->M, v3(W.x - cc->t[0], W.y - cc->t[1], W.z - cc->t[2]));
-                float u, v;
-                ProjAux a;
-                project_point(*cc, X, u, v, a);
-                float4 q = gu4[K / 2];
-                V3 gp = project_point_bwd(*cc, a, (K & 1) ? q.z : q.x, (K & 1) ? q.w : q.y);
-                gc = gc + gp;
-            }
-            g = matT_vec_add(cc->M, gc, g);
+        V3 gc = v3(0.f, 0.f, 0.f);
+        if (gc4) gc = load3<K>(gc4);           // block-uniform branch
+        if (GUV) {
+            constexpr bool kZero = origin_is_zero(OUT16[K]);
+            V3 X;
+            if constexpr (kZero) X = v0;
+            else X = mat_vec_add(MR, o, v0);
+            float u, v;
+            ProjAux a;
+            project_point(*cc, X, u, v, a);
+            float4 q = gu4[K / 2];
+            gc = gc + project_point_bwd(*cc, a, (K & 1) ? q.z : q.x, (K & 1) ? q.w : q.y);
         }
-        return matT_vec(R, g);
+        return to_chain(g, gc, gc4 != nullptr);
     }
     // same for a runtime output index (shared limb routine): scalar shared loads at runtime offsets
     DHFK_DI V3 upstream_rt(int k, V3 o) const {
@@ -416,24 +431,20 @@ struct BwdCtx {
             const float* r = reinterpret_cast<const float*>(gw4) + 3 * k;
             g = v3(r[0], r[1], r[2]);
         }
-        if (GUV || gc4) {
-            V3 gc = v3(0.f, 0.f, 0.f);
-            if (gc4) {
-                const float* r = reinterpret_cast<const float*>(gc4) + 3 * k;
-                gc = v3(r[0], r[1], r[2]);
-            }
-            if (GUV) {
-                V3 W = mat_vec_add(R, o, root);
-                V3 X = mat_vec(cc->M, v3(W.x - cc->t[0], W.y - cc->t[1], W.z - cc->t[2]));
-                float u, v;
-                ProjAux a;
-                project_point(*cc, X, u, v, a);
-                const float2 q = reinterpret_cast<const float2*>(gu4)[k];
-                gc = gc + project_point_bwd(*cc, a, q.x, q.y);
-            }
-            g = matT_vec_add(cc->M, gc, g);
+        V3 gc = v3(0.f, 0.f, 0.f);
+        if (gc4) {
+            const float* r = reinterpret_cast<const float*>(gc4) + 3 * k;
+            gc = v3(r[0], r[1], r[2]);
         }
-        return matT_vec(R, g);
+        if (GUV) {
+            V3 X = mat_vec_add(MR, o, v0);
+            float u, v;
+            ProjAux a;
+            project_point(*cc, X, u, v, a);
+            const float2 q = reinterpret_cast<const float2*>(gu4)[k];
+            gc = gc + project_point_bwd(*cc, a, q.x, q.y);
+        }
+        return to_chain(g, gc, gc4 != nullptr);
     }
     DHFK_DI void grad_angle(int j, float g) { g_ang[j] = g; }
     DHFK_DI void grad_bone(int b, float g) { g_bone[b] = g; }
@@ -506,6 +517,7 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         float sx, cx, sy, cy;
         global_rotation<TRIG>(s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
         ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
+        ctx.setup_camera();
         const Frame I = identity_frame();
         // body + head chain unrolled; at joint 18 the walker runs the shared limb loop (arms AND legs)
         Wrench wb = bwd_walk<TRIG, 10>(I, ctx);
