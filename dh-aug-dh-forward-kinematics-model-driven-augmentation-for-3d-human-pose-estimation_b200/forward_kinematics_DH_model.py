@@ -22,6 +22,15 @@ from . import tables
 from .functional import fk_world16
 from .tables import used_16key_15bone_len_table  # noqa: F401  (re-exported like the reference module)
 
+# angle ranges of the non-GAN sampler (forward_kinematics_DH_model.py:935-976): joint1..joint34, degrees;
+# row 24 ('joint24': {}) is skipped by the sampler, kept here as (0, 0)
+SAMPLER_ANGLE_RANGE = (
+    (-90, 45), (-90, 45), (-45, 120), (-135, 0), (0, 0), (-45, 90), (-45, 90), (-45, 120), (-135, 0), (0, 0),
+    (-25, 25), (-10, 90), (-20, 20), (-20, 20), (-10, 45), (-25, 25), (-20, 20), (0, 0), (-20, 20), (-90, 90),
+    (-20, 90), (-45, 45), (0, 0), (0, 0), (-135, 45), (-135, 45), (-45, 180), (0, 135), (0, 0), (-45, 135),
+    (-45, 135), (-45, 180), (0, 135), (0, 0))
+SAMPLER_GLOBAL_ROT_RANGE = ((-20, 20), (-20, 20), (-180, 180))
+
 H36M_POINTS_LEFT = [6, 7, 8, 17, 18, 19]
 H36M_POINTS_RIGHT = [1, 2, 3, 25, 26, 27]
 
@@ -34,6 +43,30 @@ def _index16(device):
     if _IDX16 is None or _IDX16.device != device:
         _IDX16 = torch.as_tensor(tables.H36M_32_To_16_Table, dtype=torch.long, device=device)
     return _IDX16
+
+
+def dh_matrix(alpha, a, d, theta, args=None):
+    """One modified-DH 4x4 transform for SCALAR inputs in degrees (the reference's numpy branch,
+    forward_kinematics_DH_model.py:54-78; the GUI uses it).  Batched tensors are not built matrix by matrix
+    here -- that is the whole point of the fused kernel -- so tensor inputs are rejected."""
+    if torch.is_tensor(theta):
+        raise NotImplementedError("dh_matrix on tensors is replaced by the fused kernel: use "
+                                  "Forward_Kinematics_DH_Model.change_3d_joint_angle / dhfk.fk_project")
+    al, th = alpha / 180 * np.pi, theta / 180 * np.pi
+    ca, sa, ct, st = np.cos(al), np.sin(al), np.cos(th), np.sin(th)
+    return np.array([[ct, -st, 0.0, a], [st * ca, ct * ca, -sa, -sa * d], [st * sa, ct * sa, ca, ca * d],
+                     [0.0, 0.0, 0.0, 1.0]])
+
+
+def rotationMatrix(angle_x, angle_y, angle_z, args=None):
+    """R = Rx(angle_x) Ry(angle_y) Rz(angle_z) for SCALAR degrees (forward_kinematics_DH_model.py:120-139)."""
+    if torch.is_tensor(angle_x):
+        raise NotImplementedError("rotationMatrix on tensors is replaced by the fused kernel")
+    ax, ay, az = (v / 180 * np.pi for v in (angle_x, angle_y, angle_z))
+    r1 = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    r2 = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    r3 = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+    return r1.dot(r2).dot(r3)
 
 
 def scatter_16_to_32(world16: torch.Tensor, root: torch.Tensor) -> torch.Tensor:
@@ -186,3 +219,74 @@ class Forward_Kinematics_DH_Model:
         subject, action, cam, frame = self.my_random_get_sigle_frame_data()
         pose = np.array(self.dataSet_world_3d_pos[subject][action][cam][frame], copy=True)
         self.root_3d_pos = pose[0].copy()
+
+    # ---- non-GAN augmentation sampler (--data_enhancement_method normal), :931-1152 ---------------------
+    def sample_normal_mode(self):
+        """Host-side draws of handler_but_generater in the reference's exact RNG order (so a seeded run
+        produces the same poses): returns (angles [W,33], global_rot [W,3], bone_len [W,15] incl. scaler,
+        root [W,3]) as float64 numpy, plus the raw lists the reference returns."""
+        args = self.args
+        W = int(args.generator_whole_number)
+        n_tab = len(SAMPLER_ANGLE_RANGE)     # 34
+        self.generator_3d_pos_angle, self.generator_global_rot_3d_pos_angle = [], []
+        self.generator_bone_len, self.generator_root = [], []
+        for frame in range(W):
+            if args.generator_choose_BoneLen:
+                self.get_bone_len_from_dataSet()
+            self.generator_bone_len.append(self.record_bone_len)
+            if args.generator_choose_root_pos:
+                self.get_root_3d_pos_from_dataSet()
+            self.generator_root.append(self.root_3d_pos)
+            n_change = self.random.randint(0, n_tab)
+            change = self.random.choice(np.arange(n_tab), size=n_change, replace=False)
+            row = []
+            for j in range(n_tab):
+                if j + 1 == 24:
+                    continue
+                if (j in change) and frame > 0:
+                    lo, hi = SAMPLER_ANGLE_RANGE[j]
+                    row.append(min(max(self.random.normal((lo + hi) / 2, 60), lo), hi))
+                else:
+                    row.append(0)
+            g = []
+            for lo, hi in SAMPLER_GLOBAL_ROT_RANGE:
+                if frame > 0 and args.generator_global_rot:
+                    g.append(min(max(self.random.normal((lo + hi) / 2, 60), lo), hi))
+                else:
+                    g.append(0)
+            self.generator_global_rot_3d_pos_angle.append(g)
+            self.generator_3d_pos_angle.append(row)
+        self.generator_3d_pos_angle = np.array(self.generator_3d_pos_angle).reshape(-1, n_tab - 1)
+        bone = np.zeros((W, 15))
+        grp = tables.BONE_SCALER_GROUP
+        for frame in range(W):
+            scaler = np.zeros(8)
+            if args.bone_len_scaler == "different":
+                scaler = np.array(self.random.randint(-200, 200, size=(8))).reshape(8) / 1000.0
+            elif args.bone_len_scaler == "same":
+                scaler = np.array(self.random.randint(-200, 200, size=(1))).reshape(1).repeat(8) / 1000.0
+            elif args.bone_len_scaler == "":
+                pass
+            else:
+                raise ValueError("args.bone_len_scaler")
+            base = np.asarray(self.generator_bone_len[frame], dtype=np.float64)
+            bone[frame] = base * np.where(grp >= 0, 1 + scaler[np.maximum(grp, 0)], 1.0)
+        root = np.asarray(self.generator_root, dtype=np.float64).reshape(W, 3)
+        glob = np.asarray(self.generator_global_rot_3d_pos_angle, dtype=np.float64).reshape(W, 3)
+        return self.generator_3d_pos_angle.astype(np.float64), glob, bone, root
+
+    def handler_but_generater(self):
+        """Same return tuple as the reference; the W forward-kinematics evaluations the reference does one
+        pose at a time in numpy (:1071-1144) are one fused kernel launch here."""
+        ang, glob, bone, root = self.sample_normal_mode()
+        if not torch.cuda.is_available():
+            raise RuntimeError("dhfk needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        f = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
+        with torch.no_grad():
+            r = f(root)
+            pos32 = scatter_16_to_32(fk_world16(f(ang), f(glob), f(bone), r), r)
+        self.record_bone_len = self.generator_bone_len[-1] if self.generator_bone_len else self.record_bone_len
+        self.root_3d_pos = self.generator_root[-1] if self.generator_root else self.root_3d_pos
+        return (pos32.cpu().numpy().astype(np.float32), self.generator_3d_pos_angle,
+                self.generator_global_rot_3d_pos_angle, self.generator_bone_len, self.generator_root)

@@ -12,6 +12,7 @@ Fixtures
   stress200.npz    200 poses, U(-180,180) on every slot, root 10*tanh(randn) (clamp active), S7/cam2
   video36.npz      multi-frame mode: B=4 clips x F=9 frames, root given as [B,F,3]
   camera_ops.npz   GAN_torch_world_to_camera / project_to_2d on their own, per-row intrinsics (9 and 16 cols)
+  sampler40.npz    handler_but_generater (non-GAN sampler) draws + poses for a fixed seed
 """
 from __future__ import annotations
 
@@ -173,6 +174,26 @@ def camera_ops_fixture():
                 w_g_x=gxw.numpy())
 
 
+def sampler_fixture():
+    """handler_but_generater (--data_enhancement_method normal) with a fixed seed, dataset look-ups off."""
+    import argparse
+    ref = rh.import_reference()
+    out = {}
+    for mode in ("different", "same"):
+        args = argparse.Namespace(batch_size=1, random_seed=5, single_or_multi_train_mode="single", architecture="3,3,3",
+                                  generator_whole_number=40, generator_choose_BoneLen=False,
+                                  generator_choose_root_pos=False, generator_global_rot=True, bone_len_scaler=mode)
+        m = ref.fk.Forward_Kinematics_DH_Model(args, ["S1"], None)
+        m.record_bone_len = [0.45, 0.45, 0.44, 0.44, 0.13, 0.13, 0.23, 0.26, 0.15, 0.15, 0.28, 0.28, 0.25, 0.25, 0.18]
+        m.root_3d_pos = np.array([0.1, -0.2, 0.9])
+        pos, ang, glob, bl, root = m.handler_but_generater()
+        out[mode + "_pos32"] = np.asarray(pos, np.float32)
+        out[mode + "_ang"] = np.asarray(ang, np.float64)
+        out[mode + "_glob"] = np.asarray(glob, np.float64)
+        out[mode + "_next_draw"] = np.array([m.random.randint(0, 1 << 30)])   # RNG position after the call
+    return out
+
+
 def main():
     from dhfk import synthetic
     os.makedirs(OUT, exist_ok=True)
@@ -188,6 +209,7 @@ def main():
              **run_case(synthetic.gan_like(36, seed=3), rh.camera_block("S8", 1), synthetic.upstream_grads(36, seed=8),
                         mode="multi", architecture="3,3", root_shape=(4, 9, 3)))
     np.savez(os.path.join(OUT, "camera_ops.npz"), **camera_ops_fixture())
+    np.savez(os.path.join(OUT, "sampler40.npz"), **sampler_fixture())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -100,3 +100,22 @@ def test_camera_functions_standalone(golden):
     assert_parity(cam.detach().cpu().numpy(), g["w_cam"], "w_cam")
     (cam * T(g["w_g_cam"])).sum().backward()
     assert_parity(xw.grad.cpu().numpy(), g["w_g_x"], "w_g_x")
+
+
+@pytest.mark.parametrize("mode", ["different", "same"])
+def test_handler_but_generater_matches_reference(golden, mode):
+    """The non-GAN sampler: same RNG draws as the reference, poses from ONE fused launch instead of 40
+    numpy FK calls; the reference computes them in float64 and casts to float32."""
+    from dhfk import Forward_Kinematics_DH_Model
+    g = golden("sampler40")
+    args = argparse.Namespace(batch_size=1, random_seed=5, single_or_multi_train_mode="single", architecture="3,3,3",
+                              generator_whole_number=40, generator_choose_BoneLen=False,
+                              generator_choose_root_pos=False, generator_global_rot=True, bone_len_scaler=mode)
+    m = Forward_Kinematics_DH_Model(args, ["S1"], None)
+    m.record_bone_len = [0.45, 0.45, 0.44, 0.44, 0.13, 0.13, 0.23, 0.26, 0.15, 0.15, 0.28, 0.28, 0.25, 0.25, 0.18]
+    m.root_3d_pos = np.array([0.1, -0.2, 0.9])
+    pos, ang, glob, bl, root = m.handler_but_generater()
+    assert pos.shape == (40, 32, 3) and pos.dtype == np.float32
+    assert np.array_equal(ang, g[mode + "_ang"])
+    assert_parity(pos, g[mode + "_pos32"], "pos32")
+    assert len(bl) == 40 and len(root) == 40 and len(glob) == 40

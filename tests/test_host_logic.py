@@ -109,3 +109,40 @@ def test_camera_dropin_assertions_match_reference():
         camera.project_to_2d(torch.zeros(4, 16, 3), torch.zeros(5, 9))       # batch mismatch
     with pytest.raises(AssertionError):
         camera.GAN_torch_world_to_camera(torch.zeros(4, 16, 3), torch.zeros(1, 3), torch.zeros(1, 3))
+
+
+def _sampler_args(mode):
+    import argparse
+    return argparse.Namespace(batch_size=1, random_seed=5, single_or_multi_train_mode="single", architecture="3,3,3",
+                              generator_whole_number=40, generator_choose_BoneLen=False,
+                              generator_choose_root_pos=False, generator_global_rot=True, bone_len_scaler=mode)
+
+
+@pytest.mark.parametrize("mode", ["different", "same"])
+def test_sampler_draws_match_reference_rng_order(golden, mode):
+    """handler_but_generater's host-side draws (forward_kinematics_DH_model.py:931-1113) must consume the
+    RandomState exactly like the reference so that seeded runs produce the same poses."""
+    g = golden("sampler40")
+    m = Forward_Kinematics_DH_Model(_sampler_args(mode), ["S1"], None)
+    m.record_bone_len = [0.45, 0.45, 0.44, 0.44, 0.13, 0.13, 0.23, 0.26, 0.15, 0.15, 0.28, 0.28, 0.25, 0.25, 0.18]
+    m.root_3d_pos = np.array([0.1, -0.2, 0.9])
+    ang, glob, bone, root = m.sample_normal_mode()
+    assert np.array_equal(ang, g[mode + "_ang"])            # bit-exact: same draws, same clipping
+    assert np.array_equal(glob, g[mode + "_glob"])
+    assert m.random.randint(0, 1 << 30) == int(g[mode + "_next_draw"][0])   # RNG left in the same state
+    assert bone.shape == (40, 15) and np.allclose(bone[:, 7], 0.26)          # thorax never scaled
+    assert (ang[0] == 0).all() and (glob[0] == 0).all()                      # frame 0 is the rest pose
+
+
+def test_scalar_dh_matrix_and_rotation_helpers(c_oracle):
+    import ctypes
+    from dhfk.forward_kinematics_DH_model import dh_matrix, rotationMatrix
+    lib = c_oracle.lib()
+    T = np.zeros(16); R = np.zeros(9)
+    d = ctypes.c_double
+    lib.dhfk_oracle_dh_matrix(d(-90.0), d(0.3), d(0.2), d(37.0), T.ctypes.data_as(ctypes.POINTER(d)))
+    assert np.allclose(dh_matrix(-90.0, 0.3, 0.2, 37.0, None), T.reshape(4, 4), atol=1e-15)
+    lib.dhfk_oracle_rotation_matrix(d(10.0), d(20.0), d(30.0), R.ctypes.data_as(ctypes.POINTER(d)))
+    assert np.allclose(rotationMatrix(10.0, 20.0, 30.0, None), R.reshape(3, 3), atol=1e-15)
+    with pytest.raises(NotImplementedError):
+        dh_matrix(torch.zeros(2), torch.zeros(2), torch.zeros(2), torch.zeros(2), None)
