@@ -1,7 +1,8 @@
 """dhfk -- B200-native DH forward kinematics + camera projection (forward & backward) for DH-AUG.
 
 Public surface:
-  fk_project, fk_world16, world_to_camera, project_to_2d, fk_project_host   (functional.py)
+  fk_project, fk_world16, generator_fk, world_to_camera, project_to_2d, fk_project_host   (functional.py)
+  Fk_generator.Fk_Generator / Video_Fk_Generator                            (reference-shaped generators, fused epilogue)
   Forward_Kinematics_DH_Model                                               (reference-shaped class)
   camera.GAN_torch_world_to_camera / camera.project_to_2d                   (reference-shaped functions)
   dropin.install()                                                          (patch the imported reference)
@@ -16,9 +17,10 @@ from . import _cabi, tables  # noqa: F401
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `import dhfk` stays cheap
     import importlib
-    if name in ("functional", "camera", "dropin", "parallel", "synthetic", "forward_kinematics_DH_model"):
+    if name in ("functional", "camera", "dropin", "parallel", "synthetic", "forward_kinematics_DH_model",
+                "Fk_generator"):
         return importlib.import_module("." + name, __name__)
-    if name in ("fk_project", "fk_world16", "world_to_camera", "project_to_2d", "fk_project_host"):
+    if name in ("fk_project", "fk_world16", "world_to_camera", "project_to_2d", "fk_project_host", "generator_fk"):
         return getattr(importlib.import_module(".functional", __name__), name)
     if name == "Forward_Kinematics_DH_Model":
         return importlib.import_module(".forward_kinematics_DH_model", __name__).Forward_Kinematics_DH_Model

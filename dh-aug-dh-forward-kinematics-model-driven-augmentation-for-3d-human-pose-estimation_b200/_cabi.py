@@ -33,6 +33,10 @@ SIGNATURES = {
     "dhfk_backward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64,
                                      _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
                                      _i64, _u32, _vp]),
+    "dhfk_generator_forward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, ctypes.c_float, _vp,
+                                              _vp, _vp, _vp, _i64, _u32, _vp]),
+    "dhfk_generator_backward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, ctypes.c_float, _vp,
+                                               _vp, _vp, _vp, _vp, _i64, _i64, _u32, _vp]),
     "dhfk_world_to_camera_forward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, _vp, _i64, _vp]),
     "dhfk_world_to_camera_backward": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _i64, _vp]),
     "dhfk_project_forward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp]),

@@ -204,6 +204,7 @@ int dhfk_forward(const float* ang, int64_t ang_stride, const float* grot, int64_
     if (!aligned16(out_world) || !aligned16(out_cam) || !aligned16(out_uv))
         return fail(DHFK_E_ALIGN, "outputs must be 16-byte aligned");
     FwdParams p;
+    memset(&p, 0, sizeof p);
     p.ang = row_src(ang, ang_stride, 33);
     p.grot = row_src(grot, grot_stride, 3);
     p.bone = row_src(bone, bone_stride, 15);
@@ -217,8 +218,8 @@ int dhfk_forward(const float* ang, int64_t ang_stride, const float* grot, int64_
     cudaStream_t st = (cudaStream_t)stream;
     const char* where = "";
     const bool oc = out_cam != nullptr, ou = out_uv != nullptr;
-    int e = (flags & DHFK_FLAG_FAST_TRIG) ? dhfk::launch_fwd_trig1(p, oc, ou, st, &where)
-                                          : dhfk::launch_fwd_trig0(p, oc, ou, st, &where);
+    int e = (flags & DHFK_FLAG_FAST_TRIG) ? dhfk::launch_fwd_t1_g0(p, oc, ou, st, &where)
+                                          : dhfk::launch_fwd_t0_g0(p, oc, ou, st, &where);
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }
 
@@ -241,6 +242,7 @@ int dhfk_backward(const float* ang, int64_t ang_stride, const float* grot, int64
     if (!aligned16(g_world) || !aligned16(g_cam) || !aligned16(g_uv))
         return fail(DHFK_E_ALIGN, "upstream gradients must be 16-byte aligned");
     BwdParams p;
+    memset(&p, 0, sizeof p);
     p.ang = row_src(ang, ang_stride, 33);
     p.grot = row_src(grot, grot_stride, 3);
     p.bone = row_src(bone, bone_stride, 15);
@@ -260,8 +262,76 @@ int dhfk_backward(const float* ang, int64_t ang_stride, const float* grot, int64
     const bool fast = (flags & DHFK_FLAG_FAST_TRIG) != 0;
     const char* where = "";
     int e;
-    if (g_bone) e = fast ? dhfk::launch_bwd_trig1_bone1(p, gu, st, &where) : dhfk::launch_bwd_trig0_bone1(p, gu, st, &where);
-    else e = fast ? dhfk::launch_bwd_trig1_bone0(p, gu, st, &where) : dhfk::launch_bwd_trig0_bone0(p, gu, st, &where);
+    if (g_bone) e = fast ? dhfk::launch_bwd_t1_b1_g0(p, gu, st, &where) : dhfk::launch_bwd_t0_b1_g0(p, gu, st, &where);
+    else e = fast ? dhfk::launch_bwd_t1_b0_g0(p, gu, st, &where) : dhfk::launch_bwd_t0_b0_g0(p, gu, st, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+
+// ---- generator-epilogue mode -----------------------------------------------------
+static int fill_gen_scale(dhfk::GenScale& gs, const float* half37, const float* mid37, float root_scale) {
+    if (!half37 || !mid37) return fail(DHFK_E_INVAL, "gen_half37 / gen_mid37 (host, 37 floats each) are required");
+    for (int i = 0; i < dhfk::GEN_NSLOT; ++i) { gs.half[i] = half37[i]; gs.mid[i] = mid37[i]; }
+    gs.root_scale = root_scale;
+    return DHFK_OK;
+}
+
+int dhfk_generator_forward(const float* net_out, int64_t net_out_stride, const float* bone, int64_t bone_stride,
+                           const float* gen_half37, const float* gen_mid37, float root_scale, const float* cam,
+                           float* out_world, float* out_cam, float* out_uv, int64_t n, uint32_t flags, void* stream) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
+    if (n == 0) return DHFK_OK;
+    if (!net_out || !bone) return fail(DHFK_E_INVAL, "net_out / bone must be non-null");
+    if (net_out_stride < dhfk::GEN_NCOL || bone_stride < 15)
+        return fail(DHFK_E_INVAL, "row strides must be >= 35 (net_out), 15 (bone)");
+    if (!out_world) return fail(DHFK_E_INVAL, "out_world is required");
+    if ((out_cam || out_uv) && !cam) return fail(DHFK_E_INVAL, "cam block required for out_cam / out_uv");
+    if (!aligned16(out_world) || !aligned16(out_cam) || !aligned16(out_uv))
+        return fail(DHFK_E_ALIGN, "outputs must be 16-byte aligned");
+    if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
+    FwdParams p;
+    memset(&p, 0, sizeof p);
+    int rc = fill_gen_scale(p.gs, gen_half37, gen_mid37, root_scale);
+    if (rc != DHFK_OK) return rc;
+    p.ang = row_src(net_out, net_out_stride, dhfk::GEN_NCOL);
+    p.bone = row_src(bone, bone_stride, 15);
+    p.out_world = out_world; p.out_cam = out_cam; p.out_uv = out_uv;
+    p.n = n;
+    p.cam = make_cam(cam);
+    const char* where = "";
+    const bool oc = out_cam != nullptr, ou = out_uv != nullptr;
+    int e = (flags & DHFK_FLAG_FAST_TRIG) ? dhfk::launch_fwd_t1_g1(p, oc, ou, (cudaStream_t)stream, &where)
+                                          : dhfk::launch_fwd_t0_g1(p, oc, ou, (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+
+int dhfk_generator_backward(const float* net_out, int64_t net_out_stride, const float* bone, int64_t bone_stride,
+                            const float* gen_half37, const float* gen_mid37, float root_scale, const float* cam,
+                            const float* g_world, const float* g_cam, const float* g_uv, float* g_net_out,
+                            int64_t g_net_out_stride, int64_t n, uint32_t flags, void* stream) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
+    if (n == 0) return DHFK_OK;
+    if (!net_out || !bone || !g_net_out) return fail(DHFK_E_INVAL, "net_out / bone / g_net_out must be non-null");
+    if (net_out_stride < dhfk::GEN_NCOL || bone_stride < 15 || g_net_out_stride < dhfk::GEN_NCOL)
+        return fail(DHFK_E_INVAL, "row strides must be >= 35 (net_out, g_net_out), 15 (bone)");
+    if (!g_world && !g_cam && !g_uv) return fail(DHFK_E_INVAL, "at least one upstream gradient is required");
+    if ((g_cam || g_uv) && !cam) return fail(DHFK_E_INVAL, "cam block required for g_cam / g_uv");
+    if (!aligned16(g_world) || !aligned16(g_cam) || !aligned16(g_uv))
+        return fail(DHFK_E_ALIGN, "upstream gradients must be 16-byte aligned");
+    if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
+    BwdParams p;
+    memset(&p, 0, sizeof p);
+    int rc = fill_gen_scale(p.gs, gen_half37, gen_mid37, root_scale);
+    if (rc != DHFK_OK) return rc;
+    p.ang = row_src(net_out, net_out_stride, dhfk::GEN_NCOL);
+    p.bone = row_src(bone, bone_stride, 15);
+    p.g_world = g_world; p.g_cam = g_cam; p.g_uv = g_uv;
+    p.g_ang = row_dst(g_net_out, g_net_out_stride, dhfk::GEN_NCOL);
+    p.n = n;
+    p.cam = make_cam(cam);
+    const char* where = "";
+    const bool gu = g_uv != nullptr;
+    int e = (flags & DHFK_FLAG_FAST_TRIG) ? dhfk::launch_bwd_t1_b0_g1(p, gu, (cudaStream_t)stream, &where)
+                                          : dhfk::launch_bwd_t0_b0_g1(p, gu, (cudaStream_t)stream, &where);
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }
 

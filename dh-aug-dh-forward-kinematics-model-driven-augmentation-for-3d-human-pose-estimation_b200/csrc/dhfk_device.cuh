@@ -284,9 +284,35 @@ DHFK_DI V3 project_point_bwd(const CamConst& cc, const ProjAux& a, float gu, flo
     return v3(gx * a.iz, gy * a.iz, -fmaf(gx, a.rx, gy * a.ry) * a.iz);
 }
 
+// tanh(x) and sech^2(x) = d tanh/dx from u = exp(-2|x|):  t = sgn(x)(1-u)/(1+u),  sech^2 = 4u/(1+u)^2
+// (the derivative is formed without cancellation, so it keeps full relative accuracy when tanh saturates;
+// tanh itself is accurate to ~1e-7 absolute: MUFU.EX2 + MUFU.RCP)
+DHFK_DI void tanh_sech2(float x, float& t, float& s2) {
+    float u;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(-2.885390043f * fabsf(x)));
+    float r = rcp_approx(1.0f + u);
+    t = copysignf((1.0f - u) * r, x);
+    s2 = 4.0f * u * r * r;
+}
+// per-slot affine map of the generator epilogue (host-filled: half = (hi-lo)/2, mid = (hi+lo)/2, or
+// 180 / 0 when GAN_whether_use_preAngle is off) and the root scale (10)
+struct GenScale {
+    float half[GEN_NSLOT];
+    float mid[GEN_NSLOT];
+    float root_scale;
+};
+static __constant__ int c_gen_src[GEN_NSLOT] = {
+    gen_src_col(0),  gen_src_col(1),  gen_src_col(2),  gen_src_col(3),  gen_src_col(4),  gen_src_col(5),
+    gen_src_col(6),  gen_src_col(7),  gen_src_col(8),  gen_src_col(9),  gen_src_col(10), gen_src_col(11),
+    gen_src_col(12), gen_src_col(13), gen_src_col(14), gen_src_col(15), gen_src_col(16), gen_src_col(17),
+    gen_src_col(18), gen_src_col(19), gen_src_col(20), gen_src_col(21), gen_src_col(22), gen_src_col(23),
+    gen_src_col(24), gen_src_col(25), gen_src_col(26), gen_src_col(27), gen_src_col(28), gen_src_col(29),
+    gen_src_col(30), gen_src_col(31), gen_src_col(32), gen_src_col(33), gen_src_col(34), gen_src_col(35),
+    gen_src_col(36)};
+
 // ---------------------------------------------------------------------------------------
 // Forward walker: depth-first over the compile-time tree.  Ctx provides
-//   const float* ang (33 joint angles, degrees), const float* bone (15 lengths)
+//   template<int J> float angle()  (joint angle, degrees), const float* bone (15 lengths)
 //   template<int K> void emit(V3 origin_in_chain_frame)
 // ---------------------------------------------------------------------------------------
 template <int TRIG, int J, class Ctx> DHFK_DI void fwd_walk(Frame F, Ctx& ctx);
@@ -307,7 +333,7 @@ DHFK_DI void fwd_walk(Frame F, Ctx& ctx) {
     if constexpr (!is_leaf(J)) {
         float s, c;
         constexpr int Q0 = THETA0_Q[J];
-        sincos_deg<TRIG, Q0>(ctx.ang[J], s, c);
+        sincos_deg<TRIG, Q0>(ctx.template angle<J>(), s, c);
         rotate_joint<J>(F, s, c);
         fwd_children<TRIG, J, 0>(F, ctx);
     }
@@ -320,8 +346,9 @@ DHFK_DI void fwd_walk(Frame F, Ctx& ctx) {
 // where (F_j, M_j) sums the outputs strictly below j (the joint's own origin does not
 // depend on its own theta), z_j is the joint axis after the alpha twist, o_j its origin.
 // Ctx provides ang, bone and
+//   template<int J> float angle() / float angle_rt(int j)
 //   template<int K> V3 upstream(V3 origin)   -- total dL/d(origin) in the chain frame
-//   void grad_angle(int j, float g)          -- j is a compile-time constant after inlining
+//   template<int J> void grad_angle(float g) / void grad_angle_rt(int j, float g), zero_grad_angle*()
 //   void grad_bone(int b, float g)           -- only called when Ctx::kBoneGrad
 // ---------------------------------------------------------------------------------------
 template <int TRIG, int J, class Ctx> DHFK_DI Wrench bwd_walk(Frame F, Ctx& ctx);
@@ -334,29 +361,29 @@ static __constant__ LimbDesc c_limbs[NLIMB] = {make_limb(0), make_limb(1), make_
 // Extra Ctx members used:  V3 upstream_rt(int k, V3 origin)
 template <int TRIG, class Ctx>
 DHFK_DI Wrench bwd_limb(const Frame& B, const LimbDesc& L, Ctx& ctx) {
-    const float* ang = ctx.ang + L.ang0;
+    const int j0 = L.ang0;
     const float sg = L.sigma;
     float s, c;
     // joint 0: hip / shoulder offset along parent x, rotation about B.Z
     const V3 o0 = axpy(L.sgn0 * ctx.bone[L.b0], B.X, B.O);
     const V3 g0 = ctx.upstream_rt(L.k0, o0);
-    sincos_deg_rt<TRIG>(ang[0], L.q0, s, c);
+    sincos_deg_rt<TRIG>(ctx.angle_rt(j0), L.q0, s, c);
     const V3 X1 = axpy(s, B.Y, scale(c, B.X));
     const V3 Y1 = axpy(c, B.Y, scale(-s, B.X));
     // joint 1: alpha = sigma*90  =>  y' = sigma z_p, z' = -sigma y_p
     const V3 zj1 = scale(-sg, Y1);
-    sincos_deg_rt<TRIG>(ang[1], -1, s, c);
+    sincos_deg_rt<TRIG>(ctx.angle_rt(j0 + 1), -1, s, c);
     const V3 X2 = axpy(s * sg, B.Z, scale(c, X1));
     const V3 Y2 = axpy(c * sg, B.Z, scale(-s, X1));
     // joint 2: same twist
     const V3 zj2 = scale(-sg, Y2);
-    sincos_deg_rt<TRIG>(ang[2], L.q2, s, c);
+    sincos_deg_rt<TRIG>(ctx.angle_rt(j0 + 2), L.q2, s, c);
     const V3 X3 = axpy(s * sg, zj1, scale(c, X2));
     const V3 Y3 = axpy(c * sg, zj1, scale(-s, X2));
     // joint 3: knee / elbow, alpha 0, axis zj2
     const V3 o3 = axpy(ctx.bone[L.b3], X3, o0);
     const V3 g3 = ctx.upstream_rt(L.k0 + 1, o3);
-    sincos_deg_rt<TRIG>(ang[3], 0, s, c);
+    sincos_deg_rt<TRIG>(ctx.angle_rt(j0 + 3), 0, s, c);
     const V3 X4 = axpy(s, Y3, scale(c, X3));
     // joint 4: foot / wrist, leaf
     const V3 o4 = axpy(ctx.bone[L.b4], X4, o3);
@@ -365,16 +392,16 @@ DHFK_DI Wrench bwd_limb(const Frame& B, const LimbDesc& L, Ctx& ctx) {
     Wrench w;
     w.F = g4;
     w.M = cross(o4, g4);
-    ctx.grad_angle(L.ang0 + 4, 0.f);
-    ctx.grad_angle(L.ang0 + 3, kDegToRad * dot(zj2, sub_cross(w.M, o3, w.F)));
+    ctx.zero_grad_angle_rt(j0 + 4);
+    ctx.grad_angle_rt(j0 + 3, kDegToRad * dot(zj2, sub_cross(w.M, o3, w.F)));
     if (Ctx::kBoneGrad) ctx.grad_bone(L.b4, dot(X4, w.F));
     w.F = w.F + g3;
     w.M = add_cross(w.M, o3, g3);
     if (Ctx::kBoneGrad) ctx.grad_bone(L.b3, dot(X3, w.F));
     const V3 tau = sub_cross(w.M, o0, w.F);
-    ctx.grad_angle(L.ang0 + 2, kDegToRad * dot(zj2, tau));
-    ctx.grad_angle(L.ang0 + 1, kDegToRad * dot(zj1, tau));
-    ctx.grad_angle(L.ang0, kDegToRad * dot(B.Z, tau));
+    ctx.grad_angle_rt(j0 + 2, kDegToRad * dot(zj2, tau));
+    ctx.grad_angle_rt(j0 + 1, kDegToRad * dot(zj1, tau));
+    ctx.grad_angle_rt(j0, kDegToRad * dot(B.Z, tau));
     w.F = w.F + g0;
     w.M = add_cross(w.M, o0, g0);
     if (Ctx::kBoneGrad) ctx.grad_bone(L.b0, L.sgn0 * dot(B.X, w.F));
@@ -447,21 +474,21 @@ DHFK_DI Wrench bwd_walk(Frame F, Ctx& ctx) {
         twist<J>(F, y1, zj);
         float s, c;
         constexpr int Q0 = THETA0_Q[J];
-        sincos_deg<TRIG, Q0>(ctx.ang[J], s, c);
+        sincos_deg<TRIG, Q0>(ctx.template angle<J>(), s, c);
         rotate_joint<J>(F, s, c);
         w = bwd_children<TRIG, J, 0>(F, ctx);
         constexpr bool kZero = origin_is_zero(J);
         V3 tau;
         if constexpr (kZero) tau = w.M;
         else tau = sub_cross(w.M, o, w.F);
-        ctx.grad_angle(J, kDegToRad * dot(zj, tau));
+        ctx.template grad_angle<J>(kDegToRad * dot(zj, tau));
         if constexpr (K >= 0) {
             w.F = w.F + gh;
             if constexpr (!kZero) w.M = add_cross(w.M, o, gh);
         }
     } else {
         static_assert(K >= 0, "every chain end is an output joint");
-        ctx.grad_angle(J, 0.f);
+        ctx.template zero_grad_angle<J>();
         w.F = gh;
         w.M = cross(o, gh);
     }

@@ -51,21 +51,23 @@ struct RowDst {
 };
 
 struct FwdParams {
-    RowSrc ang, grot, bone, root;
+    RowSrc ang, grot, bone, root;   // GEN mode: `ang` is the raw network output [N,35]; grot/root unused
     float* out_world;
     float* out_cam;
     float* out_uv;
     long long n;
     CamConst cam;
+    GenScale gs;                    // GEN mode only
 };
 struct BwdParams {
     RowSrc ang, grot, bone, root;
     const float* g_world;
     const float* g_cam;
     const float* g_uv;
-    RowDst g_ang, g_grot, g_root, g_bone;
+    RowDst g_ang, g_grot, g_root, g_bone;   // GEN mode: g_ang is d(raw network output) [N,35]
     long long n;
     CamConst cam;
+    GenScale gs;                            // GEN mode only
 };
 
 // ---- asynchronous staging: LDGSTS in, TMA bulk (UBLKCP) out, TMA L2 prefetch ---------------------
@@ -236,11 +238,26 @@ DHFK_DI void global_rotation(const float* g, float* R, float& sx, float& cx, flo
 }
 
 // ---- forward -------------------------------------------------------------------------------------
-template <bool CAM, bool UV>
+template <bool CAM, bool UV, bool GEN>
 struct FwdCtx {
-    const float* ang;
+    const float* ang;     // this pose's 33 angles, or (GEN) its 35 raw network outputs
     const float* bone;
     const CamConst* cc;
+    const GenScale* gs;
+
+    template <int J>
+    DHFK_DI float angle() const {
+        if constexpr (!GEN) return ang[J];
+        else {
+            constexpr int SRC = gen_src_col(J);
+            if constexpr (SRC < 0) return gs->mid[J];
+            else {
+                float t, s2;
+                tanh_sech2(ang[SRC], t, s2);
+                return fmaf(t, gs->half[J], gs->mid[J]);
+            }
+        }
+    }
     float R[9];
     V3 root;
     float w[48];
@@ -271,14 +288,15 @@ DHFK_DI void flush_chunks(float4* row4, const float* v) {
     for (int c = LO; c < HI; ++c) row4[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
-template <bool CAM, bool UV, int TRIG>
+template <bool CAM, bool UV, int TRIG, bool GEN>
 __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__ FwdParams p) {
+    constexpr int NANG = GEN ? GEN_NCOL : 33;      // floats per pose in the first slab
     extern __shared__ __align__(16) float smem[];
     float* s_ang = smem;
-    float* s_grot = s_ang + kTile * 33;
-    float* s_bone = s_grot + kTile * 3;
+    float* s_grot = s_ang + kTile * NANG;
+    float* s_bone = s_grot + (GEN ? 0 : kTile * 3);
     float* s_root = s_bone + kTile * 15;
-    float4* s_world = reinterpret_cast<float4*>(s_root + kTile * 3);
+    float4* s_world = reinterpret_cast<float4*>(s_root + (GEN ? 0 : kTile * 3));
     float4* s_cam = s_world + kTile * kWorldRow4;
     float4* s_uv = s_cam + (CAM ? kTile * kWorldRow4 : 0);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_uv + (UV ? kTile * kUvRow4 : 0));
@@ -287,42 +305,67 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
     const long long row0 = (long long)blockIdx.x * kTile;
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
-    // full tile of packed, aligned rows: TMA bulk path; ragged last tile / strided views: gather path
-    const bool bulk = rows == kTile && p.ang.vec && p.grot.vec && p.bone.vec && p.root.vec;
+    // full tile of packed, aligned rows: async slab path; ragged last tile / strided views: gather path
+    const bool bulk = rows == kTile && p.ang.vec && p.bone.vec && (GEN || (p.grot.vec && p.root.vec));
 
     if (bulk) {
-        ldgsts_slab<33>(s_ang, p.ang.p + row0 * 33);
+        ldgsts_slab<NANG>(s_ang, p.ang.p + row0 * NANG);
         ldgsts_slab<15>(s_bone, p.bone.p + row0 * 15);
-        ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
-        ldgsts_slab<3>(s_root, p.root.p + row0 * 3);
+        if (!GEN) {
+            ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
+            ldgsts_slab<3>(s_root, p.root.p + row0 * 3);
+        }
 #if DHFK_PREFETCH_TILES_FWD > 0
         if (lane == 0) {
             const long long rowp = row0 + (long long)DHFK_PREFETCH_TILES_FWD * kTile;
             if (rowp + kTile <= p.n) {   // the warp one resident wave later finds its slabs in L2
-                bulk_prefetch_l2(p.ang.p + rowp * 33, kTile * 33 * 4);
+                bulk_prefetch_l2(p.ang.p + rowp * NANG, kTile * NANG * 4);
                 bulk_prefetch_l2(p.bone.p + rowp * 15, kTile * 15 * 4);
-                bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
-                bulk_prefetch_l2(p.root.p + rowp * 3, kTile * 3 * 4);
+                if (!GEN) {
+                    bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
+                    bulk_prefetch_l2(p.root.p + rowp * 3, kTile * 3 * 4);
+                }
             }
         }
 #endif
         ldgsts_wait_all();
     } else {
-        stage_rows_in<33>(s_ang, p.ang, row0, rows);
-        stage_rows_in<3>(s_grot, p.grot, row0, rows);
+        stage_rows_in<NANG>(s_ang, p.ang, row0, rows);
         stage_rows_in<15>(s_bone, p.bone, row0, rows);
-        stage_rows_in<3>(s_root, p.root, row0, rows);
+        if (!GEN) {
+            stage_rows_in<3>(s_grot, p.grot, row0, rows);
+            stage_rows_in<3>(s_root, p.root, row0, rows);
+        }
     }
     __syncwarp();
 
     if (lane < rows) {
-        FwdCtx<CAM, UV> ctx;
-        ctx.ang = s_ang + lane * 33;
+        FwdCtx<CAM, UV, GEN> ctx;
+        ctx.gs = &p.gs;
+        ctx.ang = s_ang + lane * NANG;
         ctx.bone = s_bone + lane * 15;
         ctx.cc = &p.cam;
         float sx, cx, sy, cy;
-        global_rotation<TRIG>(s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
-        ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
+        if (GEN) {
+            // global rotation = slots 34..36 (columns 28..30), root = tanh(columns 32..34) * 10
+            float g[3], t, s2;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                tanh_sech2(ctx.ang[gen_src_col(GEN_GROT_SLOT) + i], t, s2);
+                g[i] = fmaf(t, p.gs.half[GEN_GROT_SLOT + i], p.gs.mid[GEN_GROT_SLOT + i]);
+            }
+            global_rotation<TRIG>(g, ctx.R, sx, cx, sy, cy);
+            float r[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                tanh_sech2(ctx.ang[GEN_ROOT_COL + i], t, s2);
+                r[i] = t * p.gs.root_scale;
+            }
+            ctx.root = v3(r[0], r[1], r[2]);
+        } else {
+            global_rotation<TRIG>(s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
+            ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
+        }
         float4* wrow = s_world + lane * kWorldRow4;
         float4* crow = s_cam + lane * kWorldRow4;
         float4* urow = s_uv + lane * kUvRow4;
@@ -357,14 +400,68 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
 }
 
 // ---- backward ------------------------------------------------------------------------------------
-template <bool GUV, bool GBONE>
+template <bool GUV, bool GBONE, bool GEN>
 struct BwdCtx {
     static constexpr bool kBoneGrad = GBONE;
-    const float* ang;
+    const float* ang;   // this pose's 33 angles, or (GEN) its 35 raw network outputs
     const float* bone;
     float* g_ang;   // same shared row as ang (in place)
     float* g_bone;  // same shared row as bone (in place)
     const CamConst* cc;
+    const GenScale* gs;
+
+    // Joint angle in degrees.  GEN: tanh + affine slot map on the fly; the slot's chain factor
+    // d(angle)/d(network output) = half * sech^2 is parked in the (now consumed) input cell so that
+    // grad_angle can turn d/d(angle) into d/d(network output) in place.
+    template <int J>
+    DHFK_DI float angle() {
+        if constexpr (!GEN) return ang[J];
+        else {
+            constexpr int SRC = gen_src_col(J);
+            if constexpr (SRC < 0) return gs->mid[J];
+            else {
+                float t, s2;
+                tanh_sech2(ang[SRC], t, s2);
+                g_ang[SRC] = s2 * gs->half[J];
+                return fmaf(t, gs->half[J], gs->mid[J]);
+            }
+        }
+    }
+    DHFK_DI float angle_rt(int j) {
+        if (!GEN) return ang[j];
+        const int src = c_gen_src[j];       // warp-uniform
+        if (src < 0) return gs->mid[j];
+        float t, s2;
+        tanh_sech2(ang[src], t, s2);
+        g_ang[src] = s2 * gs->half[j];
+        return fmaf(t, gs->half[j], gs->mid[j]);
+    }
+    template <int J>
+    DHFK_DI void grad_angle(float g) {
+        if constexpr (!GEN) g_ang[J] = g;
+        else {
+            constexpr int SRC = gen_src_col(J);
+            if constexpr (SRC >= 0) g_ang[SRC] = g * g_ang[SRC];
+        }
+    }
+    DHFK_DI void grad_angle_rt(int j, float g) {
+        if (!GEN) { g_ang[j] = g; return; }
+        const int src = c_gen_src[j];
+        if (src >= 0) g_ang[src] = g * g_ang[src];
+    }
+    template <int J>
+    DHFK_DI void zero_grad_angle() {
+        if constexpr (!GEN) g_ang[J] = 0.f;
+        else {
+            constexpr int SRC = gen_src_col(J);
+            if constexpr (SRC >= 0) g_ang[SRC] = 0.f;
+        }
+    }
+    DHFK_DI void zero_grad_angle_rt(int j) {
+        if (!GEN) { g_ang[j] = 0.f; return; }
+        const int src = c_gen_src[j];
+        if (src >= 0) g_ang[src] = 0.f;
+    }
     const float4* gw4;   // padded shared rows of the upstream gradients (may be null)
     const float4* gc4;
     const float4* gu4;
@@ -373,8 +470,14 @@ struct BwdCtx {
     float MR[9];   // M * R: chain frame -> camera frame in one 3x3 (only when GUV)
     V3 v0;         // M * (root - t)
     Wrench legs;   // filled by bwd_all_limbs
+    // d/d root = sum over the 16 outputs of the world-space gradient.  Summed directly (world part and
+    // camera part separately, one M^T at the end) instead of as R * sum(R^T g): the round trip through the
+    // fp32 rotation is only orthogonal to ~2e-7 and that error scales with |sum g|.
+    V3 sum_gw, sum_gc;
 
     DHFK_DI void setup_camera() {
+        sum_gw = v3(0.f, 0.f, 0.f);
+        sum_gc = v3(0.f, 0.f, 0.f);
         if (GUV) {
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -385,7 +488,9 @@ struct BwdCtx {
         }
     }
     // dL/d(origin) in the chain frame from the world-space gradient g and the camera-space gradient gc
-    DHFK_DI V3 to_chain(V3 g, V3 gc, bool have_gc) const {
+    DHFK_DI V3 to_chain(V3 g, V3 gc, bool have_gc) {
+        if (gw4) sum_gw = sum_gw + g;
+        if (GUV || have_gc) sum_gc = sum_gc + gc;
         V3 r = matT_vec(R, g);
         if (GUV) return matT_vec_add(MR, gc, r);                 // R^T g + (M R)^T gc
         if (have_gc) return matT_vec_add(R, matT_vec(cc->M, gc), r);
@@ -406,7 +511,7 @@ struct BwdCtx {
 
     // total dL/d(origin of output K) rotated back into the chain frame
     template <int K>
-    DHFK_DI V3 upstream(V3 o) const {
+    DHFK_DI V3 upstream(V3 o) {
         V3 g = v3(0.f, 0.f, 0.f);
         if (gw4) g = load3<K>(gw4);            // block-uniform branch
         V3 gc = v3(0.f, 0.f, 0.f);
@@ -425,7 +530,7 @@ struct BwdCtx {
         return to_chain(g, gc, gc4 != nullptr);
     }
     // same for a runtime output index (shared limb routine): scalar shared loads at runtime offsets
-    DHFK_DI V3 upstream_rt(int k, V3 o) const {
+    DHFK_DI V3 upstream_rt(int k, V3 o) {
         V3 g = v3(0.f, 0.f, 0.f);
         if (gw4) {
             const float* r = reinterpret_cast<const float*>(gw4) + 3 * k;
@@ -446,18 +551,19 @@ struct BwdCtx {
         }
         return to_chain(g, gc, gc4 != nullptr);
     }
-    DHFK_DI void grad_angle(int j, float g) { g_ang[j] = g; }
     DHFK_DI void grad_bone(int b, float g) { g_bone[b] = g; }
 };
 
-template <bool GUV, bool GBONE, int TRIG>
+template <bool GUV, bool GBONE, int TRIG, bool GEN>
 __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__ BwdParams p) {
+    static_assert(!(GEN && GBONE), "bone-length gradients are not produced in generator mode");
+    constexpr int NANG = GEN ? GEN_NCOL : 33;
     extern __shared__ __align__(16) float smem[];
     float* s_ang = smem;
-    float* s_grot = s_ang + kTile * 33;
-    float* s_bone = s_grot + kTile * 3;
+    float* s_grot = s_ang + kTile * NANG;
+    float* s_bone = s_grot + (GEN ? 0 : kTile * 3);
     float* s_root = s_bone + kTile * 15;
-    float4* s_gw = reinterpret_cast<float4*>(s_root + kTile * 3);
+    float4* s_gw = reinterpret_cast<float4*>(s_root + (GEN ? 0 : kTile * 3));
     const bool GW = p.g_world != nullptr, GCAM = p.g_cam != nullptr;
     float4* s_gc = s_gw + (GW ? kTile * kWorldRow4 : 0);
     float4* s_gu = s_gc + (GCAM ? kTile * kWorldRow4 : 0);
@@ -467,14 +573,16 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
     const long long row0 = (long long)blockIdx.x * kTile;
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
-    const bool bulk = rows == kTile && p.ang.vec && p.grot.vec && p.bone.vec && p.root.vec;
+    const bool bulk = rows == kTile && p.ang.vec && p.bone.vec && (GEN || (p.grot.vec && p.root.vec));
 
     if (bulk) {
         // one round trip: every byte of the tile is requested before anything is waited for
-        ldgsts_slab<33>(s_ang, p.ang.p + row0 * 33);
+        ldgsts_slab<NANG>(s_ang, p.ang.p + row0 * NANG);
         ldgsts_slab<15>(s_bone, p.bone.p + row0 * 15);
-        ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
-        ldgsts_slab<3>(s_root, p.root.p + row0 * 3);
+        if (!GEN) {
+            ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
+            ldgsts_slab<3>(s_root, p.root.p + row0 * 3);
+        }
         if (GW) ldgsts_padded_tile<kWorldChunks>(s_gw, p.g_world, row0);
         if (GCAM) ldgsts_padded_tile<kWorldChunks>(s_gc, p.g_cam, row0);
         if (GUV) ldgsts_padded_tile<kUvChunks>(s_gu, p.g_uv, row0);
@@ -482,10 +590,12 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         if (lane == 0) {
             const long long rowp = row0 + (long long)DHFK_PREFETCH_TILES_BWD * kTile;
             if (rowp + kTile <= p.n) {
-                bulk_prefetch_l2(p.ang.p + rowp * 33, kTile * 33 * 4);
+                bulk_prefetch_l2(p.ang.p + rowp * NANG, kTile * NANG * 4);
                 bulk_prefetch_l2(p.bone.p + rowp * 15, kTile * 15 * 4);
-                bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
-                bulk_prefetch_l2(p.root.p + rowp * 3, kTile * 3 * 4);
+                if (!GEN) {
+                    bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
+                    bulk_prefetch_l2(p.root.p + rowp * 3, kTile * 3 * 4);
+                }
                 if (GW) bulk_prefetch_l2(p.g_world + rowp * 48, kTile * 48 * 4);
                 if (GCAM) bulk_prefetch_l2(p.g_cam + rowp * 48, kTile * 48 * 4);
                 if (GUV) bulk_prefetch_l2(p.g_uv + rowp * 32, kTile * 32 * 4);
@@ -494,10 +604,12 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
 #endif
         ldgsts_wait_all();
     } else {
-        stage_rows_in<33>(s_ang, p.ang, row0, rows);
-        stage_rows_in<3>(s_grot, p.grot, row0, rows);
+        stage_rows_in<NANG>(s_ang, p.ang, row0, rows);
         stage_rows_in<15>(s_bone, p.bone, row0, rows);
-        stage_rows_in<3>(s_root, p.root, row0, rows);
+        if (!GEN) {
+            stage_rows_in<3>(s_grot, p.grot, row0, rows);
+            stage_rows_in<3>(s_root, p.root, row0, rows);
+        }
         if (GW) stage_padded_in<kWorldChunks>(s_gw, p.g_world, row0, rows);
         if (GCAM) stage_padded_in<kWorldChunks>(s_gc, p.g_cam, row0, rows);
         if (GUV) stage_padded_in<kUvChunks>(s_gu, p.g_uv, row0, rows);
@@ -505,9 +617,10 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
     __syncwarp();
 
     if (lane < rows) {
-        BwdCtx<GUV, GBONE> ctx;
-        ctx.ang = s_ang + lane * 33;
-        ctx.g_ang = s_ang + lane * 33;
+        BwdCtx<GUV, GBONE, GEN> ctx;
+        ctx.gs = &p.gs;
+        ctx.ang = s_ang + lane * NANG;
+        ctx.g_ang = s_ang + lane * NANG;
         ctx.bone = s_bone + lane * 15;
         ctx.g_bone = s_bone + lane * 15;
         ctx.cc = &p.cam;
@@ -515,43 +628,74 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         ctx.gc4 = GCAM ? s_gc + lane * kWorldRow4 : nullptr;
         ctx.gu4 = GUV ? s_gu + lane * kUvRow4 : nullptr;
         float sx, cx, sy, cy;
-        global_rotation<TRIG>(s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
-        ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
+        float chain_g[3], chain_r[3];   // GEN: d(grot_i)/d(col), d(root_i)/d(col)
+        if (GEN) {
+            float g[3], r[3], t, s2;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                tanh_sech2(ctx.ang[gen_src_col(GEN_GROT_SLOT) + i], t, s2);
+                g[i] = fmaf(t, p.gs.half[GEN_GROT_SLOT + i], p.gs.mid[GEN_GROT_SLOT + i]);
+                chain_g[i] = s2 * p.gs.half[GEN_GROT_SLOT + i];
+                tanh_sech2(ctx.ang[GEN_ROOT_COL + i], t, s2);
+                r[i] = t * p.gs.root_scale;
+                chain_r[i] = s2 * p.gs.root_scale;
+            }
+            global_rotation<TRIG>(g, ctx.R, sx, cx, sy, cy);
+            ctx.root = v3(r[0], r[1], r[2]);
+        } else {
+            global_rotation<TRIG>(s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
+            ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
+        }
         ctx.setup_camera();
         const Frame I = identity_frame();
         // body + head chain unrolled; at joint 18 the walker runs the shared limb loop (arms AND legs)
         Wrench wb = bwd_walk<TRIG, 10>(I, ctx);
         V3 Ft = wb.F + ctx.legs.F;
         V3 Mt = wb.M + ctx.legs.M;
-        // d/d root = sum_k g_k = R * sum_k (R^T g_k)
-        V3 gr = mat_vec(ctx.R, Ft);
-        s_root[lane * 3] = gr.x; s_root[lane * 3 + 1] = gr.y; s_root[lane * 3 + 2] = gr.z;
+        V3 gr = ctx.sum_gw;
+        if (GUV || GCAM) gr = matT_vec_add(p.cam.M, ctx.sum_gc, gr);
         // d/d global angles: torque about the world axes e_x, Rx e_y, Rx Ry e_z
         V3 tw = mat_vec(ctx.R, Mt);
-        s_grot[lane * 3] = kDegToRad * tw.x;
-        s_grot[lane * 3 + 1] = kDegToRad * fmaf(cx, tw.y, sx * tw.z);
-        s_grot[lane * 3 + 2] = kDegToRad * fmaf(sy, tw.x, fmaf(-sx * cy, tw.y, cx * cy * tw.z));
+        const float gg0 = kDegToRad * tw.x;
+        const float gg1 = kDegToRad * fmaf(cx, tw.y, sx * tw.z);
+        const float gg2 = kDegToRad * fmaf(sy, tw.x, fmaf(-sx * cy, tw.y, cx * cy * tw.z));
+        if (GEN) {
+            float* o = ctx.g_ang;
+            constexpr int C = gen_src_col(GEN_GROT_SLOT);
+            o[C] = gg0 * chain_g[0]; o[C + 1] = gg1 * chain_g[1]; o[C + 2] = gg2 * chain_g[2];
+            o[GEN_UNUSED_COL] = 0.f;      // column 31 never reaches a slot
+            o[GEN_ROOT_COL] = gr.x * chain_r[0]; o[GEN_ROOT_COL + 1] = gr.y * chain_r[1];
+            o[GEN_ROOT_COL + 2] = gr.z * chain_r[2];
+        } else {
+            s_root[lane * 3] = gr.x; s_root[lane * 3 + 1] = gr.y; s_root[lane * 3 + 2] = gr.z;
+            s_grot[lane * 3] = gg0; s_grot[lane * 3 + 1] = gg1; s_grot[lane * 3 + 2] = gg2;
+        }
     }
-    const bool bulk_out = rows == kTile && p.g_ang.vec && p.g_grot.vec && p.g_root.vec && (!GBONE || p.g_bone.vec);
+    const bool bulk_out = rows == kTile && p.g_ang.vec &&
+                          (GEN || (p.g_grot.vec && p.g_root.vec && (!GBONE || p.g_bone.vec)));
     if (bulk_out) {
         // results overwrote the input slabs in place; lane 0 ships the slabs
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            bulk_s2g(p.g_ang.p + row0 * 33, s_ang, kTile * 33 * 4);
-            bulk_s2g(p.g_grot.p + row0 * 3, s_grot, kTile * 3 * 4);
-            bulk_s2g(p.g_root.p + row0 * 3, s_root, kTile * 3 * 4);
-            if (GBONE) bulk_s2g(p.g_bone.p + row0 * 15, s_bone, kTile * 15 * 4);
+            bulk_s2g(p.g_ang.p + row0 * NANG, s_ang, kTile * NANG * 4);
+            if (!GEN) {
+                bulk_s2g(p.g_grot.p + row0 * 3, s_grot, kTile * 3 * 4);
+                bulk_s2g(p.g_root.p + row0 * 3, s_root, kTile * 3 * 4);
+                if (GBONE) bulk_s2g(p.g_bone.p + row0 * 15, s_bone, kTile * 15 * 4);
+            }
             bulk_commit();
             bulk_wait_read_all();
         }
         return;
     }
     __syncwarp();
-    stage_rows_out<33>(s_ang, p.g_ang, row0, rows);
-    stage_rows_out<3>(s_grot, p.g_grot, row0, rows);
-    stage_rows_out<3>(s_root, p.g_root, row0, rows);
-    if (GBONE) stage_rows_out<15>(s_bone, p.g_bone, row0, rows);
+    stage_rows_out<NANG>(s_ang, p.g_ang, row0, rows);
+    if (!GEN) {
+        stage_rows_out<3>(s_grot, p.g_grot, row0, rows);
+        stage_rows_out<3>(s_root, p.g_root, row0, rows);
+        if (GBONE) stage_rows_out<15>(s_bone, p.g_bone, row0, rows);
+    }
 }
 
 }  // namespace dhfk

@@ -4,21 +4,28 @@
 #include "dhfk_kernels.cuh"
 
 namespace dhfk {
-// return 0 or a cudaError_t; `where` receives a static string naming the failing call
-int launch_fwd_trig0(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
-int launch_fwd_trig1(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
-int launch_bwd_trig0_bone0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
-int launch_bwd_trig0_bone1(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
-int launch_bwd_trig1_bone0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
-int launch_bwd_trig1_bone1(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+// return 0 or a cudaError_t; `where` receives a static string naming the failing call.
+// Naming: launch_fwd_t<TRIG>_g<GEN>, launch_bwd_t<TRIG>_b<GBONE>_g<GEN>
+int launch_fwd_t0_g0(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
+int launch_fwd_t1_g0(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
+int launch_fwd_t0_g1(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
+int launch_fwd_t1_g1(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
+int launch_bwd_t0_b0_g0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+int launch_bwd_t0_b1_g0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+int launch_bwd_t1_b0_g0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+int launch_bwd_t1_b1_g0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+int launch_bwd_t0_b0_g1(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+int launch_bwd_t1_b0_g1(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
 
-inline size_t fwd_smem_bytes(bool cam, bool uv) {
-    return sizeof(float) * kTile * 54 +
-           sizeof(float4) * kTile * (kWorldRow4 * (1 + (cam ? 1 : 0)) + (uv ? kUvRow4 : 0)) + 16 /* mbarrier */;
+// floats per pose in the input slabs: raw mode ang33+grot3+bone15+root3, generator mode out35+bone15
+inline size_t in_floats(bool gen) { return gen ? (GEN_NCOL + 15) : 54; }
+inline size_t fwd_smem_bytes(bool cam, bool uv, bool gen) {
+    return sizeof(float) * kTile * in_floats(gen) +
+           sizeof(float4) * kTile * (kWorldRow4 * (1 + (cam ? 1 : 0)) + (uv ? kUvRow4 : 0)) + 16;
 }
-inline size_t bwd_smem_bytes(bool gw, bool gcam, bool guv) {
-    return sizeof(float) * kTile * 54 +
-           sizeof(float4) * kTile * (kWorldRow4 * ((gw ? 1 : 0) + (gcam ? 1 : 0)) + (guv ? kUvRow4 : 0)) + 16 /* mbarrier */;
+inline size_t bwd_smem_bytes(bool gw, bool gcam, bool guv, bool gen) {
+    return sizeof(float) * kTile * in_floats(gen) +
+           sizeof(float4) * kTile * (kWorldRow4 * ((gw ? 1 : 0) + (gcam ? 1 : 0)) + (guv ? kUvRow4 : 0)) + 16;
 }
 
 template <typename K, typename P>

@@ -76,6 +76,30 @@ constexpr bool origin_is_zero(int j) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Generator epilogue (models_Fk_GAN/Fk_generator.py:121-168).  The network emits 35 columns per pose:
+// 31 tanh'ed angle values scattered into a 37-slot vector (slots 4, 9, 22, 23, 28, 33 are forced to zero,
+// :136; slots 34-36 are the global rotation), then each slot is mapped affinely to its range; column 31
+// is never consumed and columns 32-34 are the root (tanh * 10, :122).
+// Slot j is DH joint j for j < 33.
+// ---------------------------------------------------------------------------------------
+constexpr int GEN_NSLOT = 37;
+constexpr int GEN_NCOL = 35;
+constexpr int GEN_GROT_SLOT = 34;   // slots 34,35,36 = global rotation x,y,z
+constexpr int GEN_ROOT_COL = 32;    // columns 32,33,34 = root x,y,z
+constexpr int GEN_UNUSED_COL = 31;
+constexpr bool gen_zero_slot(int i) { return i == 4 || i == 9 || i == 22 || i == 23 || i == 28 || i == 33; }
+// network column feeding slot i, or -1 for a zero slot
+constexpr int gen_src_col(int slot) {
+    if (gen_zero_slot(slot)) return -1;
+    int col = 0;
+    for (int i = 0; i < slot; ++i)
+        if (!gen_zero_slot(i)) ++col;
+    return col;
+}
+static_assert(gen_src_col(0) == 0 && gen_src_col(5) == 4 && gen_src_col(32) == 27 && gen_src_col(34) == 28 &&
+              gen_src_col(36) == 30, "generator slot map");
+
+// ---------------------------------------------------------------------------------------
 // Limbs.  The four 5-joint chains (right leg, left leg, right arm, left arm) have ONE structure:
 //   joint 0: length along parent x (sign sgn0), output k0, alpha0 in {0,-90}, theta0 quadrant q0
 //   joint 1: alpha = sigma*90, theta0 = -90          joint 2: alpha = sigma*90, theta0 quadrant q2

@@ -179,6 +179,81 @@ def fk_world16(angles, global_rot, bone_len, root, *, fast_trig=False):
     return _FKProject.apply(angles, global_rot, bone_len, root, None, False, False, flags)[0]
 
 
+class _GeneratorFK(torch.autograd.Function):
+    """Generator epilogue + FK (+ camera + projection) in one launch.  Inputs: raw last-layer
+    output [N,35], scaled bone lengths [N,15]; outputs like _FKProject.  Gradient flows to the network output only."""
+
+    @staticmethod
+    def forward(ctx, net_out, bone, half37, mid37, root_scale, cam, want_cam, want_uv, flags):
+        _require_cuda()
+        lib = _cabi.load()
+        device = net_out.device if net_out.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        x = _rows(net_out, 35, device)
+        n = x.shape[0]
+        bone2 = _rows(bone, 15, device)
+        if bone2.shape[0] != n:
+            raise ValueError("row counts differ: net_out %d, bone %d" % (n, bone2.shape[0]))
+        half = np.ascontiguousarray(np.asarray(half37, dtype=np.float32).reshape(37))
+        mid = np.ascontiguousarray(np.asarray(mid37, dtype=np.float32).reshape(37))
+        cam_arr = cam_block_array(cam) if (want_cam or want_uv) else None
+        world = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
+        camo = torch.empty((n, 16, 3), dtype=torch.float32, device=device) if want_cam else None
+        uv = torch.empty((n, 16, 2), dtype=torch.float32, device=device) if want_uv else None
+        with torch.cuda.device(device):
+            rc = lib.dhfk_generator_forward(
+                x.data_ptr(), _row_stride(x), bone2.data_ptr(), _row_stride(bone2), half.ctypes.data, mid.ctypes.data,
+                float(root_scale), cam_arr.ctypes.data if cam_arr is not None else None,
+                world.data_ptr(), camo.data_ptr() if want_cam else None, uv.data_ptr() if want_uv else None,
+                n, flags, _stream_ptr(device))
+        _cabi.check(rc, "dhfk_generator_forward")
+        ctx.save_for_backward(x, bone2)
+        ctx.consts = (half, mid, float(root_scale), cam_arr, flags, want_cam, want_uv)
+        ctx.in_shape, ctx.in_meta = net_out.shape, (net_out.device, net_out.dtype)
+        return (world,) + ((camo,) if want_cam else ()) + ((uv,) if want_uv else ())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        lib = _cabi.load()
+        x, bone2 = ctx.saved_tensors
+        half, mid, root_scale, cam_arr, flags, want_cam, want_uv = ctx.consts
+        device, n = x.device, x.shape[0]
+        it = iter(grads)
+        g_world = _packed(next(it), (n, 16, 3), device)
+        g_cam = _packed(next(it), (n, 16, 3), device) if want_cam else None
+        g_uv = _packed(next(it), (n, 16, 2), device) if want_uv else None
+        cols = ctx.in_shape[-1]
+        g_x = torch.zeros((n, cols), dtype=torch.float32, device=device) if cols != 35 \
+            else torch.empty((n, 35), dtype=torch.float32, device=device)
+        if g_world is None and g_cam is None and g_uv is None:
+            g_x.zero_()
+        elif n > 0:
+            with torch.cuda.device(device):
+                rc = lib.dhfk_generator_backward(
+                    x.data_ptr(), _row_stride(x), bone2.data_ptr(), _row_stride(bone2), half.ctypes.data,
+                    mid.ctypes.data, root_scale, cam_arr.ctypes.data if cam_arr is not None else None,
+                    g_world.data_ptr() if g_world is not None else None,
+                    g_cam.data_ptr() if g_cam is not None else None, g_uv.data_ptr() if g_uv is not None else None,
+                    g_x.data_ptr(), g_x.shape[1], n, flags, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_generator_backward")
+        g_x = g_x.reshape(ctx.in_shape)
+        if (g_x.device, g_x.dtype) != ctx.in_meta:
+            g_x = g_x.to(device=ctx.in_meta[0], dtype=ctx.in_meta[1])
+        return (g_x,) + (None,) * 8
+
+
+def generator_fk(net_out, bone_len, *, use_pre_angle=True, root_scale=10.0, cam=None, return_cam=False,
+                 return_uv=False, half37=None, mid37=None, fast_trig=False):
+    """Fk_generator.py:121-259 after the last Linear layer, fused: net_out [N,35] raw, bone_len [N,15] already
+    multiplied by (1 + scaler).  Returns world16 [N,16,3] (and cam16 / uv16 when requested with `cam`)."""
+    from . import tables
+    if half37 is None or mid37 is None:
+        half37, mid37 = tables.generator_slot_scale(use_pre_angle)
+    flags = _cabi.FLAG_FAST_TRIG if fast_trig else 0
+    outs = _GeneratorFK.apply(net_out, bone_len, half37, mid37, root_scale, cam, bool(return_cam), bool(return_uv), flags)
+    return outs[0] if len(outs) == 1 else outs
+
+
 class _WorldToCamera(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, q, t):

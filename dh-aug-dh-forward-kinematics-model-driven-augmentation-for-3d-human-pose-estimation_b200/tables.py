@@ -153,3 +153,25 @@ def camera_block(subject: str = "S1", cam_id: int = 0) -> np.ndarray:
     c = np.array([c[0] / res_w * 2 - 1, c[1] / res_w * 2 - res_h / res_w]).astype("float32")
     blk = np.concatenate([q, t, f, c, np.array(k, dtype=np.float64), np.array(p, dtype=np.float64)])
     return blk.astype(np.float32)
+
+
+def generator_slot_scale(use_pre_angle: bool = True):
+    """(half[37], mid[37]) of the generator's per-slot affine map (Fk_generator.py:143-168): slot i < 34 uses
+    GAN_angle_range_table row 'joint{i+1}', slots 34-36 the global rotation table; with
+    GAN_whether_use_preAngle off every slot is simply multiplied by 180."""
+    if not use_pre_angle:
+        return np.full(37, 180.0, np.float32), np.zeros(37, np.float32)
+    rng = np.concatenate([GAN_ANGLE_RANGE, GAN_GLOBAL_ROT_RANGE]).astype(np.float64)
+    return ((rng[:, 1] - rng[:, 0]) / 2).astype(np.float32), ((rng[:, 1] + rng[:, 0]) / 2).astype(np.float32)
+
+
+def generator_src_col():
+    """network column feeding each of the 37 slots (-1 for the slots forced to zero)."""
+    src, col = [], 0
+    for i in range(37):
+        if i in GAN_ZERO_SLOTS:
+            src.append(-1)
+        else:
+            src.append(col)
+            col += 1
+    return np.array(src, dtype=np.int64)

@@ -14,6 +14,10 @@
  *       GAN_torch_world_to_camera                 common/camera.py:36-38 (+ quaternion.py:6-35)
  *       project_to_2d                             common/camera.py:62-94
  *       autograd through all of the above         model_fk_gan_train.py:480 (gen_loss.backward)
+ *   dhfk_generator_forward / dhfk_generator_backward          (generator epilogue -> kernel prologue)
+ *       the post-MLP glue of Fk_Generator.forward / Video_Fk_Generator.forward,
+ *         models_Fk_GAN/Fk_generator.py:121-168 and :310-357 (tanh, tanh*10 root, 31 -> 37 slot scatter,
+ *         per-slot range map: ~37 + 37 in-place column writes per call) followed by everything above
  *   dhfk_world_to_camera_*      common/camera.py:36-38 called on its own
  *       (model_fk_gan_train.py:374,434; video_GAN_fun.py:321,440)
  *   dhfk_project_*              common/camera.py:62-94 called on its own, per-row intrinsics
@@ -107,6 +111,28 @@ int dhfk_backward(const float* ang_dev, int64_t ang_stride, const float* grot_de
                   float* g_ang_dev, int64_t g_ang_stride, float* g_grot_dev, int64_t g_grot_stride,
                   float* g_root_dev, int64_t g_root_stride, float* g_bone_dev, int64_t g_bone_stride,
                   int64_t n, uint32_t flags, void* stream);
+
+/*
+ * Generator-epilogue mode.  net_out_dev [N, >=35] is the RAW output of the generator's last Linear layer
+ * (before any activation).  Per pose the kernel forms
+ *     slot_i  = tanh(net_out[col(i)]) * gen_half37[i] + gen_mid37[i]      for the 31 fed slots i of 37
+ *     slot_i  = gen_mid37[i]                                              for slots 4, 9, 22, 23, 28, 33
+ *     root    = tanh(net_out[32..34]) * root_scale                         (column 31 is never consumed)
+ * with joint angles = slots 0..32 and global rotation = slots 34..36, then runs the same fused
+ * FK / camera / projection as dhfk_forward.  gen_half37 / gen_mid37 are HOST arrays: (hi-lo)/2 and (hi+lo)/2
+ * of GAN_angle_range_table / GAN_global_rotation_table (Fk_generator.py:35-76) as the generator applies them,
+ * or 180 / 0 when GAN_whether_use_preAngle is off; root_scale = 10 (Fk_generator.py:122).
+ * bone_dev holds the already scaled lengths boneLength * (1 + scaler) (Fk_generator.py:216-230).
+ * The backward writes d/d(net_out) into g_net_out_dev [N, >=35] (column 31 = 0).
+ */
+int dhfk_generator_forward(const float* net_out_dev, int64_t net_out_stride, const float* bone_dev, int64_t bone_stride,
+                           const float* gen_half37, const float* gen_mid37, float root_scale, const float* cam,
+                           float* out_world_dev, float* out_cam_dev, float* out_uv_dev, int64_t n, uint32_t flags,
+                           void* stream);
+int dhfk_generator_backward(const float* net_out_dev, int64_t net_out_stride, const float* bone_dev, int64_t bone_stride,
+                            const float* gen_half37, const float* gen_mid37, float root_scale, const float* cam,
+                            const float* g_world_dev, const float* g_cam_dev, const float* g_uv_dev,
+                            float* g_net_out_dev, int64_t g_net_out_stride, int64_t n, uint32_t flags, void* stream);
 
 /* world -> camera for P = prod(X.shape[:-1]) points with one camera q[4] (w,x,y,z), t[3]:
  * out = qrot(conj(q), X - t).  Backward: g_x = R(q) g_out.

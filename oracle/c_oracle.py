@@ -111,3 +111,60 @@ def tables():
                              _ptr(kind, i32), _ptr(bone, i32), _ptr(sign, i32), _ptr(out16, i32), _ptr(h, i32))
     return dict(alpha=alpha, theta0=theta0, parent=parent, len_kind=kind, len_bone=bone, len_sign=sign,
                 out16=out16, h36m_32_to_16=h)
+
+
+# ---- generator epilogue (Fk_generator.py:121-230), float64 numpy around the C oracle ----------------------
+_GEN_ZERO = (4, 9, 22, 23, 28, 33)
+
+
+def gen_decode(raw35, half37, mid37, root_scale=10.0):
+    """raw [N,35] -> (ang [N,33], grot [N,3], root [N,3], chain) where chain holds d(value)/d(raw column)."""
+    raw = np.asarray(raw35, dtype=np.float64)
+    n = raw.shape[0]
+    t = np.tanh(raw)
+    dt = 1.0 - t * t
+    slot = np.zeros((n, 37)); dslot = np.zeros((n, 37)); src = -np.ones(37, dtype=np.int64)
+    col = 0
+    for i in range(37):
+        if i in _GEN_ZERO:
+            slot[:, i] = mid37[i]
+        else:
+            slot[:, i] = t[:, col] * half37[i] + mid37[i]
+            dslot[:, i] = dt[:, col] * half37[i]
+            src[i] = col
+            col += 1
+    assert col == 31
+    root = t[:, 32:35] * root_scale
+    droot = dt[:, 32:35] * root_scale
+    return slot[:, :33], slot[:, 34:37], root, (src, dslot, droot)
+
+
+def gen_chain_factor(raw35, half37, mid37, root_scale=10.0):
+    """|d(slot or root value)/d(raw column)| per element of the raw output [N,35] (0 for column 31)."""
+    _, _, _, (src, dslot, droot) = gen_decode(raw35, half37, mid37, root_scale)
+    j = np.zeros((dslot.shape[0], 35))
+    for i in range(37):
+        if src[i] >= 0:
+            j[:, src[i]] = np.abs(dslot[:, i])
+    j[:, 32:35] = np.abs(droot)
+    return j
+
+
+def gen_forward(raw35, bone_scaled, half37, mid37, cam16=None, root_scale=10.0):
+    ang, grot, root, _ = gen_decode(raw35, half37, mid37, root_scale)
+    return forward(ang.astype(np.float32), grot.astype(np.float32), bone_scaled, root.astype(np.float32), cam16)
+
+
+def gen_backward(raw35, bone_scaled, half37, mid37, cam16=None, g_world=None, g_cam=None, g_uv=None, root_scale=10.0):
+    """d/d(raw network output) [N,35] (column 31 = 0)."""
+    ang, grot, root, (src, dslot, droot) = gen_decode(raw35, half37, mid37, root_scale)
+    b = backward(ang.astype(np.float32), grot.astype(np.float32), bone_scaled, root.astype(np.float32), cam16,
+                 g_world=g_world, g_cam=g_cam, g_uv=g_uv, want_bone=False)
+    n = ang.shape[0]
+    d = np.zeros((n, 35))
+    gslot = np.concatenate([b["g_ang"], np.zeros((n, 1)), b["g_grot"]], axis=1)
+    for i in range(37):
+        if src[i] >= 0:
+            d[:, src[i]] = gslot[:, i] * dslot[:, i]
+    d[:, 32:35] = b["g_root"] * droot
+    return d

@@ -13,6 +13,8 @@ Fixtures
   video36.npz      multi-frame mode: B=4 clips x F=9 frames, root given as [B,F,3]
   camera_ops.npz   GAN_torch_world_to_camera / project_to_2d on their own, per-row intrinsics (9 and 16 cols)
   sampler40.npz    handler_but_generater (non-GAN sampler) draws + poses for a fixed seed
+  generator.npz    Fk_Generator / Video_Fk_Generator epilogue (tanh, slot scatter, range map, scaler) + FK,
+                   outputs and d/d(raw network output), for a known raw last-layer output
 """
 from __future__ import annotations
 
@@ -194,6 +196,57 @@ def sampler_fixture():
     return out
 
 
+def generator_fixture():
+    """The reference's own Fk_Generator.forward / Video_Fk_Generator.forward (Fk_generator.py:114-261, :302-458)
+    fed with a KNOWN raw last-layer output: `deconv_out` is replaced by a module that returns a leaf tensor, so
+    everything after the MLP is the unmodified reference code and autograd yields d(loss)/d(raw output)."""
+    import argparse
+    import torch.nn as nn
+    ref = rh.import_reference()
+
+    class Feed(nn.Module):
+        def __init__(self, raw):
+            super().__init__()
+            self.raw = raw
+
+        def forward(self, x):
+            return self.raw * 1.0
+
+    out = {}
+    rng = np.random.RandomState(21)
+    from dhfk import synthetic
+    for tag, B, F, pre in (("single", 70, 1, True), ("single_nopre", 33, 1, False), ("video", 4, 9, True)):
+        args = argparse.Namespace(batch_size=B, random_seed=0, single_or_multi_train_mode="multi" if F > 1 else "single",
+                                  architecture="3,3", GAN_OUTPUT_DIM=35, Gen_DenseDim=16, GAN_whether_use_preAngle=pre,
+                                  whether_use_RT=True, bone_len_scaler="different", record_all_picture=False,
+                                  checkpoint="/tmp")
+        fk = ref.fk.Forward_Kinematics_DH_Model(args, ["S1"], None)
+        if F == 1:
+            G = ref.generator.Fk_Generator(fk, args, torch.device("cpu"))
+        else:
+            G = ref.generator.Video_Fk_Generator(F, fk, args, torch.device("cpu"))
+        G.train_num = 1                                   # skip the heat-map dump (train_num % 500 == 1)
+        raw = torch.tensor((rng.randn(B, F * 35) * 1.2).astype(np.float32), requires_grad=True)
+        G.deconv_out = Feed(raw)
+        bone = synthetic.gan_like(B * F, seed=31 + B)["bone"]
+        G.boneLength = torch.tensor(bone)
+        if F == 1:
+            torch.manual_seed(77)
+            fake = G(torch.zeros(B, 128))
+            torch.manual_seed(77)
+            scaler = (torch.randint(-200, 200, size=(B, 8)) / 1000.0).numpy()
+        else:
+            fk.random = np.random.RandomState(5)
+            fake = G(torch.zeros(B, 128))
+            scaler = np.random.RandomState(5).randint(-200, 200, size=(B, 8)).reshape(B, 8) / 1000.0
+            scaler = np.repeat(scaler[:, None, :], F, axis=1).reshape(B * F, 8)
+        g_fake = rng.randn(*fake.shape).astype(np.float32)
+        (fake * torch.tensor(g_fake)).sum().backward()
+        out.update({tag + "_raw": raw.detach().numpy(), tag + "_bone": bone, tag + "_scaler": scaler.astype(np.float32),
+                    tag + "_fake": fake.detach().numpy(), tag + "_g_fake": g_fake, tag + "_d_raw": raw.grad.numpy()})
+    return out
+
+
 def main():
     from dhfk import synthetic
     os.makedirs(OUT, exist_ok=True)
@@ -210,6 +263,7 @@ def main():
                         mode="multi", architecture="3,3", root_shape=(4, 9, 3)))
     np.savez(os.path.join(OUT, "camera_ops.npz"), **camera_ops_fixture())
     np.savez(os.path.join(OUT, "sampler40.npz"), **sampler_fixture())
+    np.savez(os.path.join(OUT, "generator.npz"), **generator_fixture())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -20,20 +20,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def rel_err(x, ref, row_scale=None):
+def rel_err(x, ref, row_scale=None, floor=1.0):
+    """max |x - ref| / max(|ref|, floor).  `floor` (scalar or array like ref) is the magnitude below which the
+    error is judged absolutely; 1 for quantities the north-star tolerance is stated on."""
     x = np.asarray(x, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert x.shape == ref.shape, (x.shape, ref.shape)
     if x.size == 0:
         return 0.0
-    e = np.abs(x - ref) / np.maximum(np.abs(ref), 1.0)
+    e = np.abs(x - ref) / np.maximum(np.abs(ref), floor)
     if row_scale is not None:
         e = e / np.asarray(row_scale, dtype=np.float64).reshape((-1,) + (1,) * (e.ndim - 1))
     return float(np.max(e))
 
 
-def assert_parity(x, ref, what="", rtol=RTOL, row_scale=None):
-    e = rel_err(x, ref, row_scale)
+def assert_parity(x, ref, what="", rtol=RTOL, row_scale=None, floor=1.0):
+    e = rel_err(x, ref, row_scale, floor)
     assert np.isfinite(e) and e <= rtol, "%s: max |x-ref|/max(|ref|,1) = %.3e > %.1e" % (what, e, rtol)
     return e
 

@@ -118,3 +118,29 @@ def test_oracle_camera_ops(golden, c_oracle):
     g = golden("camera_ops")
     assert g["clamped"].any()
     assert np.array_equal(g["uv"], g["uv16"])     # the reference only reads the first 9 of 16 columns
+
+
+def _scaled_bone(bone, scaler):
+    from dhfk import tables
+    grp = tables.BONE_SCALER_GROUP
+    return (bone * np.where(grp[None, :] >= 0, 1.0 + scaler[:, np.maximum(grp, 0)], 1.0)).astype(np.float32)
+
+
+@pytest.mark.parametrize("tag,pre", [("single", True), ("single_nopre", False), ("video", True)])
+def test_generator_epilogue_oracle_matches_reference(golden, c_oracle, tag, pre):
+    """the generator epilogue restated in the oracle (tanh, 31->37 slot scatter, range map, x10 root,
+    bone scaler) reproduces the reference's Fk_Generator / Video_Fk_Generator outputs and d/d(raw output)."""
+    from dhfk import tables
+    g = golden("generator")
+    half, mid = tables.generator_slot_scale(pre)
+    raw = g[tag + "_raw"].reshape(-1, 35)
+    bone = _scaled_bone(g[tag + "_bone"], g[tag + "_scaler"])
+    o = c_oracle.gen_forward(raw, bone, half, mid)
+    fake = g[tag + "_fake"].reshape(-1, 16, 3)
+    assert_parity(o["world16"], fake, "fake")
+    d = c_oracle.gen_backward(raw, bone, half, mid, g_world=g[tag + "_g_fake"].reshape(-1, 16, 3))
+    ref = g[tag + "_d_raw"].reshape(-1, 35)
+    assert_parity(d, ref, "d_raw")
+    assert np.all(ref[:, 31] == 0)                      # network column 31 is never consumed (SURVEY 3.6)
+    assert np.all(ref[:, [23, 27]] == 0)                # columns feeding the chain-end slots 27 / 32
+    assert np.array_equal(tables.generator_src_col()[[27, 32, 34, 36]], [23, 27, 28, 30])
