@@ -347,6 +347,45 @@ def run_native(args):
                "d2h_bytes_per_step": n * (320 + 156), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "api": "dhfk.fk_project_host -> dhfk_forward_backward_host (pinned host buffers, %d-row chunks, 4 streams)" % chunk}
 
+    # ---- extra: generator-epilogue mode, same batch, device-resident, rank 0 only ----
+    gen_extra = None
+    if rank == 0:
+        try:
+            half, mid = tables.generator_slot_scale(True)
+            g = torch.Generator(device=dev).manual_seed(99)
+            raws = [torch.randn((n, 35), generator=g, device=dev) for _ in range(2)]
+            for r_ in raws:
+                r_[:, 32:35] = torch.rand((n, 3), generator=g, device=dev) * 0.2 - 0.1
+                r_[:, 34] += 0.1
+            d_raw = torch.empty((n, 35), device=dev)
+            hp, mp = half.ctypes.data, mid.ctypes.data
+
+            def gen_step(i):
+                d = sets[i % nbuf]; r_ = raws[i % 2]
+                _cabi.check(lib.dhfk_generator_forward(r_.data_ptr(), 35, d["bone"].data_ptr(), 15, hp, mp, 10.0, cam_ptr,
+                                                       world.data_ptr(), None, uv.data_ptr(), n, flags, sp), "gen fwd")
+                _cabi.check(lib.dhfk_generator_backward(r_.data_ptr(), 35, d["bone"].data_ptr(), 15, hp, mp, 10.0, cam_ptr,
+                                                        d["g_world"].data_ptr(), None, d["g_uv"].data_ptr(),
+                                                        d_raw.data_ptr(), 35, n, flags, sp), "gen bwd")
+            for i in range(5):
+                gen_step(i)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            gsteps = min(steps, 50)
+            e0.record(stream)
+            for i in range(gsteps):
+                gen_step(i)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            gms = e0.elapsed_time(e1) / gsteps
+            gbytes = (200 + 320) + (200 + 320 + 140)     # fwd: 50 floats in, 80 out; bwd: 50 + 80 in, 35 out
+            gen_extra = {"poses_per_s": n / (gms * 1e-3), "ms_per_step": gms, "bytes_per_pose": gbytes,
+                         "hbm_gbs": gbytes * n / (gms * 1e-3) / 1e9,
+                         "what": "dhfk_generator_forward + dhfk_generator_backward: raw network output [N,35] in, "
+                                 "d(raw) out; tanh / slot scatter / range map fused (SURVEY 8 f1)"}
+        except Exception as e:      # never let the extra break the headline line
+            gen_extra = {"error": repr(e)}
+
     if distributed:
         dist.barrier()
     if rank != 0:
@@ -388,6 +427,8 @@ def run_native(args):
     }
     if e2e:
         line["e2e"] = e2e
+    if gen_extra:
+        line["generator_mode"] = gen_extra
     if not args.no_cpu_baseline:
         pps, dt, threads = time_torch_port(args.ref_chunk, 1, steps=10, warmup=2)
         line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
