@@ -20,9 +20,21 @@ _CALLERS = (
 )
 
 
-def install(verbose: bool = False):
-    """Patch the reference modules that are currently imported.  Idempotent.  Returns the names patched."""
+def install(verbose: bool = False, generators: bool = False):
+    """Patch the reference modules that are currently imported.  Idempotent.  Returns the names patched.
+    generators=True also swaps Fk_Generator / Video_Fk_Generator for the fused-epilogue versions (SURVEY 8 f1;
+    same constructor and state dict) wherever `my_get_poseFk_model` (model_fk_gan_train.py:97-173) finds them."""
     patched = []
+    if generators:
+        from . import Fk_generator as _gen
+        for name in ("models_Fk_GAN.Fk_generator", "models_Fk_GAN.model_fk_gan_train", "models_Fk_GAN.video_GAN_fun"):
+            mod = sys.modules.get(name)
+            if mod is None:
+                continue
+            for sym in ("Fk_Generator", "Video_Fk_Generator"):
+                if hasattr(mod, sym):
+                    setattr(mod, sym, getattr(_gen, sym))
+                    patched.append("%s.%s" % (name, sym))
     fkmod = sys.modules.get("models_Fk_GAN.forward_kinematics_DH_model")
     if fkmod is not None:
         fkmod.Forward_Kinematics_DH_Model = _fk.Forward_Kinematics_DH_Model
