@@ -416,7 +416,7 @@ DHFK_DI Wrench bwd_all_limbs(const Frame& P /*frame of the arms' parent joint*/,
     Frame A = P;            // arms: alpha0 = -90 folded into the base frame (y' = -z, z' = y)
     A.Y = -P.Z;
     A.Z = P.Y;
-    const Frame I = identity_frame();
+    const Frame I = ctx.base;   // legs hang off the chain root frame
     Wrench arms, legs;
     arms.F = arms.M = legs.F = legs.M = v3(0.f, 0.f, 0.f);
 #pragma unroll 1

@@ -267,9 +267,9 @@ struct FwdCtx {
     template <int K>
     DHFK_DI void emit(V3 o) {
         constexpr bool kZero = origin_is_zero(OUT16[K]);
-        V3 W;
+        V3 W;                       // the chain runs in world axes (base frame = columns of R): no R*o per joint
         if constexpr (kZero) W = root;
-        else W = mat_vec_add(R, o, root);
+        else W = o + root;
         w[3 * K] = W.x; w[3 * K + 1] = W.y; w[3 * K + 2] = W.z;
         if (CAM || UV) {
             V3 X = mat_vec(cc->M, v3(W.x - cc->t[0], W.y - cc->t[1], W.z - cc->t[2]));
@@ -369,7 +369,9 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
         float4* wrow = s_world + lane * kWorldRow4;
         float4* crow = s_cam + lane * kWorldRow4;
         float4* urow = s_uv + lane * kUvRow4;
-        const Frame I = identity_frame();
+        Frame I;                    // chain root frame: world axes rotated by the global rotation, origin = root point
+        I.X = v3(ctx.R[0], ctx.R[3], ctx.R[6]); I.Y = v3(ctx.R[1], ctx.R[4], ctx.R[7]);
+        I.Z = v3(ctx.R[2], ctx.R[5], ctx.R[8]); I.O = v3(0.f, 0.f, 0.f);
         // body, head, arms: outputs 0,7,8,9,13,14,15,10,11,12 -> joints 8..15 complete
         fwd_walk<TRIG, 10>(I, ctx);
         flush_chunks<6, 12>(wrow, ctx.w);
@@ -467,34 +469,44 @@ struct BwdCtx {
     const float4* gu4;
     float R[9];
     V3 root;
-    float MR[9];   // M * R: chain frame -> camera frame in one 3x3 (only when GUV)
-    V3 v0;         // M * (root - t)
+    // The chain is walked directly in the frame the upstream gradients live in, with the root point as origin:
+    // camera axes (base = columns of M*R) when any camera-space gradient exists, world axes (columns of R)
+    // otherwise.  Positions then need only "+ v0" to become camera coordinates and gradients need no
+    // per-joint rotation back into a chain frame.
+    Frame base;
+    bool cam_frame;
+    V3 v0;         // root point in camera coordinates, M * (root - t)
     Wrench legs;   // filled by bwd_all_limbs
-    // d/d root = sum over the 16 outputs of the world-space gradient.  Summed directly (world part and
-    // camera part separately, one M^T at the end) instead of as R * sum(R^T g): the round trip through the
-    // fp32 rotation is only orthogonal to ~2e-7 and that error scales with |sum g|.
+    // d/d root = sum over the 16 outputs of the world-space gradient, summed directly (world part and camera
+    // part separately, one M^T at the end).
     V3 sum_gw, sum_gc;
 
     DHFK_DI void setup_camera() {
         sum_gw = v3(0.f, 0.f, 0.f);
         sum_gc = v3(0.f, 0.f, 0.f);
-        if (GUV) {
+        cam_frame = GUV || gc4 != nullptr;
+        base.O = v3(0.f, 0.f, 0.f);
+        if (cam_frame) {
+            float MR[9];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
                     MR[3 * i + j] = fmaf(cc->M[3 * i], R[j], fmaf(cc->M[3 * i + 1], R[3 + j], cc->M[3 * i + 2] * R[6 + j]));
+            base.X = v3(MR[0], MR[3], MR[6]); base.Y = v3(MR[1], MR[4], MR[7]); base.Z = v3(MR[2], MR[5], MR[8]);
             v0 = mat_vec(cc->M, v3(root.x - cc->t[0], root.y - cc->t[1], root.z - cc->t[2]));
+        } else {
+            base.X = v3(R[0], R[3], R[6]); base.Y = v3(R[1], R[4], R[7]); base.Z = v3(R[2], R[5], R[8]);
+            v0 = v3(0.f, 0.f, 0.f);
         }
     }
-    // dL/d(origin) in the chain frame from the world-space gradient g and the camera-space gradient gc
-    DHFK_DI V3 to_chain(V3 g, V3 gc, bool have_gc) {
+    // total dL/d(origin) in the working frame from the world-space gradient g and the camera-space gradient gc
+    DHFK_DI V3 to_frame(V3 g, V3 gc) {
         if (gw4) sum_gw = sum_gw + g;
-        if (GUV || have_gc) sum_gc = sum_gc + gc;
-        V3 r = matT_vec(R, g);
-        if (GUV) return matT_vec_add(MR, gc, r);                 // R^T g + (M R)^T gc
-        if (have_gc) return matT_vec_add(R, matT_vec(cc->M, gc), r);
-        return r;
+        if (!cam_frame) return g;
+        sum_gc = sum_gc + gc;
+        if (gw4) return mat_vec_add(cc->M, g, gc);      // M g_w + g_c
+        return gc;
     }
 
     // 3 consecutive floats starting at float index 3K of a padded row, via 128-bit loads only
@@ -509,7 +521,7 @@ struct BwdCtx {
         return v3(a.w, b.x, b.y);
     }
 
-    // total dL/d(origin of output K) rotated back into the chain frame
+    // total dL/d(origin of output K) in the working frame; o = origin relative to the root, working axes
     template <int K>
     DHFK_DI V3 upstream(V3 o) {
         V3 g = v3(0.f, 0.f, 0.f);
@@ -520,14 +532,14 @@ struct BwdCtx {
             constexpr bool kZero = origin_is_zero(OUT16[K]);
             V3 X;
             if constexpr (kZero) X = v0;
-            else X = mat_vec_add(MR, o, v0);
+            else X = o + v0;
             float u, v;
             ProjAux a;
             project_point(*cc, X, u, v, a);
             float4 q = gu4[K / 2];
             gc = gc + project_point_bwd(*cc, a, (K & 1) ? q.z : q.x, (K & 1) ? q.w : q.y);
         }
-        return to_chain(g, gc, gc4 != nullptr);
+        return to_frame(g, gc);
     }
     // same for a runtime output index (shared limb routine): scalar shared loads at runtime offsets
     DHFK_DI V3 upstream_rt(int k, V3 o) {
@@ -542,14 +554,14 @@ struct BwdCtx {
             gc = v3(r[0], r[1], r[2]);
         }
         if (GUV) {
-            V3 X = mat_vec_add(MR, o, v0);
+            V3 X = o + v0;
             float u, v;
             ProjAux a;
             project_point(*cc, X, u, v, a);
             const float2 q = reinterpret_cast<const float2*>(gu4)[k];
             gc = gc + project_point_bwd(*cc, a, q.x, q.y);
         }
-        return to_chain(g, gc, gc4 != nullptr);
+        return to_frame(g, gc);
     }
     DHFK_DI void grad_bone(int b, float g) { g_bone[b] = g; }
 };
@@ -647,15 +659,15 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
             ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
         }
         ctx.setup_camera();
-        const Frame I = identity_frame();
         // body + head chain unrolled; at joint 18 the walker runs the shared limb loop (arms AND legs)
-        Wrench wb = bwd_walk<TRIG, 10>(I, ctx);
+        Wrench wb = bwd_walk<TRIG, 10>(ctx.base, ctx);
         V3 Ft = wb.F + ctx.legs.F;
         V3 Mt = wb.M + ctx.legs.M;
         V3 gr = ctx.sum_gw;
         if (GUV || GCAM) gr = matT_vec_add(p.cam.M, ctx.sum_gc, gr);
         // d/d global angles: torque about the world axes e_x, Rx e_y, Rx Ry e_z
-        V3 tw = mat_vec(ctx.R, Mt);
+        V3 tw = Mt;                                      // moment about the root, working axes -> world axes
+        if (ctx.cam_frame) tw = matT_vec(p.cam.M, Mt);
         const float gg0 = kDegToRad * tw.x;
         const float gg1 = kDegToRad * fmaf(cx, tw.y, sx * tw.z);
         const float gg2 = kDegToRad * fmaf(sy, tw.x, fmaf(-sx * cy, tw.y, cx * cy * tw.z));
