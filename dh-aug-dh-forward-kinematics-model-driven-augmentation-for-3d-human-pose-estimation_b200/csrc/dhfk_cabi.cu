@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(256) w2c_bwd_dev_kernel(const float* __restric
 
 DHFK_DI CamConst load_cam_row(const float* row) {
     CamConst cc;
-    cc.f[0] = row[0]; cc.f[1] = row[1]; cc.c[0] = row[2]; cc.c[1] = row[3];
-    cc.k[0] = row[4]; cc.k[1] = row[5]; cc.k[2] = row[6]; cc.p[0] = row[7]; cc.p[1] = row[8];
+    cc.f = make_float2(row[0], row[1]); cc.c = make_float2(row[2], row[3]);
+    cc.k[0] = row[4]; cc.k[1] = row[5]; cc.k[2] = row[6]; cc.p = make_float2(row[7], row[8]);
     cc.k1x2 = 2.f * cc.k[1]; cc.k2x3 = 3.f * cc.k[2];
     return cc;
 }
@@ -147,8 +147,8 @@ CamConst make_cam(const float* cam) {
     if (cam) {
         camera_matrix(cam, cc.M);
         for (int i = 0; i < 3; ++i) cc.t[i] = cam[4 + i];
-        cc.f[0] = cam[7]; cc.f[1] = cam[8]; cc.c[0] = cam[9]; cc.c[1] = cam[10];
-        cc.k[0] = cam[11]; cc.k[1] = cam[12]; cc.k[2] = cam[13]; cc.p[0] = cam[14]; cc.p[1] = cam[15];
+        cc.f = make_float2(cam[7], cam[8]); cc.c = make_float2(cam[9], cam[10]);
+        cc.k[0] = cam[11]; cc.k[1] = cam[12]; cc.k[2] = cam[13]; cc.p = make_float2(cam[14], cam[15]);
         cc.k1x2 = 2.f * cc.k[1];
         cc.k2x3 = 3.f * cc.k[2];
     }

@@ -239,12 +239,20 @@ DHFK_DI Frame identity_frame() {
 // M maps v = X_world - t to camera space exactly as qrot(conj(q), v) does
 // (common/quaternion.py:6-24, common/camera.py:36-38), valid for non-unit q too.
 // ---------------------------------------------------------------------------------------
-struct CamConst {
+struct alignas(8) CamConst {
     float M[9];
     float t[3];
-    float f[2], c[2], k[3], p[2];
+    float2 f, c, p;    // focal, principal point, tangential distortion as (x, y) pairs: FFMA2 operands
+    float k[3];
     float k1x2, k2x3;  // 2*k[1], 3*k[2]
 };
+
+// Packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): the projection works on (x, y) lanes, so every
+// per-lane product/FMA is one instruction for both lanes; scalar operands broadcast for free (".F32").
+#ifndef DHFK_PACKED_PROJ
+#define DHFK_PACKED_PROJ 1
+#endif
+DHFK_DI float2 bc2(float s) { return make_float2(s, s); }
 
 struct ProjAux { float rx, ry, x, y, r2, S, iz; };
 
@@ -257,31 +265,59 @@ DHFK_DI float rcp_approx(float x) {
 DHFK_DI void project_point(const CamConst& cc, V3 X, float& u, float& v, ProjAux& a) {
     float iz = rcp_approx(X.z);
     a.iz = iz;
+#if DHFK_PACKED_PROJ
+    const float2 r = __fmul2_rn(make_float2(X.x, X.y), bc2(iz));
+    a.rx = r.x; a.ry = r.y;
+    a.x = fminf(fmaxf(r.x, -1.f), 1.f);
+    a.y = fminf(fmaxf(r.y, -1.f), 1.f);
+    a.r2 = fmaf(a.x, a.x, a.y * a.y);
+    float radial = fmaf(a.r2, fmaf(a.r2, fmaf(a.r2, cc.k[2], cc.k[1]), cc.k[0]), 1.f);
+    float tan = fmaf(cc.p.x, a.x, cc.p.y * a.y);
+    a.S = radial + tan;
+    const float2 sxy = __ffma2_rn(make_float2(a.x, a.y), bc2(a.S), __fmul2_rn(cc.p, bc2(a.r2)));
+    const float2 uv = __ffma2_rn(cc.f, sxy, cc.c);
+    u = uv.x; v = uv.y;
+#else
     a.rx = X.x * iz;
     a.ry = X.y * iz;
     a.x = fminf(fmaxf(a.rx, -1.f), 1.f);
     a.y = fminf(fmaxf(a.ry, -1.f), 1.f);
     a.r2 = fmaf(a.x, a.x, a.y * a.y);
     float radial = fmaf(a.r2, fmaf(a.r2, fmaf(a.r2, cc.k[2], cc.k[1]), cc.k[0]), 1.f);
-    float tan = fmaf(cc.p[0], a.x, cc.p[1] * a.y);
+    float tan = fmaf(cc.p.x, a.x, cc.p.y * a.y);
     a.S = radial + tan;
-    float sx = fmaf(a.x, a.S, cc.p[0] * a.r2);
-    float sy = fmaf(a.y, a.S, cc.p[1] * a.r2);
-    u = fmaf(cc.f[0], sx, cc.c[0]);
-    v = fmaf(cc.f[1], sy, cc.c[1]);
+    float sx = fmaf(a.x, a.S, cc.p.x * a.r2);
+    float sy = fmaf(a.y, a.S, cc.p.y * a.r2);
+    u = fmaf(cc.f.x, sx, cc.c.x);
+    v = fmaf(cc.f.y, sy, cc.c.y);
+#endif
 }
 // gradient wrt the camera-space point; torch.clamp passes gradient where -1 <= x/z <= 1
 DHFK_DI V3 project_point_bwd(const CamConst& cc, const ProjAux& a, float gu, float gv) {
-    float a0 = cc.f[0] * gu, a1 = cc.f[1] * gv;
+#if DHFK_PACKED_PROJ
+    const float2 a01 = __fmul2_rn(cc.f, make_float2(gu, gv));
+    float drad = fmaf(a.r2, fmaf(a.r2, cc.k2x3, cc.k1x2), cc.k[0]);
+    float ax = fmaf(a01.x, a.x, a01.y * a.y);
+    float ap = fmaf(a01.x, cc.p.x, a01.y * cc.p.y);
+    float t2 = 2.f * fmaf(ax, drad, ap);
+    const float2 xy = make_float2(a.x, a.y);
+    float2 g = __ffma2_rn(a01, bc2(a.S), __ffma2_rn(xy, bc2(t2), __fmul2_rn(cc.p, bc2(ax))));
+    g.x = (a.x == a.rx) ? g.x : 0.f;
+    g.y = (a.y == a.ry) ? g.y : 0.f;
+    const float2 gi = __fmul2_rn(g, bc2(a.iz));
+    return v3(gi.x, gi.y, -fmaf(g.x, a.rx, g.y * a.ry) * a.iz);
+#else
+    float a0 = cc.f.x * gu, a1 = cc.f.y * gv;
     float drad = fmaf(a.r2, fmaf(a.r2, cc.k2x3, cc.k1x2), cc.k[0]);
     float ax = fmaf(a0, a.x, a1 * a.y);
-    float ap = fmaf(a0, cc.p[0], a1 * cc.p[1]);
+    float ap = fmaf(a0, cc.p.x, a1 * cc.p.y);
     float t2 = 2.f * fmaf(ax, drad, ap);
-    float gx = fmaf(a0, a.S, fmaf(a.x, t2, ax * cc.p[0]));
-    float gy = fmaf(a1, a.S, fmaf(a.y, t2, ax * cc.p[1]));
+    float gx = fmaf(a0, a.S, fmaf(a.x, t2, ax * cc.p.x));
+    float gy = fmaf(a1, a.S, fmaf(a.y, t2, ax * cc.p.y));
     gx = (a.x == a.rx) ? gx : 0.f;
     gy = (a.y == a.ry) ? gy : 0.f;
     return v3(gx * a.iz, gy * a.iz, -fmaf(gx, a.rx, gy * a.ry) * a.iz);
+#endif
 }
 
 // tanh(x) and sech^2(x) = d tanh/dx from u = exp(-2|x|):  t = sgn(x)(1-u)/(1+u),  sech^2 = 4u/(1+u)^2
