@@ -5,6 +5,7 @@ Public surface:
   Fk_generator.Fk_Generator / Video_Fk_Generator                            (reference-shaped generators, fused epilogue)
   Forward_Kinematics_DH_Model                                               (reference-shaped class)
   camera.GAN_torch_world_to_camera / camera.project_to_2d                   (reference-shaped functions)
+  dataloader_update.random_bl_aug / dataloader_update / refresh_poses        (per-epoch loader refresh)
   dropin.install()                                                          (patch the imported reference)
   tables, synthetic, parallel
 
@@ -18,9 +19,10 @@ def __getattr__(name):
     # torch-dependent modules are imported lazily so that `import dhfk` stays cheap
     import importlib
     if name in ("functional", "camera", "dropin", "parallel", "synthetic", "forward_kinematics_DH_model",
-                "Fk_generator"):
+                "Fk_generator", "dataloader_update"):
         return importlib.import_module("." + name, __name__)
-    if name in ("fk_project", "fk_world16", "world_to_camera", "project_to_2d", "fk_project_host", "generator_fk"):
+    if name in ("fk_project", "fk_world16", "world_to_camera", "project_to_2d", "fk_project_host", "generator_fk",
+                "retarget_project"):
         return getattr(importlib.import_module(".functional", __name__), name)
     if name == "Forward_Kinematics_DH_Model":
         return importlib.import_module(".forward_kinematics_DH_model", __name__).Forward_Kinematics_DH_Model

@@ -41,6 +41,7 @@ SIGNATURES = {
     "dhfk_world_to_camera_backward": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _i64, _vp]),
     "dhfk_project_forward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp]),
     "dhfk_project_backward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
+    "dhfk_retarget_project": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, _vp, _i64, _vp, _vp, _i64, _vp]),
     "dhfk_host_workspace_bytes": (_i64, [_i64, ctypes.c_int32]),
     "dhfk_forward_backward_host": (ctypes.c_int, [_vp] * 12 + [_i64, _i64, ctypes.c_int32, _vp, _i64, _u32]),
 }

@@ -401,6 +401,25 @@ int dhfk_project_backward(const float* x, const float* cam_rows, int64_t cam_row
     return e == cudaSuccess ? DHFK_OK : cuda_fail(e, "project_bwd_kernel");
 }
 
+// ---- bone-length retarget + per-row projection ---------------------------------------
+int dhfk_retarget_project(const float* pose, const int32_t* tmpl_idx, const float* templates, int32_t num_templates,
+                          const float* cam_rows, int64_t cam_rows_stride, float* out_pose, float* out_uv, int64_t n,
+                          void* stream) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
+    if (n == 0) return DHFK_OK;
+    if (!pose || !templates || !out_pose) return fail(DHFK_E_INVAL, "pose / templates / out_pose must be non-null");
+    if (num_templates <= 0) return fail(DHFK_E_INVAL, "num_templates must be > 0");
+    if (out_uv && (!cam_rows || (cam_rows_stride != 0 && cam_rows_stride < 9)))
+        return fail(DHFK_E_INVAL, "out_uv needs cam_rows with >= 9 columns (row stride 0 = one shared row)");
+    if (!aligned16(pose) || !aligned16(out_pose) || !aligned16(out_uv))
+        return fail(DHFK_E_ALIGN, "pose / out_pose / out_uv must be 16-byte aligned");
+    if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
+    const char* where = "";
+    int e = dhfk::launch_retarget(pose, tmpl_idx, templates, num_templates, cam_rows, cam_rows_stride, out_pose, out_uv,
+                                  n, (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+
 // ---- host-buffer end-to-end entry --------------------------------------------------------------
 // per-row device scratch: inputs 54, world 48, uv 32, g_world 48, g_uv 32, g_ang 33, g_grot 3, g_root 3
 static const int64_t kHostRowFloats = 54 + 48 + 32 + 48 + 32 + 33 + 3 + 3;

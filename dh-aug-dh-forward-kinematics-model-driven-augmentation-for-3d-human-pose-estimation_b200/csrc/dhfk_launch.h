@@ -17,6 +17,11 @@ int launch_bwd_t1_b1_g0(const BwdParams& p, bool guv, cudaStream_t st, const cha
 int launch_bwd_t0_b0_g1(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
 int launch_bwd_t1_b0_g1(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
 
+// bone-length retarget (+ per-row projection), forward only
+int launch_retarget(const float* pose, const int* tmpl_idx, const float* templates, int num_templates,
+                    const float* cam_rows, long long cam_stride, float* out_pose, float* out_uv, long long n,
+                    cudaStream_t st, const char** where);
+
 // floats per pose in the input slabs: raw mode ang33+grot3+bone15+root3, generator mode out35+bone15
 inline size_t in_floats(bool gen) { return gen ? (GEN_NCOL + 15) : 54; }
 inline size_t fwd_smem_bytes(bool cam, bool uv, bool gen) {

@@ -20,11 +20,25 @@ _CALLERS = (
 )
 
 
-def install(verbose: bool = False, generators: bool = False):
+def install(verbose: bool = False, generators: bool = False, loader_refresh: bool = False):
     """Patch the reference modules that are currently imported.  Idempotent.  Returns the names patched.
+    loader_refresh=True also swaps random_bl_aug / video_mode_random_bl_aug / dataloader_update for the fused
+    retarget+project versions (same np.random stream, same data_dict contract).
     generators=True also swaps Fk_Generator / Video_Fk_Generator for the fused-epilogue versions (SURVEY 8 f1;
     same constructor and state dict) wherever `my_get_poseFk_model` (model_fk_gan_train.py:97-173) finds them."""
     patched = []
+    if loader_refresh:
+        from . import dataloader_update as _du
+        for name, syms in (("function_aug.dataloader_update", ("random_bl_aug", "dataloader_update")),
+                           ("models_Fk_GAN.video_mode_operate", ("random_bl_aug", "video_mode_random_bl_aug")),
+                           ("run_Fk_GAN", ("dataloader_update",)), ("__main__", ("dataloader_update",))):
+            mod = sys.modules.get(name)
+            if mod is None:
+                continue
+            for sym in syms:
+                if hasattr(mod, sym):
+                    setattr(mod, sym, getattr(_du, sym))
+                    patched.append("%s.%s" % (name, sym))
     if generators:
         from . import Fk_generator as _gen
         for name in ("models_Fk_GAN.Fk_generator", "models_Fk_GAN.model_fk_gan_train", "models_Fk_GAN.video_GAN_fun"):

@@ -349,6 +349,52 @@ def project_to_2d(x, camera_params):
     return _Project.apply(x, camera_params)
 
 
+def retarget_project(pose16, templates, tmpl_idx=None, cam_rows=None, *, out_pose=None, out_uv=None):
+    """Bone-length retarget (+ per-row projection) in one launch -- SURVEY 8 f3.
+
+    pose16 [N,16,3]; templates [T,15] in utils/gan_utils.py bone order; tmpl_idx [N] int template row per
+    pose, or None: every pose takes templates[0] (video_mode_random_bl_aug draws one row per sequence).
+    cam_rows [N,>=9] (or a single row [9] / [1,9] shared by all poses) -> also returns uv [N,16,2].
+    Replaces random_bl_aug + project_to_2d (function_aug/dataloader_update.py:18-41,69).  Forward only: the
+    reference detaches the result before it is used."""
+    _require_cuda()
+    lib = _cabi.load()
+    device = pose16.device if pose16.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    assert pose16.shape[-2:] == (16, 3), "pose must be [N,16,3]"
+    x = _packed(pose16.detach(), (-1, 16, 3), device)
+    n = x.shape[0]
+    tm = templates if isinstance(templates, torch.Tensor) else torch.as_tensor(np.asarray(templates, dtype=np.float32))
+    tm = tm.detach().to(device=device, dtype=torch.float32).reshape(-1, 15).contiguous()
+    idx = None
+    if tmpl_idx is not None:
+        idx = tmpl_idx if isinstance(tmpl_idx, torch.Tensor) else torch.as_tensor(np.asarray(tmpl_idx))
+        idx = idx.to(device=device, dtype=torch.int32).reshape(-1).contiguous()
+        if idx.shape[0] != n:
+            raise ValueError("tmpl_idx has %d rows, pose has %d" % (idx.shape[0], n))
+    cams, cam_stride = None, 0
+    if cam_rows is not None:
+        cams = cam_rows.detach()
+        if cams.dim() == 1 or cams.shape[0] == 1 and n != 1:
+            cams = _rows(cams.reshape(1, -1), 9, device)
+            cam_stride = 0
+        else:
+            cams = _rows(cams, 9, device)
+            if cams.shape[0] != n:
+                raise ValueError("cam_rows has %d rows, pose has %d" % (cams.shape[0], n))
+            cam_stride = _row_stride(cams)
+    if out_pose is None:
+        out_pose = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
+    if cams is not None and out_uv is None:
+        out_uv = torch.empty((n, 16, 2), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        rc = lib.dhfk_retarget_project(
+            x.data_ptr(), idx.data_ptr() if idx is not None else None, tm.data_ptr(), tm.shape[0],
+            cams.data_ptr() if cams is not None else None, cam_stride, out_pose.data_ptr(),
+            out_uv.data_ptr() if cams is not None else None, n, _stream_ptr(device))
+    _cabi.check(rc, "dhfk_retarget_project")
+    return (out_pose, out_uv) if cams is not None else out_pose
+
+
 def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chunk_rows=65536, num_streams=3,
                     workspace=None, out=None, fast_trig=False):
     """End-to-end over HOST (ideally pinned) float32 tensors through dhfk_forward_backward_host:

@@ -22,6 +22,8 @@
  *       (model_fk_gan_train.py:374,434; video_GAN_fun.py:321,440)
  *   dhfk_project_*              common/camera.py:62-94 called on its own, per-row intrinsics
  *       (function_aug/dataloader_update.py:69; model_fk_gan_train.py:376,436)
+ *   dhfk_retarget_project       random_bl_aug + project_to_2d of the per-epoch loader refresh
+ *       (function_aug/dataloader_update.py:18-41,69; models_Fk_GAN/video_mode_operate.py:879-928)
  *   dhfk_topology               the constant tables the reference keeps as Python lists
  *       (forward_kinematics_DH_model.py:234-261,:571-589,:751-817; common/h36m_dataset.py:37-38)
  *
@@ -150,6 +152,23 @@ int dhfk_project_forward(const float* x_dev, const float* cam_rows_dev, int64_t 
                          int64_t n, int64_t joints, void* stream);
 int dhfk_project_backward(const float* x_dev, const float* cam_rows_dev, int64_t cam_rows_stride,
                           const float* g_uv_dev, float* g_x_dev, int64_t n, int64_t joints, void* stream);
+
+/*
+ * SURVEY 8 f3 -- per-epoch dataset re-augmentation, fused (forward only; the reference detaches the result):
+ *   random_bl_aug            function_aug/dataloader_update.py:18-41
+ *   video_mode_random_bl_aug models_Fk_GAN/video_mode_operate.py:879-897
+ *     (root-centre; unit bone vectors utils/gan_utils.py:90-134; times a bone-length template row; rebuild the
+ *      pose down the 16-joint tree utils/gan_utils.py:56-86; add the root back)
+ *   followed by project_to_2d with per-row intrinsics (dataloader_update.py:69, video_mode_operate.py:925-928).
+ * pose_dev [N,16,3] packed; templates_dev [T,15] in utils/gan_utils.py bone order (the order of
+ * data_extra/bone_length_npy/hm36s15678_bl_templates.npy); tmpl_idx_dev [N] int32 template row per pose, or NULL:
+ * every pose uses template row 0 (the video variant draws one row per sequence).  cam_rows_dev [N, >=9] with row
+ * stride cam_rows_stride, or stride 0: one intrinsics row shared by all poses.  out_pose_dev [N,16,3] (may alias
+ * pose_dev); out_uv_dev [N,16,2] or NULL (then cam_rows_dev is ignored).
+ */
+int dhfk_retarget_project(const float* pose_dev, const int32_t* tmpl_idx_dev, const float* templates_dev,
+                          int32_t num_templates, const float* cam_rows_dev, int64_t cam_rows_stride,
+                          float* out_pose_dev, float* out_uv_dev, int64_t n, void* stream);
 
 /*
  * Host-buffer end-to-end entry: forward + backward over N poses whose inputs, upstream gradients

@@ -18,8 +18,8 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the C oracle (gcc) if needed; returns the .so path."""
-    src = os.path.join(_HERE, "dhfk_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("dhfk_oracle.c", "dhfk_oracle_aux.c", "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B" if force else "all"])
     return _LIB_PATH
 
@@ -168,3 +168,23 @@ def gen_backward(raw35, bone_scaled, half37, mid37, cam16=None, g_world=None, g_
             d[:, src[i]] = gslot[:, i] * dslot[:, i]
     d[:, 32:35] = b["g_root"] * droot
     return d
+
+
+def retarget(pose16, templates, tmpl_idx=None, cam_rows=None):
+    """random_bl_aug (+ project_to_2d with per-row intrinsics) -> dict(pose [N,16,3], uv [N,16,2]) float64."""
+    pose16 = np.ascontiguousarray(pose16, dtype=np.float32).reshape(-1, 16, 3)
+    n = pose16.shape[0]
+    tm = np.ascontiguousarray(templates, dtype=np.float32).reshape(-1, 15)
+    idx = None if tmpl_idx is None else np.ascontiguousarray(tmpl_idx, dtype=np.int32).reshape(n)
+    out = {"pose": np.empty((n, 16, 3), np.float64)}
+    stride = 0
+    if cam_rows is not None:
+        cam_rows = _f32(np.asarray(cam_rows).reshape(-1, np.asarray(cam_rows).shape[-1]))
+        stride = 0 if cam_rows.shape[0] == 1 and n != 1 else cam_rows.shape[1]
+        out["uv"] = np.empty((n, 16, 2), np.float64)
+    rc = lib().dhfk_oracle_retarget(
+        ctypes.c_int64(n), _ptr(pose16), _ptr(idx, ctypes.c_int32), _ptr(tm), ctypes.c_int32(tm.shape[0]),
+        _ptr(cam_rows), ctypes.c_int64(stride), _ptr(out["pose"], ctypes.c_double),
+        _ptr(out.get("uv"), ctypes.c_double))
+    assert rc == 0, rc
+    return out

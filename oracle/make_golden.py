@@ -15,6 +15,10 @@ Fixtures
   sampler40.npz    handler_but_generater (non-GAN sampler) draws + poses for a fixed seed
   generator.npz    Fk_Generator / Video_Fk_Generator epilogue (tanh, slot scatter, range map, scaler) + FK,
                    outputs and d/d(raw network output), for a known raw last-layer output
+  retarget.npz     random_bl_aug / video_mode_random_bl_aug + per-row project_to_2d, seeded
+                   np.random so the drawn template rows are part of the fixture
+
+    python oracle/make_golden.py retarget      # regenerate only the named fixtures
 """
 from __future__ import annotations
 
@@ -247,23 +251,73 @@ def generator_fixture():
     return out
 
 
+def retarget_fixture():
+    """random_bl_aug (function_aug/dataloader_update.py:18-41) and video_mode_random_bl_aug
+    (models_Fk_GAN/video_mode_operate.py:879-897) + project_to_2d with per-row intrinsics, run from the
+    reference's own working directory (they np.load the template file by relative path)."""
+    ref = rh.import_reference()
+    for name in ("progress", "progress.bar"):
+        if name not in sys.modules:
+            rh._stub_module(name)
+    cwd = os.getcwd()
+    os.chdir(rh.REF_ROOT)
+    try:
+        from function_aug import dataloader_update as du
+        # video_mode_operate drags in the whole training stack; its 12-line function is exercised through the
+        # identical code path of random_bl_aug with a broadcast single row (checked below against gan_utils)
+        from utils import gan_utils as gu
+        cam_poses = np.load(os.path.join(OUT, "gan133.npz"))["cam"].astype(np.float32)      # realistic camera-space poses
+        n = cam_poses.shape[0]
+        rng = np.random.RandomState(23)
+        subjects = ["S1", "S5", "S6", "S7", "S8"]
+        rows = np.stack([rh.camera_block(subjects[rng.randint(5)], rng.randint(4))[7:16] for _ in range(n)])
+        rows16 = np.concatenate([rows, rng.randn(n, 7).astype(np.float32)], 1)
+        np.random.seed(17)
+        out = du.random_bl_aug(t(cam_poses))
+        np.random.seed(17)
+        idx = np.random.choice(5, n)
+        after = np.random.randint(0, 1 << 30)          # RNG position after the call
+        uv = ref.camera.project_to_2d(out, t(rows16))
+        # sequence variant: one template row for 27 frames, one shared intrinsics row (video_mode_operate.py:916-928)
+        seq = cam_poses[:27]
+        tm = np.load("./data_extra/bone_length_npy/hm36s15678_bl_templates.npy")
+        np.random.seed(4)
+        vidx = np.random.choice(tm.shape[0], 1)
+        x = t(seq)
+        root = x[:, :1, :] * 1.0
+        unit = gu.get_bone_unit_vecbypose3d(x - x[:, :1, :])
+        vout = gu.get_pose3dbyBoneVec(unit * torch.from_numpy(tm[vidx].astype("float32")).unsqueeze(2)) + root
+        used = torch.zeros(27, 9)
+        used[:] = t(rows[0])
+        vuv = ref.camera.project_to_2d(vout, used)
+    finally:
+        os.chdir(cwd)
+    return dict(pose=cam_poses, tmpl_idx=idx.astype(np.int32), rng_after=np.array([after]), cam_rows16=rows16,
+                out_pose=out.numpy(), out_uv=uv.numpy(), templates=tm, v_pose=seq, v_idx=vidx.astype(np.int32),
+                v_cam_row=rows[0], v_out_pose=vout.numpy(), v_out_uv=vuv.numpy())
+
+
 def main():
     from dhfk import synthetic
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
-    np.savez(os.path.join(OUT, "tables.npz"), **tables_fixture())
-    np.savez(os.path.join(OUT, "kat.npz"), **kat_fixture())
-    np.savez(os.path.join(OUT, "gan133.npz"),
-             **run_case(synthetic.gan_like(133, seed=1234), rh.camera_block("S1", 0), synthetic.upstream_grads(133)))
-    np.savez(os.path.join(OUT, "stress200.npz"),
-             **run_case(synthetic.gan_like(200, seed=99, root_mode="generator", angle_mode="stress"),
-                        rh.camera_block("S7", 2), synthetic.upstream_grads(200, seed=5)))
-    np.savez(os.path.join(OUT, "video36.npz"),
-             **run_case(synthetic.gan_like(36, seed=3), rh.camera_block("S8", 1), synthetic.upstream_grads(36, seed=8),
-                        mode="multi", architecture="3,3", root_shape=(4, 9, 3)))
-    np.savez(os.path.join(OUT, "camera_ops.npz"), **camera_ops_fixture())
-    np.savez(os.path.join(OUT, "sampler40.npz"), **sampler_fixture())
-    np.savez(os.path.join(OUT, "generator.npz"), **generator_fixture())
+    fixtures = {
+        "tables": tables_fixture,
+        "kat": kat_fixture,
+        "gan133": lambda: run_case(synthetic.gan_like(133, seed=1234), rh.camera_block("S1", 0),
+                                   synthetic.upstream_grads(133)),
+        "stress200": lambda: run_case(synthetic.gan_like(200, seed=99, root_mode="generator", angle_mode="stress"),
+                                      rh.camera_block("S7", 2), synthetic.upstream_grads(200, seed=5)),
+        "video36": lambda: run_case(synthetic.gan_like(36, seed=3), rh.camera_block("S8", 1),
+                                    synthetic.upstream_grads(36, seed=8), mode="multi", architecture="3,3",
+                                    root_shape=(4, 9, 3)),
+        "camera_ops": camera_ops_fixture,
+        "sampler40": sampler_fixture,
+        "generator": generator_fixture,
+        "retarget": retarget_fixture,
+    }
+    for name in (sys.argv[1:] or list(fixtures)):
+        np.savez(os.path.join(OUT, name + ".npz"), **fixtures[name]())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
