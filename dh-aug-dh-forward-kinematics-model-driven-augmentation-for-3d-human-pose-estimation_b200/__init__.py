@@ -6,6 +6,7 @@ Public surface:
   Forward_Kinematics_DH_Model                                               (reference-shaped class)
   camera.GAN_torch_world_to_camera / camera.project_to_2d                   (reference-shaped functions)
   dataloader_update.random_bl_aug / dataloader_update / refresh_poses        (per-epoch loader refresh)
+  Fk_discriminator.special_KCS_Input_transform / critic_views, functional.critic_input / flip_pose   
   dropin.install()                                                          (patch the imported reference)
   tables, synthetic, parallel
 
@@ -19,10 +20,10 @@ def __getattr__(name):
     # torch-dependent modules are imported lazily so that `import dhfk` stays cheap
     import importlib
     if name in ("functional", "camera", "dropin", "parallel", "synthetic", "forward_kinematics_DH_model",
-                "Fk_generator", "dataloader_update"):
+                "Fk_generator", "dataloader_update", "Fk_discriminator"):
         return importlib.import_module("." + name, __name__)
     if name in ("fk_project", "fk_world16", "world_to_camera", "project_to_2d", "fk_project_host", "generator_fk",
-                "retarget_project"):
+                "retarget_project", "critic_input", "flip_pose"):
         return getattr(importlib.import_module(".functional", __name__), name)
     if name == "Forward_Kinematics_DH_Model":
         return importlib.import_module(".forward_kinematics_DH_model", __name__).Forward_Kinematics_DH_Model

@@ -15,6 +15,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 ABI_VERSION = 1
 FLAG_FAST_TRIG = 0x1
+CRITIC_CENTRE, CRITIC_FLIP = 0x1, 0x2
 E_INVAL, E_ALIGN, E_UNSUPPORTED = -1, -2, -3
 
 _c_f32p = ctypes.c_void_p  # raw device/host addresses are passed as integers
@@ -42,6 +43,10 @@ SIGNATURES = {
     "dhfk_project_forward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp]),
     "dhfk_project_backward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "dhfk_retarget_project": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "dhfk_critic_input_forward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, _i64, _u32, _vp]),
+    "dhfk_critic_input_backward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, _vp, _i64, _u32, _vp]),
+    "dhfk_critic_input_jvp": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int32, _i64, _u32, _vp]),
+    "dhfk_flip_pose": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int32, _vp]),
     "dhfk_host_workspace_bytes": (_i64, [_i64, ctypes.c_int32]),
     "dhfk_forward_backward_host": (ctypes.c_int, [_vp] * 12 + [_i64, _i64, ctypes.c_int32, _vp, _i64, _u32]),
 }

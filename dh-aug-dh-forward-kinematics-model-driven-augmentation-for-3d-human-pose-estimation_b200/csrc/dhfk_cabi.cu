@@ -420,6 +420,70 @@ int dhfk_retarget_project(const float* pose, const int32_t* tmpl_idx, const floa
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }
 
+// ---- critic input transforms -----------------------------------------------------------
+static int critic_common(int32_t kcs_cols, int64_t n, uint32_t flags) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
+    if (kcs_cols != 0 && kcs_cols != 15 && kcs_cols != 30) return fail(DHFK_E_INVAL, "kcs_cols must be 0, 15 or 30");
+    if (flags & ~(DHFK_CRITIC_CENTRE | DHFK_CRITIC_FLIP)) return fail(DHFK_E_INVAL, "unknown critic flag");
+    if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
+    return DHFK_OK;
+}
+int dhfk_critic_input_forward(const float* pose, float* out_pos, float* out_kcs, int32_t kcs_cols, int64_t n,
+                              uint32_t flags, void* stream) {
+    if (int rc = critic_common(kcs_cols, n, flags)) return rc;
+    if (n == 0) return DHFK_OK;
+    if (!pose) return fail(DHFK_E_INVAL, "pose must be non-null");
+    if ((kcs_cols > 0) != (out_kcs != nullptr)) return fail(DHFK_E_INVAL, "out_kcs must be given iff kcs_cols > 0");
+    if (!out_pos && !out_kcs) return fail(DHFK_E_INVAL, "nothing to compute: out_pos and out_kcs are both null");
+    if (!aligned16(pose) || !aligned16(out_pos) || !aligned16(out_kcs))
+        return fail(DHFK_E_ALIGN, "pose / out_pos / out_kcs must be 16-byte aligned");
+    const char* where = "";
+    int e = dhfk::launch_critic(0, kcs_cols, out_pos != nullptr, pose, nullptr, nullptr, out_pos, out_kcs, n, flags,
+                                (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+int dhfk_critic_input_backward(const float* pose, const float* g_pos, const float* g_kcs, int32_t kcs_cols,
+                               float* g_pose, int64_t n, uint32_t flags, void* stream) {
+    if (int rc = critic_common(kcs_cols, n, flags)) return rc;
+    if (n == 0) return DHFK_OK;
+    if (!pose || !g_pose) return fail(DHFK_E_INVAL, "pose / g_pose must be non-null");
+    if ((kcs_cols > 0) != (g_kcs != nullptr)) return fail(DHFK_E_INVAL, "g_kcs must be given iff kcs_cols > 0");
+    if (!g_pos && !g_kcs) return fail(DHFK_E_INVAL, "no upstream gradient: g_pos and g_kcs are both null");
+    if (!aligned16(pose) || !aligned16(g_pos) || !aligned16(g_kcs) || !aligned16(g_pose))
+        return fail(DHFK_E_ALIGN, "pose / g_pos / g_kcs / g_pose must be 16-byte aligned");
+    const char* where = "";
+    int e = dhfk::launch_critic(1, kcs_cols, g_pos != nullptr, pose, g_pos, g_kcs, g_pose, nullptr, n, flags,
+                                (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+int dhfk_critic_input_jvp(const float* pose, const float* v_pose, float* t_pos, float* t_kcs, int32_t kcs_cols,
+                          int64_t n, uint32_t flags, void* stream) {
+    if (int rc = critic_common(kcs_cols, n, flags)) return rc;
+    if (n == 0) return DHFK_OK;
+    if (!pose || !v_pose) return fail(DHFK_E_INVAL, "pose / v_pose must be non-null");
+    if ((kcs_cols > 0) != (t_kcs != nullptr)) return fail(DHFK_E_INVAL, "t_kcs must be given iff kcs_cols > 0");
+    if (!t_pos && !t_kcs) return fail(DHFK_E_INVAL, "nothing to compute: t_pos and t_kcs are both null");
+    if (!aligned16(pose) || !aligned16(v_pose) || !aligned16(t_pos) || !aligned16(t_kcs))
+        return fail(DHFK_E_ALIGN, "pose / v_pose / t_pos / t_kcs must be 16-byte aligned");
+    const char* where = "";
+    int e = dhfk::launch_critic(2, kcs_cols, t_pos != nullptr, pose, v_pose, nullptr, t_pos, t_kcs, n, flags,
+                                (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+int dhfk_flip_pose(const float* x, float* out, int64_t n, int32_t dims, void* stream) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
+    if (dims != 2 && dims != 3) return fail(DHFK_E_INVAL, "dims must be 2 or 3");
+    if (n == 0) return DHFK_OK;
+    if (!x || !out) return fail(DHFK_E_INVAL, "x / out must be non-null");
+    if (x == out) return fail(DHFK_E_INVAL, "flip cannot run in place");
+    if (n > (1LL << 34)) return fail(DHFK_E_INVAL, "n too large for one launch");
+    if (dims == 2 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 7u))
+        return fail(DHFK_E_ALIGN, "x / out must be 8-byte aligned");
+    const char* where = "";
+    int e = dhfk::launch_flip(x, out, n, dims, (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+
 // ---- host-buffer end-to-end entry --------------------------------------------------------------
 // per-row device scratch: inputs 54, world 48, uv 32, g_world 48, g_uv 32, g_ang 33, g_grot 3, g_root 3
 static const int64_t kHostRowFloats = 54 + 48 + 32 + 48 + 32 + 33 + 3 + 3;

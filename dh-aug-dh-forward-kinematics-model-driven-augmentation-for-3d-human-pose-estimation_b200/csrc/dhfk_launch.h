@@ -22,6 +22,11 @@ int launch_retarget(const float* pose, const int* tmpl_idx, const float* templat
                     const float* cam_rows, long long cam_stride, float* out_pose, float* out_uv, long long n,
                     cudaStream_t st, const char** where);
 
+// critic input transforms (flip / root-centre / KCS features): mode 0 forward, 1 vjp, 2 jvp
+int launch_critic(int mode, int kc, bool pos, const float* pose, const float* a, const float* b, float* out_pos,
+                  float* out_kcs, long long n, unsigned flags, cudaStream_t st, const char** where);
+int launch_flip(const float* x, float* out, long long n, int dims, cudaStream_t st, const char** where);
+
 // floats per pose in the input slabs: raw mode ang33+grot3+bone15+root3, generator mode out35+bone15
 inline size_t in_floats(bool gen) { return gen ? (GEN_NCOL + 15) : 54; }
 inline size_t fwd_smem_bytes(bool cam, bool uv, bool gen) {

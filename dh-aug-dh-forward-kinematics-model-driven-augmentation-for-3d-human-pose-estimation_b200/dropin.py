@@ -20,13 +20,21 @@ _CALLERS = (
 )
 
 
-def install(verbose: bool = False, generators: bool = False, loader_refresh: bool = False):
+def install(verbose: bool = False, generators: bool = False, loader_refresh: bool = False, critics: bool = False):
     """Patch the reference modules that are currently imported.  Idempotent.  Returns the names patched.
     loader_refresh=True also swaps random_bl_aug / video_mode_random_bl_aug / dataloader_update for the fused
     retarget+project versions (same np.random stream, same data_dict contract).
+    critics=True rebinds special_KCS_Input_transform / video_mode_special_KCS_Input_transform.
     generators=True also swaps Fk_Generator / Video_Fk_Generator for the fused-epilogue versions (SURVEY 8 f1;
     same constructor and state dict) wherever `my_get_poseFk_model` (model_fk_gan_train.py:97-173) finds them."""
     patched = []
+    if critics:   # SURVEY 8 f2: the critic classes call these two as module globals (Fk_discriminator.py:190, :443)
+        from . import Fk_discriminator as _dis
+        mod = sys.modules.get("models_Fk_GAN.Fk_discriminator")
+        if mod is not None:
+            for sym in ("special_KCS_Input_transform", "video_mode_special_KCS_Input_transform"):
+                setattr(mod, sym, getattr(_dis, sym))
+                patched.append("models_Fk_GAN.Fk_discriminator.%s" % sym)
     if loader_refresh:
         from . import dataloader_update as _du
         for name, syms in (("function_aug.dataloader_update", ("random_bl_aug", "dataloader_update")),

@@ -395,6 +395,136 @@ def retarget_project(pose16, templates, tmpl_idx=None, cam_rows=None, *, out_pos
     return (out_pose, out_uv) if cams is not None else out_pose
 
 
+# ---- critic input transforms ---------------------------------------------------------------------
+def _critic_flags(centre, flip):
+    return (_cabi.CRITIC_CENTRE if centre else 0) | (_cabi.CRITIC_FLIP if flip else 0)
+
+
+class _CriticInput(torch.autograd.Function):
+    """pose [N,16,3] -> (pos' = centre(flip(pose)), kcs [N,kcs_cols]).  Differentiable twice w.r.t. the upstream
+    gradients (what WGAN-GP needs); once w.r.t. the pose."""
+
+    @staticmethod
+    def forward(ctx, pose, flags, kcs_cols, want_pos):
+        _require_cuda()
+        lib = _cabi.load()
+        device = pose.device if pose.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        x = _packed(pose, (-1, 16, 3), device)
+        n = x.shape[0]
+        pos = torch.empty((n, 16, 3), dtype=torch.float32, device=device) if want_pos else None
+        kcs = torch.empty((n, kcs_cols), dtype=torch.float32, device=device) if kcs_cols else None
+        with torch.cuda.device(device):
+            rc = lib.dhfk_critic_input_forward(x.data_ptr(), pos.data_ptr() if want_pos else None,
+                                               kcs.data_ptr() if kcs_cols else None, kcs_cols, n, flags,
+                                               _stream_ptr(device))
+        _cabi.check(rc, "dhfk_critic_input_forward")
+        ctx.save_for_backward(x)
+        ctx.cfg = (flags, kcs_cols, want_pos, pose.shape, pose.device, pose.dtype)
+        return tuple(o for o in (pos, kcs) if o is not None)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (x,) = ctx.saved_tensors
+        flags, kcs_cols, want_pos, shape, dev, dtype = ctx.cfg
+        it = iter(grads)
+        g_pos = next(it) if want_pos else None
+        g_kcs = next(it) if kcs_cols else None
+        if g_pos is None and g_kcs is None:
+            return None, None, None, None
+        gx = _CriticInputVJP.apply(x, g_pos, g_kcs, flags, kcs_cols).reshape(shape)
+        if (gx.device, gx.dtype) != (dev, dtype):
+            gx = gx.to(device=dev, dtype=dtype)
+        return gx, None, None, None
+
+
+class _CriticInputVJP(torch.autograd.Function):
+    """g_pose = J(pose)^T (g_pos, g_kcs).  Linear in (g_pos, g_kcs); its derivative w.r.t. them is the JVP kernel.
+    The second derivative w.r.t. the pose itself is not propagated (nothing in the reference consumes it: WGAN-GP's
+    `interpolates` is a throw-away leaf, Fk_discriminator.py:221-231)."""
+
+    @staticmethod
+    def forward(ctx, x, g_pos, g_kcs, flags, kcs_cols):
+        lib = _cabi.load()
+        device, n = x.device, x.shape[0]
+        gp = _packed(g_pos, (n, 16, 3), device)
+        gk = _packed(g_kcs, (n, kcs_cols), device) if g_kcs is not None else None
+        gx = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
+        if n > 0:
+            with torch.cuda.device(device):
+                rc = lib.dhfk_critic_input_backward(x.data_ptr(), gp.data_ptr() if gp is not None else None,
+                                                    gk.data_ptr() if gk is not None else None,
+                                                    kcs_cols if gk is not None else 0, gx.data_ptr(), n, flags,
+                                                    _stream_ptr(device))
+            _cabi.check(rc, "dhfk_critic_input_backward")
+        ctx.save_for_backward(x)
+        ctx.cfg = (flags, kcs_cols, g_pos is not None, g_kcs is not None)
+        return gx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, v):
+        lib = _cabi.load()
+        (x,) = ctx.saved_tensors
+        flags, kcs_cols, has_pos, has_kcs = ctx.cfg
+        device, n = x.device, x.shape[0]
+        v = _packed(v, (n, 16, 3), device)
+        t_pos = torch.empty((n, 16, 3), dtype=torch.float32, device=device) if has_pos else None
+        t_kcs = torch.empty((n, kcs_cols), dtype=torch.float32, device=device) if has_kcs else None
+        if n > 0:
+            with torch.cuda.device(device):
+                rc = lib.dhfk_critic_input_jvp(x.data_ptr(), v.data_ptr(), t_pos.data_ptr() if has_pos else None,
+                                               t_kcs.data_ptr() if has_kcs else None, kcs_cols if has_kcs else 0, n,
+                                               flags, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_critic_input_jvp")
+        return None, t_pos, t_kcs, None, None
+
+
+def critic_input(pose16, *, centre=False, flip=False, kcs_cols=30, return_pos=True):
+    """Fused critic input transform.  pose16 [...,16,3] (or [...,48]) -> (pos' [N,16,3], kcs [N,kcs_cols]):
+    pos' = root-centred (model_fk_gan_train.py:312) and/or left-right flipped (:320-327) pose, kcs = the 15 bone-pair
+    cosines (+ 15 bone lengths when kcs_cols = 30) of Fk_discriminator.py:36-146 / :269-377 computed on pos'.
+    kcs_cols = 0 returns pos' only; return_pos=False returns kcs only."""
+    if kcs_cols not in (0, 15, 30):
+        raise ValueError("kcs_cols must be 0, 15 or 30")
+    if not return_pos and not kcs_cols:
+        raise ValueError("nothing to compute")
+    outs = _CriticInput.apply(pose16, _critic_flags(centre, flip), int(kcs_cols), bool(return_pos))
+    return outs[0] if len(outs) == 1 else outs
+
+
+class _FlipPose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda()
+        lib = _cabi.load()
+        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        dims = x.shape[-1]
+        xs = x.to(device=device, dtype=torch.float32).contiguous()
+        if xs.data_ptr() % 8:
+            xs = xs.clone()
+        out = torch.empty_like(xs)
+        n = xs.numel() // (16 * dims)
+        with torch.cuda.device(device):
+            rc = lib.dhfk_flip_pose(xs.data_ptr(), out.data_ptr(), n, dims, _stream_ptr(device))
+        _cabi.check(rc, "dhfk_flip_pose")
+        ctx.meta = (x.device, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = _FlipPose.apply(g)          # the flip is its own transpose
+        if (gx.device, gx.dtype) != ctx.meta:
+            gx = gx.to(device=ctx.meta[0], dtype=ctx.meta[1])
+        return gx
+
+
+def flip_pose(x):
+    """Left/right flip of [...,16,2|3] keypoints: negate x, swap joints [4,5,6,10,11,12] <-> [1,2,3,13,14,15]
+    (model_fk_gan_train.py:320-331, 393-405).  Returns a new tensor (the reference flips a detached clone)."""
+    assert x.shape[-2] == 16 and x.shape[-1] in (2, 3), "expected [...,16,2] or [...,16,3]"
+    return _FlipPose.apply(x)
+
+
 def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chunk_rows=65536, num_streams=3,
                     workspace=None, out=None, fast_trig=False):
     """End-to-end over HOST (ideally pinned) float32 tensors through dhfk_forward_backward_host:

@@ -24,6 +24,8 @@
  *       (function_aug/dataloader_update.py:69; model_fk_gan_train.py:376,436)
  *   dhfk_retarget_project       random_bl_aug + project_to_2d of the per-epoch loader refresh
  *       (function_aug/dataloader_update.py:18-41,69; models_Fk_GAN/video_mode_operate.py:879-928)
+ *   dhfk_critic_input_* / dhfk_flip_pose   flip, root-centring and KCS features of the critics' inputs
+ *       (models_Fk_GAN/Fk_discriminator.py:36-146,269-377; model_fk_gan_train.py:311-331,393-405)
  *   dhfk_topology               the constant tables the reference keeps as Python lists
  *       (forward_kinematics_DH_model.py:234-261,:571-589,:751-817; common/h36m_dataset.py:37-38)
  *
@@ -169,6 +171,33 @@ int dhfk_project_backward(const float* x_dev, const float* cam_rows_dev, int64_t
 int dhfk_retarget_project(const float* pose_dev, const int32_t* tmpl_idx_dev, const float* templates_dev,
                           int32_t num_templates, const float* cam_rows_dev, int64_t cam_rows_stride,
                           float* out_pose_dev, float* out_uv_dev, int64_t n, void* stream);
+
+/*
+ * SURVEY 8 f2 -- critic input transforms, fused (one thread per pose):
+ *   left/right flip      model_fk_gan_train.py:320-331 (negate x, swap joints [4,5,6,10,11,12] <-> [1,2,3,13,14,15])
+ *   root-centring        model_fk_gan_train.py:295,312,437 (x - x[:, :1])
+ *   KCS features         Fk_discriminator.py:36-146 special_KCS_Input_transform: 15 bone-pair cosines followed by the
+ *                        15 bone lengths (kcs_cols = 30), or Fk_discriminator.py:269-377
+ *                        video_mode_special_KCS_Input_transform: the 15 cosines only (kcs_cols = 15); bones from
+ *                        special_operate.py:513-539 Fk_get_boneVecByPose3d (used_16key_15bone_len_table order)
+ * forward : pos' = centre(flip(pose)) (each step only if its flag is set), kcs = KCS(pos').
+ *           out_pos_dev [N,16,3] or NULL; out_kcs_dev [N,kcs_cols] iff kcs_cols > 0.
+ * backward: g_pose = d( <g_pos, pos'> + <g_kcs, kcs> ) / d pose; g_pos_dev or g_kcs_dev may be NULL (= zero), not both.
+ * jvp     : (t_pos, t_kcs) = J(pose) v_pose -- the derivative of `backward` w.r.t. its upstream gradients, which is
+ *           what double-backward through the critic needs (WGAN-GP, Fk_discriminator.py:208-233, create_graph=True).
+ * All tensors packed, 16-byte aligned.  out_pos_dev may alias pose_dev.
+ */
+#define DHFK_CRITIC_CENTRE 0x1u
+#define DHFK_CRITIC_FLIP 0x2u
+int dhfk_critic_input_forward(const float* pose_dev, float* out_pos_dev, float* out_kcs_dev, int32_t kcs_cols,
+                              int64_t n, uint32_t flags, void* stream);
+int dhfk_critic_input_backward(const float* pose_dev, const float* g_pos_dev, const float* g_kcs_dev,
+                               int32_t kcs_cols, float* g_pose_dev, int64_t n, uint32_t flags, void* stream);
+int dhfk_critic_input_jvp(const float* pose_dev, const float* v_pose_dev, float* t_pos_dev, float* t_kcs_dev,
+                          int32_t kcs_cols, int64_t n, uint32_t flags, void* stream);
+/* The flip alone for [N,16,dims] keypoints, dims = 2 (the 2D critic's inputs, model_fk_gan_train.py:393-405) or 3.
+ * Not in place.  The flip is its own transpose: the backward is the same call on the upstream gradient. */
+int dhfk_flip_pose(const float* x_dev, float* out_dev, int64_t n, int32_t dims, void* stream);
 
 /*
  * Host-buffer end-to-end entry: forward + backward over N poses whose inputs, upstream gradients

@@ -188,3 +188,60 @@ def retarget(pose16, templates, tmpl_idx=None, cam_rows=None):
         _ptr(out.get("uv"), ctypes.c_double))
     assert rc == 0, rc
     return out
+
+
+CRITIC_CENTRE, CRITIC_FLIP = 1, 2
+
+
+def critic_forward(pose16, flags=0, kcs_cols=30):
+    """centre / flip / KCS features -> dict(pos [N,16,3], kcs [N,kcs_cols]) float64."""
+    pose16 = np.ascontiguousarray(pose16, dtype=np.float32).reshape(-1, 16, 3)
+    n = pose16.shape[0]
+    out = {"pos": np.empty((n, 16, 3), np.float64)}
+    if kcs_cols:
+        out["kcs"] = np.empty((n, kcs_cols), np.float64)
+    rc = lib().dhfk_oracle_critic_forward(ctypes.c_int64(n), _ptr(pose16), ctypes.c_uint32(flags),
+                                          ctypes.c_int32(kcs_cols), _ptr(out["pos"], ctypes.c_double),
+                                          _ptr(out.get("kcs"), ctypes.c_double))
+    assert rc == 0, rc
+    return out
+
+
+def critic_jvp(pose16, v, flags=0, kcs_cols=30):
+    pose16 = np.ascontiguousarray(pose16, dtype=np.float32).reshape(-1, 16, 3)
+    v = np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 16, 3)
+    n = pose16.shape[0]
+    out = {"pos": np.empty((n, 16, 3), np.float64)}
+    if kcs_cols:
+        out["kcs"] = np.empty((n, kcs_cols), np.float64)
+    rc = lib().dhfk_oracle_critic_jvp(ctypes.c_int64(n), _ptr(pose16), _ptr(v), ctypes.c_uint32(flags),
+                                      ctypes.c_int32(kcs_cols), _ptr(out["pos"], ctypes.c_double),
+                                      _ptr(out.get("kcs"), ctypes.c_double))
+    assert rc == 0, rc
+    return out
+
+
+def critic_backward(pose16, g_pos=None, g_kcs=None, flags=0):
+    pose16 = np.ascontiguousarray(pose16, dtype=np.float32).reshape(-1, 16, 3)
+    n = pose16.shape[0]
+    g_pos = None if g_pos is None else np.ascontiguousarray(g_pos, dtype=np.float32).reshape(n, 16, 3)
+    kcs_cols = 0
+    if g_kcs is not None:
+        g_kcs = np.ascontiguousarray(g_kcs, dtype=np.float32).reshape(n, -1)
+        kcs_cols = g_kcs.shape[1]
+    out = np.empty((n, 16, 3), np.float64)
+    rc = lib().dhfk_oracle_critic_backward(ctypes.c_int64(n), _ptr(pose16), _ptr(g_pos), _ptr(g_kcs),
+                                           ctypes.c_uint32(flags), ctypes.c_int32(kcs_cols),
+                                           _ptr(out, ctypes.c_double))
+    assert rc == 0, rc
+    return out
+
+
+def flip(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    dims = x.shape[-1]
+    out = np.empty(x.shape, np.float64)
+    rc = lib().dhfk_oracle_flip(ctypes.c_int64(x.size // (16 * dims)), _ptr(x), ctypes.c_int32(dims),
+                                _ptr(out, ctypes.c_double))
+    assert rc == 0, rc
+    return out

@@ -16,7 +16,10 @@ Fixtures
   generator.npz    Fk_Generator / Video_Fk_Generator epilogue (tanh, slot scatter, range map, scaler) + FK,
                    outputs and d/d(raw network output), for a known raw last-layer output
   retarget.npz     random_bl_aug / video_mode_random_bl_aug + per-row project_to_2d, seeded
-                   np.random so the drawn template rows are part of the fixture
+                   np.random so the drawn template rows are part of the fixture  critic.npz       critic input transforms: special_KCS_Input_transform (30 cols) and its video variant
+                   (15 cols), the train loop's root-centring and left/right flip, autograd gradients, and the
+                   reference Fk_3D_Discriminator's WGAN-GP gradient penalty + parameter gradients (double backward
+                   through the KCS transform) for a seeded state dict
 
     python oracle/make_golden.py retarget      # regenerate only the named fixtures
 """
@@ -297,6 +300,84 @@ def retarget_fixture():
                 v_cam_row=rows[0], v_out_pose=vout.numpy(), v_out_uv=vuv.numpy())
 
 
+def critic_fixture():
+    import argparse
+    rh.import_reference()
+    for name in ("progress", "progress.bar"):
+        if name not in sys.modules:
+            rh._stub_module(name)
+    from models_Fk_GAN import Fk_discriminator as fd
+    cpu = torch.device("cpu")
+    g = np.load(os.path.join(OUT, "gan133.npz"))
+    world = g["world16"].astype(np.float32)
+    n = world.shape[0]
+    rng = np.random.RandomState(41)
+    g_pos = rng.randn(n, 16, 3).astype(np.float32)
+    g_kcs = rng.randn(n, 30).astype(np.float32)
+    out = dict(pose=world, g_pos=g_pos, g_kcs=g_kcs)
+    left, right = [4, 5, 6, 10, 11, 12], [1, 2, 3, 13, 14, 15]
+
+    def transform(x, centre, flip):
+        if centre:
+            x = x[:, :, :] - x[:, :1, :]                      # model_fk_gan_train.py:312
+        if flip:                                              # :325-327 (on a clone; autograd-friendly restatement
+            x = x * torch.tensor([-1.0, 1.0, 1.0])            #  of `[:, :, 0] *= -1`)
+            idx = list(range(16))
+            for d, s_ in zip(left + right, right + left):
+                idx[d] = s_
+            x = x[:, idx, :]
+        return x
+
+    for centre in (0, 1):
+        for flip in (0, 1):
+            tag = "c%df%d" % (centre, flip)
+            x = t(world, True)
+            pos = transform(x, centre, flip)
+            kcs = fd.special_KCS_Input_transform(pos, cpu)
+            vk = fd.video_mode_special_KCS_Input_transform(pos, cpu)
+            out[tag + "_pos"] = pos.detach().numpy()
+            out[tag + "_kcs"] = kcs.detach().numpy()
+            out[tag + "_vkcs"] = vk.detach().numpy()
+            (gx,) = torch.autograd.grad((pos * t(g_pos)).sum() + (kcs * t(g_kcs)).sum(), x, retain_graph=True)
+            out[tag + "_g_pose"] = gx.numpy()
+            (gk,) = torch.autograd.grad((kcs * t(g_kcs)).sum(), x, retain_graph=True)
+            out[tag + "_g_pose_kcs_only"] = gk.numpy()
+            (gv,) = torch.autograd.grad((vk * t(g_kcs[:, :15])).sum(), x)
+            out[tag + "_g_pose_vkcs_only"] = gv.numpy()
+    # the in-place flip exactly as the train loop writes it, 3-D and 2-D (model_fk_gan_train.py:324-327, 399-405)
+    f3 = t(world).detach().clone()
+    f3[:, :, 0] *= -1
+    f3[:, left + right, :] = f3[:, right + left, :]
+    uv = g["uv"].astype(np.float32)
+    f2 = t(uv).detach().clone()
+    f2[:, :, 0] *= -1
+    f2[:, left + right, :] = f2[:, right + left, :]
+    out.update(flip3=f3.numpy(), uv=uv, flip2=f2.numpy())
+    # reference 3-D critic, seeded weights: outputs, WGAN-GP penalty and its parameter gradients
+    B = 40
+    args = argparse.Namespace(Dis_DenseDim_3D=32)
+    torch.manual_seed(12)
+    D = fd.Fk_3D_Discriminator(cpu, args)
+    real = t(world[:B]) - t(world[:B])[:, :1]
+    fake = t(world[B:2 * B]) - t(world[B:2 * B])[:, :1]
+    d_real = D(real)
+    D.zero_grad()
+    torch.manual_seed(3)
+    gp = fd.calc_gradient_penalty(D, real.data, fake.data, B, 10, cpu)
+    gp.backward()
+    torch.manual_seed(3)
+    alpha = torch.rand(B, 1)
+    names = [k for k, _ in D.named_parameters()]
+    out.update(d3d_real=real.numpy(), d3d_fake=fake.numpy(), d3d_out_real=d_real.detach().numpy(),
+               d3d_gp=np.array([gp.item()], np.float64), d3d_alpha=alpha.numpy(),
+               d3d_param_names=np.array(names))
+    for k, v in D.state_dict().items():
+        out["d3d_w_" + k] = v.numpy()
+    for k, v in D.named_parameters():
+        out["d3d_g_" + k] = v.grad.numpy() if v.grad is not None else np.zeros(tuple(v.shape), np.float32)
+    return out
+
+
 def main():
     from dhfk import synthetic
     os.makedirs(OUT, exist_ok=True)
@@ -315,6 +396,7 @@ def main():
         "sampler40": sampler_fixture,
         "generator": generator_fixture,
         "retarget": retarget_fixture,
+        "critic": critic_fixture,
     }
     for name in (sys.argv[1:] or list(fixtures)):
         np.savez(os.path.join(OUT, name + ".npz"), **fixtures[name]())

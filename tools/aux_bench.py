@@ -1,0 +1,70 @@
+"""Time the kernels either side of the hot path on one GPU: CUDA events, 4 rotating buffer
+sets (> L2), algorithmic bytes / time against the measured copy peak.  Prints one JSON object."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import dhfk  # noqa: E402
+from dhfk import tables  # noqa: E402
+from dhfk.functional import _cabi  # noqa: E402
+
+
+def timeit(fn, sets, steps=50, warmup=5):
+    for i in range(warmup):
+        fn(sets[i % len(sets)])
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        fn(sets[i % len(sets)])
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+    dev = torch.device("cuda:0")
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6528.7)
+    lib = _cabi.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device=dev).manual_seed(1)
+    sets = []
+    for _ in range(4):
+        pose = torch.randn(n, 16, 3, device=dev, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 4.5], device=dev)
+        sets.append(dict(pose=pose, idx=torch.randint(0, 5, (n,), device=dev, dtype=torch.int32, generator=g),
+                         cam=torch.tensor(tables.camera_block("S1", 0)[7:16], device=dev).repeat(n, 1).contiguous(),
+                         gp=torch.randn(n, 16, 3, device=dev, generator=g), gk=torch.randn(n, 30, device=dev, generator=g),
+                         o48=torch.empty(n, 16, 3, device=dev), o32=torch.empty(n, 16, 2, device=dev),
+                         o30=torch.empty(n, 30, device=dev)))
+    tm = torch.tensor(tables.BONE_TEMPLATES_GANUTILS_ORDER, device=dev)
+    P = lambda t: t.data_ptr()
+    cases = {
+        "retarget+project (f3)": (lambda s: lib.dhfk_retarget_project(P(s["pose"]), P(s["idx"]), P(tm), 5, P(s["cam"]), 9,
+                                                                      P(s["o48"]), P(s["o32"]), n, st), 192 + 4 + 36 + 192 + 128),
+        "critic fwd centre+flip+kcs30 (f2)": (lambda s: lib.dhfk_critic_input_forward(P(s["pose"]), P(s["o48"]), P(s["o30"]), 30, n, 3, st),
+                                              192 + 192 + 120),
+        "critic fwd kcs30 only (f2)": (lambda s: lib.dhfk_critic_input_forward(P(s["pose"]), None, P(s["o30"]), 30, n, 0, st), 192 + 120),
+        "critic vjp pos+kcs30 (f2)": (lambda s: lib.dhfk_critic_input_backward(P(s["pose"]), P(s["gp"]), P(s["gk"]), 30, P(s["o48"]), n, 1, st),
+                                      192 + 192 + 120 + 192),
+        "critic jvp pos+kcs30 (f2)": (lambda s: lib.dhfk_critic_input_jvp(P(s["pose"]), P(s["gp"]), P(s["o48"]), P(s["o30"]), 30, n, 1, st),
+                                      192 + 192 + 192 + 120),
+        "flip 3d (f2)": (lambda s: lib.dhfk_flip_pose(P(s["pose"]), P(s["o48"]), n, 3, st), 384),
+        "flip 2d (f2)": (lambda s: lib.dhfk_flip_pose(P(s["gp"]), P(s["o32"]), n, 2, st), 256),
+    }
+    out = {"poses": n, "peak_gbs": peak, "kernels": {}}
+    for name, (fn, bpp) in cases.items():
+        ms = timeit(fn, sets)
+        gbs = n * bpp / ms / 1e6
+        out["kernels"][name] = {"ms": round(ms, 5), "bytes_per_pose": bpp, "gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
+                                "poses_per_s": round(n / ms * 1e3)}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
