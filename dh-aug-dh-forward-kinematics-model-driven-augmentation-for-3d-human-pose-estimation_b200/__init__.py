@@ -7,6 +7,7 @@ Public surface:
   camera.GAN_torch_world_to_camera / camera.project_to_2d                   (reference-shaped functions)
   dataloader_update.random_bl_aug / dataloader_update / refresh_poses        (per-epoch loader refresh)
   Fk_discriminator.special_KCS_Input_transform / critic_views, functional.critic_input / flip_pose   
+  pose_buffer.DevicePoseBuffer / shuffled_order / gather_pairs              (device-resident fake-pair bank)
   dropin.install()                                                          (patch the imported reference)
   tables, synthetic, parallel
 
@@ -20,7 +21,8 @@ def __getattr__(name):
     # torch-dependent modules are imported lazily so that `import dhfk` stays cheap
     import importlib
     if name in ("functional", "camera", "dropin", "parallel", "synthetic", "forward_kinematics_DH_model",
-                "Fk_generator", "dataloader_update", "Fk_discriminator"):
+                "Fk_generator", "dataloader_update", "Fk_discriminator",
+                "pose_buffer"):
         return importlib.import_module("." + name, __name__)
     if name in ("fk_project", "fk_world16", "world_to_camera", "project_to_2d", "fk_project_host", "generator_fk",
                 "retarget_project", "critic_input", "flip_pose"):

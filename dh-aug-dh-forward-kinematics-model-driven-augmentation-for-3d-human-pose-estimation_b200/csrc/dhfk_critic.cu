@@ -24,6 +24,8 @@ __device__ constexpr int KP1[15] = {2, 3, 4, 5, 5, 6, 6, 7, 14, 8, 9, 10, 11, 12
 // joint j of the flipped pose = mirrored joint FLIP16[j] (out_left/out_right swap, model_fk_gan_train.py:321-327)
 __device__ constexpr int FLIP16[16] = {0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 13, 14, 15, 10, 11, 12};
 
+__constant__ int c_flip16[16] = {0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 13, 14, 15, 10, 11, 12};   // runtime-indexed copy
+
 constexpr unsigned kCentre = 1u, kFlip = 2u;
 
 struct CriticParams {
@@ -288,21 +290,30 @@ __global__ void __launch_bounds__(kTile) dhfk_critic_jvp_kernel(const __grid_con
     }
 }
 
-// left/right flip of [N,16,D] keypoints (D = 2 or 3): one thread per joint.  Its own transpose.
+// left/right flip of [N,16,D] keypoints (D = 2 or 3): one thread per 16-byte chunk of the output (128-bit
+// coalesced stores; the permuted source elements of a pose sit in the same 128/192-byte row).  Its own transpose.
 template <int D>
-__global__ void dhfk_flip_kernel(const float* __restrict__ x, float* __restrict__ out, long long njoints) {
+__global__ void dhfk_flip_kernel(const float* __restrict__ x, float* __restrict__ out, long long nchunks) {
+    constexpr int CH = 4 * D;                        // 16-byte chunks per pose: 8 (D=2) or 12 (D=3)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= njoints) return;
-    const long long n = i >> 4;
-    const int j = (int)(i & 15);
-    const float* s = x + (n * 16 + FLIP16[j]) * D;
-    float* d = out + i * D;
+    if (i >= nchunks) return;
+    const long long n = i / CH;
+    const int c = (int)(i - n * CH);
+    const float* row = x + n * 16 * D;
+    float v[4];
     if (D == 2) {
-        float2 v = *reinterpret_cast<const float2*>(s);
-        *reinterpret_cast<float2*>(d) = make_float2(-v.x, v.y);
+        const float2 a = *reinterpret_cast<const float2*>(row + 2 * c_flip16[2 * c]);
+        const float2 b = *reinterpret_cast<const float2*>(row + 2 * c_flip16[2 * c + 1]);
+        v[0] = -a.x; v[1] = a.y; v[2] = -b.x; v[3] = b.y;
     } else {
-        d[0] = -s[0]; d[1] = s[1]; d[2] = s[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = 4 * c + k, j = e / 3, a = e - 3 * j;
+            const float s = __ldg(row + 3 * c_flip16[j] + a);
+            v[k] = a == 0 ? -s : s;
+        }
     }
+    __stcs(reinterpret_cast<float4*>(out) + i, make_float4(v[0], v[1], v[2], v[3]));
 }
 
 template <int KC, bool POS>
@@ -337,10 +348,10 @@ int launch_critic(int mode, int kc, bool pos, const float* pose, const float* a,
 }
 
 int launch_flip(const float* x, float* out, long long n, int dims, cudaStream_t st, const char** where) {
-    const long long nj = n * 16;
-    const unsigned blocks = (unsigned)((nj + 255) / 256);
-    if (dims == 2) dhfk_flip_kernel<2><<<blocks, 256, 0, st>>>(x, out, nj);
-    else dhfk_flip_kernel<3><<<blocks, 256, 0, st>>>(x, out, nj);
+    const long long nc = n * 4 * dims;
+    const unsigned blocks = (unsigned)((nc + 255) / 256);
+    if (dims == 2) dhfk_flip_kernel<2><<<blocks, 256, 0, st>>>(x, out, nc);
+    else dhfk_flip_kernel<3><<<blocks, 256, 0, st>>>(x, out, nc);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *where = "dhfk_flip_kernel"; return (int)e; }
     return 0;

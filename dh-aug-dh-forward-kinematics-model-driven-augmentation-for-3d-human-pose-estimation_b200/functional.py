@@ -500,7 +500,7 @@ class _FlipPose(torch.autograd.Function):
         device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
         dims = x.shape[-1]
         xs = x.to(device=device, dtype=torch.float32).contiguous()
-        if xs.data_ptr() % 8:
+        if xs.data_ptr() % 16:
             xs = xs.clone()
         out = torch.empty_like(xs)
         n = xs.numel() // (16 * dims)

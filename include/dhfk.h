@@ -26,6 +26,8 @@
  *       (function_aug/dataloader_update.py:18-41,69; models_Fk_GAN/video_mode_operate.py:879-928)
  *   dhfk_critic_input_* / dhfk_flip_pose   flip, root-centring and KCS features of the critics' inputs
  *       (models_Fk_GAN/Fk_discriminator.py:36-146,269-377; model_fk_gan_train.py:311-331,393-405)
+ *   dhfk_bank_gather            mini-batch out of the device-resident fake-pair bank
+ *       (model_fk_gan_train.py:486-510; common/data_loader.py:9-36)
  *   dhfk_topology               the constant tables the reference keeps as Python lists
  *       (forward_kinematics_DH_model.py:234-261,:571-589,:751-817; common/h36m_dataset.py:37-38)
  *
@@ -198,6 +200,18 @@ int dhfk_critic_input_jvp(const float* pose_dev, const float* v_pose_dev, float*
 /* The flip alone for [N,16,dims] keypoints, dims = 2 (the 2D critic's inputs, model_fk_gan_train.py:393-405) or 3.
  * Not in place.  The flip is its own transpose: the backward is the same call on the upstream gradient. */
 int dhfk_flip_pose(const float* x_dev, float* out_dev, int64_t n, int32_t dims, void* stream);
+
+/*
+ * SURVEY 8 f4 -- device-resident fake-pair bank.  The reference copies every iteration's pos_3d_cam / uv / cam to
+ * host numpy (model_fk_gan_train.py:486-488) and re-serves them through a CPU DataLoader (:504-510;
+ * common/data_loader.py:9-36: PoseDataSet).  Here they stay in HBM; this call serves one (shuffled) mini-batch:
+ *   out3d[b] = bank3d[idx[b]]  ([16,3]),  out2d[b] = bank2d[idx[b]]  ([16,2]),  out_cam[b] = bank_cam[idx[b]]
+ * idx_dev [nb] int64 (what torch.randperm yields).  An index outside [0, bank_rows) produces a NaN row.
+ * bank_cam_dev / out_cam_dev [*, cam_cols] packed (cam_cols <= 20), or both NULL.
+ */
+int dhfk_bank_gather(const float* bank3d_dev, const float* bank2d_dev, const float* bank_cam_dev, int32_t cam_cols,
+                     const int64_t* idx_dev, int64_t nb, int64_t bank_rows, float* out3d_dev, float* out2d_dev,
+                     float* out_cam_dev, void* stream);
 
 /*
  * Host-buffer end-to-end entry: forward + backward over N poses whose inputs, upstream gradients
