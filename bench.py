@@ -328,14 +328,14 @@ def run_native(args):
         h_gw, h_gu = pin(up["g_world"]), pin(up["g_uv"])
         out = {}
         e2e_steps = max(3, min(steps, 10))
-        chunk = 1 << 16
+        chunk, slots = 1 << 17, 3
         for _ in range(2):
-            out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=4,
+            out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=slots,
                                        workspace=out.get("_workspace"), out=out, fast_trig=args.fast_trig)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=4,
+            out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=slots,
                                        workspace=out["_workspace"], out=out, fast_trig=args.fast_trig)
         torch.cuda.synchronize(dev)
         e2e_s = (time.perf_counter() - t0) / e2e_steps
@@ -345,7 +345,8 @@ def run_native(args):
         e2e_s = float(te.item())
         e2e = {"value": n * world_size / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * (FWD_BYTES - 320 + 320),
                "d2h_bytes_per_step": n * (320 + 156), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "api": "dhfk.fk_project_host -> dhfk_forward_backward_host (pinned host buffers, %d-row chunks, 4 streams)" % chunk}
+               "api": "dhfk.fk_project_host -> dhfk_forward_backward_host (pinned host buffers, %d-row chunks through an "
+                      "upload / compute / download stream pipeline over %d device slots)" % (chunk, slots)}
 
     # ---- extra: generator-epilogue mode, same batch, device-resident, rank 0 only ----
     gen_extra = None

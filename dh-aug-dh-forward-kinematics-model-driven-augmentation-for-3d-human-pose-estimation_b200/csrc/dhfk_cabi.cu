@@ -529,23 +529,42 @@ int dhfk_forward_backward_host(const float* ang_h, const float* grot_h, const fl
         return fail(DHFK_E_INVAL, "workspace too small (see dhfk_host_workspace_bytes)");
     if (!aligned16(workspace)) return fail(DHFK_E_ALIGN, "workspace must be 16-byte aligned");
 
-    cudaStream_t streams[8];
-    cudaError_t e = cudaSuccess;
-    int made = 0;
-    for (; made < num_streams; ++made) {
-        e = cudaStreamCreateWithFlags(&streams[made], cudaStreamNonBlocking);
-        if (e != cudaSuccess) break;
-    }
+    // Three-stage pipeline over a ring of `num_streams` device slots: one stream only uploads, one only computes,
+    // one only downloads, chained by events.  Each chunk moves in two half-steps -- inputs up, forward, world/uv
+    // down; upstream gradients up, backward, gradients down -- so the first download starts after 216 B/row have
+    // arrived and the last one is only 156 B/row (short pipeline fill and drain), and each DMA engine sees one
+    // in-order queue of copies that are ready when they reach its head.
+    const int slots = num_streams;
+    cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
+    enum { kUpIn, kUpGrad, kFwd, kBwd, kDown, kNumEv };
+    cudaEvent_t ev[8][kNumEv];
+    int n_ev = 0;
     int rc = DHFK_OK;
-    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamCreate");
+    cudaError_t e = cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking);
+    for (; e == cudaSuccess && n_ev < slots * kNumEv; ++n_ev)
+        e = cudaEventCreateWithFlags(&ev[n_ev / kNumEv][n_ev % kNumEv], cudaEventDisableTiming);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamCreate / cudaEventCreate");
 
     const size_t F = sizeof(float);
     const int64_t slot_floats = chunk_rows * kHostRowFloats;
     int64_t chunk_idx = 0;
+#define DHFK_CP(dst, src, cnt, kind, st)                                                  \
+    if (rc == DHFK_OK) {                                                                  \
+        e = cudaMemcpyAsync(dst, src, (size_t)(cnt)*F, kind, st);                         \
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync");                       \
+    }
+#define DHFK_EV(call)                                                                     \
+    if (rc == DHFK_OK) {                                                                  \
+        e = call;                                                                         \
+        if (e != cudaSuccess) rc = cuda_fail(e, #call);                                   \
+    }
     for (int64_t r0 = 0; r0 < n && rc == DHFK_OK; r0 += chunk_rows, ++chunk_idx) {
         const int64_t rows = (n - r0 < chunk_rows) ? (n - r0) : chunk_rows;
-        cudaStream_t st = streams[chunk_idx % num_streams];
-        float* base = reinterpret_cast<float*>(workspace) + (chunk_idx % num_streams) * slot_floats;
+        const int slot = (int)(chunk_idx % slots);
+        cudaEvent_t* E = ev[slot];
+        float* base = reinterpret_cast<float*>(workspace) + slot * slot_floats;
         float* d_ang = base;
         float* d_grot = d_ang + chunk_rows * 33;
         float* d_bone = d_grot + chunk_rows * 3;
@@ -557,37 +576,50 @@ int dhfk_forward_backward_host(const float* ang_h, const float* grot_h, const fl
         float* d_gang = d_gu + chunk_rows * 32;
         float* d_ggrot = d_gang + chunk_rows * 33;
         float* d_groot = d_ggrot + chunk_rows * 3;
-#define DHFK_CP(dst, src, cnt, kind)                                                      \
-    if (rc == DHFK_OK) {                                                                  \
-        e = cudaMemcpyAsync(dst, src, (size_t)(cnt)*F, kind, st);                         \
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync");                       \
-    }
-        DHFK_CP(d_ang, ang_h + r0 * 33, rows * 33, cudaMemcpyHostToDevice)
-        DHFK_CP(d_grot, grot_h + r0 * 3, rows * 3, cudaMemcpyHostToDevice)
-        DHFK_CP(d_bone, bone_h + r0 * 15, rows * 15, cudaMemcpyHostToDevice)
-        DHFK_CP(d_root, root_h + r0 * 3, rows * 3, cudaMemcpyHostToDevice)
+        // the slot is free once the last download of the chunk that used it before has finished
+        if (chunk_idx >= slots) DHFK_EV(cudaStreamWaitEvent(s_up, E[kDown], 0))
+        DHFK_CP(d_ang, ang_h + r0 * 33, rows * 33, cudaMemcpyHostToDevice, s_up)
+        DHFK_CP(d_grot, grot_h + r0 * 3, rows * 3, cudaMemcpyHostToDevice, s_up)
+        DHFK_CP(d_bone, bone_h + r0 * 15, rows * 15, cudaMemcpyHostToDevice, s_up)
+        DHFK_CP(d_root, root_h + r0 * 3, rows * 3, cudaMemcpyHostToDevice, s_up)
+        DHFK_EV(cudaEventRecord(E[kUpIn], s_up))
+        if (do_bwd) {
+            DHFK_CP(d_gw, g_world_h + r0 * 48, rows * 48, cudaMemcpyHostToDevice, s_up)
+            DHFK_CP(d_gu, g_uv_h + r0 * 32, rows * 32, cudaMemcpyHostToDevice, s_up)
+            DHFK_EV(cudaEventRecord(E[kUpGrad], s_up))
+        }
+        DHFK_EV(cudaStreamWaitEvent(s_run, E[kUpIn], 0))
         if (rc == DHFK_OK)
             rc = dhfk_forward(d_ang, 33, d_grot, 3, d_bone, 15, d_root, 3, cam, nullptr, 0, d_world, nullptr, d_uv,
-                              rows, flags, st);
-        DHFK_CP(out_world_h + r0 * 48, d_world, rows * 48, cudaMemcpyDeviceToHost)
-        DHFK_CP(out_uv_h + r0 * 32, d_uv, rows * 32, cudaMemcpyDeviceToHost)
+                              rows, flags, s_run);
+        DHFK_EV(cudaEventRecord(E[kFwd], s_run))
         if (do_bwd) {
-            DHFK_CP(d_gw, g_world_h + r0 * 48, rows * 48, cudaMemcpyHostToDevice)
-            DHFK_CP(d_gu, g_uv_h + r0 * 32, rows * 32, cudaMemcpyHostToDevice)
+            DHFK_EV(cudaStreamWaitEvent(s_run, E[kUpGrad], 0))
             if (rc == DHFK_OK)
                 rc = dhfk_backward(d_ang, 33, d_grot, 3, d_bone, 15, d_root, 3, cam, nullptr, 0, d_gw, nullptr, d_gu,
-                                   d_gang, 33, d_ggrot, 3, d_groot, 3, nullptr, 0, rows, flags, st);
-            DHFK_CP(g_ang_h + r0 * 33, d_gang, rows * 33, cudaMemcpyDeviceToHost)
-            DHFK_CP(g_grot_h + r0 * 3, d_ggrot, rows * 3, cudaMemcpyDeviceToHost)
-            DHFK_CP(g_root_h + r0 * 3, d_groot, rows * 3, cudaMemcpyDeviceToHost)
+                                   d_gang, 33, d_ggrot, 3, d_groot, 3, nullptr, 0, rows, flags, s_run);
+            DHFK_EV(cudaEventRecord(E[kBwd], s_run))
         }
+        DHFK_EV(cudaStreamWaitEvent(s_down, E[kFwd], 0))
+        DHFK_CP(out_world_h + r0 * 48, d_world, rows * 48, cudaMemcpyDeviceToHost, s_down)
+        DHFK_CP(out_uv_h + r0 * 32, d_uv, rows * 32, cudaMemcpyDeviceToHost, s_down)
+        if (do_bwd) {
+            DHFK_EV(cudaStreamWaitEvent(s_down, E[kBwd], 0))
+            DHFK_CP(g_ang_h + r0 * 33, d_gang, rows * 33, cudaMemcpyDeviceToHost, s_down)
+            DHFK_CP(g_grot_h + r0 * 3, d_ggrot, rows * 3, cudaMemcpyDeviceToHost, s_down)
+            DHFK_CP(g_root_h + r0 * 3, d_groot, rows * 3, cudaMemcpyDeviceToHost, s_down)
+        }
+        DHFK_EV(cudaEventRecord(E[kDown], s_down))
+    }
 #undef DHFK_CP
-    }
-    for (int i = 0; i < made; ++i) {
-        e = cudaStreamSynchronize(streams[i]);
+#undef DHFK_EV
+    for (cudaStream_t st : {s_up, s_run, s_down}) {
+        if (!st) continue;
+        e = cudaStreamSynchronize(st);
         if (e != cudaSuccess && rc == DHFK_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
-        cudaStreamDestroy(streams[i]);
+        cudaStreamDestroy(st);
     }
+    for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i / kNumEv][i % kNumEv]);
     return rc;
 }
 

@@ -35,8 +35,9 @@ static_assert(nth_child(-1, 0) == 0 && nth_child(-1, 1) == 5 && nth_child(-1, 2)
 #ifndef DHFK_PREFETCH_TILES_FWD
 #define DHFK_PREFETCH_TILES_FWD 1776
 #endif
+// backward: a third of a wave ahead measured +3 % (0.1353 -> 0.1313 ms); one wave ahead (1776) measured nothing
 #ifndef DHFK_PREFETCH_TILES_BWD
-#define DHFK_PREFETCH_TILES_BWD 0
+#define DHFK_PREFETCH_TILES_BWD 592
 #endif
 
 struct RowSrc {

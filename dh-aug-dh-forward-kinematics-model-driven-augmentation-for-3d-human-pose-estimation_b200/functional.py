@@ -525,10 +525,11 @@ def flip_pose(x):
     return _FlipPose.apply(x)
 
 
-def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chunk_rows=65536, num_streams=3,
+def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chunk_rows=131072, num_streams=3,
                     workspace=None, out=None, fast_trig=False):
     """End-to-end over HOST (ideally pinned) float32 tensors through dhfk_forward_backward_host:
-    chunk-pipelined H2D -> fused forward -> D2H and H2D(grads) -> fused backward -> D2H.
+    chunks move through an upload / compute / download stream pipeline over `num_streams` device slots
+    (H2D inputs -> fused forward -> D2H world, uv; H2D grads -> fused backward -> D2H grads).
     Returns dict(world, uv[, g_ang, g_grot, g_root]) of host tensors (pinned if allocated here)."""
     _require_cuda()
     lib = _cabi.load()

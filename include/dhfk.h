@@ -215,11 +215,12 @@ int dhfk_bank_gather(const float* bank3d_dev, const float* bank2d_dev, const flo
 
 /*
  * Host-buffer end-to-end entry: forward + backward over N poses whose inputs, upstream gradients
- * and results all live in HOST memory (pinned for full speed).  The rows are cut into chunks that
- * are pipelined H2D -> fused forward -> D2H(world, uv) and H2D(grads) -> fused backward ->
- * D2H(grads) on `num_streams` internal streams.  `workspace_dev` is caller-owned device scratch
- * of at least dhfk_host_workspace_bytes(chunk_rows, num_streams) bytes.  Synchronous: returns when
- * all results are in host memory.  g_world_host / g_uv_host may be NULL to run forward only.
+ * and results all live in HOST memory (pinned for full speed).  The rows are cut into chunks that move through a
+ * three-stage pipeline -- an upload stream (H2D of the chunk's inputs and upstream gradients), a compute stream
+ * (fused forward + backward) and a download stream (D2H of world, uv and the gradients), chained per chunk by
+ * events -- over a ring of `num_streams` (1..8) device slots, so both PCIe directions stay busy.  `workspace_dev`
+ * is caller-owned device scratch of at least dhfk_host_workspace_bytes(chunk_rows, num_streams) bytes.
+ * Synchronous: returns when all results are in host memory.  g_world_host / g_uv_host may be NULL to run forward only.
  */
 int64_t dhfk_host_workspace_bytes(int64_t chunk_rows, int32_t num_streams);
 int dhfk_forward_backward_host(const float* ang_host, const float* grot_host, const float* bone_host,
