@@ -387,6 +387,30 @@ def run_native(args):
         except Exception as e:      # never let the extra break the headline line
             gen_extra = {"error": repr(e)}
 
+    # ---- extra (N > 1): the only exchange of the data-parallel GAN step, the flat gradient all-reduce of a
+    # generator/critic-sized model (1-4 MB, latency-bound), outside the timed region ----
+    allreduce_extra = None
+    if distributed:
+        from dhfk import parallel
+        net = torch.nn.Sequential(torch.nn.Linear(128, 256), *[torch.nn.Linear(256, 256) for _ in range(7)],
+                                  torch.nn.Linear(256, 35)).to(dev)           # Fk_Generator-sized (dense 256)
+        for p_ in net.parameters():
+            p_.grad = torch.ones_like(p_)
+        for _ in range(3):
+            parallel.allreduce_grads_flat(list(net.parameters()))
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(20):
+            nel = parallel.allreduce_grads_flat(list(net.parameters()))
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        ta = torch.tensor([a0.elapsed_time(a1) / 20], device=dev, dtype=torch.float64)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        allreduce_extra = {"bytes": int(nel) * 4, "ms": float(ta.item()), "backend": "nccl",
+                           "what": "dhfk.parallel.allreduce_grads_flat of a dense-256 generator's gradients "
+                                   "(cat + one all-reduce + scatter back); not part of the timed FK region"}
+
     if distributed:
         dist.barrier()
     if rank != 0:
@@ -430,6 +454,8 @@ def run_native(args):
         line["e2e"] = e2e
     if gen_extra:
         line["generator_mode"] = gen_extra
+    if allreduce_extra:
+        line["grad_allreduce"] = allreduce_extra
     if not args.no_cpu_baseline:
         pps, dt, threads = time_torch_port(args.ref_chunk, 1, steps=10, warmup=2)
         line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",

@@ -30,11 +30,12 @@ def allreduce_grads_flat(params, group=None, average: bool = True):
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat /= dist.get_world_size(group)
-    off = 0
+    views, off = [], 0
     for g in grads:
         k = g.numel()
-        g.copy_(flat[off:off + k].view_as(g))
+        views.append(flat[off:off + k].view_as(g))
         off += k
+    torch._foreach_copy_(grads, views)      # one multi-tensor launch instead of one copy per parameter
     return flat.numel()
 
 
