@@ -15,8 +15,19 @@ namespace dhfk {
 int DHFK_CAT(launch_bwd_t, DHFK_TRIG, _b, DHFK_GBONE, _g, DHFK_GEN)(const BwdParams& p, bool guv, cudaStream_t st,
                                                                     const char** where) {
     constexpr bool G = DHFK_GEN != 0, B = DHFK_GBONE != 0;
-    const size_t smem = bwd_smem_bytes(p.g_world != nullptr, p.g_cam != nullptr, guv, G);
-    if (guv) return launch_tiles(dhfk_bwd_kernel<true, B, DHFK_TRIG, G>, smem, p, st, where);
-    return launch_tiles(dhfk_bwd_kernel<false, B, DHFK_TRIG, G>, smem, p, st, where);
+    const bool gw = p.g_world != nullptr, gc = p.g_cam != nullptr;
+    const size_t smem = bwd_smem_bytes(gw, gc, guv, G);
+    // which upstream gradients exist is a compile-time property of the kernel (7 combinations)
+#define DHFK_BWD(W, C, U) return launch_tiles(dhfk_bwd_kernel<W, C, U, B, DHFK_TRIG, G>, smem, p, st, where)
+    if (gw && !gc && guv) DHFK_BWD(true, false, true);       // the GAN step: world + 2D critics
+    if (gw && !gc && !guv) DHFK_BWD(true, false, false);     // FK only
+    if (gw && gc && guv) DHFK_BWD(true, true, true);
+    if (gw && gc && !guv) DHFK_BWD(true, true, false);
+    if (!gw && gc && guv) DHFK_BWD(false, true, true);
+    if (!gw && gc && !guv) DHFK_BWD(false, true, false);
+    if (!gw && !gc && guv) DHFK_BWD(false, false, true);
+#undef DHFK_BWD
+    *where = "no upstream gradient";
+    return (int)cudaErrorInvalidValue;
 }
 }  // namespace dhfk

@@ -456,7 +456,10 @@ DHFK_DI Wrench bwd_all_limbs(const Frame& P /*frame of the arms' parent joint*/,
     Wrench arms, legs;
     arms.F = arms.M = legs.F = legs.M = v3(0.f, 0.f, 0.f);
 #pragma unroll 1
-    for (int l = 0; l < NLIMB; ++l) {
+#ifndef DHFK_EXPERIMENT_LIMBS      // sensitivity experiment only (wrong results): run fewer limbs
+#define DHFK_EXPERIMENT_LIMBS NLIMB
+#endif
+    for (int l = 0; l < DHFK_EXPERIMENT_LIMBS; ++l) {
         const bool arm = l >= 2;
         Frame B;
         B.X = arm ? A.X : I.X; B.Y = arm ? A.Y : I.Y; B.Z = arm ? A.Z : I.Z; B.O = arm ? A.O : I.O;
