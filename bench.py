@@ -387,6 +387,39 @@ def run_native(args):
         except Exception as e:      # never let the extra break the headline line
             gen_extra = {"error": repr(e)}
 
+    # ---- extra: the same step with DHFK_FLAG_FAST_TRIG (MUFU sin/cos after exact range reduction; as close to exact
+    # arithmetic as the reference's own fp32 results -- tools/trig_parity.py), rank 0 only, not the headline ----
+    fast_extra = None
+    if rank == 0 and not args.fast_trig:
+        try:
+            ff = _cabi.FLAG_FAST_TRIG
+
+            def fast_step(i):
+                d = sets[i % nbuf]
+                _cabi.check(lib.dhfk_forward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
+                                             d["root"].data_ptr(), 3, cam_ptr, None, 0, world.data_ptr(), None,
+                                             uv.data_ptr(), n, ff, sp), "fwd")
+                _cabi.check(lib.dhfk_backward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
+                                              d["root"].data_ptr(), 3, cam_ptr, None, 0, d["g_world"].data_ptr(), None,
+                                              d["g_uv"].data_ptr(), g_ang.data_ptr(), 33, g_grot.data_ptr(), 3,
+                                              g_root.data_ptr(), 3, None, 15, n, ff, sp), "bwd")
+            for i in range(5):
+                fast_step(i)
+            torch.cuda.synchronize(dev)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fsteps = min(steps, 50)
+            f0.record(stream)
+            for i in range(fsteps):
+                fast_step(i)
+            f1.record(stream)
+            torch.cuda.synchronize(dev)
+            fms = f0.elapsed_time(f1) / fsteps
+            fast_extra = {"poses_per_s": n / (fms * 1e-3), "ms_per_step": fms,
+                          "hbm_gbs": (FWD_BYTES + BWD_BYTES) * n / (fms * 1e-3) / 1e9,
+                          "what": "same step with DHFK_FLAG_FAST_TRIG (MUFU.SIN/COS after exact degree reduction, abs err ~4e-7)"}
+        except Exception as e:
+            fast_extra = {"error": repr(e)}
+
     # ---- extra (N > 1): the only exchange of the data-parallel GAN step, the flat gradient all-reduce of a
     # generator/critic-sized model (1-4 MB, latency-bound), outside the timed region ----
     allreduce_extra = None
@@ -454,6 +487,8 @@ def run_native(args):
         line["e2e"] = e2e
     if gen_extra:
         line["generator_mode"] = gen_extra
+    if fast_extra:
+        line["fast_trig_variant"] = fast_extra
     if allreduce_extra:
         line["grad_allreduce"] = allreduce_extra
     if not args.no_cpu_baseline:

@@ -449,24 +449,27 @@ DHFK_DI Wrench bwd_limb(const Frame& B, const LimbDesc& L, Ctx& ctx) {
 // arms' wrench; the legs' wrench is left in ctx.legs.
 template <int TRIG, class Ctx>
 DHFK_DI Wrench bwd_all_limbs(const Frame& P /*frame of the arms' parent joint*/, Ctx& ctx) {
-    Frame A = P;            // arms: alpha0 = -90 folded into the base frame (y' = -z, z' = y)
-    A.Y = -P.Z;
-    A.Z = P.Y;
-    const Frame I = ctx.base;   // legs hang off the chain root frame
-    Wrench arms, legs;
-    arms.F = arms.M = legs.F = legs.M = v3(0.f, 0.f, 0.f);
+    Wrench acc[2];          // [0] legs (hang off the chain root frame), [1] arms
+    Frame B = ctx.base;
 #pragma unroll 1
-#ifndef DHFK_EXPERIMENT_LIMBS      // sensitivity experiment only (wrong results): run fewer limbs
-#define DHFK_EXPERIMENT_LIMBS NLIMB
+    for (int half = 0; half < 2; ++half) {
+        if (half == 1) {    // arms: alpha0 = -90 folded into the base frame (y' = -z, z' = y)
+            B.X = P.X; B.Y = -P.Z; B.Z = P.Y; B.O = P.O;
+        }
+        Wrench w0;
+        w0.F = w0.M = v3(0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int i = 0; i < 2; ++i) {
+#ifdef DHFK_EXPERIMENT_LIMBS      // sensitivity experiment only (wrong results): run fewer limbs
+            if (2 * half + i >= DHFK_EXPERIMENT_LIMBS) break;
 #endif
-    for (int l = 0; l < DHFK_EXPERIMENT_LIMBS; ++l) {
-        const bool arm = l >= 2;
-        Frame B;
-        B.X = arm ? A.X : I.X; B.Y = arm ? A.Y : I.Y; B.Z = arm ? A.Z : I.Z; B.O = arm ? A.O : I.O;
-        const Wrench w = bwd_limb<TRIG>(B, c_limbs[l], ctx);
-        if (arm) { arms.F = arms.F + w.F; arms.M = arms.M + w.M; }
-        else { legs.F = legs.F + w.F; legs.M = legs.M + w.M; }
+            const Wrench w = bwd_limb<TRIG>(B, c_limbs[2 * half + i], ctx);
+            w0.F = w0.F + w.F;
+            w0.M = w0.M + w.M;
+        }
+        if (half == 0) acc[0] = w0; else acc[1] = w0;
     }
+    const Wrench legs = acc[0], arms = acc[1];
     ctx.legs = legs;
     return arms;
 }

@@ -310,7 +310,6 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
     float4* s_world = reinterpret_cast<float4*>(s_root + (GEN ? 0 : kTile * 3));
     float4* s_cam = s_world + kTile * kWorldRow4;
     float4* s_uv = s_cam + (CAM ? kTile * kWorldRow4 : 0);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_uv + (UV ? kTile * kUvRow4 : 0));
 
     const int lane = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kTile;
@@ -490,13 +489,11 @@ struct BwdCtx {
     static constexpr bool cam_frame = GUV || GCAM;
     V3 v0;         // root point in camera coordinates, M * (root - t)
     Wrench legs;   // filled by bwd_all_limbs
-    // d/d root = sum over the 16 outputs of the world-space gradient, summed directly (world part and camera
-    // part separately, one M^T at the end).
-    V3 sum_gw, sum_gc;
+    // d/d root = sum over the 16 outputs of the world-space gradient: see root_grad()
+    V3 sum_gw;
 
     DHFK_DI void setup_camera() {
         sum_gw = v3(0.f, 0.f, 0.f);
-        sum_gc = v3(0.f, 0.f, 0.f);
         base.O = v3(0.f, 0.f, 0.f);
         if constexpr (cam_frame) {
             float MR[9];
@@ -512,14 +509,23 @@ struct BwdCtx {
             v0 = v3(0.f, 0.f, 0.f);
         }
     }
-    // total dL/d(origin) in the working frame from the world-space gradient g and the camera-space gradient gc
+    // total dL/d(origin) in the working frame from the world-space gradient g and the camera-space gradient gc.
+    // Only the world-space part is summed on the side (for d/d root); the camera-space sum falls out of the
+    // total force at the end:  sum_gc = F_total - M sum_gw.
     DHFK_DI V3 to_frame(V3 g, V3 gc) {
-        if constexpr (GW) sum_gw = sum_gw + g;
         if constexpr (!cam_frame) return g;
+        else if constexpr (GW) {
+            sum_gw = sum_gw + g;
+            return mat_vec_add(cc->M, g, gc);      // M g_w + g_c
+        } else return gc;
+    }
+    // d/d root (world axes) from the total force over the 16 outputs (working frame)
+    DHFK_DI V3 root_grad(V3 Ft) const {
+        if constexpr (!cam_frame) return Ft;                       // working frame = world axes
+        else if constexpr (!GW) return matT_vec(cc->M, Ft);        // M^T sum_gc
         else {
-            sum_gc = sum_gc + gc;
-            if constexpr (GW) return mat_vec_add(cc->M, g, gc);      // M g_w + g_c
-            else return gc;
+            const V3 mg = mat_vec(cc->M, sum_gw);
+            return matT_vec_add(cc->M, v3(Ft.x - mg.x, Ft.y - mg.y, Ft.z - mg.z), sum_gw);
         }
     }
 
@@ -593,7 +599,6 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
     float4* s_gw = reinterpret_cast<float4*>(s_root + (GEN ? 0 : kTile * 3));
     float4* s_gc = s_gw + (GW ? kTile * kWorldRow4 : 0);
     float4* s_gu = s_gc + (GCAM ? kTile * kWorldRow4 : 0);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_gu + (GUV ? kTile * kUvRow4 : 0));
 
     const int lane = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kTile;
@@ -677,8 +682,7 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         Wrench wb = bwd_walk<TRIG, 10>(ctx.base, ctx);
         V3 Ft = wb.F + ctx.legs.F;
         V3 Mt = wb.M + ctx.legs.M;
-        V3 gr = ctx.sum_gw;
-        if (GUV || GCAM) gr = matT_vec_add(p.cam.M, ctx.sum_gc, gr);
+        const V3 gr = ctx.root_grad(Ft);
         // d/d global angles: torque about the world axes e_x, Rx e_y, Rx Ry e_z
         V3 tw = Mt;                                      // moment about the root, working axes -> world axes
         if (ctx.cam_frame) tw = matT_vec(p.cam.M, Mt);
