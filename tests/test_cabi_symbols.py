@@ -65,3 +65,47 @@ def test_argument_validation_without_gpu():
         _cabi.check(_cabi.E_UNSUPPORTED, "x")
     with pytest.raises(RuntimeError):
         _cabi.check(700, "x")
+
+
+def test_argument_validation_of_the_widened_entry_points_without_gpu():
+    """SURVEY 8 f2-f4 entry points: every argument error is detected before any CUDA call."""
+    lib = _cabi.load()
+    z = None
+    buf = np.zeros(4096, np.float32)
+    p = buf.ctypes.data
+    # n == 0: no-op success
+    assert lib.dhfk_retarget_project(z, z, z, 5, z, 9, z, z, 0, z) == 0
+    assert lib.dhfk_critic_input_forward(z, z, z, 30, 0, 0, z) == 0
+    assert lib.dhfk_critic_input_backward(z, z, z, 30, z, 0, 0, z) == 0
+    assert lib.dhfk_critic_input_jvp(z, z, z, z, 30, 0, 0, z) == 0
+    assert lib.dhfk_flip_pose(z, z, 0, 3, z) == 0
+    assert lib.dhfk_bank_gather(z, z, z, 9, z, 0, 10, z, z, z, z) == 0
+    # retarget
+    assert lib.dhfk_retarget_project(p, p, p, 5, p, 9, p, p, -1, z) == _cabi.E_INVAL
+    assert lib.dhfk_retarget_project(z, p, p, 5, p, 9, p, p, 4, z) == _cabi.E_INVAL
+    assert lib.dhfk_retarget_project(p, p, p, 0, p, 9, p, p, 4, z) == _cabi.E_INVAL          # no templates
+    assert lib.dhfk_retarget_project(p, p, p, 5, p, 8, p, p, 4, z) == _cabi.E_INVAL          # cam stride < 9
+    assert "9 columns" in _cabi.last_error()
+    assert lib.dhfk_retarget_project(p, p, p, 5, z, 9, p, p, 4, z) == _cabi.E_INVAL          # uv without intrinsics
+    assert lib.dhfk_retarget_project(p + 4, p, p, 5, p, 9, p, p, 4, z) == _cabi.E_ALIGN
+    # critic inputs
+    assert lib.dhfk_critic_input_forward(p, p, p, 16, 4, 0, z) == _cabi.E_INVAL              # kcs_cols not 0/15/30
+    assert "kcs_cols" in _cabi.last_error()
+    assert lib.dhfk_critic_input_forward(p, p, p, 30, 4, 8, z) == _cabi.E_INVAL              # unknown flag
+    assert lib.dhfk_critic_input_forward(p, p, z, 30, 4, 0, z) == _cabi.E_INVAL              # kcs wanted, no buffer
+    assert lib.dhfk_critic_input_forward(p, z, z, 0, 4, 0, z) == _cabi.E_INVAL               # nothing to compute
+    assert lib.dhfk_critic_input_forward(p, p + 4, p, 30, 4, 0, z) == _cabi.E_ALIGN
+    assert lib.dhfk_critic_input_backward(p, z, z, 0, p, 4, 0, z) == _cabi.E_INVAL           # no upstream gradient
+    assert "upstream" in _cabi.last_error()
+    assert lib.dhfk_critic_input_backward(p, p, p, 30, z, 4, 0, z) == _cabi.E_INVAL
+    assert lib.dhfk_critic_input_jvp(p, z, p, p, 30, 4, 0, z) == _cabi.E_INVAL               # no tangent
+    assert lib.dhfk_critic_input_jvp(p, p, z, z, 0, 4, 0, z) == _cabi.E_INVAL
+    # flip
+    assert lib.dhfk_flip_pose(p, p + 256, 4, 4, z) == _cabi.E_INVAL                          # dims
+    assert lib.dhfk_flip_pose(p, p, 4, 2, z) == _cabi.E_INVAL                                # 2-D in place
+    assert lib.dhfk_flip_pose(p + 4, p + 256, 4, 2, z) == _cabi.E_ALIGN
+    # bank gather
+    assert lib.dhfk_bank_gather(p, p, p, 9, z, 4, 10, p, p, p, z) == _cabi.E_INVAL           # no indices
+    assert lib.dhfk_bank_gather(p, p, p, 9, p, 4, 10, p, p, z, z) == _cabi.E_INVAL           # cam in without cam out
+    assert lib.dhfk_bank_gather(p, p, p, 21, p, 4, 10, p, p, p, z) == _cabi.E_INVAL          # cam_cols > 20
+    assert lib.dhfk_bank_gather(p, p + 4, z, 0, p, 4, 10, p, p, z, z) == _cabi.E_ALIGN
