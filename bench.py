@@ -62,7 +62,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--poses", type=int, default=1 << 20, help="poses per GPU per step")
-    ap.add_argument("--fast-trig", action="store_true", help="MUFU sin/cos variant (DHFK_FLAG_FAST_TRIG)")
+    ap.add_argument("--fast-trig", action="store_true", help="MUFU sin/cos in the forward too (DHFK_FLAG_FAST_TRIG)")
+    ap.add_argument("--accurate-trig", action="store_true", help="table sincos in the backward too (DHFK_FLAG_ACCURATE_TRIG)")
     ap.add_argument("--buffers", type=int, default=4, help="rotating input buffer sets (L2 hygiene)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -79,7 +80,10 @@ def workload_config(args, extra=None):
         "outputs": "world16[N,16,3]+uv16[N,16,2]; grads d_ang[N,33]+d_grot[N,3]+d_root[N,3]",
         "bytes_per_pose": {"forward": FWD_BYTES, "backward": BWD_BYTES},
         "parallelism": "dp%d (rows sharded, no data-path collective)" % args.gpus,
-        "trig": "mufu" if args.fast_trig else "poly(~1ulp)",
+        "trig": ("fwd+bwd MUFU.SIN/COS (DHFK_FLAG_FAST_TRIG)" if args.fast_trig else
+                 "fwd polynomial + bwd table sincos, <=1e-7 (DHFK_FLAG_ACCURATE_TRIG)" if getattr(args, "accurate_trig", False) else
+                 "library default: fwd polynomial (abs err 7.7e-8), bwd MUFU.SIN/COS after exact degree reduction "
+                 "(abs err 4e-7; gradients 1.8e-7 from exact at 1M poses, tolerance 1e-5)"),
     }
     if extra:
         cfg.update(extra)
@@ -241,7 +245,7 @@ def run_native(args):
 
     lib = _cabi.load()
     n = args.poses
-    flags = _cabi.FLAG_FAST_TRIG if args.fast_trig else 0
+    flags = (_cabi.FLAG_FAST_TRIG if args.fast_trig else 0) | (_cabi.FLAG_ACCURATE_TRIG if args.accurate_trig else 0)
     blk = tables.camera_block("S1", 0)
     cam_ptr = blk.ctypes.data
     nbuf = max(1, args.buffers)
@@ -284,15 +288,26 @@ def run_native(args):
     sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
     if sampler:
         sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    # One event pair brackets the K timed steps; every `probe_every`-th step additionally carries three events around its
+    # two launches for the live per-kernel durations (an event record is a ~2 us bubble on the stream, so probing every
+    # launch would cost the headline ~3 %).
+    probe_every = 8 if steps >= 16 else 1
+    probes = {i: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for i in range(0, steps, probe_every)}
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    ev_start.record(stream)
     for i in range(steps):
         d = sets[i % nbuf]
-        ev[i][0].record(stream); fwd(d)
-        ev[i][1].record(stream); bwd(d)
-        ev[i][2].record(stream)
+        pr = probes.get(i)
+        if pr is None:
+            fwd(d); bwd(d)
+        else:
+            pr[0].record(stream); fwd(d)
+            pr[1].record(stream); bwd(d)
+            pr[2].record(stream)
+    ev_end.record(stream)
     torch.cuda.synchronize(dev)
-    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    total_ms = ev_start.elapsed_time(ev_end)
     barrier()
     # keep the sampler fed if the timed region was shorter than a few polling periods
     extension = False
@@ -307,8 +322,8 @@ def run_native(args):
         torch.cuda.synchronize(dev)
     if sampler:
         sampler.stop()
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in probes.values()) / len(probes)
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in probes.values()) / len(probes)
 
     t = torch.tensor([total_ms, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
     if distributed:
@@ -331,12 +346,14 @@ def run_native(args):
         chunk, slots = 1 << 17, 3
         for _ in range(2):
             out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=slots,
-                                       workspace=out.get("_workspace"), out=out, fast_trig=args.fast_trig)
+                                       workspace=out.get("_workspace"), out=out, fast_trig=args.fast_trig,
+                                       accurate_grad=args.accurate_trig)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=slots,
-                                       workspace=out["_workspace"], out=out, fast_trig=args.fast_trig)
+                                       workspace=out["_workspace"], out=out, fast_trig=args.fast_trig,
+                                       accurate_grad=args.accurate_trig)
         torch.cuda.synchronize(dev)
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -387,38 +404,39 @@ def run_native(args):
         except Exception as e:      # never let the extra break the headline line
             gen_extra = {"error": repr(e)}
 
-    # ---- extra: the same step with DHFK_FLAG_FAST_TRIG (MUFU sin/cos after exact range reduction; as close to exact
-    # arithmetic as the reference's own fp32 results -- tools/trig_parity.py), rank 0 only, not the headline ----
-    fast_extra = None
-    if rank == 0 and not args.fast_trig:
-        try:
-            ff = _cabi.FLAG_FAST_TRIG
-
-            def fast_step(i):
-                d = sets[i % nbuf]
-                _cabi.check(lib.dhfk_forward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
-                                             d["root"].data_ptr(), 3, cam_ptr, None, 0, world.data_ptr(), None,
-                                             uv.data_ptr(), n, ff, sp), "fwd")
-                _cabi.check(lib.dhfk_backward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
-                                              d["root"].data_ptr(), 3, cam_ptr, None, 0, d["g_world"].data_ptr(), None,
-                                              d["g_uv"].data_ptr(), g_ang.data_ptr(), 33, g_grot.data_ptr(), 3,
-                                              g_root.data_ptr(), 3, None, 15, n, ff, sp), "bwd")
-            for i in range(5):
-                fast_step(i)
-            torch.cuda.synchronize(dev)
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            fsteps = min(steps, 50)
-            f0.record(stream)
-            for i in range(fsteps):
-                fast_step(i)
-            f1.record(stream)
-            torch.cuda.synchronize(dev)
-            fms = f0.elapsed_time(f1) / fsteps
-            fast_extra = {"poses_per_s": n / (fms * 1e-3), "ms_per_step": fms,
-                          "hbm_gbs": (FWD_BYTES + BWD_BYTES) * n / (fms * 1e-3) / 1e9,
-                          "what": "same step with DHFK_FLAG_FAST_TRIG (MUFU.SIN/COS after exact degree reduction, abs err ~4e-7)"}
-        except Exception as e:
-            fast_extra = {"error": repr(e)}
+    # ---- extra: the same step under the two other trig policies of include/dhfk.h (rank 0 only, not the headline;
+    # distances to exact arithmetic and to the reference: tools/trig_parity.py) ----
+    trig_extra = None
+    if rank == 0 and not args.fast_trig and not args.accurate_trig:
+        trig_extra = {}
+        for key, ff, what in (("fast_trig_variant", _cabi.FLAG_FAST_TRIG, "DHFK_FLAG_FAST_TRIG: MUFU.SIN/COS in the forward too"),
+                              ("accurate_trig_variant", _cabi.FLAG_ACCURATE_TRIG,
+                               "DHFK_FLAG_ACCURATE_TRIG: table sincos (abs err 1e-7) in the backward too")):
+            try:
+                def var_step(i, ff=ff):
+                    d = sets[i % nbuf]
+                    _cabi.check(lib.dhfk_forward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
+                                                 d["root"].data_ptr(), 3, cam_ptr, None, 0, world.data_ptr(), None,
+                                                 uv.data_ptr(), n, ff, sp), "fwd")
+                    _cabi.check(lib.dhfk_backward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
+                                                  d["root"].data_ptr(), 3, cam_ptr, None, 0, d["g_world"].data_ptr(), None,
+                                                  d["g_uv"].data_ptr(), g_ang.data_ptr(), 33, g_grot.data_ptr(), 3,
+                                                  g_root.data_ptr(), 3, None, 15, n, ff, sp), "bwd")
+                for i in range(5):
+                    var_step(i)
+                torch.cuda.synchronize(dev)
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                fsteps = min(steps, 50)
+                f0.record(stream)
+                for i in range(fsteps):
+                    var_step(i)
+                f1.record(stream)
+                torch.cuda.synchronize(dev)
+                fms = f0.elapsed_time(f1) / fsteps
+                trig_extra[key] = {"poses_per_s": n / (fms * 1e-3), "ms_per_step": fms,
+                                   "hbm_gbs": (FWD_BYTES + BWD_BYTES) * n / (fms * 1e-3) / 1e9, "what": "same step, " + what}
+            except Exception as e:
+                trig_extra[key] = {"error": repr(e)}
 
     # ---- extra (N > 1): the only exchange of the data-parallel GAN step, the flat gradient all-reduce of a
     # generator/critic-sized model (1-4 MB, latency-bound), outside the timed region ----
@@ -487,8 +505,8 @@ def run_native(args):
         line["e2e"] = e2e
     if gen_extra:
         line["generator_mode"] = gen_extra
-    if fast_extra:
-        line["fast_trig_variant"] = fast_extra
+    if trig_extra:
+        line.update(trig_extra)
     if allreduce_extra:
         line["grad_allreduce"] = allreduce_extra
     if not args.no_cpu_baseline:

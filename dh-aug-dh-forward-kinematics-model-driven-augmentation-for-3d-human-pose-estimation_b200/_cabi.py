@@ -15,6 +15,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 ABI_VERSION = 1
 FLAG_FAST_TRIG = 0x1
+FLAG_ACCURATE_TRIG = 0x2
 CRITIC_CENTRE, CRITIC_FLIP = 0x1, 0x2
 E_INVAL, E_ALIGN, E_UNSUPPORTED = -1, -2, -3
 

@@ -113,6 +113,9 @@ int cuda_fail(cudaError_t e, const char* where) {
     return (int)e;
 }
 
+bool bad_trig_flags(uint32_t flags) {
+    return (flags & DHFK_FLAG_FAST_TRIG) && (flags & DHFK_FLAG_ACCURATE_TRIG);
+}
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 RowSrc row_src(const float* p, int64_t stride, int ncols) {
@@ -198,6 +201,7 @@ int dhfk_forward(const float* ang, int64_t ang_stride, const float* grot, int64_
     int rc = check_inputs(ang, ang_stride, grot, grot_stride, bone, bone_stride, root, root_stride, n);
     if (rc != DHFK_OK) return rc;
     if (n == 0) return DHFK_OK;
+    if (bad_trig_flags(flags)) return fail(DHFK_E_INVAL, "DHFK_FLAG_FAST_TRIG and DHFK_FLAG_ACCURATE_TRIG are mutually exclusive");
     if (cam_rows) return fail(DHFK_E_UNSUPPORTED, "per-row intrinsics are not supported in the fused path; use dhfk_project_*");
     if (!out_world) return fail(DHFK_E_INVAL, "out_world is required");
     if ((out_cam || out_uv) && !cam) return fail(DHFK_E_INVAL, "cam block required for out_cam / out_uv");
@@ -233,6 +237,7 @@ int dhfk_backward(const float* ang, int64_t ang_stride, const float* grot, int64
     int rc = check_inputs(ang, ang_stride, grot, grot_stride, bone, bone_stride, root, root_stride, n);
     if (rc != DHFK_OK) return rc;
     if (n == 0) return DHFK_OK;
+    if (bad_trig_flags(flags)) return fail(DHFK_E_INVAL, "DHFK_FLAG_FAST_TRIG and DHFK_FLAG_ACCURATE_TRIG are mutually exclusive");
     if (cam_rows) return fail(DHFK_E_UNSUPPORTED, "per-row intrinsics are not supported in the fused path; use dhfk_project_*");
     if (!g_world && !g_cam && !g_uv) return fail(DHFK_E_INVAL, "at least one upstream gradient is required");
     if ((g_cam || g_uv) && !cam) return fail(DHFK_E_INVAL, "cam block required for g_cam / g_uv");
@@ -259,7 +264,7 @@ int dhfk_backward(const float* ang, int64_t ang_stride, const float* grot, int64
     if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
     const bool gu = g_uv != nullptr;
-    const bool fast = (flags & DHFK_FLAG_FAST_TRIG) != 0;
+    const bool fast = (flags & DHFK_FLAG_ACCURATE_TRIG) == 0;   // backward default: MUFU trig (see dhfk.h)
     const char* where = "";
     int e;
     if (g_bone) e = fast ? dhfk::launch_bwd_t1_b1_g0(p, gu, st, &where) : dhfk::launch_bwd_t0_b1_g0(p, gu, st, &where);
@@ -280,6 +285,7 @@ int dhfk_generator_forward(const float* net_out, int64_t net_out_stride, const f
                            float* out_world, float* out_cam, float* out_uv, int64_t n, uint32_t flags, void* stream) {
     if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
     if (n == 0) return DHFK_OK;
+    if (bad_trig_flags(flags)) return fail(DHFK_E_INVAL, "DHFK_FLAG_FAST_TRIG and DHFK_FLAG_ACCURATE_TRIG are mutually exclusive");
     if (!net_out || !bone) return fail(DHFK_E_INVAL, "net_out / bone must be non-null");
     if (net_out_stride < dhfk::GEN_NCOL || bone_stride < 15)
         return fail(DHFK_E_INVAL, "row strides must be >= 35 (net_out), 15 (bone)");
@@ -310,6 +316,7 @@ int dhfk_generator_backward(const float* net_out, int64_t net_out_stride, const 
                             int64_t g_net_out_stride, int64_t n, uint32_t flags, void* stream) {
     if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
     if (n == 0) return DHFK_OK;
+    if (bad_trig_flags(flags)) return fail(DHFK_E_INVAL, "DHFK_FLAG_FAST_TRIG and DHFK_FLAG_ACCURATE_TRIG are mutually exclusive");
     if (!net_out || !bone || !g_net_out) return fail(DHFK_E_INVAL, "net_out / bone / g_net_out must be non-null");
     if (net_out_stride < dhfk::GEN_NCOL || bone_stride < 15 || g_net_out_stride < dhfk::GEN_NCOL)
         return fail(DHFK_E_INVAL, "row strides must be >= 35 (net_out, g_net_out), 15 (bone)");
@@ -330,7 +337,7 @@ int dhfk_generator_backward(const float* net_out, int64_t net_out_stride, const 
     p.cam = make_cam(cam);
     const char* where = "";
     const bool gu = g_uv != nullptr;
-    int e = (flags & DHFK_FLAG_FAST_TRIG) ? dhfk::launch_bwd_t1_b0_g1(p, gu, (cudaStream_t)stream, &where)
+    int e = !(flags & DHFK_FLAG_ACCURATE_TRIG) ? dhfk::launch_bwd_t1_b0_g1(p, gu, (cudaStream_t)stream, &where)
                                           : dhfk::launch_bwd_t0_b0_g1(p, gu, (cudaStream_t)stream, &where);
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }
@@ -518,6 +525,7 @@ int dhfk_forward_backward_host(const float* ang_h, const float* grot_h, const fl
                                uint32_t flags) {
     if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
     if (n == 0) return DHFK_OK;
+    if (bad_trig_flags(flags)) return fail(DHFK_E_INVAL, "DHFK_FLAG_FAST_TRIG and DHFK_FLAG_ACCURATE_TRIG are mutually exclusive");
     if (!ang_h || !grot_h || !bone_h || !root_h || !cam || !out_world_h || !out_uv_h)
         return fail(DHFK_E_INVAL, "null host argument");
     const bool do_bwd = g_world_h != nullptr || g_uv_h != nullptr;

@@ -17,6 +17,14 @@ from torch.autograd.function import once_differentiable
 from . import _cabi
 
 
+def _trig_flags(fast_trig=False, accurate_grad=False) -> int:
+    """C-ABI trig flags (include/dhfk.h): default = accurate forward + MUFU backward; fast_trig = MUFU in the forward
+    too; accurate_grad = table sincos in the backward too."""
+    if fast_trig and accurate_grad:
+        raise ValueError("fast_trig and accurate_grad are mutually exclusive")
+    return (_cabi.FLAG_FAST_TRIG if fast_trig else 0) | (_cabi.FLAG_ACCURATE_TRIG if accurate_grad else 0)
+
+
 def _require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError("dhfk needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -158,24 +166,24 @@ class _FKProject(torch.autograd.Function):
                 None, None, None, None)
 
 
-def fk_project(angles, global_rot, bone_len, root, cam, *, return_cam=True, fast_trig=False):
+def fk_project(angles, global_rot, bone_len, root, cam, *, return_cam=True, fast_trig=False, accurate_grad=False):
     """Fused DH-FK -> global rotation/translation -> world->camera -> pinhole projection.
 
     angles [N,>=33] deg, global_rot [N,3] deg, bone_len [N,15] m, root [N,3] (or [B,F,3]) m,
     cam: 16 floats (see tables.camera_block).  Returns (world16 [N,16,3], cam16 [N,16,3] or None,
     uv16 [N,16,2]).  Replaces Fk_generator.py:232-259 + model_fk_gan_train.py:374-376 in one launch.
     """
-    flags = _cabi.FLAG_FAST_TRIG if fast_trig else 0
+    flags = _trig_flags(fast_trig, accurate_grad)
     outs = _FKProject.apply(angles, global_rot, bone_len, root, cam, bool(return_cam), True, flags)
     if return_cam:
         return outs[0], outs[1], outs[2]
     return outs[0], None, outs[1]
 
 
-def fk_world16(angles, global_rot, bone_len, root, *, fast_trig=False):
+def fk_world16(angles, global_rot, bone_len, root, *, fast_trig=False, accurate_grad=False):
     """DH-FK only: world-space 16 joints [N,16,3] (forward_kinematics_DH_model.py:562-822 followed by
     the [:, H36M_32_To_16_Table] gather of Fk_generator.py:259)."""
-    flags = _cabi.FLAG_FAST_TRIG if fast_trig else 0
+    flags = _trig_flags(fast_trig, accurate_grad)
     return _FKProject.apply(angles, global_rot, bone_len, root, None, False, False, flags)[0]
 
 
@@ -243,13 +251,13 @@ class _GeneratorFK(torch.autograd.Function):
 
 
 def generator_fk(net_out, bone_len, *, use_pre_angle=True, root_scale=10.0, cam=None, return_cam=False,
-                 return_uv=False, half37=None, mid37=None, fast_trig=False):
+                 return_uv=False, half37=None, mid37=None, fast_trig=False, accurate_grad=False):
     """Fk_generator.py:121-259 after the last Linear layer, fused: net_out [N,35] raw, bone_len [N,15] already
     multiplied by (1 + scaler).  Returns world16 [N,16,3] (and cam16 / uv16 when requested with `cam`)."""
     from . import tables
     if half37 is None or mid37 is None:
         half37, mid37 = tables.generator_slot_scale(use_pre_angle)
-    flags = _cabi.FLAG_FAST_TRIG if fast_trig else 0
+    flags = _trig_flags(fast_trig, accurate_grad)
     outs = _GeneratorFK.apply(net_out, bone_len, half37, mid37, root_scale, cam, bool(return_cam), bool(return_uv), flags)
     return outs[0] if len(outs) == 1 else outs
 
@@ -526,7 +534,7 @@ def flip_pose(x):
 
 
 def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chunk_rows=131072, num_streams=3,
-                    workspace=None, out=None, fast_trig=False):
+                    workspace=None, out=None, fast_trig=False, accurate_grad=False):
     """End-to-end over HOST (ideally pinned) float32 tensors through dhfk_forward_backward_host:
     chunks move through an upload / compute / download stream pipeline over `num_streams` device slots
     (H2D inputs -> fused forward -> D2H world, uv; H2D grads -> fused backward -> D2H grads).
@@ -563,7 +571,7 @@ def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chun
         rc = lib.dhfk_forward_backward_host(
             p(ang), p(grot), p(bone), p(root), cam_arr.ctypes.data, p(g_world), p(g_uv), p(world), p(uv),
             p(g_ang), p(g_grot), p(g_root), n, chunk_rows, num_streams, workspace.data_ptr(),
-            workspace.numel() * workspace.element_size(), _cabi.FLAG_FAST_TRIG if fast_trig else 0)
+            workspace.numel() * workspace.element_size(), _trig_flags(fast_trig, accurate_grad))
     _cabi.check(rc, "dhfk_forward_backward_host")
     out["_workspace"] = workspace
     return out

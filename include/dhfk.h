@@ -65,9 +65,16 @@ extern "C" {
 #define DHFK_E_ALIGN (-2)       /* a packed output or gradient pointer is not 16-byte aligned  */
 #define DHFK_E_UNSUPPORTED (-3) /* combination not implemented                                 */
 
-/* flags */
-#define DHFK_FLAG_FAST_TRIG 0x1u /* MUFU.SIN/COS after exact degree range reduction (abs err ~4e-7)
-                                    instead of the ~1 ulp polynomial path                        */
+/* flags: which sin/cos the fused kernels use (every variant reduces the angle exactly in degrees first).
+ *   default (0)              forward: degree-scaled minimax polynomials, max abs err 7.7e-8 (the forward is HBM-bound,
+ *                            accuracy is free there); backward: MUFU.SIN/COS, abs err ~4e-7 -- gradients then sit
+ *                            1.8e-7 from exact arithmetic (1M poses, relative to max(|ref|,1); the reference's own fp32
+ *                            autograd sits 6.7e-8 away, the tolerance is 1e-5) and the backward runs ~10 % faster
+ *   DHFK_FLAG_FAST_TRIG      forward also uses MUFU.SIN/COS (positions 1.5e-6 from exact; the reference itself: 1.0e-6)
+ *   DHFK_FLAG_ACCURATE_TRIG  backward uses the table sincos (128-entry fp32 table + remainder, max abs err 1.0e-7)
+ * The two flags are mutually exclusive.  Numbers: tools/trig_parity.py, tests/test_parity_gpu.py (1M poses). */
+#define DHFK_FLAG_FAST_TRIG 0x1u
+#define DHFK_FLAG_ACCURATE_TRIG 0x2u
 
 #define DHFK_NUM_JOINTS 33
 #define DHFK_NUM_OUT 16

@@ -54,6 +54,9 @@ def test_argument_validation_without_gpu():
     assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, p, z, p, 4, 0, z) == _cabi.E_INVAL   # uv without cam
     assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, p, p, 9, p, z, p, 4, 0, z) == _cabi.E_UNSUPPORTED  # cam_rows
     assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, p + 4, z, z, 4, 0, z) == _cabi.E_ALIGN
+    both = _cabi.FLAG_FAST_TRIG | _cabi.FLAG_ACCURATE_TRIG          # contradictory trig policies
+    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, p, z, z, 4, both, z) == _cabi.E_INVAL
+    assert "mutually exclusive" in _cabi.last_error()
     assert lib.dhfk_backward(p, 33, p, 3, p, 15, p, 3, z, z, 0, z, z, z, p, 33, p, 3, p, 3, z, 15, 4, 0, z) == _cabi.E_INVAL
     assert "upstream" in _cabi.last_error()
     assert lib.dhfk_project_forward(p, p, 8, p, 4, 16, z) == _cabi.E_INVAL

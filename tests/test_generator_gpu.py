@@ -22,14 +22,14 @@ def _scaled_bone(bone, scaler):
     return (bone * np.where(grp[None, :] >= 0, 1.0 + scaler[:, np.maximum(grp, 0)], 1.0)).astype(np.float32)
 
 
-@pytest.mark.parametrize("fast", [False, True], ids=["accurate", "mufu"])
+@pytest.mark.parametrize("trig", [dict(accurate_grad=True), {}, dict(fast_trig=True)], ids=["accurate", "default", "mufu"])
 @pytest.mark.parametrize("tag,pre", [("single", True), ("single_nopre", False), ("video", True)])
-def test_fused_generator_epilogue_matches_reference(golden, tag, pre, fast):
+def test_fused_generator_epilogue_matches_reference(golden, tag, pre, trig):
     import dhfk
     g = golden("generator")
     raw = T(g[tag + "_raw"].reshape(-1, 35), True)
     bone = T(_scaled_bone(g[tag + "_bone"], g[tag + "_scaler"]))
-    world = dhfk.generator_fk(raw, bone, use_pre_angle=pre, fast_trig=fast)
+    world = dhfk.generator_fk(raw, bone, use_pre_angle=pre, **trig)
     assert_parity(world.detach().cpu().numpy(), g[tag + "_fake"].reshape(-1, 16, 3), "fake")
     (world * T(g[tag + "_g_fake"].reshape(-1, 16, 3))).sum().backward()
     assert_parity(raw.grad.cpu().numpy(), g[tag + "_d_raw"].reshape(-1, 35), "d_raw")

@@ -23,12 +23,16 @@ def T(x, grad=False):
     return torch.tensor(np.asarray(x, dtype=np.float32), device=dev(), requires_grad=grad)
 
 
-def run_fused(g, fast, grads):
+TRIG = {"accurate": dict(accurate_grad=True), "default": {}, "mufu": dict(fast_trig=True)}   # include/dhfk.h flags
+TRIG_IDS = list(TRIG)
+
+
+def run_fused(g, trig, grads):
     """grads: subset string of 'wcu' -> returns outputs and input gradients as numpy."""
     import dhfk
     ang, grot, root = T(g["ang"], True), T(g["grot"], True), T(g["root"], True)
     bone = T(g["bone"])
-    world, cam, uv = dhfk.fk_project(ang, grot, bone, root, g["cam_block"], return_cam=True, fast_trig=fast)
+    world, cam, uv = dhfk.fk_project(ang, grot, bone, root, g["cam_block"], return_cam=True, **TRIG[trig])
     loss = (world * T(g["g_world"])).sum()
     if "c" in grads:
         loss = loss + (cam * T(g["g_cam"])).sum()
@@ -39,22 +43,22 @@ def run_fused(g, fast, grads):
             ang.grad.cpu().numpy(), grot.grad.cpu().numpy(), root.grad.cpu().numpy())
 
 
-@pytest.mark.parametrize("fast", [False, True], ids=["poly", "mufu"])
+@pytest.mark.parametrize("trig", TRIG_IDS)
 @pytest.mark.parametrize("case", CASES)
-def test_forward_matches_reference_golden(golden, case, fast):
+def test_forward_matches_reference_golden(golden, case, trig):
     g = golden(case)
-    world, cam, uv, *_ = run_fused(g, fast, "w")
+    world, cam, uv, *_ = run_fused(g, trig, "w")
     assert_parity(world, g["world16"], "world16")
     assert_parity(cam, g["cam"], "cam")
     assert_parity(uv, g["uv"], "uv")
 
 
-@pytest.mark.parametrize("fast", [False, True], ids=["poly", "mufu"])
+@pytest.mark.parametrize("trig", TRIG_IDS)
 @pytest.mark.parametrize("tag", ["w", "wu", "wcu"])
 @pytest.mark.parametrize("case", CASES)
-def test_backward_matches_reference_autograd(golden, case, tag, fast):
+def test_backward_matches_reference_autograd(golden, case, tag, trig):
     g = golden(case)
-    *_, g_ang, g_grot, g_root = run_fused(g, fast, tag)
+    *_, g_ang, g_grot, g_root = run_fused(g, trig, tag)
     cond = projection_conditioning(g["cam"], g["world16"], g["cam_block"], g["g_uv"]) if "u" in tag else None
     assert_parity(g_ang, g["g_ang_" + tag], "g_ang", row_scale=cond)
     assert_parity(g_grot, g["g_grot_" + tag], "g_grot", row_scale=cond)
@@ -71,7 +75,7 @@ def test_kat_tpose_and_bent(golden):
     assert np.abs(w.cpu().numpy()[0] - g["tpose32"][idx]).max() < 1e-6
     for pre in ("bent_", "bent2_"):
         gg = {k[len(pre):]: v for k, v in g.items() if k.startswith(pre)}
-        world, cam, uv, *_ = run_fused(gg, False, "w")
+        world, cam, uv, *_ = run_fused(gg, "default", "w")
         assert_parity(world, gg["world16"], pre + "world16")
         assert_parity(uv, gg["uv"], pre + "uv")
 
@@ -85,7 +89,7 @@ def test_ragged_sizes_vs_c_oracle(c_oracle, n):
     up = synthetic.upstream_grads(n, seed=7 + n)
     blk = tables.camera_block("S5", 1)
     g = dict(inp, cam_block=blk, **up)
-    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, False, "wcu")
+    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, "default", "wcu")
     o = c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
     b = c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"],
                           g_cam=up["g_cam"], g_uv=up["g_uv"])
@@ -149,8 +153,8 @@ def test_fk_only_and_no_cam_variants_agree():
         assert np.abs(L - inp["bone"][:, bi]).max() < 2e-6, bi
 
 
-@pytest.mark.parametrize("fast", [False, True], ids=["poly", "mufu"])
-def test_full_size_1m_vs_c_oracle(c_oracle, fast):
+@pytest.mark.parametrize("trig", TRIG_IDS)
+def test_full_size_1m_vs_c_oracle(c_oracle, trig):
     """BASELINE config 2 size (1,048,576 poses): forward and backward against the float64 oracle on
     every pose, plus size-independent properties (linearity of the backward in the upstream gradient,
     root-translation equivariance)."""
@@ -161,7 +165,7 @@ def test_full_size_1m_vs_c_oracle(c_oracle, fast):
     up = synthetic.upstream_grads(n, seed=4321)
     blk = tables.camera_block("S1", 0)
     g = dict(inp, cam_block=blk, **up)
-    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, fast, "wu")
+    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, trig, "wu")
     o = c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
     assert (np.abs(o["cam"][..., :2] / o["cam"][..., 2:]) < 1).all()     # in-volume roots: clamp inactive
     e = [assert_parity(world, o["world16"], "world16"), assert_parity(cam, o["cam"], "cam"),
@@ -170,15 +174,16 @@ def test_full_size_1m_vs_c_oracle(c_oracle, fast):
                           g_uv=up["g_uv"], want_bone=False)
     e += [assert_parity(g_ang, b["g_ang"], "g_ang"), assert_parity(g_grot, b["g_grot"], "g_grot"),
           assert_parity(g_root, b["g_root"], "g_root")]
-    print("\n[1M %s] max rel err world/cam/uv/g_ang/g_grot/g_root = %s" % ("mufu" if fast else "poly",
+    print("\n[1M %s] max rel err world/cam/uv/g_ang/g_grot/g_root = %s" % (trig,
                                                                           " ".join("%.2e" % x for x in e)))
     # linearity: backward(2*g) == 2*backward(g) bit-exactly (power-of-two scaling commutes with fp32 rounding)
     g2 = dict(g, g_world=2 * up["g_world"], g_uv=2 * up["g_uv"])
-    *_, a2, r2, t2 = run_fused(g2, fast, "wu")
+    *_, a2, r2, t2 = run_fused(g2, trig, "wu")
     assert np.array_equal(a2, 2 * g_ang) and np.array_equal(r2, 2 * g_grot) and np.array_equal(t2, 2 * g_root)
 
 
-def test_stress_1m_clamp_active(c_oracle):
+@pytest.mark.parametrize("trig", TRIG_IDS)
+def test_stress_1m_clamp_active(c_oracle, trig):
     """1M poses with roots 10*tanh(randn): most poses leave the image (clamp active) or sit behind the
     camera.  Forward must match everywhere.  Gradients are compared with the conditioning multiplier;
     poses with a point whose x/z sits on the clamp edge within fp32 resolution are excluded, because
@@ -191,7 +196,7 @@ def test_stress_1m_clamp_active(c_oracle):
     up = synthetic.upstream_grads(n, seed=78)
     blk = tables.camera_block("S8", 3)
     g = dict(inp, cam_block=blk, **up)
-    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, False, "wu")
+    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, trig, "wu")
     o = c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
     assert_parity(world, o["world16"], "world16"); assert_parity(cam, o["cam"], "cam")
     ratio = np.abs(o["cam"][..., :2] / o["cam"][..., 2:])
@@ -227,7 +232,7 @@ def test_host_pipeline_matches_device_path():
     res = dhfk.fk_project_host(pin(inp["ang"]), pin(inp["grot"]), pin(inp["bone"]), pin(inp["root"]), blk,
                                pin(up["g_world"]), pin(up["g_uv"]), chunk_rows=8192, num_streams=3)
     g = dict(inp, cam_block=blk, **up)
-    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, False, "wu")
+    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, "default", "wu")
     assert np.array_equal(res["world"].numpy(), world) and np.array_equal(res["uv"].numpy(), uv)
     assert np.array_equal(res["g_ang"].numpy(), g_ang) and np.array_equal(res["g_grot"].numpy(), g_grot)
     assert np.array_equal(res["g_root"].numpy(), g_root)
