@@ -17,9 +17,9 @@ o = c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
 b = c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"], g_uv=up["g_uv"], want_bone=False)
 exact = dict(world=o["world16"], uv=o["uv"], g_ang=b["g_ang"], g_grot=b["g_grot"], g_root=b["g_root"])
 T = lambda a, g=False: torch.tensor(a, device="cuda:0", requires_grad=g)
-def run(fast):
+def run(kw):
     a, g, r = T(inp["ang"], True), T(inp["grot"], True), T(inp["root"], True)
-    w, _, uv = dhfk.fk_project(a, g, T(inp["bone"]), r, blk, return_cam=False, fast_trig=fast)
+    w, _, uv = dhfk.fk_project(a, g, T(inp["bone"]), r, blk, return_cam=False, **kw)
     ((w * T(up["g_world"])).sum() + (uv * T(up["g_uv"])).sum()).backward()
     return dict(world=w.detach().cpu().numpy(), uv=uv.detach().cpu().numpy(), g_ang=a.grad.cpu().numpy(),
                 g_grot=g.grad.cpu().numpy(), g_root=r.grad.cpu().numpy())
@@ -37,7 +37,8 @@ ref = {k: np.concatenate(v).astype(np.float64) for k, v in ref.items()}
 print("n = %d poses; max |x-ref|/max(|ref|,1)" % n)
 print("%-34s" % "" + "".join("%10s" % k for k in exact))
 print("%-34s" % "reference fp32  vs exact" + "".join("%10.2e" % rel(ref[k], exact[k]) for k in exact))
-for name, fast in (("kernels accurate", False), ("kernels MUFU", True)):
-    got = run(fast)
+for name, kw in (("kernels ACCURATE_TRIG flag", dict(accurate_grad=True)), ("kernels default", {}),
+                 ("kernels FAST_TRIG flag", dict(fast_trig=True))):
+    got = run(kw)
     print("%-34s" % (name + " vs exact") + "".join("%10.2e" % rel(got[k], exact[k]) for k in exact))
     print("%-34s" % (name + " vs reference fp32") + "".join("%10.2e" % rel(got[k], ref[k]) for k in exact))
