@@ -48,6 +48,32 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this rank's host threads to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned buffer is
+    allocated (first touch places the pages there).  The e2e leg is a PCIe/host-memory stream: with several ranks on
+    one box, buffers on the far socket halve it.  Returns a short description (or None when sysfs says nothing)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception:
+        return None
+
+
 METRIC = "augmented poses/sec (FK+proj fwd+bwd)"
 UNIT = "poses/s"
 FWD_BYTES = 536    # per pose: 54 floats in, 48 + 32 floats out           (SURVEY 8d / BASELINE.md 4)
@@ -239,6 +265,7 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world_size > 1
+    numa = bind_to_gpu_numa_node(local_rank) if distributed else None
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -364,6 +391,8 @@ def run_native(args):
                "d2h_bytes_per_step": n * (320 + 156), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "api": "dhfk.fk_project_host -> dhfk_forward_backward_host (pinned host buffers, %d-row chunks through an "
                       "upload / compute / download stream pipeline over %d device slots)" % (chunk, slots)}
+        if numa:
+            e2e["host_affinity"] = numa
 
     # ---- extra: generator-epilogue mode, same batch, device-resident, rank 0 only ----
     gen_extra = None
