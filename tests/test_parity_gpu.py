@@ -236,3 +236,32 @@ def test_host_pipeline_matches_device_path():
     assert np.array_equal(res["world"].numpy(), world) and np.array_equal(res["uv"].numpy(), uv)
     assert np.array_equal(res["g_ang"].numpy(), g_ang) and np.array_equal(res["g_grot"].numpy(), g_grot)
     assert np.array_equal(res["g_root"].numpy(), g_root)
+
+
+def test_multi_million_batch_crosses_2gib_offsets(c_oracle):
+    """BASELINE config 5 shards 16 M poses over 2-8 GPUs (2-8 M per GPU).  One launch over 11.3 M poses puts byte
+    offsets of world16 beyond 2^31 and element offsets of the angle tensor beyond 2^28: spot-check windows at
+    the start, the end and around the 2^31-byte offsets against the float64 oracle (64-bit indexing everywhere)."""
+    import dhfk
+    from dhfk import synthetic, tables
+    n = (1 << 31) // 192 + 150_001
+    d = synthetic.gan_like_torch(n, dev(), seed=3)
+    blk = tables.camera_block("S5", 2)
+    a, g, r = d["ang"].requires_grad_(True), d["grot"].requires_grad_(True), d["root"].requires_grad_(True)
+    w, _, uv = dhfk.fk_project(a, g, d["bone"], r, blk, return_cam=False)
+    gen = torch.Generator(device=dev()).manual_seed(5)
+    gw = torch.randn((n, 16, 3), device=dev(), generator=gen)
+    gu = torch.randn((n, 16, 2), device=dev(), generator=gen)
+    ((w * gw).sum() + (uv * gu).sum()).backward()
+    for lo in (0, n - 2048, (1 << 31) // 192 - 1024, (1 << 31) // 192 + 100_000, (1 << 30) // 132 - 1024):
+        sl = slice(lo, lo + 2048)
+        c = lambda t: t[sl].detach().cpu().numpy()
+        o = c_oracle.forward(c(a), c(g), c(d["bone"]), c(r), blk)
+        b = c_oracle.backward(c(a), c(g), c(d["bone"]), c(r), blk, g_world=c(gw), g_uv=c(gu), want_bone=False)
+        assert_parity(c(w), o["world16"], "world16 @%d" % lo)
+        assert_parity(c(uv), o["uv"], "uv @%d" % lo)
+        assert_parity(c(a.grad), b["g_ang"], "g_ang @%d" % lo)
+        assert_parity(c(g.grad), b["g_grot"], "g_grot @%d" % lo)
+        assert_parity(c(r.grad), b["g_root"], "g_root @%d" % lo)
+    del a, g, r, w, uv, gw, gu, d
+    torch.cuda.empty_cache()
