@@ -146,3 +146,49 @@ def test_scalar_dh_matrix_and_rotation_helpers(c_oracle):
     assert np.allclose(rotationMatrix(10.0, 20.0, 30.0, None), R.reshape(3, 3), atol=1e-15)
     with pytest.raises(NotImplementedError):
         dh_matrix(torch.zeros(2), torch.zeros(2), torch.zeros(2), torch.zeros(2), None)
+
+
+def test_dropin_install_widening_flags(monkeypatch):
+    """install(generators/critics/loader_refresh=True) rebinds exactly the symbols INTEGRATION.md lists and nothing
+    else; without the flags those symbols are left alone."""
+    from dhfk import Fk_discriminator, Fk_generator, dataloader_update, dropin
+    sentinel = object()
+    mods = {}
+    for name, syms in (("models_Fk_GAN.Fk_discriminator", ("special_KCS_Input_transform", "video_mode_special_KCS_Input_transform",
+                                                           "Fk_3D_Discriminator", "calc_gradient_penalty")),
+                       ("models_Fk_GAN.Fk_generator", ("Fk_Generator", "Video_Fk_Generator", "GAN_angle_range_table")),
+                       ("function_aug.dataloader_update", ("random_bl_aug", "dataloader_update", "project_to_2d")),
+                       ("models_Fk_GAN.video_mode_operate", ("random_bl_aug", "video_mode_random_bl_aug",
+                                                             "video_mode_dataloader_update")),
+                       ("run_Fk_GAN", ("dataloader_update",))):
+        m = types.ModuleType(name)
+        for s in syms:
+            setattr(m, s, sentinel)
+        monkeypatch.setitem(sys.modules, name, m)
+        mods[name] = m
+    dropin.install()
+    assert mods["models_Fk_GAN.Fk_discriminator"].special_KCS_Input_transform is sentinel
+    assert mods["models_Fk_GAN.Fk_generator"].Fk_Generator is sentinel
+    assert mods["function_aug.dataloader_update"].random_bl_aug is sentinel
+    patched = dropin.install(generators=True, critics=True, loader_refresh=True)
+    d, g = mods["models_Fk_GAN.Fk_discriminator"], mods["models_Fk_GAN.Fk_generator"]
+    assert d.special_KCS_Input_transform is Fk_discriminator.special_KCS_Input_transform
+    assert d.video_mode_special_KCS_Input_transform is Fk_discriminator.video_mode_special_KCS_Input_transform
+    assert d.Fk_3D_Discriminator is sentinel and d.calc_gradient_penalty is sentinel      # critic classes stay the reference's
+    assert g.Fk_Generator is Fk_generator.Fk_Generator and g.Video_Fk_Generator is Fk_generator.Video_Fk_Generator
+    assert g.GAN_angle_range_table is sentinel
+    du, vo = mods["function_aug.dataloader_update"], mods["models_Fk_GAN.video_mode_operate"]
+    assert du.random_bl_aug is dataloader_update.random_bl_aug and du.dataloader_update is dataloader_update.dataloader_update
+    assert vo.random_bl_aug is dataloader_update.random_bl_aug
+    assert vo.video_mode_random_bl_aug is dataloader_update.video_mode_random_bl_aug
+    assert vo.video_mode_dataloader_update is sentinel
+    assert mods["run_Fk_GAN"].dataloader_update is dataloader_update.dataloader_update
+    assert any("special_KCS_Input_transform" in p for p in patched)
+
+
+def test_bone_length_templates_table_matches_reference_file(golden):
+    """The in-package copy of data_extra/bone_length_npy/hm36s15678_bl_templates.npy is bit-identical to the file."""
+    from dhfk import dataloader_update, tables
+    g = golden("tables")
+    assert np.array_equal(tables.BONE_TEMPLATES_GANUTILS_ORDER, g["bone_templates"].astype(np.float32))
+    assert np.array_equal(dataloader_update.bone_length_templates(), g["bone_templates"].astype(np.float32))
