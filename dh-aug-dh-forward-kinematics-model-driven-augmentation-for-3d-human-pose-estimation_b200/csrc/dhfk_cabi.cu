@@ -491,20 +491,21 @@ int dhfk_flip_pose(const float* x, float* out, int64_t n, int32_t dims, void* st
 }
 
 // ---- device-resident fake-pair bank ----------------------------------------------------
-int dhfk_bank_gather(const float* bank3d, const float* bank2d, const float* bank_cam, int32_t cam_cols,
-                     const int64_t* idx, int64_t nb, int64_t bank_rows, float* out3d, float* out2d, float* out_cam,
-                     void* stream) {
+int dhfk_bank_gather(const float* bank, int64_t rec_floats, int32_t cam_cols, const int64_t* idx, int64_t nb,
+                     int64_t bank_rows, float* out3d, float* out2d, float* out_cam, void* stream) {
     if (nb < 0 || bank_rows < 0) return fail(DHFK_E_INVAL, "nb / bank_rows must be >= 0");
     if (nb == 0) return DHFK_OK;
-    if (!bank3d || !bank2d || !idx || !out3d || !out2d) return fail(DHFK_E_INVAL, "bank3d / bank2d / idx / out3d / out2d must be non-null");
-    if ((out_cam != nullptr) != (bank_cam != nullptr)) return fail(DHFK_E_INVAL, "bank_cam and out_cam go together");
-    if (out_cam && (cam_cols < 1 || cam_cols > 20)) return fail(DHFK_E_INVAL, "cam_cols must be in 1..20");
-    if (!aligned16(bank3d) || !aligned16(bank2d) || !aligned16(out3d) || !aligned16(out2d))
-        return fail(DHFK_E_ALIGN, "bank3d / bank2d / out3d / out2d must be 16-byte aligned");
+    if (!bank || !idx || !out3d || !out2d) return fail(DHFK_E_INVAL, "bank / idx / out3d / out2d must be non-null");
+    if (out_cam && (cam_cols < 1 || cam_cols > 32)) return fail(DHFK_E_INVAL, "cam_cols must be in 1..32");
+    const int64_t need = 80 + (out_cam ? (cam_cols + 3) / 4 * 4 : 0);
+    if (rec_floats < need || rec_floats % 4 != 0 || rec_floats > (1 << 20))
+        return fail(DHFK_E_INVAL, "rec_floats must be a multiple of 4 and >= 80 + cam_cols rounded up to 4");
+    if (!aligned16(bank) || !aligned16(out3d) || !aligned16(out2d))
+        return fail(DHFK_E_ALIGN, "bank / out3d / out2d must be 16-byte aligned");
     if (nb > (1LL << 33)) return fail(DHFK_E_INVAL, "nb too large for one launch");
     const char* where = "";
-    int e = dhfk::launch_bank_gather(bank3d, bank2d, bank_cam, cam_cols, reinterpret_cast<const long long*>(idx), nb,
-                                     bank_rows, out3d, out2d, out_cam, (cudaStream_t)stream, &where);
+    int e = dhfk::launch_bank_gather(bank, rec_floats, cam_cols, reinterpret_cast<const long long*>(idx), nb, bank_rows,
+                                     out3d, out2d, out_cam, (cudaStream_t)stream, &where);
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }
 

@@ -28,9 +28,9 @@ int launch_critic(int mode, int kc, bool pos, const float* pose, const float* a,
 int launch_flip(const float* x, float* out, long long n, int dims, cudaStream_t st, const char** where);
 
 // shuffled mini-batch gather out of the device-resident fake-pair bank
-int launch_bank_gather(const float* bank3d, const float* bank2d, const float* bank_cam, int cam_cols,
-                       const long long* idx, long long nb, long long bank_rows, float* out3d, float* out2d,
-                       float* out_cam, cudaStream_t st, const char** where);
+int launch_bank_gather(const float* bank, long long rec_floats, int cam_cols, const long long* idx, long long nb,
+                       long long bank_rows, float* out3d, float* out2d, float* out_cam, cudaStream_t st,
+                       const char** where);
 
 // floats per pose in the input slabs: raw mode ang33+grot3+bone15+root3, generator mode out35+bone15
 inline size_t in_floats(bool gen) { return gen ? (GEN_NCOL + 15) : 54; }

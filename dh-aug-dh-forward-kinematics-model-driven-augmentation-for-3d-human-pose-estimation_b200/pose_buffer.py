@@ -5,7 +5,8 @@ The reference appends every iteration's ``pos_3d_cam`` / ``uv`` / ``cam_para_tem
 to ``train_posenet`` through ``DataLoader(PoseDataSet(...), batch_size, shuffle=True, pin_memory=True)``
 (:504-510; common/data_loader.py:9-36) -- one D2H copy per iteration and one H2D copy per batch.
 
-``DevicePoseBuffer`` keeps the pairs in HBM (bounded ring, sized for 180 GB per GPU: 356 B per pose) and
+``DevicePoseBuffer`` keeps the pairs in HBM (bounded ring of 384-byte records, one per pose: a shuffled batch
+reads one contiguous span per pose; 180 GB per GPU holds 4.7e8 pairs) and
 ``DevicePoseBuffer.loader()`` yields batches with the same wire format and -- for the same torch seed -- the SAME
 sample order as the reference's shuffled DataLoader under the installed torch: the iterator draws a base seed,
 RandomSampler draws its own int64 seed from torch's default RNG and permutes with ``torch.randperm(n, generator=g)``
@@ -30,24 +31,31 @@ def shuffled_order(n: int) -> torch.Tensor:
     return torch.randperm(n, generator=g)
 
 
-def gather_pairs(bank3d, bank2d, bank_cam, idx, rows=None):
-    """(bank3d[idx], bank2d[idx], bank_cam[idx]) in one launch; idx int64 on the device; `rows` = valid bank rows."""
+REC_3D, REC_2D = 48, 80          # record layout (floats): pose3d [0,48) | pose2d [48,80) | cam [80, 80+cam_cols) | pad
+
+
+def record_floats(cam_cols: int) -> int:
+    """Floats per bank record: 80 + cam_cols rounded up so that a record is a whole number of 128-byte lines
+    (9 camera columns -> 96 floats = 384 bytes)."""
+    return (80 + int(cam_cols) + 31) // 32 * 32
+
+
+def gather_pairs(records, idx, cam_cols=9, rows=None, want_cam=True):
+    """(pose3d [nb,16,3], pose2d [nb,16,2], cam [nb,cam_cols]) = the records `idx` of the bank, in one launch.
+    records: [capacity, rec_floats] float32 CUDA, contiguous; idx int64 on the device; `rows` = valid bank rows."""
     _require_cuda()
     lib = _cabi.load()
-    device = bank3d.device
+    if not (records.is_cuda and records.dtype == torch.float32 and records.is_contiguous() and records.dim() == 2):
+        raise ValueError("records must be a contiguous 2-D float32 CUDA tensor")
+    device = records.device
     idx = idx.to(device=device, dtype=torch.int64).contiguous()
     nb = idx.shape[0]
-    rows = bank3d.shape[0] if rows is None else int(rows)
+    rows = records.shape[0] if rows is None else int(rows)
     o3 = torch.empty((nb, 16, 3), dtype=torch.float32, device=device)
     o2 = torch.empty((nb, 16, 2), dtype=torch.float32, device=device)
-    oc = torch.empty((nb, bank_cam.shape[1]), dtype=torch.float32, device=device) if bank_cam is not None else None
-    for t in (bank3d, bank2d) + ((bank_cam,) if bank_cam is not None else ()):
-        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
-            raise ValueError("bank tensors must be contiguous float32 CUDA tensors")
+    oc = torch.empty((nb, cam_cols), dtype=torch.float32, device=device) if want_cam else None
     with torch.cuda.device(device):
-        rc = lib.dhfk_bank_gather(bank3d.data_ptr(), bank2d.data_ptr(),
-                                  bank_cam.data_ptr() if bank_cam is not None else None,
-                                  bank_cam.shape[1] if bank_cam is not None else 0, idx.data_ptr(), nb, rows,
+        rc = lib.dhfk_bank_gather(records.data_ptr(), records.shape[1], cam_cols, idx.data_ptr(), nb, rows,
                                   o3.data_ptr(), o2.data_ptr(), oc.data_ptr() if oc is not None else None,
                                   _stream_ptr(device))
     _cabi.check(rc, "dhfk_bank_gather")
@@ -55,15 +63,17 @@ def gather_pairs(bank3d, bank2d, bank_cam, idx, rows=None):
 
 
 class DevicePoseBuffer:
-    """Append-only (ring when full) bank of (pose3d_cam [16,3], pose2d [16,2], cam [cam_cols]) rows in HBM."""
+    """Append-only (ring when full) bank of (pose3d_cam [16,3], pose2d [16,2], cam [cam_cols]) records in HBM.
+    `pose3d` / `pose2d` / `cam` are strided views into the record array."""
 
     def __init__(self, capacity: int, device=None, cam_cols: int = 9):
         _require_cuda()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.capacity, self.cam_cols = int(capacity), int(cam_cols)
-        self.pose3d = torch.empty((self.capacity, 16, 3), dtype=torch.float32, device=self.device)
-        self.pose2d = torch.empty((self.capacity, 16, 2), dtype=torch.float32, device=self.device)
-        self.cam = torch.empty((self.capacity, self.cam_cols), dtype=torch.float32, device=self.device)
+        self.records = torch.zeros((self.capacity, record_floats(cam_cols)), dtype=torch.float32, device=self.device)
+        self.pose3d = self.records[:, :REC_3D].unflatten(1, (16, 3))
+        self.pose2d = self.records[:, REC_3D:REC_2D].unflatten(1, (16, 2))
+        self.cam = self.records[:, REC_2D:REC_2D + self.cam_cols]
         self.reset()
 
     def reset(self):
@@ -112,5 +122,5 @@ class DeviceBatchLoader:
         order = order.to(self.bank.device, non_blocking=True)
         for b in range(len(self)):
             idx = order[b * self.batch_size:(b + 1) * self.batch_size]
-            p3, p2, cam = gather_pairs(self.bank.pose3d, self.bank.pose2d, self.bank.cam, idx, rows=n)
+            p3, p2, cam = gather_pairs(self.bank.records, idx, self.bank.cam_cols, rows=n)
             yield p3, p2, ["none"] * idx.shape[0], cam

@@ -211,14 +211,15 @@ int dhfk_flip_pose(const float* x_dev, float* out_dev, int64_t n, int32_t dims, 
 /*
  * SURVEY 8 f4 -- device-resident fake-pair bank.  The reference copies every iteration's pos_3d_cam / uv / cam to
  * host numpy (model_fk_gan_train.py:486-488) and re-serves them through a CPU DataLoader (:504-510;
- * common/data_loader.py:9-36: PoseDataSet).  Here they stay in HBM; this call serves one (shuffled) mini-batch:
- *   out3d[b] = bank3d[idx[b]]  ([16,3]),  out2d[b] = bank2d[idx[b]]  ([16,2]),  out_cam[b] = bank_cam[idx[b]]
+ * common/data_loader.py:9-36: PoseDataSet).  Here they stay in HBM, one record of rec_floats floats per pose:
+ *   [ pose3d 16x3 | pose2d 16x2 | cam (cam_cols floats, padded to the record end) ]      (default 96 floats = 384 B)
+ * and this call serves one (shuffled) mini-batch as three packed tensors -- the wire format of
+ * PoseDataSet.__getitem__:  out3d[b] = rec[idx[b]][0:48], out2d[b] = rec[idx[b]][48:80], out_cam[b] = rec[idx[b]][80:80+cam_cols].
  * idx_dev [nb] int64 (what torch.randperm yields).  An index outside [0, bank_rows) produces a NaN row.
- * bank_cam_dev / out_cam_dev [*, cam_cols] packed (cam_cols <= 20), or both NULL.
+ * out_cam_dev may be NULL (cameras not wanted).  rec_floats: multiple of 4, >= 80 + cam_cols rounded up to 4.
  */
-int dhfk_bank_gather(const float* bank3d_dev, const float* bank2d_dev, const float* bank_cam_dev, int32_t cam_cols,
-                     const int64_t* idx_dev, int64_t nb, int64_t bank_rows, float* out3d_dev, float* out2d_dev,
-                     float* out_cam_dev, void* stream);
+int dhfk_bank_gather(const float* bank_dev, int64_t rec_floats, int32_t cam_cols, const int64_t* idx_dev, int64_t nb,
+                     int64_t bank_rows, float* out3d_dev, float* out2d_dev, float* out_cam_dev, void* stream);
 
 /*
  * Host-buffer end-to-end entry: forward + backward over N poses whose inputs, upstream gradients

@@ -82,7 +82,7 @@ def test_argument_validation_of_the_widened_entry_points_without_gpu():
     assert lib.dhfk_critic_input_backward(z, z, z, 30, z, 0, 0, z) == 0
     assert lib.dhfk_critic_input_jvp(z, z, z, z, 30, 0, 0, z) == 0
     assert lib.dhfk_flip_pose(z, z, 0, 3, z) == 0
-    assert lib.dhfk_bank_gather(z, z, z, 9, z, 0, 10, z, z, z, z) == 0
+    assert lib.dhfk_bank_gather(z, 96, 9, z, 0, 10, z, z, z, z) == 0
     # retarget
     assert lib.dhfk_retarget_project(p, p, p, 5, p, 9, p, p, -1, z) == _cabi.E_INVAL
     assert lib.dhfk_retarget_project(z, p, p, 5, p, 9, p, p, 4, z) == _cabi.E_INVAL
@@ -108,7 +108,9 @@ def test_argument_validation_of_the_widened_entry_points_without_gpu():
     assert lib.dhfk_flip_pose(p, p, 4, 2, z) == _cabi.E_INVAL                                # 2-D in place
     assert lib.dhfk_flip_pose(p + 4, p + 256, 4, 2, z) == _cabi.E_ALIGN
     # bank gather
-    assert lib.dhfk_bank_gather(p, p, p, 9, z, 4, 10, p, p, p, z) == _cabi.E_INVAL           # no indices
-    assert lib.dhfk_bank_gather(p, p, p, 9, p, 4, 10, p, p, z, z) == _cabi.E_INVAL           # cam in without cam out
-    assert lib.dhfk_bank_gather(p, p, p, 21, p, 4, 10, p, p, p, z) == _cabi.E_INVAL          # cam_cols > 20
-    assert lib.dhfk_bank_gather(p, p + 4, z, 0, p, 4, 10, p, p, z, z) == _cabi.E_ALIGN
+    assert lib.dhfk_bank_gather(p, 96, 9, z, 4, 10, p, p, p, z) == _cabi.E_INVAL             # no indices
+    assert lib.dhfk_bank_gather(p, 88, 9, p, 4, 10, p, p, p, z) == _cabi.E_INVAL             # record too short for 9 cam cols
+    assert "rec_floats" in _cabi.last_error()
+    assert lib.dhfk_bank_gather(p, 98, 9, p, 4, 10, p, p, p, z) == _cabi.E_INVAL             # not a multiple of 4
+    assert lib.dhfk_bank_gather(p, 96, 33, p, 4, 10, p, p, p, z) == _cabi.E_INVAL            # cam_cols > 32
+    assert lib.dhfk_bank_gather(p + 4, 96, 9, p, 4, 10, p, p, p, z) == _cabi.E_ALIGN

@@ -48,16 +48,28 @@ def test_gather_is_bit_exact_and_guards_indices():
     from dhfk import pose_buffer as pb
     rng = np.random.RandomState(0)
     p3, p2, cams = _iterations(rng, 1, 5000)
+    bank = pb.DevicePoseBuffer(5000, device="cuda:0")
+    assert bank.records.shape == (5000, 96) and pb.record_floats(9) == 96 and pb.record_floats(16) == 96 and pb.record_floats(17) == 128
+    bank.append(*(torch.tensor(a[0], device="cuda:0") for a in (p3, p2, cams)))
     b3, b2, bc = (torch.tensor(a[0], device="cuda:0") for a in (p3, p2, cams))
+    assert torch.equal(bank.pose3d, b3) and torch.equal(bank.pose2d, b2) and torch.equal(bank.cam, bc)
     idx = torch.tensor(rng.randint(0, 5000, 777), device="cuda:0")
-    o3, o2, oc = pb.gather_pairs(b3, b2, bc, idx)
+    o3, o2, oc = pb.gather_pairs(bank.records, idx)
     assert torch.equal(o3, b3[idx]) and torch.equal(o2, b2[idx]) and torch.equal(oc, bc[idx])
-    o3, o2, oc = pb.gather_pairs(b3, b2, bc, torch.tensor([0, 4999, 5000, -1], device="cuda:0"))
+    o3, o2, oc = pb.gather_pairs(bank.records, torch.tensor([0, 4999, 5000, -1], device="cuda:0"))
     assert torch.equal(o3[:2], b3[[0, 4999]]) and torch.isnan(o3[2:]).all() and torch.isnan(o2[2:]).all() and torch.isnan(oc[2:]).all()
-    e3, e2, ec = pb.gather_pairs(b3, b2, bc, torch.zeros(0, dtype=torch.int64, device="cuda:0"))
+    o3, o2, oc = pb.gather_pairs(bank.records, idx, rows=100)          # only the first 100 records are valid
+    bad = idx >= 100
+    assert torch.isnan(o3[bad]).all() and torch.equal(o3[~bad], b3[idx[~bad]])
+    e3, e2, ec = pb.gather_pairs(bank.records, torch.zeros(0, dtype=torch.int64, device="cuda:0"))
     assert e3.shape == (0, 16, 3) and e2.shape == (0, 16, 2) and ec.shape == (0, 9)
-    n3, n2, nc = pb.gather_pairs(b3, b2, None, idx)
+    n3, n2, nc = pb.gather_pairs(bank.records, idx, want_cam=False)
     assert nc is None and torch.equal(n3, b3[idx])
+    wide = pb.DevicePoseBuffer(64, device="cuda:0", cam_cols=16)        # the reference's 16-column camera rows
+    c16 = torch.randn(64, 16, device="cuda:0")
+    wide.append(b3[:64], b2[:64], c16)
+    w3, w2, wc = pb.gather_pairs(wide.records, torch.arange(63, -1, -1, device="cuda:0"), cam_cols=16)
+    assert torch.equal(wc, c16.flip(0)) and torch.equal(w3, b3[:64].flip(0))
 
 
 @pytest.mark.gpu

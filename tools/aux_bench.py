@@ -57,6 +57,15 @@ def main():
         "flip 3d (f2)": (lambda s: lib.dhfk_flip_pose(P(s["pose"]), P(s["o48"]), n, 3, st), 384),
         "flip 2d (f2)": (lambda s: lib.dhfk_flip_pose(P(s["gp"]), P(s["o32"]), n, 2, st), 256),
     }
+    # f4: shuffled mini-batch out of a 4x larger device-resident bank (one 384-byte record per pose)
+    bank_rows = 4 * n
+    rec = torch.randn(bank_rows, 96, device=dev, generator=g)
+    for s_ in sets:
+        s_["perm"] = torch.randperm(bank_rows, device=dev, generator=g)[:n].contiguous()
+        s_["o9"] = torch.empty(n, 9, device=dev)
+    cases["bank gather, shuffled batch (f4)"] = (
+        lambda s: lib.dhfk_bank_gather(P(rec), 96, 9, P(s["perm"]), n, bank_rows, P(s["o48"]), P(s["o32"]), P(s["o9"]), st),
+        8 + 2 * (192 + 128 + 36))
     out = {"poses": n, "peak_gbs": peak, "kernels": {}}
     for name, (fn, bpp) in cases.items():
         ms = timeit(fn, sets)
