@@ -211,6 +211,31 @@ def time_torch_port(chunk, chunks, steps, warmup, threads=None):
     return chunk * chunks / dt, dt, threads
 
 
+def time_torch_port_gpu(dev, chunk=16384, reps=3):
+    """Context only: the reference's op sequence (oracle/torch_port.py) in torch EAGER on the GPU, every tensor created
+    on the device (kinder than the reference's own CUDA branch, which builds each of its 34 matrices on the host and
+    copies it over).  ~7 000 ATen launches forward, ~13 000 with autograd: launch-bound at any batch that fits."""
+    import torch
+    import torch_port
+    from dhfk import synthetic, tables
+    blk = tables.camera_block("S1", 0)
+    inp = synthetic.gan_like(chunk, seed=1234)
+    up = synthetic.upstream_grads(chunk, seed=4321)
+    ang, grot, bone, root = (torch.tensor(inp[k], device=dev) for k in ("ang", "grot", "bone", "root"))
+    gw, gu = torch.tensor(up["g_world"], device=dev), torch.tensor(up["g_uv"], device=dev)
+    best = float("inf")
+    for it in range(reps + 1):
+        a = ang.clone().requires_grad_(True); g = grot.clone().requires_grad_(True); r = root.clone().requires_grad_(True)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        _, w16, _, uv = torch_port.pipeline(a, g, bone, r, blk)
+        ((w16 * gw).sum() + (uv * gu).sum()).backward()
+        torch.cuda.synchronize(dev)
+        if it > 0:
+            best = min(best, time.perf_counter() - t0)
+    return chunk / best, best
+
+
 def time_c_oracle(n=131072):
     """Extra context: the float64 C oracle (OpenMP, all cores) forward+backward."""
     import c_oracle
@@ -542,6 +567,13 @@ def run_native(args):
         pps, dt, threads = time_torch_port(args.ref_chunk, 1, steps=10, warmup=2)
         line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "10 x %d-pose torch calls (reference batch size), fwd+bwd, oracle/torch_port.py" % args.ref_chunk}
+        try:
+            gps, gdt = time_torch_port_gpu(dev)
+            line["torch_eager_gpu"] = {"value": gps, "unit": UNIT, "ms_per_call": gdt * 1e3, "kind": "port",
+                                       "sample": "16384-pose torch-eager calls on this GPU, fwd+bwd, best of 3 "
+                                                 "(the reference's op sequence, oracle/torch_port.py; context, not an arm)"}
+        except Exception as e:
+            line["torch_eager_gpu"] = {"error": repr(e)}
         try:
             cps, cthreads = time_c_oracle()
             line["cpu_baseline_c"] = {"value": cps, "unit": UNIT, "cores": cthreads, "kind": "port",

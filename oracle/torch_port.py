@@ -70,9 +70,14 @@ H36M_32_TO_16 = [0, 1, 2, 3, 6, 7, 8, 12, 13, 15, 17, 18, 19, 25, 26, 27]  # com
 class RefFKPort:
     """Stateful like the reference object (tables replicated to [N,n]; lengths written in place)."""
 
-    def __init__(self, n: int):
+    def __init__(self, n: int, device=None):
         self.n = n
-        rep = lambda rows: torch.tensor(np.tile(np.asarray(rows, dtype=np.float64), (n, 1)), dtype=torch.float32)
+        # device=None / cpu: the reference's CPU branch (what the parity pin and the CPU baseline use).  A CUDA device
+        # runs the same op sequence in torch eager on the GPU with every tensor created in place -- a generous
+        # stand-in for the reference's own CUDA branch, which builds each matrix on the host and copies it over
+        # (forward_kinematics_DH_model.py:93-97,154-156); used only as context by bench.py.
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        rep = lambda rows: torch.tensor(np.tile(np.asarray(rows, dtype=np.float64), (n, 1)), dtype=torch.float32).to(self.device)
         self.alpha = [rep(r) for r in _ALPHA]
         self.a = [rep(r) for r in _A0]
         self.d = [rep(r) for r in _D0]
@@ -81,8 +86,8 @@ class RefFKPort:
     # forward_kinematics_DH_model.py:80-116 (torch branch of dh_matrix)
     def _dh(self, alpha, a, d, theta):
         alpha = alpha / 180 * np.pi
-        theta = theta / 180 * torch.tensor(np.pi, dtype=torch.float32)
-        m = torch.tensor(np.zeros((self.n, 4, 4)), dtype=torch.float32)
+        theta = theta / 180 * torch.tensor(np.pi, dtype=torch.float32, device=self.device)
+        m = torch.zeros((self.n, 4, 4), dtype=torch.float32, device=self.device)
         m[:, 0, 0] = torch.cos(theta)
         m[:, 0, 1] = -torch.sin(theta)
         m[:, 0, 2] = 0
@@ -107,10 +112,10 @@ class RefFKPort:
         ay = ay / 180 * np.pi
         az = az / 180 * np.pi
         n = self.n
-        r1 = torch.zeros((n, 3, 3), dtype=torch.float32)
-        r2 = torch.zeros((n, 3, 3), dtype=torch.float32)
-        r3 = torch.zeros((n, 3, 3), dtype=torch.float32)
-        r1[:, 0:] = torch.tensor([1, 0, 0], dtype=torch.float32)
+        r1 = torch.zeros((n, 3, 3), dtype=torch.float32, device=self.device)
+        r2 = torch.zeros((n, 3, 3), dtype=torch.float32, device=self.device)
+        r3 = torch.zeros((n, 3, 3), dtype=torch.float32, device=self.device)
+        r1[:, 0:] = torch.tensor([1, 0, 0], dtype=torch.float32, device=self.device)
         r1[:, 1, 0] = 0
         r1[:, 1, 1] = torch.cos(ax)
         r1[:, 1, 2] = -torch.sin(ax)
@@ -120,7 +125,7 @@ class RefFKPort:
         r2[:, 0, 0] = torch.cos(ay)
         r2[:, 0, 1] = 0
         r2[:, 0, 2] = torch.sin(ay)
-        r2[:, 1:] = torch.tensor([0, 1, 0], dtype=torch.float32)
+        r2[:, 1:] = torch.tensor([0, 1, 0], dtype=torch.float32, device=self.device)
         r2[:, 2, 0] = -torch.sin(ay)
         r2[:, 2, 1] = 0
         r2[:, 2, 2] = torch.cos(ay)
@@ -130,7 +135,7 @@ class RefFKPort:
         r3[:, 1, 0] = torch.sin(az)
         r3[:, 1, 1] = torch.cos(az)
         r3[:, 1, 2] = 0
-        r3[:, 2:] = torch.tensor([0, 0, 1], dtype=torch.float32)
+        r3[:, 2:] = torch.tensor([0, 0, 1], dtype=torch.float32, device=self.device)
         return r1.bmm(r2).bmm(r3)
 
     # forward_kinematics_DH_model.py:562-822
@@ -145,7 +150,7 @@ class RefFKPort:
         for c in (1, 0, 2):
             lo, hi = _ANG_SLICE[c]
             ang = angles33[:, lo:hi]
-            h = torch.zeros((n, hi - lo, 4, 4), dtype=torch.float32)
+            h = torch.zeros((n, hi - lo, 4, 4), dtype=torch.float32, device=self.device)
             for i in range(hi - lo):
                 h[:, i] = self._dh(self.alpha[c][:, i], self.a[c][:, i], self.d[c][:, i],
                                    self.theta0[c][:, i] + ang[:, i])
@@ -153,7 +158,7 @@ class RefFKPort:
         for c in (3, 4):
             lo, hi = _ANG_SLICE[c]
             ang = angles33[:, lo:hi]
-            h = torch.zeros((n, 9 + 5, 4, 4), dtype=torch.float32)
+            h = torch.zeros((n, 9 + 5, 4, 4), dtype=torch.float32, device=self.device)
             h[:, 0:9] = torch.clone(hm[2][:, 0:9])
             for i in range(5):
                 h[:, i + 9] = self._dh(self.alpha[c][:, i], self.a[c][:, i], self.d[c][:, i],
@@ -169,12 +174,12 @@ class RefFKPort:
             x = torch.clone(h[:, :, 0, 3])
             y = torch.clone(h[:, :, 1, 3])
             z = torch.clone(h[:, :, 2, 3])
-            p = torch.zeros((n, 3, h.shape[1]), dtype=torch.float32)
+            p = torch.zeros((n, 3, h.shape[1]), dtype=torch.float32, device=self.device)
             p[:, 0, :] = x[:, :]
             p[:, 1, :] = y[:, :]
             p[:, 2, :] = z[:, :]
             pos[c] = rg.bmm(p)
-        out = torch.zeros((n, 32, 3), dtype=torch.float32)
+        out = torch.zeros((n, 32, 3), dtype=torch.float32, device=self.device)
         for slot, c, i in _SCATTER:
             for ax in range(3):
                 out[:, slot, ax] = pos[c][:, ax, i]
@@ -216,8 +221,8 @@ def project_to_2d(x, camera_params):
 def pipeline(angles33, grot3, bone15, root3, cam16):
     """FK -> gather 16 -> world->camera -> project.  cam16 = [q4,t3,f2,c2,k3,p2] (array-like)."""
     n = angles33.shape[0]
-    cam16 = torch.as_tensor(np.asarray(cam16, dtype=np.float32))
-    w32 = RefFKPort(n).fk32(angles33, grot3, bone15.detach(), root3)
+    cam16 = torch.as_tensor(np.asarray(cam16, dtype=np.float32)).to(angles33.device)
+    w32 = RefFKPort(n, angles33.device).fk32(angles33, grot3, bone15.detach(), root3)
     w16 = w32[:, H36M_32_TO_16]
     q = cam16[0:4].view(1, 4)
     t = cam16[4:7].view(1, 3)
