@@ -1,0 +1,90 @@
+"""Build-container only (skipped where /root/reference is absent, e.g. on the GPU box): dropin.install() against
+the REAL reference modules -- every symbol INTEGRATION.md lists exists there under that name, gets rebound, and the
+reference's own classes then route into the native entry points (which, without a GPU, raise instead of falling
+back to any CPU path)."""
+import argparse
+import importlib
+import sys
+
+import pytest
+import torch
+
+import ref_harness as rh
+
+pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not mounted")
+
+REF_MODULES = ("models_Fk_GAN.model_fk_gan_train", "models_Fk_GAN.video_GAN_fun", "function_aug.dataloader_update",
+               "models_Fk_GAN.video_mode_operate", "models_Fk_GAN.Fk_discriminator", "models_Fk_GAN.Fk_generator",
+               "common.camera", "models_Fk_GAN.forward_kinematics_DH_model")
+
+
+@pytest.fixture()
+def reference_modules():
+    rh.import_reference()
+    for name in ("progress", "progress.bar"):
+        if name not in sys.modules:
+            rh._stub_module(name)
+    mods = {m: importlib.import_module(m) for m in REF_MODULES}
+    saved = {m: dict(vars(mod)) for m, mod in mods.items()}
+    yield mods
+    for m, mod in mods.items():          # undo the patching: other tests use the unmodified reference
+        for k, v in saved[m].items():
+            setattr(mod, k, v)
+
+
+def test_install_rebinds_the_real_reference_symbols(reference_modules):
+    from dhfk import Fk_discriminator, Fk_generator, camera, dataloader_update, dropin
+    from dhfk import Forward_Kinematics_DH_Model
+    m = reference_modules
+    before = m["models_Fk_GAN.Fk_discriminator"].special_KCS_Input_transform
+    patched = dropin.install(generators=True, critics=True, loader_refresh=True)
+    assert m["models_Fk_GAN.forward_kinematics_DH_model"].Forward_Kinematics_DH_Model is Forward_Kinematics_DH_Model
+    for name in ("models_Fk_GAN.model_fk_gan_train", "models_Fk_GAN.video_GAN_fun"):
+        assert m[name].GAN_torch_world_to_camera is camera.GAN_torch_world_to_camera
+        assert m[name].project_to_2d is camera.project_to_2d
+        assert m[name].Fk_Generator is Fk_generator.Fk_Generator
+        assert m[name].Video_Fk_Generator is Fk_generator.Video_Fk_Generator
+    assert m["common.camera"].project_to_2d is camera.project_to_2d
+    assert m["function_aug.dataloader_update"].project_to_2d is camera.project_to_2d
+    assert m["function_aug.dataloader_update"].random_bl_aug is dataloader_update.random_bl_aug
+    assert m["function_aug.dataloader_update"].dataloader_update is dataloader_update.dataloader_update
+    assert m["models_Fk_GAN.video_mode_operate"].video_mode_random_bl_aug is dataloader_update.video_mode_random_bl_aug
+    d = m["models_Fk_GAN.Fk_discriminator"]
+    assert d.special_KCS_Input_transform is Fk_discriminator.special_KCS_Input_transform is not before
+    assert d.video_mode_special_KCS_Input_transform is Fk_discriminator.video_mode_special_KCS_Input_transform
+    assert len(patched) >= 20
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_reference_critic_routes_into_the_native_transform(reference_modules):
+    """The reference's Fk_3D_Discriminator looks special_KCS_Input_transform up as a module global
+    (Fk_discriminator.py:190): after install(critics=True) its forward reaches the native entry point, which
+    refuses to run without a CUDA device."""
+    from dhfk import dropin
+    d = reference_modules["models_Fk_GAN.Fk_discriminator"]
+    D = d.Fk_3D_Discriminator(torch.device("cpu"), argparse.Namespace(Dis_DenseDim_3D=16))
+    x = torch.randn(4, 16, 3)
+    assert D(x).shape == (4, 1)                                   # the unmodified reference runs on the CPU
+    dropin.install(critics=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        D(x)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_reference_generator_class_is_state_dict_compatible(reference_modules):
+    """Same constructor, sub-module names and parameter shapes as the reference generator (Fk_generator.py:80-112),
+    so checkpoints move both ways."""
+    from dhfk import Fk_generator as native
+    g = reference_modules["models_Fk_GAN.Fk_generator"]
+    fkmod = reference_modules["models_Fk_GAN.forward_kinematics_DH_model"]
+    args = argparse.Namespace(batch_size=8, random_seed=0, single_or_multi_train_mode="single", architecture="3,3,3",
+                              GAN_OUTPUT_DIM=35, Gen_DenseDim=32, GAN_whether_use_preAngle=True, whether_use_RT=True,
+                              bone_len_scaler="different", record_all_picture=False, checkpoint="/tmp")
+    ref_fk = fkmod.Forward_Kinematics_DH_Model(args, ["S1"], None)
+    G_ref = g.Fk_Generator(ref_fk, args, torch.device("cpu"))
+    from dhfk import Forward_Kinematics_DH_Model
+    G_nat = native.Fk_Generator(Forward_Kinematics_DH_Model(args, ["S1"], None), args, torch.device("cpu"))
+    sd_ref, sd_nat = G_ref.state_dict(), G_nat.state_dict()
+    assert list(sd_ref) == list(sd_nat)
+    assert all(sd_ref[k].shape == sd_nat[k].shape for k in sd_ref)
+    G_nat.load_state_dict(sd_ref)
