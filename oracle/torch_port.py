@@ -255,3 +255,30 @@ def time_pipeline(inputs, cam16, g_world, g_uv, backward=True, repeats=3, warmup
         if it >= warmup:
             best = min(best, dt)
     return best, n
+
+
+# ---- critic input transform (context baseline for tools/gan_step_bench.py) -------------------------------------------
+# models_Fk_GAN/special_operate.py:513-539 (Ct rows: bone = x[second] - x[first]) and
+# models_Fk_GAN/Fk_discriminator.py:36-146 (30 row writes into a [30,N] buffer, then a transpose)
+_KCS_BONES = ((5, 6), (2, 3), (4, 5), (1, 2), (0, 4), (0, 1), (0, 7), (7, 8), (8, 10), (8, 13), (10, 11), (13, 14),
+              (11, 12), (14, 15), (8, 9))
+_KCS_PAIRS = ((0, 2), (1, 3), (2, 4), (3, 5), (4, 5), (4, 6), (5, 6), (6, 7), (7, 14), (7, 8), (7, 9), (8, 10), (9, 11),
+              (10, 12), (11, 13))
+
+
+def special_kcs(pos_16_3d):
+    """special_KCS_Input_transform restated with the reference's op sequence: incidence matmul, norms, one row write per
+    feature.  Pinned to tests/golden/critic.npz by tests/test_oracle_golden.py."""
+    x = pos_16_3d.view(-1, 16, 3)
+    ct = torch.zeros(15, 16, device=x.device)
+    for b, (i, j) in enumerate(_KCS_BONES):
+        ct[b, i] = -1.0
+        ct[b, j] = 1.0
+    c = ct.transpose(1, 0).repeat([x.size(0), 1, 1]).view(-1, 16, 15)
+    bone = torch.matmul(x.permute(0, 2, 1).contiguous(), c).permute(0, 2, 1).transpose(1, 0)   # [15, N, 3]
+    length = torch.sqrt(torch.sum(bone ** 2, dim=-1))
+    out = torch.zeros((30, x.shape[0]), dtype=torch.float32, device=x.device)
+    for q, (i, j) in enumerate(_KCS_PAIRS):
+        out[q] = torch.sum(bone[i] * bone[j], dim=-1) / (length[i] * length[j])
+    out[15:] = length[0:]
+    return out.transpose(0, 1)

@@ -144,3 +144,16 @@ def test_generator_epilogue_oracle_matches_reference(golden, c_oracle, tag, pre)
     assert np.all(ref[:, 31] == 0)                      # network column 31 is never consumed
     assert np.all(ref[:, [23, 27]] == 0)                # columns feeding the chain-end slots 27 / 32
     assert np.array_equal(tables.generator_src_col()[[27, 32, 34, 36]], [23, 27, 28, 30])
+
+
+def test_torch_port_kcs_matches_reference(golden):
+    """oracle/torch_port.py::special_kcs (the eager context baseline of tools/gan_step_bench.py) against the golden
+    produced by the reference's special_KCS_Input_transform, outputs and gradients."""
+    import torch_port
+    g = golden("critic")
+    x = torch.tensor(g["c1f0_pos"], requires_grad=True)
+    k = torch_port.special_kcs(x)
+    assert_parity(k.detach().numpy(), g["c1f0_kcs"], "kcs")
+    x0 = torch.tensor(g["pose"], requires_grad=True)
+    (torch_port.special_kcs(x0) * torch.tensor(g["g_kcs"])).sum().backward()
+    assert_parity(x0.grad.numpy(), g["c0f0_g_pose_kcs_only"], "g_pose")
