@@ -22,6 +22,15 @@ GAN_angle_range_table = {
     "joint%d" % (i + 1): {"range": (int(lo), int(hi))} for i, (lo, hi) in enumerate(tables.GAN_ANGLE_RANGE)}
 
 _GROUP = torch.as_tensor(tables.BONE_SCALER_GROUP)
+_GROUP_ON = {}      # per-device copies (a host->device copy per call would also break CUDA-graph capture)
+
+
+def _group_on(device):
+    g = _GROUP_ON.get(device)
+    if g is None:
+        idx = _GROUP.to(device)
+        g = _GROUP_ON[device] = (idx.clamp(min=0), (idx >= 0).to(torch.float32))
+    return g
 
 
 class myResNet(nn.Module):
@@ -49,9 +58,8 @@ def bone_vectors_to_lengths(pose16):
 
 def scaled_bone_lengths(bone, scaler):
     """boneLength[:, i] * (1 + scaler[:, group(i)]), thorax unscaled (Fk_generator.py:216-230)."""
-    grp = _GROUP.to(bone.device)
-    factor = torch.where(grp >= 0, 1.0 + scaler[:, grp.clamp(min=0)], torch.ones((), device=bone.device))
-    return bone * factor
+    col, scaled = _group_on(bone.device)
+    return bone * (1.0 + scaler[:, col] * scaled)
 
 
 class _GeneratorBase(nn.Module):
@@ -91,6 +99,11 @@ class _GeneratorBase(nn.Module):
             mid[34:] = 0.0
         return half, mid
 
+    # Optional hook: a callable (rows, frames) -> [rows*frames, 8] tensor already on the compute device.  The reference
+    # draws the scalers on the HOST every call (below); a caller that captures the training step in a CUDA graph sets
+    # this to a device-side draw (no host RNG, no H2D copy inside the captured region).
+    scaler_source = None
+
     def _draw_scaler(self, rows, frames):
         """[rows*frames, 8] scaler, RNG use as in the reference (torch.randint on the global CPU generator for the
         single-frame 'different' mode, :197; FK_DH_Class.random otherwise, :201,:383-393)."""
@@ -126,7 +139,8 @@ class Fk_Generator(_GeneratorBase):
     def forward(self, input):
         net_out = self._mlp(input)                                   # [B, 35] raw
         self.train_num += 1
-        scaler = self._draw_scaler(net_out.shape[0], 1).to(net_out.device)
+        scaler = (self.scaler_source(net_out.shape[0], 1) if self.scaler_source is not None
+                  else self._draw_scaler(net_out.shape[0], 1).to(net_out.device))
         bone = scaled_bone_lengths(self.boneLength.to(net_out.device), scaler)
         half, mid = self._slot_scale()
         world16 = generator_fk(net_out, bone, half37=half, mid37=mid, root_scale=10.0)
@@ -149,7 +163,8 @@ class Video_Fk_Generator(_GeneratorBase):
         net_out = self._mlp(input).contiguous().view(-1, self.OUTPUT_DIM)   # [B*F, 35] raw
         self.train_num += 1
         rows = net_out.shape[0] // self.video_frame_num
-        scaler = self._draw_scaler(rows, self.video_frame_num).to(net_out.device)
+        scaler = (self.scaler_source(rows, self.video_frame_num) if self.scaler_source is not None
+                  else self._draw_scaler(rows, self.video_frame_num).to(net_out.device))
         bone = scaled_bone_lengths(self.boneLength.to(net_out.device), scaler)
         half, mid = self._slot_scale()
         world16 = generator_fk(net_out, bone, half37=half, mid37=mid, root_scale=10.0)

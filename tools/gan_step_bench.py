@@ -89,7 +89,7 @@ def gradient_penalty(D, real, fake, lam=10.0):          # Fk_discriminator.py:20
 
 
 def critic_step(D, opt, real, fake):                     # model_fk_gan_train.py:177-232
-    D.zero_grad()
+    D.zero_grad(set_to_none=True)
     (-D(real).mean()).backward()
     D(fake).mean().backward()
     gradient_penalty(D, real.data, fake.data).backward()
@@ -148,10 +148,11 @@ def make_arm(kind, G_native, bone, dense, dev, state):
     D3, D2 = Critic3D(dense, kcs).to(dev), Critic2D(dense).to(dev)
     D3.load_state_dict(state["d3"]); D2.load_state_dict(state["d2"])
     return dict(G=G, D3=D3, D2=D2, w2c=w2c, proj=proj, centre=centre, flip3=flip3, flip2=flip2,
-                o3=torch.optim.Adam(D3.parameters(), 1e-4), o2=torch.optim.Adam(D2.parameters(), 1e-4))
+                o3=torch.optim.Adam(D3.parameters(), 1e-4, capturable=True),
+                o2=torch.optim.Adam(D2.parameters(), 1e-4, capturable=True))
 
 
-def iteration(arm, kind, oG, real3d, real2d, cam_q, cam_t, cam_rows, bank, host_lists, batch, dev):
+def iteration(arm, kind, oG, real3d, real2d, cam_q, cam_t, cam_rows, bank, host_lists, batch, dev, append=True):
     G, D3, D2 = arm["G"], arm["D3"], arm["D2"]
     with torch.no_grad():
         fake = G(torch.randn(batch, 128, device=dev)).view(-1, 16, 3)
@@ -165,7 +166,7 @@ def iteration(arm, kind, oG, real3d, real2d, cam_q, cam_t, cam_rows, bank, host_
     # generator step (model_fk_gan_train.py:415-482)
     for p in list(D3.parameters()) + list(D2.parameters()):
         p.requires_grad_(False)
-    oG.zero_grad()
+    oG.zero_grad(set_to_none=True)
     fake = G(torch.randn(batch, 128, device=dev)).view(-1, 16, 3)
     uv_g = arm["proj"](arm["w2c"](fake, cam_q, cam_t), cam_rows)
     fc = arm["centre"](fake)
@@ -175,6 +176,8 @@ def iteration(arm, kind, oG, real3d, real2d, cam_q, cam_t, cam_rows, bank, host_
     for p in list(D3.parameters()) + list(D2.parameters()):
         p.requires_grad_(True)
     # fake-pair buffer (model_fk_gan_train.py:486-488)
+    if not append:
+        return cam, uv
     if kind == "native":
         bank.append(cam, uv, cam_rows)
     else:
@@ -225,6 +228,37 @@ def main():
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) / iters * 1e3
         out[kind] = {"ms_per_iteration": ms, "poses_per_s": 2 * a.batch / (ms * 1e-3), "iterations": iters}
+    # native pieces with the whole iteration captured in ONE CUDA graph (the C-ABI launches are plain stream work, so
+    # torch.cuda.graph captures them with the cuBLAS kernels; only the bank append stays outside: it moves a host-side
+    # ring head).  Scalers are drawn on the device (Fk_Generator.scaler_source) -- no host RNG inside the capture.
+    try:
+        G.scaler_source = lambda rows, frames: torch.randint(-200, 200, (rows * frames, 8), device=dev) / 1000.0
+        arm = make_arm("native", G, bone, a.dense, dev, state)
+        oG = torch.optim.Adam(G.parameters(), 1e-4, capturable=True)
+        bank = pose_buffer.DevicePoseBuffer(a.batch * (a.iters + 2), device=dev)
+        core = lambda: iteration(arm, "native", oG, real3d, real2d, cam_q, cam_t, cam_rows, bank, None, a.batch, dev, append=False)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                core()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            cam_s, uv_s = core()
+        for _ in range(2):
+            graph.replay(); bank.append(cam_s, uv_s, cam_rows)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.iters):
+            graph.replay(); bank.append(cam_s, uv_s, cam_rows)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / a.iters * 1e3
+        out["native_cuda_graph"] = {"ms_per_iteration": ms, "poses_per_s": 2 * a.batch / (ms * 1e-3), "iterations": a.iters}
+    except Exception as e:                      # context only: never let it break the two measured arms
+        out["native_cuda_graph"] = {"error": repr(e)[:300]}
+    finally:
+        G.scaler_source = None
     out["speedup"] = out["eager"]["ms_per_iteration"] / out["native"]["ms_per_iteration"]
     print(json.dumps(out, indent=1))
 
