@@ -88,11 +88,16 @@ def gradient_penalty(D, real, fake, lam=10.0):          # Fk_discriminator.py:20
     return ((g.norm(2, dim=1) - 1) ** 2).mean() * lam
 
 
+ALLREDUCE = [None]      # set under torchrun: dhfk.parallel.allreduce_grads_flat (one flat NCCL all-reduce per model step)
+
+
 def critic_step(D, opt, real, fake):                     # model_fk_gan_train.py:177-232
     D.zero_grad(set_to_none=True)
     (-D(real).mean()).backward()
     D(fake).mean().backward()
     gradient_penalty(D, real.data, fake.data).backward()
+    if ALLREDUCE[0] is not None:
+        ALLREDUCE[0](list(D.parameters()))
     opt.step()
 
 
@@ -172,6 +177,8 @@ def iteration(arm, kind, oG, real3d, real2d, cam_q, cam_t, cam_rows, bank, host_
     fc = arm["centre"](fake)
     loss = (D3(fc).mean() + D3(arm["flip3"](fc)).mean()) / 2 + 0.2 * (D2(uv_g).mean() + D2(arm["flip2"](uv_g)).mean()) / 2
     (-loss).backward()
+    if ALLREDUCE[0] is not None:
+        ALLREDUCE[0](list(G.parameters()))
     oG.step()
     for p in list(D3.parameters()) + list(D2.parameters()):
         p.requires_grad_(True)
@@ -191,7 +198,16 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--eager-iters", type=int, default=5)
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:       # data-parallel GAN iteration (BASELINE configs[4]): every rank its own batch, grads all-reduced
+        import torch.distributed as dist
+        from dhfk import parallel
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        ALLREDUCE[0] = parallel.allreduce_grads_flat
     torch.manual_seed(0)
     args = argparse.Namespace(batch_size=a.batch, random_seed=0, single_or_multi_train_mode="single", architecture="3,3,3",
                               GAN_OUTPUT_DIM=35, Gen_DenseDim=a.dense, GAN_whether_use_preAngle=True, whether_use_RT=True,
@@ -201,7 +217,9 @@ def main():
     with torch.no_grad():                          # keep the fakes in front of the camera
         G.deconv_out.weight.mul_(0.05)
         G.deconv_out.bias[-3:] = torch.tensor([0.0, 0.0, 0.1])
-    inp = synthetic.gan_like(a.batch, seed=3)
+    state = {"d3": Critic3D(a.dense, None).state_dict(), "d2": Critic2D(a.dense).state_dict()}
+    torch.manual_seed(1 + rank)                    # same weights everywhere, different noise / data per rank
+    inp = synthetic.gan_like(a.batch, seed=3 + rank)
     bone = torch.tensor(inp["bone"], device=dev)
     G.boneLength = bone
     blk = tables.camera_block("S1", 0)
@@ -211,10 +229,11 @@ def main():
     w, _, uv = dhfk.fk_project(*(torch.tensor(inp[k], device=dev) for k in ("ang", "grot", "bone", "root")), blk, return_cam=False)
     real3d = (w - w[:, :1]).detach()
     real2d = uv.detach()
-    state = {"d3": Critic3D(a.dense, None).state_dict(), "d2": Critic2D(a.dense).state_dict()}
     out = {"config": "BASELINE configs[2]: single-frame DH-AUG GAN iteration, Gen/Dis dense %d, batch %d" % (a.dense, a.batch),
            "iteration": "D3D step + flip pass, D2D step + flip pass (WGAN-GP each), generator step, fake-pair append"}
-    for kind, iters in (("native", a.iters), ("eager", a.eager_iters)):
+    if world > 1:
+        out["data_parallel"] = "%d ranks x batch %d, one flat NCCL all-reduce per optimiser step (5 per iteration)" % (world, a.batch)
+    for kind, iters in ((("native", a.iters),) if world > 1 else (("native", a.iters), ("eager", a.eager_iters))):
         arm = make_arm(kind, G, bone, a.dense, dev, state)
         oG = torch.optim.Adam(G.parameters(), 1e-4)
         bank = pose_buffer.DevicePoseBuffer(a.batch * (iters + 2), device=dev)
@@ -227,7 +246,19 @@ def main():
             iteration(arm, kind, oG, real3d, real2d, cam_q, cam_t, cam_rows, bank, host_lists, a.batch, dev)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) / iters * 1e3
-        out[kind] = {"ms_per_iteration": ms, "poses_per_s": 2 * a.batch / (ms * 1e-3), "iterations": iters}
+        out[kind] = {"ms_per_iteration": ms, "poses_per_s": 2 * a.batch * world / (ms * 1e-3), "iterations": iters}
+    if world > 1:
+        import torch.distributed as dist
+        # replicas must still agree after the all-reduced steps
+        flat = torch.cat([p.detach().reshape(-1) for m in (G, arm["D3"], arm["D2"]) for p in m.parameters()])
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        out["replicas_in_sync"] = bool(torch.equal(flat, ref))
+        dist.barrier()
+        if rank == 0:
+            print(json.dumps(out, indent=1))
+        dist.destroy_process_group()
+        return
     # native pieces with the whole iteration captured in ONE CUDA graph (the C-ABI launches are plain stream work, so
     # torch.cuda.graph captures them with the cuBLAS kernels; only the bank append stays outside: it moves a host-side
     # ring head).  Scalers are drawn on the device (Fk_Generator.scaler_source) -- no host RNG inside the capture.
