@@ -215,3 +215,30 @@ def test_kernels_match_oracle_ragged_and_large(c_oracle, n):
         assert_parity(t_pos.cpu().numpy(), reft["pos"], "t_pos")
         tscale = np.maximum(1.0, np.abs(reft["kcs"]).max(axis=1))
         assert_parity(t_kcs.cpu().numpy(), reft["kcs"], "t_kcs", row_scale=tscale)
+
+
+@pytest.mark.gpu
+def test_input_shapes_devices_and_leading_dims(golden):
+    """[N,48] rows (what the critic's interpolates look like), CPU tensors (moved to the device like every other entry
+    point) and clip-shaped [B,F,16,d] inputs of the flip."""
+    import dhfk
+    g = golden("critic")
+    x48 = T(g["pose"]).view(-1, 48).clone().requires_grad_(True)
+    pos, kcs = dhfk.critic_input(x48, centre=True, kcs_cols=30)
+    assert pos.shape == (133, 16, 3)
+    assert_parity(kcs.detach().cpu().numpy(), g["c1f0_kcs"], "kcs from [N,48]")
+    (kcs * T(g["g_kcs"])).sum().backward()
+    assert x48.grad.shape == (133, 48)
+    assert_parity(x48.grad.view(-1, 16, 3).cpu().numpy(), g["c1f0_g_pose_kcs_only"], "g_pose [N,48]")
+    xc = torch.tensor(g["pose"], requires_grad=True)                       # CPU leaf
+    k = dhfk.critic_input(xc, kcs_cols=15, return_pos=False)
+    assert k.is_cuda
+    (k * T(g["g_kcs"][:, :15])).sum().backward()
+    assert not xc.grad.is_cuda
+    assert_parity(xc.grad.numpy(), g["c0f0_g_pose_vkcs_only"], "g_pose on the CPU leaf")
+    clip2 = T(g["uv"][:132]).view(12, 11, 16, 2)
+    assert np.array_equal(dhfk.flip_pose(clip2).cpu().numpy().reshape(-1, 16, 2), g["flip2"][:132])
+    clip3 = T(g["pose"][:132]).view(4, 33, 16, 3)
+    assert np.array_equal(dhfk.flip_pose(clip3).cpu().numpy().reshape(-1, 16, 3), g["flip3"][:132])
+    with pytest.raises(ValueError):
+        dhfk.critic_input(T(g["pose"]), kcs_cols=7)

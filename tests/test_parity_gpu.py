@@ -306,3 +306,30 @@ def test_cuda_graph_capture_of_forward_and_backward():
         ((w * gw).sum() + (uv * gu).sum()).backward()
         for x, ref in zip(got, (w, uv, e_ang.grad, e_grot.grad, e_root.grad)):
             assert torch.equal(x, ref.detach())
+
+
+@pytest.mark.parametrize("n,chunk,slots,bwd", [(1, 4096, 1, True), (5000, 4096, 1, True), (5000, 4096, 2, False),
+                                               (20000, 4096, 3, True), (4096, 4096, 8, True)])
+def test_host_pipeline_shapes(n, chunk, slots, bwd):
+    """dhfk_forward_backward_host: single slot, ragged last chunk, fewer rows than one chunk, forward-only mode and
+    more slots than chunks all give the device path's results bit for bit."""
+    import dhfk
+    from dhfk import synthetic, tables
+    inp = synthetic.gan_like(n, seed=n)
+    up = synthetic.upstream_grads(n, seed=n + 1)
+    blk = tables.camera_block("S5", 3)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    res = dhfk.fk_project_host(pin(inp["ang"]), pin(inp["grot"]), pin(inp["bone"]), pin(inp["root"]), blk,
+                               pin(up["g_world"]) if bwd else None, pin(up["g_uv"]) if bwd else None,
+                               chunk_rows=chunk, num_streams=slots)
+    g = dict(inp, cam_block=blk, **up)
+    world, cam, uv, g_ang, g_grot, g_root = run_fused(g, "default", "wu")
+    assert np.array_equal(res["world"].numpy(), world) and np.array_equal(res["uv"].numpy(), uv)
+    if bwd:
+        assert np.array_equal(res["g_ang"].numpy(), g_ang) and np.array_equal(res["g_grot"].numpy(), g_grot)
+        assert np.array_equal(res["g_root"].numpy(), g_root)
+    else:
+        assert "g_ang" not in res
+    with pytest.raises(ValueError):
+        dhfk.fk_project_host(pin(inp["ang"]), pin(inp["grot"]), pin(inp["bone"]), pin(inp["root"]), blk,
+                             pin(up["g_world"]), None)
