@@ -20,13 +20,16 @@ from . import _cabi, tables  # noqa: F401
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `import dhfk` stays cheap
     import importlib
+    def keep(value):                 # resolve once: later lookups hit the module dict, not this hook
+        globals()[name] = value
+        return value
     if name in ("functional", "camera", "dropin", "parallel", "synthetic", "forward_kinematics_DH_model",
                 "Fk_generator", "dataloader_update", "Fk_discriminator",
                 "pose_buffer"):
-        return importlib.import_module("." + name, __name__)
+        return keep(importlib.import_module("." + name, __name__))
     if name in ("fk_project", "fk_world16", "world_to_camera", "project_to_2d", "fk_project_host", "generator_fk",
                 "retarget_project", "critic_input", "flip_pose"):
-        return getattr(importlib.import_module(".functional", __name__), name)
+        return keep(getattr(importlib.import_module(".functional", __name__), name))
     if name == "Forward_Kinematics_DH_Model":
-        return importlib.import_module(".forward_kinematics_DH_model", __name__).Forward_Kinematics_DH_Model
+        return keep(importlib.import_module(".forward_kinematics_DH_model", __name__).Forward_Kinematics_DH_Model)
     raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -31,7 +31,28 @@ def _require_cuda():
 
 
 def _stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """cudaStream_t of torch's current stream on `device` (the raw getter: torch.cuda.current_stream() builds a
+    Stream object per call, ~10 us -- comparable to the small-batch kernels themselves)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+class _on_device:
+    """`with torch.cuda.device(d)` only when `d` is not already current (the context manager costs ~5 us)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        idx = device.index
+        self.ctx = None if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
 
 
 def _rows(t: torch.Tensor, ncols: int, device) -> torch.Tensor:
@@ -94,7 +115,7 @@ class _FKProject(torch.autograd.Function):
         world = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
         camo = torch.empty((n, 16, 3), dtype=torch.float32, device=device) if want_cam else None
         uv = torch.empty((n, 16, 2), dtype=torch.float32, device=device) if want_uv else None
-        with torch.cuda.device(device):
+        with _on_device(device):
             rc = lib.dhfk_forward(
                 ang2.data_ptr(), _row_stride(ang2), grot2.data_ptr(), _row_stride(grot2),
                 bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
@@ -133,7 +154,7 @@ class _FKProject(torch.autograd.Function):
             if g_bone is not None:
                 g_bone.zero_()
         elif n > 0:
-            with torch.cuda.device(device):
+            with _on_device(device):
                 rc = lib.dhfk_backward(
                     ang2.data_ptr(), _row_stride(ang2), grot2.data_ptr(), _row_stride(grot2),
                     bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
@@ -207,7 +228,7 @@ class _GeneratorFK(torch.autograd.Function):
         world = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
         camo = torch.empty((n, 16, 3), dtype=torch.float32, device=device) if want_cam else None
         uv = torch.empty((n, 16, 2), dtype=torch.float32, device=device) if want_uv else None
-        with torch.cuda.device(device):
+        with _on_device(device):
             rc = lib.dhfk_generator_forward(
                 x.data_ptr(), _row_stride(x), bone2.data_ptr(), _row_stride(bone2), half.ctypes.data, mid.ctypes.data,
                 float(root_scale), cam_arr.ctypes.data if cam_arr is not None else None,
@@ -236,7 +257,7 @@ class _GeneratorFK(torch.autograd.Function):
         if g_world is None and g_cam is None and g_uv is None:
             g_x.zero_()
         elif n > 0:
-            with torch.cuda.device(device):
+            with _on_device(device):
                 rc = lib.dhfk_generator_backward(
                     x.data_ptr(), _row_stride(x), bone2.data_ptr(), _row_stride(bone2), half.ctypes.data,
                     mid.ctypes.data, root_scale, cam_arr.ctypes.data if cam_arr is not None else None,
@@ -273,7 +294,7 @@ class _WorldToCamera(torch.autograd.Function):
         t = t.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
         out = torch.empty_like(xs)
         npts = xs.numel() // 3
-        with torch.cuda.device(device):
+        with _on_device(device):
             rc = lib.dhfk_world_to_camera_forward(xs.data_ptr(), q.data_ptr(), t.data_ptr(), 1, out.data_ptr(),
                                                   npts, _stream_ptr(device))
         _cabi.check(rc, "dhfk_world_to_camera_forward")
@@ -289,7 +310,7 @@ class _WorldToCamera(torch.autograd.Function):
         device = q.device
         g = g.to(device=device, dtype=torch.float32).contiguous()
         gx = torch.empty_like(g)
-        with torch.cuda.device(device):
+        with _on_device(device):
             rc = lib.dhfk_world_to_camera_backward(g.data_ptr(), q.data_ptr(), 1, gx.data_ptr(), g.numel() // 3,
                                                    _stream_ptr(device))
         _cabi.check(rc, "dhfk_world_to_camera_backward")
@@ -320,7 +341,7 @@ class _Project(torch.autograd.Function):
         n = xs.shape[0]
         joints = xs.numel() // (3 * n) if n > 0 else 0
         uv = torch.empty(tuple(xs.shape[:-1]) + (2,), dtype=torch.float32, device=device)
-        with torch.cuda.device(device):
+        with _on_device(device):
             rc = lib.dhfk_project_forward(xs.data_ptr(), cams.data_ptr(), _row_stride(cams), uv.data_ptr(), n, joints,
                                           _stream_ptr(device))
         _cabi.check(rc, "dhfk_project_forward")
@@ -338,7 +359,7 @@ class _Project(torch.autograd.Function):
         joints = xs.numel() // (3 * n) if n > 0 else 0
         g = g.to(device=device, dtype=torch.float32).contiguous()
         gx = torch.empty_like(xs)
-        with torch.cuda.device(device):
+        with _on_device(device):
             rc = lib.dhfk_project_backward(xs.data_ptr(), cams.data_ptr(), _row_stride(cams), g.data_ptr(),
                                            gx.data_ptr(), n, joints, _stream_ptr(device))
         _cabi.check(rc, "dhfk_project_backward")
@@ -394,7 +415,7 @@ def retarget_project(pose16, templates, tmpl_idx=None, cam_rows=None, *, out_pos
         out_pose = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
     if cams is not None and out_uv is None:
         out_uv = torch.empty((n, 16, 2), dtype=torch.float32, device=device)
-    with torch.cuda.device(device):
+    with _on_device(device):
         rc = lib.dhfk_retarget_project(
             x.data_ptr(), idx.data_ptr() if idx is not None else None, tm.data_ptr(), tm.shape[0],
             cams.data_ptr() if cams is not None else None, cam_stride, out_pose.data_ptr(),
@@ -421,7 +442,7 @@ class _CriticInput(torch.autograd.Function):
         n = x.shape[0]
         pos = torch.empty((n, 16, 3), dtype=torch.float32, device=device) if want_pos else None
         kcs = torch.empty((n, kcs_cols), dtype=torch.float32, device=device) if kcs_cols else None
-        with torch.cuda.device(device):
+        with _on_device(device):
             rc = lib.dhfk_critic_input_forward(x.data_ptr(), pos.data_ptr() if want_pos else None,
                                                kcs.data_ptr() if kcs_cols else None, kcs_cols, n, flags,
                                                _stream_ptr(device))
@@ -458,7 +479,7 @@ class _CriticInputVJP(torch.autograd.Function):
         gk = _packed(g_kcs, (n, kcs_cols), device) if g_kcs is not None else None
         gx = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
         if n > 0:
-            with torch.cuda.device(device):
+            with _on_device(device):
                 rc = lib.dhfk_critic_input_backward(x.data_ptr(), gp.data_ptr() if gp is not None else None,
                                                     gk.data_ptr() if gk is not None else None,
                                                     kcs_cols if gk is not None else 0, gx.data_ptr(), n, flags,
@@ -479,7 +500,7 @@ class _CriticInputVJP(torch.autograd.Function):
         t_pos = torch.empty((n, 16, 3), dtype=torch.float32, device=device) if has_pos else None
         t_kcs = torch.empty((n, kcs_cols), dtype=torch.float32, device=device) if has_kcs else None
         if n > 0:
-            with torch.cuda.device(device):
+            with _on_device(device):
                 rc = lib.dhfk_critic_input_jvp(x.data_ptr(), v.data_ptr(), t_pos.data_ptr() if has_pos else None,
                                                t_kcs.data_ptr() if has_kcs else None, kcs_cols if has_kcs else 0, n,
                                                flags, _stream_ptr(device))
@@ -512,7 +533,7 @@ class _FlipPose(torch.autograd.Function):
             xs = xs.clone()
         out = torch.empty_like(xs)
         n = xs.numel() // (16 * dims)
-        with torch.cuda.device(device):
+        with _on_device(device):
             rc = lib.dhfk_flip_pose(xs.data_ptr(), out.data_ptr(), n, dims, _stream_ptr(device))
         _cabi.check(rc, "dhfk_flip_pose")
         ctx.meta = (x.device, x.dtype)
@@ -567,7 +588,7 @@ def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chun
     g_grot = host("g_grot", (n, 3)) if do_bwd else None
     g_root = host("g_root", (n, 3)) if do_bwd else None
     p = lambda t: t.data_ptr() if t is not None else None
-    with torch.cuda.device(device):
+    with _on_device(device):
         rc = lib.dhfk_forward_backward_host(
             p(ang), p(grot), p(bone), p(root), cam_arr.ctypes.data, p(g_world), p(g_uv), p(world), p(uv),
             p(g_ang), p(g_grot), p(g_root), n, chunk_rows, num_streams, workspace.data_ptr(),

@@ -17,7 +17,7 @@ from __future__ import annotations
 import torch
 
 from . import _cabi
-from .functional import _require_cuda, _stream_ptr
+from .functional import _on_device, _require_cuda, _stream_ptr
 
 
 def shuffled_order(n: int) -> torch.Tensor:
@@ -54,7 +54,7 @@ def gather_pairs(records, idx, cam_cols=9, rows=None, want_cam=True):
     o3 = torch.empty((nb, 16, 3), dtype=torch.float32, device=device)
     o2 = torch.empty((nb, 16, 2), dtype=torch.float32, device=device)
     oc = torch.empty((nb, cam_cols), dtype=torch.float32, device=device) if want_cam else None
-    with torch.cuda.device(device):
+    with _on_device(device):
         rc = lib.dhfk_bank_gather(records.data_ptr(), records.shape[1], cam_cols, idx.data_ptr(), nb, rows,
                                   o3.data_ptr(), o2.data_ptr(), oc.data_ptr() if oc is not None else None,
                                   _stream_ptr(device))
