@@ -378,11 +378,9 @@ def critic_fixture():
     return out
 
 
-def main():
+def fixtures_table():
     from dhfk import synthetic
-    os.makedirs(OUT, exist_ok=True)
-    torch.set_num_threads(1)
-    fixtures = {
+    return {
         "tables": tables_fixture,
         "kat": kat_fixture,
         "gan133": lambda: run_case(synthetic.gan_like(133, seed=1234), rh.camera_block("S1", 0),
@@ -398,6 +396,12 @@ def main():
         "retarget": retarget_fixture,
         "critic": critic_fixture,
     }
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    fixtures = fixtures_table()
     for name in (sys.argv[1:] or list(fixtures)):
         np.savez(os.path.join(OUT, name + ".npz"), **fixtures[name]())
     for f in sorted(os.listdir(OUT)):
