@@ -4,6 +4,7 @@ Reference-shaped names:
   random_bl_aug(x)                      function_aug/dataloader_update.py:18-41
   video_mode_random_bl_aug(x)           models_Fk_GAN/video_mode_operate.py:879-897
   dataloader_update(args, data_dict, device)          function_aug/dataloader_update.py:43-107
+  video_mode_dataloader_update(args, data_dict, device)   models_Fk_GAN/video_mode_operate.py:898-968
   refresh_poses(poses, cams, ...)       the same work for a device-resident pose bank (no loader round trip)
 
 The reference root-centres each pose, takes unit bone vectors with two [N,3,16]x[N,16,15] matmuls, multiplies
@@ -89,4 +90,39 @@ def dataloader_update(args, data_dict, device):
         PoseDataSet(buffer_poses_train, buffer_poses_train_2d, actions, buffer_cams_train), **kw)
     data_dict["target_3d_loader"] = DataLoader(PoseTarget(buffer_poses_train), **kw)
     data_dict["target_2d_loader"] = DataLoader(PoseTarget(buffer_poses_train_2d), **kw)
+    return
+
+
+def video_mode_dataloader_update(args, data_dict, device):
+    """Same contract as the reference's video_mode_dataloader_update: every training sequence gets the bone lengths of
+    ONE random template row (choice(T, 1) per sequence, in sequence order -- the reference's random stream) and is
+    re-projected with its own camera; data_dict['target_GAN_loader'] is rebuilt from the result.  The reference makes
+    ~25 torch calls and three .cpu() copies PER SEQUENCE; here the whole training set goes through ONE fused launch
+    (per-pose template index, per-pose intrinsics row) and comes back once.  The chunked generator class is the
+    reference's own (imported at call time)."""
+    import copy
+
+    from models_Fk_GAN.video_mode_operate import GAN_video_ChunkedGenerator, video_receptive_field  # reference module
+
+    tm = bone_length_templates()
+    poses = [np.asarray(p, dtype="float32") for p in data_dict["poses_train"]]
+    cams = [np.asarray(c, dtype="float32") for c in data_dict["cams_train"]]
+    actions = list(data_dict["actions_train"])
+    assert len(poses) == len(cams) == len(actions)
+    sizes = [p.shape[0] for p in poses]
+    rows = np.concatenate([np.full(k, np.random.choice(tm.shape[0], 1)[0], dtype=np.int32) for k in sizes])
+    cam_rows = np.concatenate([np.repeat(c[None, :9], k, axis=0) for c, k in zip(cams, sizes)])
+    out_pose, out_uv = retarget_project(torch.from_numpy(np.concatenate(poses)).to(device), tm, rows,
+                                        torch.from_numpy(cam_rows).to(device))
+    cuts = np.cumsum(sizes)[:-1]
+    buffer_poses_train = list(np.split(out_pose.cpu().numpy(), cuts))
+    buffer_poses_train_2d = list(np.split(out_uv.cpu().numpy(), cuts))
+    buffer_cams_train = cams
+    joints_left = out_left = [4, 5, 6, 10, 11, 12]
+    joints_right = out_right = [1, 2, 3, 13, 14, 15]
+    pad = (video_receptive_field([int(x) for x in args.architecture.split(",")]) - 1) // 2
+    data_dict["target_GAN_loader"] = GAN_video_ChunkedGenerator(
+        args.batch_size // 1, copy.deepcopy(buffer_cams_train), copy.deepcopy(buffer_poses_train),
+        copy.deepcopy(buffer_poses_train_2d), chunk_length=1, pad=pad, causal_shift=0, shuffle=True, augment=False,
+        kps_left=out_left, kps_right=out_right, joints_left=joints_left, joints_right=joints_right)
     return

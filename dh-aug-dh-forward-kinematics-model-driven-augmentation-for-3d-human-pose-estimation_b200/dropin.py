@@ -38,8 +38,10 @@ def install(verbose: bool = False, generators: bool = False, loader_refresh: boo
     if loader_refresh:
         from . import dataloader_update as _du
         for name, syms in (("function_aug.dataloader_update", ("random_bl_aug", "dataloader_update")),
-                           ("models_Fk_GAN.video_mode_operate", ("random_bl_aug", "video_mode_random_bl_aug")),
-                           ("run_Fk_GAN", ("dataloader_update",)), ("__main__", ("dataloader_update",))):
+                           ("models_Fk_GAN.video_mode_operate", ("random_bl_aug", "video_mode_random_bl_aug",
+                                                                 "video_mode_dataloader_update")),
+                           ("run_Fk_GAN", ("dataloader_update", "video_mode_dataloader_update")),
+                           ("__main__", ("dataloader_update", "video_mode_dataloader_update"))):
             mod = sys.modules.get(name)
             if mod is None:
                 continue

@@ -49,6 +49,11 @@ def test_install_rebinds_the_real_reference_symbols(reference_modules):
     assert m["function_aug.dataloader_update"].random_bl_aug is dataloader_update.random_bl_aug
     assert m["function_aug.dataloader_update"].dataloader_update is dataloader_update.dataloader_update
     assert m["models_Fk_GAN.video_mode_operate"].video_mode_random_bl_aug is dataloader_update.video_mode_random_bl_aug
+    assert (m["models_Fk_GAN.video_mode_operate"].video_mode_dataloader_update
+            is dataloader_update.video_mode_dataloader_update)
+    # what the native video refresh borrows from the reference at call time exists under those names
+    assert callable(m["models_Fk_GAN.video_mode_operate"].GAN_video_ChunkedGenerator)
+    assert m["models_Fk_GAN.video_mode_operate"].video_receptive_field([3, 3, 3]) == 27
     d = m["models_Fk_GAN.Fk_discriminator"]
     assert d.special_KCS_Input_transform is Fk_discriminator.special_KCS_Input_transform is not before
     assert d.video_mode_special_KCS_Input_transform is Fk_discriminator.video_mode_special_KCS_Input_transform

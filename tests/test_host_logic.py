@@ -181,7 +181,7 @@ def test_dropin_install_widening_flags(monkeypatch):
     assert du.random_bl_aug is dataloader_update.random_bl_aug and du.dataloader_update is dataloader_update.dataloader_update
     assert vo.random_bl_aug is dataloader_update.random_bl_aug
     assert vo.video_mode_random_bl_aug is dataloader_update.video_mode_random_bl_aug
-    assert vo.video_mode_dataloader_update is sentinel
+    assert vo.video_mode_dataloader_update is dataloader_update.video_mode_dataloader_update
     assert mods["run_Fk_GAN"].dataloader_update is dataloader_update.dataloader_update
     assert any("special_KCS_Input_transform" in p for p in patched)
 

@@ -133,3 +133,99 @@ def test_degenerate_bone_gives_nan_like_reference():
     assert np.isnan(out[1, 2]).all() and np.isnan(out[1, 3]).all()
     assert np.isfinite(out[1, [0, 1, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]]).all()
     assert np.isfinite(out[[0, 2, 3]]).all()
+
+
+# ---- the two loader-refresh entry points with stand-ins for the reference's own Dataset / generator classes ---------
+class _PoseDataSet:                      # common/data_loader.py:9-36
+    def __init__(self, poses_3d, poses_2d, actions, cams):
+        self._p3, self._p2, self._cams = np.concatenate(poses_3d), np.concatenate(poses_2d), np.concatenate(cams)
+        self._actions = sum((list(a) for a in actions), [])
+
+    def __getitem__(self, i):
+        return torch.from_numpy(self._p3[i]).float(), torch.from_numpy(self._p2[i]).float(), self._actions[i], self._cams[i]
+
+    def __len__(self):
+        return len(self._actions)
+
+
+class _PoseTarget:                       # common/data_loader.py:62-74
+    def __init__(self, poses):
+        self._poses = np.concatenate(poses)
+
+    def __getitem__(self, i):
+        return torch.from_numpy(self._poses[i]).float()
+
+    def __len__(self):
+        return len(self._poses)
+
+
+@pytest.mark.gpu
+def test_dataloader_update_contract(c_oracle, monkeypatch):
+    import argparse
+    import sys
+    import types
+    from torch.utils.data import DataLoader
+    import dhfk.dataloader_update as du
+    from dhfk import tables
+    mod = types.ModuleType("common.data_loader")
+    mod.PoseDataSet, mod.PoseTarget = _PoseDataSet, _PoseTarget
+    monkeypatch.setitem(sys.modules, "common", types.ModuleType("common"))
+    monkeypatch.setitem(sys.modules, "common.data_loader", mod)
+    rng = np.random.RandomState(3)
+    n = 300
+    p3 = rng.randn(n, 16, 3).astype(np.float32) * 0.3 + np.array([0, 0, 5], np.float32)
+    cams = np.stack([tables.camera_block(tables.TRAIN_SUBJECTS[rng.randint(5)], rng.randint(4))[7:16] for _ in range(n)])
+    acts = ["act%d" % (i % 7) for i in range(n)]
+    data_dict = {"train_gt2d3d_loader": DataLoader(_PoseDataSet([p3], [np.zeros((n, 16, 2), np.float32)], [acts], [cams]),
+                                                   batch_size=128, shuffle=False)}
+    args = argparse.Namespace(batch_size=64, num_workers=0)
+    np.random.seed(5)
+    du.dataloader_update(args, data_dict, torch.device("cuda:0"))
+    np.random.seed(5)
+    idx = np.concatenate([np.random.choice(5, k) for k in (128, 128, 44)])      # one choice() per batch, like the reference
+    ref = c_oracle.retarget(p3, tables.BONE_TEMPLATES_GANUTILS_ORDER, idx, cams)
+    ds = data_dict["train_gt2d3d_loader"].dataset
+    assert_parity(ds._p3, ref["pose"], "refreshed poses")
+    assert_parity(ds._p2, ref["uv"], "refreshed 2-D")
+    assert np.array_equal(ds._cams, cams) and ds._actions == acts
+    assert np.array_equal(data_dict["target_3d_loader"].dataset._poses, ds._p3)
+    assert np.array_equal(data_dict["target_2d_loader"].dataset._poses, ds._p2)
+    assert data_dict["train_gt2d3d_loader"].batch_size == 64
+
+
+@pytest.mark.gpu
+def test_video_mode_dataloader_update_contract(c_oracle, monkeypatch):
+    import argparse
+    import sys
+    import types
+    import dhfk.dataloader_update as du
+    from dhfk import tables
+    made = {}
+
+    class Gen:                           # stands in for GAN_video_ChunkedGenerator (video_mode_operate.py:35)
+        def __init__(self, batch_size, cameras, poses_3d, poses_2d, **kw):
+            made.update(batch_size=batch_size, cameras=cameras, poses_3d=poses_3d, poses_2d=poses_2d, kw=kw)
+
+    mod = types.ModuleType("models_Fk_GAN.video_mode_operate")
+    mod.GAN_video_ChunkedGenerator = Gen
+    mod.video_receptive_field = lambda fw: int(np.prod(fw))
+    monkeypatch.setitem(sys.modules, "models_Fk_GAN", types.ModuleType("models_Fk_GAN"))
+    monkeypatch.setitem(sys.modules, "models_Fk_GAN.video_mode_operate", mod)
+    rng = np.random.RandomState(8)
+    lens = [57, 1, 200, 33]
+    seqs = [rng.randn(k, 16, 3).astype(np.float32) * 0.3 + np.array([0, 0, 4.5], np.float32) for k in lens]
+    cams = [np.concatenate([tables.camera_block("S%d" % s, c)[7:16], rng.randn(7).astype(np.float32)])
+            for s, c in ((1, 0), (5, 1), (6, 2), (8, 3))]                        # 16-column camera rows, first 9 used
+    data_dict = {"poses_train": seqs, "poses_train_2d": [None] * 4, "actions_train": ["a", "b", "c", "d"], "cams_train": cams}
+    args = argparse.Namespace(batch_size=32, architecture="3,3,3")
+    np.random.seed(21)
+    du.video_mode_dataloader_update(args, data_dict, torch.device("cuda:0"))
+    np.random.seed(21)
+    picks = [np.random.choice(5, 1)[0] for _ in lens]                            # one row per sequence
+    assert made["batch_size"] == 32 and made["kw"]["pad"] == 13 and made["kw"]["shuffle"] is True
+    assert [p.shape[0] for p in made["poses_3d"]] == lens
+    for seq, cam, pick, got3, got2, gotc in zip(seqs, cams, picks, made["poses_3d"], made["poses_2d"], made["cameras"]):
+        ref = c_oracle.retarget(seq, tables.BONE_TEMPLATES_GANUTILS_ORDER[[pick]], None, cam[None, :9])
+        assert_parity(got3, ref["pose"], "sequence poses")
+        assert_parity(got2, ref["uv"], "sequence 2-D")
+        assert np.array_equal(gotc, cam)
