@@ -29,13 +29,19 @@ __global__ void __launch_bounds__(kTile) dhfk_retarget_kernel(const __grid_const
     extern __shared__ __align__(16) float smem[];
     float4* s_pose = reinterpret_cast<float4*>(smem);                 // padded rows, 13 chunks
     float4* s_uv = s_pose + kTile * kWorldRow4;                        // padded rows, 9 chunks
+    float* s_cam = reinterpret_cast<float*>(s_uv + (PROJ ? kTile * kUvRow4 : 0));   // exact image of 32 packed 9-float rows
     const int lane = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kTile;
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
 
+    // packed [N,9] intrinsics rows are staged as one 1152-byte slab (coalesced 128-bit requests instead of nine
+    // 36-byte-strided scalar loads per lane); wider / shared / unaligned rows are read in place
+    const bool cam_slab = PROJ && rows == kTile && p.cam_stride == 9 &&
+                          (reinterpret_cast<unsigned long long>(p.cam_rows) & 15ull) == 0;
     if (rows == kTile) {
         ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
+        if (cam_slab) ldgsts_slab<9>(s_cam, p.cam_rows + row0 * 9);
         ldgsts_wait_all();
     } else {
         stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
@@ -67,11 +73,19 @@ __global__ void __launch_bounds__(kTile) dhfk_retarget_kernel(const __grid_const
 #pragma unroll
         for (int c = 0; c < 12; ++c) prow[c] = make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
         if (PROJ) {
-            const float* cr = p.cam_rows + (row0 + lane) * p.cam_stride;
+            float cr[9];
+            if (cam_slab) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) cr[i] = s_cam[lane * 9 + i];
+            } else {
+                const float* g = p.cam_rows + (row0 + lane) * p.cam_stride;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) cr[i] = __ldg(g + i);
+            }
             CamConst cc;
-            cc.f = make_float2(__ldg(cr), __ldg(cr + 1)); cc.c = make_float2(__ldg(cr + 2), __ldg(cr + 3));
-            cc.k[0] = __ldg(cr + 4); cc.k[1] = __ldg(cr + 5); cc.k[2] = __ldg(cr + 6);
-            cc.p = make_float2(__ldg(cr + 7), __ldg(cr + 8));
+            cc.f = make_float2(cr[0], cr[1]); cc.c = make_float2(cr[2], cr[3]);
+            cc.k[0] = cr[4]; cc.k[1] = cr[5]; cc.k[2] = cr[6];
+            cc.p = make_float2(cr[7], cr[8]);
             float4* urow = s_uv + lane * kUvRow4;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -100,7 +114,7 @@ int launch_retarget(const float* pose, const int* tmpl_idx, const float* templat
     p.pose = pose; p.tmpl_idx = tmpl_idx; p.templates = templates; p.num_templates = num_templates;
     p.cam_rows = cam_rows; p.cam_stride = cam_stride; p.out_pose = out_pose; p.out_uv = out_uv; p.n = n;
     const bool proj = out_uv != nullptr;
-    const size_t smem = sizeof(float4) * kTile * (kWorldRow4 + (proj ? kUvRow4 : 0));
+    const size_t smem = sizeof(float4) * kTile * (kWorldRow4 + (proj ? kUvRow4 : 0)) + (proj ? sizeof(float) * kTile * 9 : 0);
     if (proj) return launch_tiles(dhfk_retarget_kernel<true>, smem, p, st, where);
     return launch_tiles(dhfk_retarget_kernel<false>, smem, p, st, where);
 }
