@@ -347,6 +347,19 @@ int dhfk_world_to_camera_forward(const float* x, const float* cam_q, const float
     if (num_points < 0) return fail(DHFK_E_INVAL, "num_points must be >= 0");
     if (num_points == 0) return DHFK_OK;
     if (!x || !cam_q || !cam_t || !out) return fail(DHFK_E_INVAL, "null argument");
+    const bool tiles = num_points % 16 == 0 && aligned16(x) && aligned16(out);   // 16-joint poses: tiled kernel
+    if (tiles) {
+        dhfk::RotConst rc = {};
+        if (!cam_on_device) {
+            camera_matrix(cam_q, rc.M);
+            for (int i = 0; i < 3; ++i) rc.t[i] = cam_t[i];
+        }
+        const char* where = "";
+        int e = dhfk::launch_camera_tiles(0, x, nullptr, nullptr, 0, cam_on_device ? cam_q : nullptr,
+                                          cam_on_device ? cam_t : nullptr, rc.M, rc.t, out, num_points / 16,
+                                          (cudaStream_t)stream, &where);
+        return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+    }
     if (cam_on_device) {
         long long nb = (num_points + 255) / 256;
         dhfk::w2c_fwd_dev_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(x, out, num_points, cam_q, cam_t);
@@ -366,6 +379,14 @@ int dhfk_world_to_camera_backward(const float* g_out, const float* cam_q, int32_
     if (num_points < 0) return fail(DHFK_E_INVAL, "num_points must be >= 0");
     if (num_points == 0) return DHFK_OK;
     if (!g_out || !cam_q || !g_x) return fail(DHFK_E_INVAL, "null argument");
+    if (num_points % 16 == 0 && aligned16(g_out) && aligned16(g_x)) {
+        dhfk::RotConst rc = {};
+        if (!cam_on_device) camera_matrix(cam_q, rc.M);
+        const char* where = "";
+        int e = dhfk::launch_camera_tiles(1, g_out, nullptr, nullptr, 0, cam_on_device ? cam_q : nullptr, nullptr, rc.M,
+                                          nullptr, g_x, num_points / 16, (cudaStream_t)stream, &where);
+        return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+    }
     if (cam_on_device) {
         long long nb = (num_points + 255) / 256;
         dhfk::w2c_bwd_dev_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(g_out, g_x, num_points, cam_q);
@@ -388,6 +409,12 @@ int dhfk_project_forward(const float* x, const float* cam_rows, int64_t cam_rows
     if (!x || !cam_rows || !uv) return fail(DHFK_E_INVAL, "null argument");
     if (cam_rows_stride < 9) return fail(DHFK_E_INVAL, "camera rows need >= 9 columns");
     if ((reinterpret_cast<uintptr_t>(uv) & 7u) != 0) return fail(DHFK_E_ALIGN, "uv must be 8-byte aligned");
+    if (joints == 16 && aligned16(x) && aligned16(uv) && n <= 2147483647LL * 32) {
+        const char* where = "";
+        int e = dhfk::launch_camera_tiles(2, x, nullptr, cam_rows, cam_rows_stride, nullptr, nullptr, nullptr, nullptr, uv,
+                                          n, (cudaStream_t)stream, &where);
+        return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+    }
     long long npts = n * joints, blocks = (npts + 255) / 256;
     dhfk::project_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, cam_rows, cam_rows_stride, uv,
                                                                                 npts, (int)joints);
@@ -401,6 +428,12 @@ int dhfk_project_backward(const float* x, const float* cam_rows, int64_t cam_row
     if (!x || !cam_rows || !g_uv || !g_x) return fail(DHFK_E_INVAL, "null argument");
     if (cam_rows_stride < 9) return fail(DHFK_E_INVAL, "camera rows need >= 9 columns");
     if ((reinterpret_cast<uintptr_t>(g_uv) & 7u) != 0) return fail(DHFK_E_ALIGN, "g_uv must be 8-byte aligned");
+    if (joints == 16 && aligned16(x) && aligned16(g_uv) && aligned16(g_x) && n <= 2147483647LL * 32) {
+        const char* where = "";
+        int e = dhfk::launch_camera_tiles(3, x, g_uv, cam_rows, cam_rows_stride, nullptr, nullptr, nullptr, nullptr, g_x,
+                                          n, (cudaStream_t)stream, &where);
+        return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+    }
     long long npts = n * joints, blocks = (npts + 255) / 256;
     dhfk::project_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, cam_rows, cam_rows_stride, g_uv,
                                                                                 g_x, npts, (int)joints);

@@ -32,6 +32,11 @@ int launch_bank_gather(const float* bank, long long rec_floats, int cam_cols, co
                        long long bank_rows, float* out3d, float* out2d, float* out_cam, cudaStream_t st,
                        const char** where);
 
+// tiled standalone camera ops for 16-joint poses: mode 0 w2c fwd, 1 w2c bwd, 2 project fwd, 3 project bwd
+int launch_camera_tiles(int mode, const float* x, const float* g_uv, const float* cam_rows, long long cam_stride,
+                        const float* q_dev, const float* t_dev, const float* M, const float* t, float* out,
+                        long long n, cudaStream_t st, const char** where);
+
 // floats per pose in the input slabs: raw mode ang33+grot3+bone15+root3, generator mode out35+bone15
 inline size_t in_floats(bool gen) { return gen ? (GEN_NCOL + 15) : 54; }
 inline size_t fwd_smem_bytes(bool cam, bool uv, bool gen) {

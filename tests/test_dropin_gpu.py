@@ -119,3 +119,37 @@ def test_handler_but_generater_matches_reference(golden, mode):
     assert np.array_equal(ang, g[mode + "_ang"])
     assert_parity(pos, g[mode + "_pos32"], "pos32")
     assert len(bl) == 40 and len(root) == 40 and len(glob) == 40
+
+
+def test_camera_ops_other_joint_counts_take_the_point_kernels(golden):
+    """16-joint poses run the tiled kernels; any other joint count (or an unaligned view) runs the one-thread-per-point
+    kernels.  Both must give the reference's numbers: compare with the torch port (the reference's op sequence) on
+    17- and 5-joint inputs and on an unaligned 16-joint view."""
+    import torch_port
+    from dhfk import camera
+    g = golden("camera_ops")
+    rng = np.random.RandomState(4)
+    q, t = g["w_q"], g["w_t"]
+    for joints in (17, 5):
+        x = rng.uniform(-2, 2, (50, joints, 3)).astype(np.float32)
+        x[..., 2] = rng.uniform(1.5, 6.0, (50, joints))
+        rows = g["cam_rows9"][:50]
+        xt, xc = T(x, True), torch.tensor(x, requires_grad=True)
+        uv = camera.project_to_2d(xt, T(rows))
+        ref = torch_port.project_to_2d(xc, torch.tensor(rows))
+        assert_parity(uv.detach().cpu().numpy(), ref.detach().numpy(), "uv J=%d" % joints)
+        gu = rng.randn(50, joints, 2).astype(np.float32)
+        (uv * T(gu)).sum().backward(); (ref * torch.tensor(gu)).sum().backward()
+        assert_parity(xt.grad.cpu().numpy(), xc.grad.numpy(), "g_x J=%d" % joints)
+        wt, wc = T(x, True), torch.tensor(x, requires_grad=True)
+        cam = camera.GAN_torch_world_to_camera(wt, T(q).view(1, 4), T(t).view(1, 3))
+        refc = torch_port.world_to_camera(wc, torch.tensor(q).view(1, 4), torch.tensor(t).view(1, 3))
+        assert_parity(cam.detach().cpu().numpy(), refc.detach().numpy(), "cam J=%d" % joints)
+        gc = rng.randn(50, joints, 3).astype(np.float32)
+        (cam * T(gc)).sum().backward(); (refc * torch.tensor(gc)).sum().backward()
+        assert_parity(wt.grad.cpu().numpy(), wc.grad.numpy(), "g_world J=%d" % joints)
+    # tiled and point kernels agree on the golden 16-joint case (bit for bit is not required, parity is)
+    uv16 = camera.project_to_2d(T(g["x"]), T(g["cam_rows9"]))
+    assert_parity(uv16.cpu().numpy(), g["uv"], "uv tiled")
+    uv17 = camera.project_to_2d(torch.cat([T(g["x"]), T(g["x"][:, :1])], 1), T(g["cam_rows9"]))     # 17 joints: point kernel
+    assert_parity(uv17[:, :16].cpu().numpy(), g["uv"], "uv point kernel")

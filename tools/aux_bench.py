@@ -57,6 +57,19 @@ def main():
         "flip 3d (f2)": (lambda s: lib.dhfk_flip_pose(P(s["pose"]), P(s["o48"]), n, 3, st), 384),
         "flip 2d (f2)": (lambda s: lib.dhfk_flip_pose(P(s["gp"]), P(s["o32"]), n, 2, st), 256),
     }
+    # standalone camera ops of the drop-in path (common/camera.py:36-38, :62-94)
+    blk_dev_q = torch.tensor(tables.camera_block("S1", 0)[0:4], device=dev)
+    blk_dev_t = torch.tensor(tables.camera_block("S1", 0)[4:7], device=dev)
+    cases["world->camera fwd (standalone)"] = (
+        lambda s: lib.dhfk_world_to_camera_forward(P(s["pose"]), P(blk_dev_q), P(blk_dev_t), 1, P(s["o48"]), n * 16, st), 384)
+    cases["world->camera bwd (standalone)"] = (
+        lambda s: lib.dhfk_world_to_camera_backward(P(s["gp"]), P(blk_dev_q), 1, P(s["o48"]), n * 16, st), 384)
+    cases["project fwd, per-row intrinsics (standalone)"] = (
+        lambda s: lib.dhfk_project_forward(P(s["pose"]), P(s["cam"]), 9, P(s["o32"]), n, 16, st), 192 + 36 + 128)
+    for s_ in sets:
+        s_["gu"] = torch.randn(n, 16, 2, device=dev, generator=g)
+    cases["project bwd, per-row intrinsics (standalone)"] = (
+        lambda s: lib.dhfk_project_backward(P(s["pose"]), P(s["cam"]), 9, P(s["gu"]), P(s["o48"]), n, 16, st), 192 + 36 + 128 + 192)
     # f4: shuffled mini-batch out of a 4x larger device-resident bank (one 384-byte record per pose)
     bank_rows = 4 * n
     rec = torch.randn(bank_rows, 96, device=dev, generator=g)
