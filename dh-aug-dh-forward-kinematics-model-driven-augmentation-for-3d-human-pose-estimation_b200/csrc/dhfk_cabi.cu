@@ -515,8 +515,7 @@ int dhfk_flip_pose(const float* x, float* out, int64_t n, int32_t dims, void* st
     if (dims != 2 && dims != 3) return fail(DHFK_E_INVAL, "dims must be 2 or 3");
     if (n == 0) return DHFK_OK;
     if (!x || !out) return fail(DHFK_E_INVAL, "x / out must be non-null");
-    if (x == out && dims == 2) return fail(DHFK_E_INVAL, "the 2-D flip cannot run in place");
-    if (n > (1LL << 34)) return fail(DHFK_E_INVAL, "n too large for one launch");
+    if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
     if (!aligned16(x) || !aligned16(out)) return fail(DHFK_E_ALIGN, "x / out must be 16-byte aligned");
     const char* where = "";
     int e = dhfk::launch_flip(x, out, n, dims, (cudaStream_t)stream, &where);

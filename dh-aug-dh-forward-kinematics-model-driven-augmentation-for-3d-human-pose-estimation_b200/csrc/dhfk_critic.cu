@@ -24,8 +24,6 @@ __device__ constexpr int KP1[15] = {2, 3, 4, 5, 5, 6, 6, 7, 14, 8, 9, 10, 11, 12
 // joint j of the flipped pose = mirrored joint FLIP16[j] (out_left/out_right swap, model_fk_gan_train.py:321-327)
 __device__ constexpr int FLIP16[16] = {0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 13, 14, 15, 10, 11, 12};
 
-__constant__ int c_flip16[16] = {0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 13, 14, 15, 10, 11, 12};   // runtime-indexed copy
-
 constexpr unsigned kCentre = 1u, kFlip = 2u;
 
 struct CriticParams {
@@ -290,17 +288,43 @@ __global__ void __launch_bounds__(kTile) dhfk_critic_jvp_kernel(const __grid_con
     }
 }
 
-// left/right flip of [N,16,2] keypoints: one thread per 16-byte chunk (two joints) of the output, two 8-byte
-// loads from the same 128-byte row, one 128-bit coalesced store.  Its own transpose.
-__global__ void dhfk_flip2d_kernel(const float* __restrict__ x, float* __restrict__ out, long long nchunks) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nchunks) return;
-    const long long n = i >> 3;
-    const int c = (int)(i & 7);
-    const float* row = x + n * 32;
-    const float2 a = *reinterpret_cast<const float2*>(row + 2 * c_flip16[2 * c]);
-    const float2 b = *reinterpret_cast<const float2*>(row + 2 * c_flip16[2 * c + 1]);
-    __stcs(reinterpret_cast<float4*>(out) + i, make_float4(-a.x, a.y, -b.x, b.y));
+// left/right flip of [N,16,2] keypoints: same tile staging as everything else (one thread per pose permutes its
+// 32 floats in registers; 128-bit coalesced both ways).  A one-thread-per-chunk gather measured 87 %.
+struct Flip2dParams {
+    const float* x;
+    float* out;
+    long long n;
+};
+__global__ void __launch_bounds__(kTile) dhfk_flip2d_tile_kernel(const __grid_constant__ Flip2dParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float4* s_uv = reinterpret_cast<float4*>(smem);
+    const int lane = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * kTile;
+    const long long left = p.n - row0;
+    const int rows = left < kTile ? (int)left : kTile;
+    if (rows == kTile) {
+        ldgsts_padded_tile<kUvChunks>(s_uv, p.x, row0);
+        ldgsts_wait_all();
+    } else {
+        stage_padded_in<kUvChunks>(s_uv, p.x, row0, rows);
+    }
+    __syncwarp();
+    if (lane < rows) {
+        float4* row = s_uv + lane * kUvRow4;
+        float x[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 v = row[c];
+            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            row[c] = make_float4(-x[2 * FLIP16[2 * c]], x[2 * FLIP16[2 * c] + 1], -x[2 * FLIP16[2 * c + 1]],
+                                 x[2 * FLIP16[2 * c + 1] + 1]);
+    }
+    __syncwarp();
+    if (rows == kTile) store_padded_tile<kUvChunks>(s_uv, p.out, row0);
+    else stage_padded_out<kUvChunks>(s_uv, p.out, row0, rows);
 }
 
 template <int KC, bool POS>
@@ -336,14 +360,11 @@ int launch_critic(int mode, int kc, bool pos, const float* pose, const float* a,
 
 int launch_flip(const float* x, float* out, long long n, int dims, cudaStream_t st, const char** where) {
     // 3-D: the tiled critic kernel with only the flip flag (smem-staged, 128-bit both ways: ~98 % of copy peak;
-    // a per-chunk gather of 12-byte joints measured 41 %).  2-D: joints are 8 bytes, the per-chunk kernel does it.
+    // a per-chunk gather of 12-byte joints measured 41 %).  2-D: its own tiled kernel.
     if (dims == 3) return launch_critic(0, 0, true, x, nullptr, nullptr, out, nullptr, n, kFlip, st, where);
-    const long long nc = n * 8;
-    const unsigned blocks = (unsigned)((nc + 255) / 256);
-    dhfk_flip2d_kernel<<<blocks, 256, 0, st>>>(x, out, nc);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { *where = "dhfk_flip2d_kernel"; return (int)e; }
-    return 0;
+    Flip2dParams p;
+    p.x = x; p.out = out; p.n = n;
+    return launch_tiles(dhfk_flip2d_tile_kernel, sizeof(float4) * kTile * kUvRow4, p, st, where);
 }
 
 }  // namespace dhfk

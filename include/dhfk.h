@@ -205,7 +205,7 @@ int dhfk_critic_input_backward(const float* pose_dev, const float* g_pos_dev, co
 int dhfk_critic_input_jvp(const float* pose_dev, const float* v_pose_dev, float* t_pos_dev, float* t_kcs_dev,
                           int32_t kcs_cols, int64_t n, uint32_t flags, void* stream);
 /* The flip alone for [N,16,dims] keypoints, dims = 2 (the 2D critic's inputs, model_fk_gan_train.py:393-405) or 3.
- * The 2-D flip cannot run in place.  The flip is its own transpose: the backward is the same call on the upstream gradient. */
+ * out_dev may alias x_dev.  The flip is its own transpose: the backward is the same call on the upstream gradient. */
 int dhfk_flip_pose(const float* x_dev, float* out_dev, int64_t n, int32_t dims, void* stream);
 
 /*
