@@ -57,6 +57,29 @@ def main():
         "flip 3d (f2)": (lambda s: lib.dhfk_flip_pose(P(s["pose"]), P(s["o48"]), n, 3, st), 384),
         "flip 2d (f2)": (lambda s: lib.dhfk_flip_pose(P(s["gp"]), P(s["o32"]), n, 2, st), 256),
     }
+    # the fused forward with all three outputs (the critic step buffers pos_3d_cam as well) and the FK-only forward / backward
+    from dhfk import synthetic
+    blk = tables.camera_block("S1", 0)
+    for i, s_ in enumerate(sets):
+        s_.update(synthetic.gan_like_torch(n, dev, seed=50 + i))
+        s_["o48b"] = torch.empty(n, 16, 3, device=dev)
+        s_["g33"], s_["g3a"], s_["g3b"] = torch.empty(n, 33, device=dev), torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+    cases["FK forward: world + cam + uv"] = (
+        lambda s: lib.dhfk_forward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, blk.ctypes.data, None, 0,
+                                   P(s["o48"]), P(s["o48b"]), P(s["o32"]), n, 0, st), 216 + 192 + 192 + 128)
+    cases["FK forward: world only"] = (
+        lambda s: lib.dhfk_forward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, None, None, 0,
+                                   P(s["o48"]), None, None, n, 0, st), 216 + 192)
+    cases["FK backward: g_world only"] = (
+        lambda s: lib.dhfk_backward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, None, None, 0,
+                                    P(s["gp"]), None, None, P(s["g33"]), 33, P(s["g3a"]), 3, P(s["g3b"]), 3, None, 15, n, 0, st),
+        216 + 192 + 156)
+    cases["FK backward: g_world + g_cam + g_uv"] = (
+        lambda s: lib.dhfk_backward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, blk.ctypes.data, None, 0,
+                                    P(s["gp"]), P(s["pose"]), P(s["gu2"]), P(s["g33"]), 33, P(s["g3a"]), 3, P(s["g3b"]), 3, None, 15,
+                                    n, 0, st), 216 + 192 + 192 + 128 + 156)
+    for s_ in sets:
+        s_["gu2"] = torch.randn(n, 16, 2, device=dev, generator=g)
     # standalone camera ops of the drop-in path (common/camera.py:36-38, :62-94)
     blk_dev_q = torch.tensor(tables.camera_block("S1", 0)[0:4], device=dev)
     blk_dev_t = torch.tensor(tables.camera_block("S1", 0)[4:7], device=dev)
