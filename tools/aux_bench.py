@@ -102,6 +102,10 @@ def main():
     cases["bank gather, shuffled batch (f4)"] = (
         lambda s: lib.dhfk_bank_gather(P(rec), 96, 9, P(s["perm"]), n, bank_rows, P(s["o48"]), P(s["o32"]), P(s["o9"]), st),
         8 + 2 * (192 + 128 + 36))
+    for s_ in sets:
+        s_["o96"] = torch.empty(n, 96, device=dev)
+    cases["context: torch.index_select of the same records (384 B in, 384 B out)"] = (
+        lambda s: torch.index_select(rec, 0, s["perm"], out=s["o96"]), 8 + 2 * 384)
     out = {"poses": n, "peak_gbs": peak, "kernels": {}}
     for name, (fn, bpp) in cases.items():
         ms = timeit(fn, sets)
