@@ -43,6 +43,8 @@ SIGNATURES = {
     "dhfk_world_to_camera_backward": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _i64, _vp]),
     "dhfk_project_forward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp]),
     "dhfk_project_backward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
+    "dhfk_scatter32_forward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "dhfk_scatter32_backward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "dhfk_retarget_project": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, _vp, _i64, _vp, _vp, _i64, _vp]),
     "dhfk_critic_input_forward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, _i64, _u32, _vp]),
     "dhfk_critic_input_backward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, _vp, _i64, _u32, _vp]),

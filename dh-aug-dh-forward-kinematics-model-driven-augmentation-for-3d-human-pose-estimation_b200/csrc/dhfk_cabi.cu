@@ -441,6 +441,31 @@ int dhfk_project_backward(const float* x, const float* cam_rows, int64_t cam_row
     return e == cudaSuccess ? DHFK_OK : cuda_fail(e, "project_bwd_kernel");
 }
 
+// ---- the reference's [N,32,3] output layout -----------------------------------------------------
+int dhfk_scatter32_forward(const float* world16, const float* root, int64_t root_stride, float* world32, int64_t n,
+                           void* stream) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
+    if (n == 0) return DHFK_OK;
+    if (!world16 || !root || !world32) return fail(DHFK_E_INVAL, "world16 / root / world32 must be non-null");
+    if (root_stride < 3) return fail(DHFK_E_INVAL, "root row stride must be >= 3");
+    if (!aligned16(world16) || !aligned16(world32)) return fail(DHFK_E_ALIGN, "world16 / world32 must be 16-byte aligned");
+    if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
+    const char* where = "";
+    int e = dhfk::launch_scatter32(false, world16, root, root_stride, world32, nullptr, n, (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+int dhfk_scatter32_backward(const float* g_world32, float* g_world16, float* g_root, int64_t n, void* stream) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
+    if (n == 0) return DHFK_OK;
+    if (!g_world32 || !g_world16 || !g_root) return fail(DHFK_E_INVAL, "g_world32 / g_world16 / g_root must be non-null");
+    if (!aligned16(g_world32) || !aligned16(g_world16))
+        return fail(DHFK_E_ALIGN, "g_world32 / g_world16 must be 16-byte aligned");
+    if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
+    const char* where = "";
+    int e = dhfk::launch_scatter32(true, g_world32, nullptr, 0, g_world16, g_root, n, (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+
 // ---- bone-length retarget + per-row projection ---------------------------------------
 int dhfk_retarget_project(const float* pose, const int32_t* tmpl_idx, const float* templates, int32_t num_templates,
                           const float* cam_rows, int64_t cam_rows_stride, float* out_pose, float* out_uv, int64_t n,

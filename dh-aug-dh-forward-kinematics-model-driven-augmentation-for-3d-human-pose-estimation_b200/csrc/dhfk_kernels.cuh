@@ -141,17 +141,24 @@ DHFK_DI void for_each_tile_chunk(F&& f) {
     //   CH = 8 :  gi / 8  = 4 m + lane / 8
     //   CH = 12:  32 m = 12 (2 m + 2 (m / 3)) + {0, 8, 16}[m % 3]  =>  gi / 12 = 2 m + 2 (m / 3) + {l/12, (l+8)/12, 1 + (l+4)/12}
     const int lane = threadIdx.x;
-    static_assert(CH == 8 || CH == 12, "closed forms are written for the 32- and 48-float rows");
+    static_assert(CH == 8 || CH == 12 || CH == 24, "closed forms are written for 32-, 48- and 96-float rows");
     if constexpr (CH == 8) {
         const int b = lane + (lane >> 3);
 #pragma unroll
         for (int m = 0; m < CH; ++m) f(m * 32 + lane, m * 36 + b);
-    } else {
+    } else if constexpr (CH == 12) {
         const int b0 = lane + lane / 12, b1 = lane + (lane + 8) / 12, b2 = lane + (lane + 4) / 12;
 #pragma unroll
         for (int m = 0; m < CH; ++m) {
             const int k = m / 3, r = m % 3;
             f(m * 32 + lane, 34 * m + 2 * k + (r == 2 ? 1 : 0) + (r == 0 ? b0 : (r == 1 ? b1 : b2)));
+        }
+    } else {   // CH = 24: 32 m = 24 (m + m / 3) + {0, 8, 16}[m % 3]  =>  gi / 24 = m + m / 3 + (8 (m % 3) + lane) / 24
+        const int b0 = lane + lane / 24, b1 = lane + (lane + 8) / 24, b2 = lane + (lane + 16) / 24;
+#pragma unroll
+        for (int m = 0; m < CH; ++m) {
+            const int k = m / 3, r = m % 3;
+            f(m * 32 + lane, 33 * m + k + (r == 0 ? b0 : (r == 1 ? b1 : b2)));
         }
     }
 }

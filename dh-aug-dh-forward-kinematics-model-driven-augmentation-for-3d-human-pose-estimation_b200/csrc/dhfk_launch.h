@@ -37,6 +37,10 @@ int launch_camera_tiles(int mode, const float* x, const float* g_uv, const float
                         const float* q_dev, const float* t_dev, const float* M, const float* t, float* out,
                         long long n, cudaStream_t st, const char** where);
 
+// the reference's 32-slot output layout: forward world16 + root -> world32, backward g32 -> g16 + g_root
+int launch_scatter32(bool bwd, const float* in, const float* root, long long root_stride, float* out, float* g_root,
+                     long long n, cudaStream_t st, const char** where);
+
 // floats per pose in the input slabs: raw mode ang33+grot3+bone15+root3, generator mode out35+bone15
 inline size_t in_floats(bool gen) { return gen ? (GEN_NCOL + 15) : 54; }
 inline size_t fwd_smem_bytes(bool cam, bool uv, bool gen) {

@@ -20,6 +20,7 @@ import torch
 
 from . import tables
 from .functional import fk_world16
+from .functional import scatter_16_to_32 as _scatter32
 from .tables import used_16key_15bone_len_table  # noqa: F401  (re-exported like the reference module)
 
 # angle ranges of the non-GAN sampler (forward_kinematics_DH_model.py:935-976): joint1..joint34, degrees;
@@ -71,12 +72,9 @@ def rotationMatrix(angle_x, angle_y, angle_z, args=None):
 
 def scatter_16_to_32(world16: torch.Tensor, root: torch.Tensor) -> torch.Tensor:
     """[N,16,3] -> the reference's [N,32,3] layout (:745-820): gathered slots hold the joints, slot 14
-    duplicates the head joint (slot 15), every other slot equals root (0 + root)."""
-    n = world16.shape[0]
-    out = root.reshape(n, 1, 3).expand(n, 32, 3).clone()
-    out = out.index_copy(1, _index16(world16.device), world16)
-    out[:, 14] = world16[:, tables.H36M_EXTRA_SLOT_14_OUT]
-    return out
+    duplicates the head joint (slot 15), every other slot equals root (0 + root).  One launch each way
+    (dhfk_scatter32_*) instead of expand + clone + index_copy + slice write and their autograd mirror."""
+    return _scatter32(world16, root.reshape(world16.shape[0], 3))
 
 
 class Forward_Kinematics_DH_Model:

@@ -554,6 +554,52 @@ def flip_pose(x):
     return _FlipPose.apply(x)
 
 
+class _Scatter32(torch.autograd.Function):
+    """world16 [N,16,3], root [N,3] -> the reference's [N,32,3] slot layout, one launch each way."""
+
+    @staticmethod
+    def forward(ctx, world16, root):
+        _require_cuda()
+        lib = _cabi.load()
+        device = world16.device
+        w = _packed(world16, (-1, 16, 3), device)
+        n = w.shape[0]
+        r = _rows(root, 3, device)
+        if r.shape[0] != n:
+            raise ValueError("row counts differ: world16 %d, root %d" % (n, r.shape[0]))
+        out = torch.empty((n, 32, 3), dtype=torch.float32, device=device)
+        with _on_device(device):
+            rc = lib.dhfk_scatter32_forward(w.data_ptr(), r.data_ptr(), _row_stride(r), out.data_ptr(), n, _stream_ptr(device))
+        _cabi.check(rc, "dhfk_scatter32_forward")
+        ctx.meta = (root.shape, root.device, root.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g32):
+        lib = _cabi.load()
+        device = g32.device
+        n = g32.shape[0]
+        g = _packed(g32, (n, 32, 3), device)
+        g16 = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
+        g_root = torch.empty((n, 3), dtype=torch.float32, device=device)
+        if n > 0:
+            with _on_device(device):
+                rc = lib.dhfk_scatter32_backward(g.data_ptr(), g16.data_ptr(), g_root.data_ptr(), n, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_scatter32_backward")
+        shape, dev, dtype = ctx.meta
+        g_root = g_root.reshape(shape)
+        if (g_root.device, g_root.dtype) != (dev, dtype):
+            g_root = g_root.to(device=dev, dtype=dtype)
+        return g16, g_root
+
+
+def scatter_16_to_32(world16, root):
+    """[N,16,3] + root [N,3] -> the reference's [N,32,3] layout (forward_kinematics_DH_model.py:745-820): the 16 joints
+    in their H36M slots, slot 14 = the head joint again, every other slot = root."""
+    return _Scatter32.apply(world16, root)
+
+
 def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chunk_rows=131072, num_streams=3,
                     workspace=None, out=None, fast_trig=False, accurate_grad=False):
     """End-to-end over HOST (ideally pinned) float32 tensors through dhfk_forward_backward_host:

@@ -28,6 +28,7 @@
  *       (models_Fk_GAN/Fk_discriminator.py:36-146,269-377; model_fk_gan_train.py:311-331,393-405)
  *   dhfk_bank_gather            mini-batch out of the device-resident fake-pair bank
  *       (model_fk_gan_train.py:486-510; common/data_loader.py:9-36)
+ *   dhfk_scatter32_*            the [N,32,3] H36M slot layout change_3d_joint_angle returns (...:745-820), both ways
  *   dhfk_topology               the constant tables the reference keeps as Python lists
  *       (forward_kinematics_DH_model.py:234-261,:571-589,:751-817; common/h36m_dataset.py:37-38)
  *
@@ -163,6 +164,17 @@ int dhfk_project_forward(const float* x_dev, const float* cam_rows_dev, int64_t 
                          int64_t n, int64_t joints, void* stream);
 int dhfk_project_backward(const float* x_dev, const float* cam_rows_dev, int64_t cam_rows_stride,
                           const float* g_uv_dev, float* g_x_dev, int64_t n, int64_t joints, void* stream);
+
+/*
+ * The reference's 32-slot output layout (Forward_Kinematics_DH_Model.change_3d_joint_angle returns [N,32,3],
+ * forward_kinematics_DH_model.py:745-820): the 16 joints in their H36M slots (common/h36m_dataset.py:37-38), slot 14 =
+ * the head joint again, every other slot = root.  forward: world16_dev [N,16,3] + root_dev [N, root_stride] -> world32_dev
+ * [N,32,3].  backward: g_world32_dev -> g_world16_dev [N,16,3] (slot 14 folded into the head joint) and g_root_dev [N,3]
+ * = the sum over the 15 free slots (the part of d/d root that does not already flow through world16).
+ */
+int dhfk_scatter32_forward(const float* world16_dev, const float* root_dev, int64_t root_stride, float* world32_dev,
+                           int64_t n, void* stream);
+int dhfk_scatter32_backward(const float* g_world32_dev, float* g_world16_dev, float* g_root_dev, int64_t n, void* stream);
 
 /*
  * SURVEY 8 f3 -- per-epoch dataset re-augmentation, fused (forward only; the reference detaches the result):

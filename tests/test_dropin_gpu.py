@@ -153,3 +153,38 @@ def test_camera_ops_other_joint_counts_take_the_point_kernels(golden):
     assert_parity(uv16.cpu().numpy(), g["uv"], "uv tiled")
     uv17 = camera.project_to_2d(torch.cat([T(g["x"]), T(g["x"][:, :1])], 1), T(g["cam_rows9"]))     # 17 joints: point kernel
     assert_parity(uv17[:, :16].cpu().numpy(), g["uv"], "uv point kernel")
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 1000])
+def test_scatter_32_layout_and_gradient(n):
+    """dhfk_scatter32_*: the [N,32,3] slot layout and its adjoint are exact (copies and sums of copies), checked
+    against the index arithmetic the reference's column writes amount to."""
+    from dhfk.forward_kinematics_DH_model import scatter_16_to_32
+    rng = np.random.RandomState(n)
+    w = T(rng.randn(n, 16, 3), True)
+    r = T(rng.randn(n, 3), True)
+    out = scatter_16_to_32(w, r)
+    idx = [0, 1, 2, 3, 6, 7, 8, 12, 13, 15, 17, 18, 19, 25, 26, 27]
+    ref = r.detach().view(n, 1, 3).expand(n, 32, 3).clone()
+    ref[:, idx] = w.detach()
+    ref[:, 14] = w.detach()[:, 9]
+    assert torch.equal(out, ref)
+    g = T(rng.randn(n, 32, 3))
+    (out * g).sum().backward()
+    g16 = g[:, idx].clone()
+    g16[:, 9] += g[:, 14]
+    free = [s for s in range(32) if s not in idx + [14]]
+    assert len(free) == 15
+    assert torch.allclose(w.grad, g16, rtol=0, atol=1e-6) and torch.equal(w.grad[:, :9], g16[:, :9])
+    assert torch.allclose(r.grad, g[:, free].sum(1), rtol=1e-6, atol=1e-6)
+
+
+def test_scatter_16_to_32_reproduces_the_reference_tensor(golden):
+    """Against the reference's own [N,32,3] output (goldens): pure data movement, bit-exact; root given as [B,F,3] too."""
+    from dhfk.forward_kinematics_DH_model import scatter_16_to_32
+    g = golden("gan133")
+    out = scatter_16_to_32(T(g["world16"]), T(g["root"]))
+    assert np.array_equal(out.cpu().numpy(), g["world32"])
+    gv = golden("video36")
+    out = scatter_16_to_32(T(gv["world16"]), T(gv["root"]).view(4, 9, 3))
+    assert np.array_equal(out.cpu().numpy(), gv["world32"])

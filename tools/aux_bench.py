@@ -80,6 +80,13 @@ def main():
                                     n, 0, st), 216 + 192 + 192 + 128 + 156)
     for s_ in sets:
         s_["gu2"] = torch.randn(n, 16, 2, device=dev, generator=g)
+    for s_ in sets:
+        s_["o96b"] = torch.empty(n, 32, 3, device=dev)
+        s_["g32"] = torch.randn(n, 32, 3, device=dev, generator=g)
+    cases["32-slot layout forward (change_3d_joint_angle's return tensor)"] = (
+        lambda s: lib.dhfk_scatter32_forward(P(s["pose"]), P(s["root"]), 3, P(s["o96b"]), n, st), 192 + 12 + 384)
+    cases["32-slot layout backward"] = (
+        lambda s: lib.dhfk_scatter32_backward(P(s["g32"]), P(s["o48"]), P(s["g3a"]), n, st), 384 + 192 + 12)
     # standalone camera ops of the drop-in path (common/camera.py:36-38, :62-94)
     blk_dev_q = torch.tensor(tables.camera_block("S1", 0)[0:4], device=dev)
     blk_dev_t = torch.tensor(tables.camera_block("S1", 0)[4:7], device=dev)
