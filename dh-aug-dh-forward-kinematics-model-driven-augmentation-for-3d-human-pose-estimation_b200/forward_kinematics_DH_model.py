@@ -70,6 +70,26 @@ def rotationMatrix(angle_x, angle_y, angle_z, args=None):
     return r1.dot(r2).dot(r3)
 
 
+def _shared_angle_view(rleg, lleg, body, rhand, lhand):
+    """The generator passes the five angle kwargs as column slices of ONE [N,37] tensor (Fk_generator.py:179-184).
+    When that is the case return the [N,33] view of their common base in kernel order (right leg, left leg, body, right
+    hand, left hand) -- no torch.cat, no split in the backward, the kernel reads the base tensor with its row stride.
+    Returns None when the five tensors are anything else."""
+    parts = (rleg, lleg, body, rhand, lhand)
+    base = rleg._base
+    if base is None or base.dim() != 2 or base.stride(1) != 1 or any(t._base is not base for t in parts):
+        return None
+    n, stride = base.shape[0], base.stride(0)
+    col0 = rleg.storage_offset() - base.storage_offset()
+    if col0 < 0 or col0 + 33 > base.shape[1]:
+        return None
+    for t, off, width in zip(parts, (0, 5, 10, 23, 28), (5, 5, 13, 5, 5)):
+        if (t.dim() != 2 or t.shape != (n, width) or t.stride(1) != 1 or (n > 1 and t.stride(0) != stride)
+                or t.storage_offset() - base.storage_offset() != col0 + off):
+            return None
+    return base[:, col0:col0 + 33]
+
+
 def scatter_16_to_32(world16: torch.Tensor, root: torch.Tensor) -> torch.Tensor:
     """[N,16,3] -> the reference's [N,32,3] layout (:745-820): gathered slots hold the joints, slot 14
     duplicates the head joint (slot 15), every other slot equals root (0 + root).  One launch each way
@@ -140,8 +160,11 @@ class Forward_Kinematics_DH_Model:
         if dev.type != "cuda":
             dev = torch.device("cuda", torch.cuda.current_device())
         to = lambda t: t if t.device == dev else t.to(dev)
-        ang = torch.cat([to(right_leg_joints_angle), to(left_leg_joints_angle), to(body_joints_angle),
-                         to(right_hand_joints_angle), to(left_hand_joints_angle)], dim=1)
+        ang = _shared_angle_view(right_leg_joints_angle, left_leg_joints_angle, body_joints_angle,
+                                 right_hand_joints_angle, left_hand_joints_angle)
+        if ang is None or ang.device != dev:
+            ang = torch.cat([to(right_leg_joints_angle), to(left_leg_joints_angle), to(body_joints_angle),
+                             to(right_hand_joints_angle), to(left_hand_joints_angle)], dim=1)
         n = ang.shape[0]
         grot = to(generator_global_rot_3d_pos_angle)
         cols = []

@@ -183,3 +183,21 @@ def test_bone_length_templates_table_matches_reference_file(golden):
     g = golden("tables")
     assert np.array_equal(tables.BONE_TEMPLATES_GANUTILS_ORDER, g["bone_templates"].astype(np.float32))
     assert np.array_equal(dataloader_update.bone_length_templates(), g["bone_templates"].astype(np.float32))
+
+
+def test_shared_angle_view_detection():
+    """The five angle kwargs as column slices of one [N,37] tensor (how the generator passes them) are recognised and
+    replaced by ONE strided view of their base -- in kernel order, no torch.cat; anything else is left to torch.cat."""
+    from dhfk.forward_kinematics_DH_model import _shared_angle_view as view
+    g = torch.randn(7, 37, requires_grad=True) * 1.0
+    sl = lambda a, b: g[:, a:b]
+    v = view(sl(0, 5), sl(5, 10), sl(10, 23), sl(23, 28), sl(28, 33))
+    assert v is not None and v.shape == (7, 33) and v.data_ptr() == g.data_ptr() and v.stride() == (37, 1)
+    assert v._base is g                                             # autograd flows to the generator's tensor
+    g2 = torch.randn(4, 40)
+    v2 = view(g2[:, 2:7], g2[:, 7:12], g2[:, 12:25], g2[:, 25:30], g2[:, 30:35])
+    assert v2.shape == (4, 33) and v2.storage_offset() == 2
+    assert view(sl(5, 10), sl(0, 5), sl(10, 23), sl(23, 28), sl(28, 33)) is None          # not in generator order
+    assert view(g2[:4, 0:5], sl(5, 10), sl(10, 23), sl(23, 28), sl(28, 33)) is None       # different bases
+    assert view(*(torch.randn(7, w) for w in (5, 5, 13, 5, 5))) is None                   # independent tensors
+    assert view(sl(0, 5), sl(5, 10), sl(10, 23), sl(23, 28), g[:, 28:33][::2]) is None    # a row-strided slice
