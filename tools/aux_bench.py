@@ -81,6 +81,12 @@ def main():
     for s_ in sets:
         s_["gu2"] = torch.randn(n, 16, 2, device=dev, generator=g)
     for s_ in sets:
+        s_["g37"] = torch.zeros(n, 37, device=dev)
+        s_["g37"][:, :33] = s_["ang"]; s_["g37"][:, 34:] = s_["grot"]
+    cases["FK forward world only, angles / global rotation as views of one [N,37] tensor"] = (
+        lambda s: lib.dhfk_forward(P(s["g37"]), 37, P(s["g37"]) + 34 * 4, 37, P(s["bone"]), 15, P(s["root"]), 3, None, None, 0,
+                                   P(s["o48"]), None, None, n, 0, st), 148 + 60 + 12 + 192)
+    for s_ in sets:
         s_["o96b"] = torch.empty(n, 32, 3, device=dev)
         s_["g32"] = torch.randn(n, 32, 3, device=dev, generator=g)
     cases["32-slot layout forward (change_3d_joint_angle's return tensor)"] = (
