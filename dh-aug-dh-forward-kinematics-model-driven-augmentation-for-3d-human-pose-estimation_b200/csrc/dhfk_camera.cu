@@ -45,11 +45,11 @@ __global__ void __launch_bounds__(kTile) dhfk_camera_tile_kernel(const __grid_co
         ldgsts_padded_tile<kWorldChunks>(s_x, p.x, row0);
         if (MODE == 3) ldgsts_padded_tile<kUvChunks>(s_uv, p.g_uv, row0);
         if (cam_slab) ldgsts_slab<9>(s_cam, p.cam_rows + row0 * 9);
-        ldgsts_wait_all();
     } else {
         stage_padded_in<kWorldChunks>(s_x, p.x, row0, rows);
         if (MODE == 3) stage_padded_in<kUvChunks>(s_uv, p.g_uv, row0, rows);
     }
+    ldgsts_wait_all();     // full tiles and ragged tiles alike: everything above was queued with cp.async
     __syncwarp();
     if (lane < rows) {
         float4* xrow = s_x + lane * kWorldRow4;

@@ -108,10 +108,10 @@ __global__ void __launch_bounds__(kTile) dhfk_critic_fwd_kernel(const __grid_con
     const int rows = left < kTile ? (int)left : kTile;
     if (rows == kTile) {
         ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
-        ldgsts_wait_all();
     } else {
         stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
     }
+    ldgsts_wait_all();     // full tiles and ragged tiles alike: everything above was queued with cp.async
     __syncwarp();
     if (lane < rows) {
         float x[48], y[48];
@@ -183,7 +183,6 @@ __global__ void __launch_bounds__(kTile) dhfk_critic_bwd_kernel(const __grid_con
         ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
         if (GPOS) ldgsts_padded_tile<kWorldChunks>(s_gp, p.a, row0);
         if (KC > 0) ldgsts_slab<(KC > 0 ? KC : 4)>(s_gk, p.b + row0 * KC);
-        ldgsts_wait_all();
     } else {
         stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
         if (GPOS) stage_padded_in<kWorldChunks>(s_gp, p.a, row0, rows);
@@ -192,6 +191,7 @@ __global__ void __launch_bounds__(kTile) dhfk_critic_bwd_kernel(const __grid_con
             stage_rows_in<(KC > 0 ? KC : 1)>(s_gk, s, row0, rows);
         }
     }
+    ldgsts_wait_all();     // full tiles and ragged tiles alike: everything above was queued with cp.async
     __syncwarp();
     if (lane < rows) {
         float x[48], y[48], g[48];
@@ -238,11 +238,11 @@ __global__ void __launch_bounds__(kTile) dhfk_critic_jvp_kernel(const __grid_con
     if (rows == kTile) {
         if (KC > 0) ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
         ldgsts_padded_tile<kWorldChunks>(s_v, p.a, row0);
-        ldgsts_wait_all();
     } else {
         if (KC > 0) stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
         stage_padded_in<kWorldChunks>(s_v, p.a, row0, rows);
     }
+    ldgsts_wait_all();     // full tiles and ragged tiles alike: everything above was queued with cp.async
     __syncwarp();
     if (lane < rows) {
         float v[48], ty[48];
@@ -304,10 +304,10 @@ __global__ void __launch_bounds__(kTile) dhfk_flip2d_tile_kernel(const __grid_co
     const int rows = left < kTile ? (int)left : kTile;
     if (rows == kTile) {
         ldgsts_padded_tile<kUvChunks>(s_uv, p.x, row0);
-        ldgsts_wait_all();
     } else {
         stage_padded_in<kUvChunks>(s_uv, p.x, row0, rows);
     }
+    ldgsts_wait_all();     // full tiles and ragged tiles alike: everything above was queued with cp.async
     __syncwarp();
     if (lane < rows) {
         float4* row = s_uv + lane * kUvRow4;

@@ -125,6 +125,9 @@ DHFK_DI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;"
 DHFK_DI void ldgsts16(void* sdst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
 }
+DHFK_DI void ldgsts4(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
 DHFK_DI void ldgsts_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -190,6 +193,10 @@ DHFK_DI void store_padded_tile(const float4* s4, float* gbase, long long row0) {
 }
 
 // Generic (ragged last tile, strided / unaligned views) paths: plain loads and stores.
+// Asynchronous like the slab path: every element is requested with cp.async (16-byte chunks when the rows are packed,
+// 4-byte otherwise) and the CALLER waits once with ldgsts_wait_all() after all arrays of the tile have been queued --
+// one DRAM round trip per tile also for ragged tiles and strided views (synchronous LDG -> STS staging serialised one
+// round trip per array: the [N,37]-view forward measured 40 % of the copy roofline with it).
 template <int NCOLS>
 DHFK_DI void stage_rows_in(float* s, const RowSrc& src, long long row0, int rows) {
     const int lane = threadIdx.x;
@@ -199,12 +206,12 @@ DHFK_DI void stage_rows_in(float* s, const RowSrc& src, long long row0, int rows
         const int nv = nfl >> 2;
         const float4* g4 = reinterpret_cast<const float4*>(g);
         float4* s4 = reinterpret_cast<float4*>(s);
-        for (int i = lane; i < nv; i += kTile) s4[i] = __ldcs(g4 + i);
-        for (int i = (nv << 2) + lane; i < nfl; i += kTile) s[i] = __ldcs(g + i);
+        for (int i = lane; i < nv; i += kTile) ldgsts16(s4 + i, g4 + i);
+        for (int i = (nv << 2) + lane; i < nfl; i += kTile) ldgsts4(s + i, g + i);
     } else {
         for (int i = lane; i < nfl; i += kTile) {
             int r = i / NCOLS, c = i - r * NCOLS;
-            s[i] = __ldg(g + (long long)r * src.stride + c);
+            ldgsts4(s + i, g + (long long)r * src.stride + c);
         }
     }
 }
@@ -229,9 +236,9 @@ DHFK_DI void stage_rows_out(const float* s, const RowDst& dst, long long row0, i
 template <int CH>
 DHFK_DI void stage_padded_in(float4* s4, const float* gbase, long long row0, int rows) {
     const float4* g4 = reinterpret_cast<const float4*>(gbase) + row0 * CH;
-    for (int i = threadIdx.x; i < rows * CH; i += kTile) {
+    for (int i = threadIdx.x; i < rows * CH; i += kTile) {   // cp.async: the caller waits with ldgsts_wait_all()
         int r = i / CH, c = i - r * CH;
-        s4[r * (CH + 1) + c] = __ldcs(g4 + i);
+        ldgsts16(s4 + r * (CH + 1) + c, g4 + i);
     }
 }
 template <int CH>
@@ -353,6 +360,7 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
             stage_rows_in<3>(s_grot, p.grot, row0, rows);
             stage_rows_in<3>(s_root, p.root, row0, rows);
         }
+        ldgsts_wait_all();
     }
     __syncwarp();
 
@@ -651,6 +659,7 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         if (GW) stage_padded_in<kWorldChunks>(s_gw, p.g_world, row0, rows);
         if (GCAM) stage_padded_in<kWorldChunks>(s_gc, p.g_cam, row0, rows);
         if (GUV) stage_padded_in<kUvChunks>(s_gu, p.g_uv, row0, rows);
+        ldgsts_wait_all();
     }
     __syncwarp();
 

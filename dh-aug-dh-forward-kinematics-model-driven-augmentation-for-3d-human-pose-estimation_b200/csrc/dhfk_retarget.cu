@@ -42,10 +42,10 @@ __global__ void __launch_bounds__(kTile) dhfk_retarget_kernel(const __grid_const
     if (rows == kTile) {
         ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
         if (cam_slab) ldgsts_slab<9>(s_cam, p.cam_rows + row0 * 9);
-        ldgsts_wait_all();
     } else {
         stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
     }
+    ldgsts_wait_all();     // full tiles and ragged tiles alike: everything above was queued with cp.async
     __syncwarp();
 
     if (lane < rows) {

@@ -49,11 +49,11 @@ __global__ void __launch_bounds__(kTile) dhfk_scatter32_kernel(const __grid_cons
     if (rows == kTile) {
         if (BWD) ldgsts_padded_tile<kW32Chunks>(s32, p.in, row0);
         else ldgsts_padded_tile<kWorldChunks>(s16, p.in, row0);
-        ldgsts_wait_all();
     } else {
         if (BWD) stage_padded_in<kW32Chunks>(s32, p.in, row0, rows);
         else stage_padded_in<kWorldChunks>(s16, p.in, row0, rows);
     }
+    ldgsts_wait_all();     // full tiles and ragged tiles alike: everything above was queued with cp.async
     __syncwarp();
     if (lane < rows) {
         float4* r16 = s16 + lane * kWorldRow4;
