@@ -211,6 +211,25 @@ def time_torch_port(chunk, chunks, steps, warmup, threads=None):
     return chunk * chunks / dt, dt, threads
 
 
+def time_torch_port_forward_only(chunk=1024, reps=5, warmup=2, threads=None):
+    """SURVEY 8d asks for the reference's forward (no_grad) next to forward+backward: best of `reps` calls."""
+    import torch
+    import torch_port
+    from dhfk import synthetic, tables
+    torch.set_num_threads(threads or host_threads())
+    blk = tables.camera_block("S1", 0)
+    inp = synthetic.gan_like(chunk, seed=1234)
+    ang, grot, bone, root = (torch.tensor(inp[k]) for k in ("ang", "grot", "bone", "root"))
+    best = float("inf")
+    with torch.no_grad():
+        for it in range(warmup + reps):
+            t0 = time.perf_counter()
+            torch_port.pipeline(ang, grot, bone, root, blk)
+            if it >= warmup:
+                best = min(best, time.perf_counter() - t0)
+    return chunk / best, torch.get_num_threads()
+
+
 def time_torch_port_gpu(dev, chunk=16384, reps=3):
     """Context only: the reference's op sequence (oracle/torch_port.py) in torch EAGER on the GPU, every tensor created
     on the device (kinder than the reference's own CUDA branch, which builds each of its 34 matrices on the host and
@@ -567,6 +586,12 @@ def run_native(args):
         pps, dt, threads = time_torch_port(args.ref_chunk, 1, steps=10, warmup=2)
         line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "10 x %d-pose torch calls (reference batch size), fwd+bwd, oracle/torch_port.py" % args.ref_chunk}
+        try:
+            fps, fthreads = time_torch_port_forward_only(args.ref_chunk)
+            line["cpu_baseline_forward_only"] = {"value": fps, "unit": UNIT, "cores": fthreads, "kind": "port",
+                                                 "sample": "best of 5 %d-pose torch calls under no_grad (forward only)" % args.ref_chunk}
+        except Exception as e:
+            line["cpu_baseline_forward_only"] = {"error": repr(e)}
         try:
             gps, gdt = time_torch_port_gpu(dev)
             line["torch_eager_gpu"] = {"value": gps, "unit": UNIT, "ms_per_call": gdt * 1e3, "kind": "port",
