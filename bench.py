@@ -351,6 +351,26 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # parity before any timing is reported: the first rows of buffer set 0 against the float64 C oracle,
+    # as the checker only (part of the cpu_baseline leg: skipped with --no-cpu-baseline)
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import c_oracle
+        m = min(n, 4096)
+        d = sets[0]
+        fwd(d); bwd(d)
+        torch.cuda.synchronize(dev)
+        host = {k: d[k][:m].cpu().numpy() for k in ("ang", "grot", "bone", "root", "g_world", "g_uv")}
+        o = c_oracle.forward(host["ang"], host["grot"], host["bone"], host["root"], blk)
+        b = c_oracle.backward(host["ang"], host["grot"], host["bone"], host["root"], blk, g_world=host["g_world"],
+                              g_uv=host["g_uv"], want_bone=False)
+        rel = lambda x, r: float((np.abs(x[:m].cpu().numpy().astype(np.float64) - r) / np.maximum(np.abs(r), 1.0)).max())
+        errs = {"world": rel(world, o["world16"]), "uv": rel(uv, o["uv"]), "g_ang": rel(g_ang, b["g_ang"]),
+                "g_grot": rel(g_grot, b["g_grot"]), "g_root": rel(g_root, b["g_root"])}
+        if not all(v <= 1e-5 for v in errs.values()):
+            raise SystemExit("bench.py: parity check against the oracle failed before timing: %r" % errs)
+        parity = {"checked_poses": m, "tolerance": 1e-5, "max_rel_err": errs, "oracle": "oracle/dhfk_oracle.c (float64)"}
+
     steps, warmup = max(args.steps, 1), max(args.warmup, 3)
     for i in range(warmup):
         fwd(sets[i % nbuf]); bwd(sets[i % nbuf])
@@ -574,6 +594,8 @@ def run_native(args):
         "clocks": dict(sampler.summary(), window="timed region" + (" + 1 s extension of the same loop" if extension else "")),
         "gpu_launches": 2 * steps,
     }
+    if parity:
+        line["parity"] = parity
     if e2e:
         line["e2e"] = e2e
     if gen_extra:
