@@ -14,29 +14,50 @@ namespace dhfk {
 constexpr int kRec3d = kWorldChunks;              // chunks 0..11  : pose3d
 constexpr int kRec2d = kWorldChunks + kUvChunks;  // chunks 12..19 : pose2d;  chunks 20.. : camera row
 
-// One thread per 16-byte chunk of a record.  rec_chunks = record stride in 16-byte chunks (>= 20 + ceil(cam_cols/4)).
-__global__ void dhfk_bank_gather_kernel(const float4* __restrict__ bank, int rec_chunks, int cam_cols,
-                                        const long long* __restrict__ idx, long long nb, long long bank_rows,
-                                        float4* __restrict__ out3d, float4* __restrict__ out2d,
-                                        float* __restrict__ out_cam) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per 16-byte chunk of a record, kBankUnroll chunks per thread a whole block apart: the kBankUnroll index
+// loads are issued back to back, then the kBankUnroll record loads, then the stores -- a random gather is latency-bound,
+// so throughput is bytes in flight.  (r1: one chunk per thread = 32 KB in flight per SM = 64 % of the streaming peak.)
+// rec_chunks = record stride in 16-byte chunks (>= 20 + ceil(cam_cols/4)).
+constexpr int kBankThreads = 256;
+constexpr int kBankUnroll = 4;
+
+__global__ void __launch_bounds__(kBankThreads)
+dhfk_bank_gather_kernel(const float4* __restrict__ bank, int rec_chunks, int cam_cols, const long long* __restrict__ idx,
+                        long long nb, long long bank_rows, float4* __restrict__ out3d, float4* __restrict__ out2d,
+                        float* __restrict__ out_cam) {
     const int used = kRec2d + (out_cam ? (cam_cols + 3) / 4 : 0);   // chunks of a record that are consumed
-    if (i >= nb * used) return;
-    const long long b = i / used;
-    const int c = (int)(i - b * used);
-    const long long r = idx[b];
-    const bool ok = r >= 0 && r < bank_rows;          // an out-of-range index yields a NaN row, never a wild read
+    const long long total = nb * used;
+    const long long i0 = (long long)blockIdx.x * (kBankThreads * kBankUnroll) + threadIdx.x;
+    long long b[kBankUnroll], r[kBankUnroll];
+    int c[kBankUnroll];
+#pragma unroll
+    for (int u = 0; u < kBankUnroll; ++u) {
+        const long long i = i0 + (long long)u * kBankThreads;
+        b[u] = i / used;
+        c[u] = (int)(i - b[u] * used);
+        r[u] = i < total ? __ldg(idx + b[u]) : -1;
+    }
     const float nan = __int_as_float(0x7fc00000);
-    const float4 v = ok ? __ldg(bank + r * rec_chunks + c) : make_float4(nan, nan, nan, nan);
-    if (c < kRec3d) out3d[b * kWorldChunks + c] = v;
-    else if (c < kRec2d) out2d[b * kUvChunks + (c - kRec3d)] = v;
-    else {
-        const int k0 = 4 * (c - kRec2d);
-        float* o = out_cam + b * cam_cols + k0;
-        if (k0 < cam_cols) o[0] = v.x;
-        if (k0 + 1 < cam_cols) o[1] = v.y;
-        if (k0 + 2 < cam_cols) o[2] = v.z;
-        if (k0 + 3 < cam_cols) o[3] = v.w;
+    float4 v[kBankUnroll];
+#pragma unroll
+    for (int u = 0; u < kBankUnroll; ++u) {
+        const bool ok = r[u] >= 0 && r[u] < bank_rows;   // an out-of-range index yields a NaN row, never a wild read
+        v[u] = ok ? __ldg(bank + r[u] * rec_chunks + c[u]) : make_float4(nan, nan, nan, nan);
+    }
+#pragma unroll
+    for (int u = 0; u < kBankUnroll; ++u) {
+        if (i0 + (long long)u * kBankThreads >= total) continue;
+        const int cu = c[u];
+        if (cu < kRec3d) __stcs(out3d + b[u] * kWorldChunks + cu, v[u]);
+        else if (cu < kRec2d) __stcs(out2d + b[u] * kUvChunks + (cu - kRec3d), v[u]);
+        else {
+            const int k0 = 4 * (cu - kRec2d);
+            float* o = out_cam + b[u] * cam_cols + k0;
+            if (k0 < cam_cols) o[0] = v[u].x;
+            if (k0 + 1 < cam_cols) o[1] = v[u].y;
+            if (k0 + 2 < cam_cols) o[2] = v[u].z;
+            if (k0 + 3 < cam_cols) o[3] = v[u].w;
+        }
     }
 }
 
@@ -45,10 +66,11 @@ int launch_bank_gather(const float* bank, long long rec_floats, int cam_cols, co
                        const char** where) {
     const int used = kRec2d + (out_cam ? (cam_cols + 3) / 4 : 0);
     const long long nthreads = nb * used;
-    const unsigned blocks = (unsigned)((nthreads + 255) / 256);
-    dhfk_bank_gather_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(bank), (int)(rec_floats / 4), cam_cols,
-                                                    idx, nb, bank_rows, reinterpret_cast<float4*>(out3d),
-                                                    reinterpret_cast<float4*>(out2d), out_cam);
+    const long long per_block = kBankThreads * kBankUnroll;
+    const unsigned blocks = (unsigned)((nthreads + per_block - 1) / per_block);
+    dhfk_bank_gather_kernel<<<blocks, kBankThreads, 0, st>>>(reinterpret_cast<const float4*>(bank), (int)(rec_floats / 4),
+                                                            cam_cols, idx, nb, bank_rows, reinterpret_cast<float4*>(out3d),
+                                                            reinterpret_cast<float4*>(out2d), out_cam);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *where = "dhfk_bank_gather_kernel"; return (int)e; }
     return 0;

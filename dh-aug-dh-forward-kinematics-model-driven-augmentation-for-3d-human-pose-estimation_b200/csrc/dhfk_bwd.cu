@@ -16,7 +16,7 @@ int DHFK_CAT(launch_bwd_t, DHFK_TRIG, _b, DHFK_GBONE, _g, DHFK_GEN)(const BwdPar
                                                                     const char** where) {
     constexpr bool G = DHFK_GEN != 0, B = DHFK_GBONE != 0;
     const bool gw = p.g_world != nullptr, gc = p.g_cam != nullptr;
-    const size_t smem = bwd_smem_bytes(gw, gc, guv, G);
+    const size_t smem = bwd_smem_bytes(gw, gc, guv, G, p.w);
     // which upstream gradients exist is a compile-time property of the kernel (7 combinations)
 #define DHFK_BWD(W, C, U) return launch_tiles(dhfk_bwd_kernel<W, C, U, B, DHFK_TRIG, G>, smem, p, st, where)
     if (gw && !gc && guv) DHFK_BWD(true, false, true);       // the GAN step: world + 2D critics

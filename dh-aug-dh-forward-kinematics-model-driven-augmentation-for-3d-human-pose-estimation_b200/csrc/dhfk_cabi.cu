@@ -3,10 +3,47 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/dhfk.h"
 #include "dhfk_launch.h"
 
 namespace dhfk {
+
+// ---- per-(kernel, device) "attributes already set" set: open addressing over atomics, never shrinks -----------
+namespace {
+constexpr int kAttrDevices = 16, kAttrSlots = 256;     // ~90 kernel instantiations in the library
+std::atomic<uintptr_t> g_attr_keys[kAttrDevices][kAttrSlots];
+constexpr uintptr_t kTombstone = ~uintptr_t(0);
+int attr_slot(uintptr_t key) { return (int)(((unsigned long long)key * 0x9E3779B97F4A7C15ull) >> 56) & (kAttrSlots - 1); }
+}  // namespace
+
+bool func_attrs_done(const void* kernel, int device) {
+    if (device < 0 || device >= kAttrDevices) return false;          // unknown ordinal: set the attributes every time
+    std::atomic<uintptr_t>* keys = g_attr_keys[device];
+    const uintptr_t key = reinterpret_cast<uintptr_t>(kernel);
+    int s = attr_slot(key);
+    for (int probe = 0; probe < kAttrSlots; ++probe, s = (s + 1) & (kAttrSlots - 1)) {
+        uintptr_t cur = keys[s].load(std::memory_order_acquire);
+        if (cur == key) return true;
+        if (cur == 0) {
+            if (keys[s].compare_exchange_strong(cur, key, std::memory_order_acq_rel)) return false;
+            if (cur == key) return true;
+        }
+    }
+    return false;   // table full: fall back to setting the attributes on every launch
+}
+void func_attrs_forget(const void* kernel, int device) {
+    if (device < 0 || device >= kAttrDevices) return;
+    std::atomic<uintptr_t>* keys = g_attr_keys[device];
+    const uintptr_t key = reinterpret_cast<uintptr_t>(kernel);
+    int s = attr_slot(key);
+    for (int probe = 0; probe < kAttrSlots; ++probe, s = (s + 1) & (kAttrSlots - 1)) {
+        uintptr_t cur = keys[s].load(std::memory_order_acquire);
+        if (cur == key) { keys[s].store(kTombstone, std::memory_order_release); return; }
+        if (cur == 0) return;
+    }
+}
 
 // ---- standalone camera ops (common/camera.py used on its own) ---------------------------------
 struct RotConst { float M[9]; float t[3]; };
@@ -158,6 +195,20 @@ CamConst make_cam(const float* cam) {
     return cc;
 }
 
+// Angles and global rotation handed over as column slices of ONE 16-byte aligned [N,S] tensor (the generator's [N,37]
+// layout): stage it as a slab.  Max S keeps 12 CTAs per SM only for S <= 37; larger rows still work, at lower occupancy.
+WideRows detect_wide(const float* ang, int64_t as, const float* grot, int64_t gs, const float* bone, int64_t bs,
+                     const float* root, int64_t rs, int64_t n) {
+    WideRows w = {0, 0, 1};
+    if (as == gs && as > 33 && as <= 64 && aligned16(ang) && grot >= ang + 33 && grot + 3 <= ang + as) {
+        w.wide = (int)as;
+        w.goff = (int)(grot - ang);
+        // no ragged last tile and every tile takes the slab path => the separate [32,3] slab is never touched
+        w.grot_slab = (n % dhfk::kTile == 0 && bs == 15 && aligned16(bone) && rs == 3 && aligned16(root)) ? 0 : 1;
+    }
+    return w;
+}
+
 int check_inputs(const float* ang, int64_t as, const float* grot, int64_t gs, const float* bone, int64_t bs,
                  const float* root, int64_t rs, int64_t n) {
     if (n < 0) return fail(DHFK_E_INVAL, "n must be >= 0");
@@ -213,6 +264,7 @@ int dhfk_forward(const float* ang, int64_t ang_stride, const float* grot, int64_
     p.grot = row_src(grot, grot_stride, 3);
     p.bone = row_src(bone, bone_stride, 15);
     p.root = row_src(root, root_stride, 3);
+    p.w = detect_wide(ang, ang_stride, grot, grot_stride, bone, bone_stride, root, root_stride, n);
     p.out_world = out_world;
     p.out_cam = out_cam;
     p.out_uv = out_uv;
@@ -259,6 +311,10 @@ int dhfk_backward(const float* ang, int64_t ang_stride, const float* grot, int64
     p.g_grot = row_dst(g_grot, g_grot_stride, 3);
     p.g_root = row_dst(g_root, g_root_stride, 3);
     p.g_bone = row_dst(g_bone, g_bone_stride, 15);
+    p.w = detect_wide(ang, ang_stride, grot, grot_stride, bone, bone_stride, root, root_stride, n);
+    // the gradient of the wide tensor as one [N,S] tensor: same stride, d(global rotation) at the same column
+    p.g_wide = (p.w.wide && g_ang_stride == p.w.wide && g_grot_stride == p.w.wide && g_grot == g_ang + p.w.goff &&
+                aligned16(g_ang)) ? 1 : 0;
     p.n = n;
     p.cam = make_cam(cam);
     if ((n + dhfk::kTile - 1) / dhfk::kTile > 2147483647LL) return fail(DHFK_E_INVAL, "n too large for one launch");
@@ -544,6 +600,84 @@ int dhfk_flip_pose(const float* x, float* out, int64_t n, int32_t dims, void* st
     if (!aligned16(x) || !aligned16(out)) return fail(DHFK_E_ALIGN, "x / out must be 16-byte aligned");
     const char* where = "";
     int e = dhfk::launch_flip(x, out, n, dims, (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+
+// ---- SURVEY 8 f2, video part: motion-critic inputs ---------------------------------------------------
+static int video_common(int32_t frames, uint32_t flags, int64_t n) {
+    if (n < 0) return fail(DHFK_E_INVAL, "n_rows must be >= 0");
+    if (frames < 1) return fail(DHFK_E_INVAL, "frames must be >= 1");
+    if (n % frames != 0) return fail(DHFK_E_INVAL, "n_rows must be a multiple of frames");
+    if (flags & ~DHFK_VIDEO_REVERSE) return fail(DHFK_E_INVAL, "unknown video flag");
+    if ((n + dhfk::kTile - 2) / (dhfk::kTile - 1) > 2147483647LL) return fail(DHFK_E_INVAL, "n_rows too large for one launch");
+    return DHFK_OK;
+}
+int dhfk_video_critic_forward(const float* pose, int32_t frames, uint32_t flags, float* out_kcs, float* out_dkcs,
+                              float* out_dpos, float* out_pos, int64_t n, void* stream) {
+    if (int rc = video_common(frames, flags, n)) return rc;
+    if (n == 0) return DHFK_OK;
+    if (!pose || !out_kcs) return fail(DHFK_E_INVAL, "pose / out_kcs must be non-null");
+    if (frames > 1 && !out_dkcs) return fail(DHFK_E_INVAL, "out_dkcs must be non-null when frames > 1");
+    if (!aligned16(pose) || !aligned16(out_dpos) || !aligned16(out_pos))
+        return fail(DHFK_E_ALIGN, "pose / out_dpos / out_pos must be 16-byte aligned");
+    const char* where = "";
+    int e = dhfk::launch_video_critic(0, pose, nullptr, frames, flags, out_kcs, out_dkcs, frames > 1 ? out_dpos : nullptr,
+                                      out_pos, n, (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+int dhfk_video_critic_jvp(const float* pose, const float* v_pose, int32_t frames, uint32_t flags, float* t_kcs,
+                          float* t_dkcs, float* t_dpos, float* t_pos, int64_t n, void* stream) {
+    if (int rc = video_common(frames, flags, n)) return rc;
+    if (n == 0) return DHFK_OK;
+    if (!pose || !v_pose || !t_kcs) return fail(DHFK_E_INVAL, "pose / v_pose / t_kcs must be non-null");
+    if (frames > 1 && !t_dkcs) return fail(DHFK_E_INVAL, "t_dkcs must be non-null when frames > 1");
+    if (!aligned16(pose) || !aligned16(v_pose) || !aligned16(t_dpos) || !aligned16(t_pos))
+        return fail(DHFK_E_ALIGN, "pose / v_pose / t_dpos / t_pos must be 16-byte aligned");
+    const char* where = "";
+    int e = dhfk::launch_video_critic(2, pose, v_pose, frames, flags, t_kcs, t_dkcs, frames > 1 ? t_dpos : nullptr, t_pos,
+                                      n, (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+int dhfk_video_critic_backward(const float* pose, int32_t frames, uint32_t flags, const float* g_kcs, const float* g_dkcs,
+                               const float* g_dpos, const float* g_pos, float* g_pose, int64_t n, void* stream) {
+    if (int rc = video_common(frames, flags, n)) return rc;
+    if (n == 0) return DHFK_OK;
+    if (!pose || !g_pose) return fail(DHFK_E_INVAL, "pose / g_pose must be non-null");
+    if (frames == 1) { g_dkcs = nullptr; g_dpos = nullptr; }
+    if (!g_kcs && !g_dkcs && !g_dpos && !g_pos) return fail(DHFK_E_INVAL, "at least one upstream gradient is required");
+    if (!aligned16(pose) || !aligned16(g_dpos) || !aligned16(g_pos) || !aligned16(g_pose))
+        return fail(DHFK_E_ALIGN, "pose / g_dpos / g_pos / g_pose must be 16-byte aligned");
+    const char* where = "";
+    int e = dhfk::launch_video_critic_bwd(pose, frames, flags, g_kcs, g_dkcs, g_dpos, g_pos, g_pose, n,
+                                          (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+int dhfk_video_root_diff_forward(const float* uv, int32_t frames, uint32_t flags, float* out_diff, float* out_uv,
+                                 int64_t n, void* stream) {
+    if (int rc = video_common(frames, flags, n)) return rc;
+    if (n == 0) return DHFK_OK;
+    if (!uv) return fail(DHFK_E_INVAL, "uv must be non-null");
+    if (frames > 1 && !out_diff) return fail(DHFK_E_INVAL, "out_diff must be non-null when frames > 1");
+    if (!aligned16(uv) || !aligned16(out_uv) || (reinterpret_cast<uintptr_t>(out_diff) & 7u))
+        return fail(DHFK_E_ALIGN, "uv / out_uv must be 16-byte aligned, out_diff 8-byte aligned");
+    if (frames == 1 && !out_uv) return DHFK_OK;
+    const char* where = "";
+    int e = dhfk::launch_video_root_diff(false, uv, nullptr, nullptr, frames, flags, out_diff, out_uv, nullptr, n,
+                                         (cudaStream_t)stream, &where);
+    return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
+}
+int dhfk_video_root_diff_backward(const float* g_diff, const float* g_uv_playback, int32_t frames, uint32_t flags,
+                                  float* g_uv, int64_t n, void* stream) {
+    if (int rc = video_common(frames, flags, n)) return rc;
+    if (n == 0) return DHFK_OK;
+    if (!g_uv) return fail(DHFK_E_INVAL, "g_uv must be non-null");
+    if (frames == 1) g_diff = nullptr;
+    if (!g_diff && !g_uv_playback && frames > 1) return fail(DHFK_E_INVAL, "at least one upstream gradient is required");
+    if (!aligned16(g_uv) || !aligned16(g_uv_playback) || (reinterpret_cast<uintptr_t>(g_diff) & 7u))
+        return fail(DHFK_E_ALIGN, "g_uv / g_uv_playback must be 16-byte aligned, g_diff 8-byte aligned");
+    const char* where = "";
+    int e = dhfk::launch_video_root_diff(true, nullptr, g_diff, g_uv_playback, frames, flags, nullptr, nullptr, g_uv, n,
+                                         (cudaStream_t)stream, &where);
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }
 

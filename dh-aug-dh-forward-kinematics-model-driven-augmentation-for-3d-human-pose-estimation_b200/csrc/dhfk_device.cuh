@@ -320,16 +320,22 @@ DHFK_DI V3 project_point_bwd(const CamConst& cc, const ProjAux& a, float gu, flo
 #endif
 }
 
-// tanh(x) and sech^2(x) = d tanh/dx from u = exp(-2|x|):  t = sgn(x)(1-u)/(1+u),  sech^2 = 4u/(1+u)^2
-// (the derivative is formed without cancellation, so it keeps full relative accuracy when tanh saturates;
-// tanh itself is accurate to ~1e-7 absolute: MUFU.EX2 + MUFU.RCP)
-DHFK_DI void tanh_sech2(float x, float& t, float& s2) {
-    float u;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(-2.885390043f * fabsf(x)));
-    float r = rcp_approx(1.0f + u);
-    t = copysignf((1.0f - u) * r, x);
-    s2 = 4.0f * u * r * r;
+// tanh of two values at once: t = 1 - 2 / (1 + 2^(2x log2 e)), packed fp32x2 arithmetic around MUFU.EX2 / MUFU.RCP
+// (7 instructions per pair).  Saturates cleanly (2^+big = inf -> rcp 0 -> 1; 2^-big = 0 -> -1), NaN stays NaN.
+// Absolute error ~1.5e-7 (ex2.approx is 2^-22 relative on a value near 1, so no formula built on it is relatively
+// accurate around 0; as an angle that is 3e-5 degrees at the widest slot range).
+DHFK_DI float2 tanh2(float2 x) {
+    const float2 a = __fmul2_rn(x, bc2(2.885390043f));
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+    const float2 d = __fadd2_rn(e, bc2(1.0f));
+    const float2 r = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+    return __ffma2_rn(r, bc2(-2.0f), bc2(1.0f));
 }
+// sech^2 = d tanh / dx from the stored tanh value: 1 - t^2 (absolute error ~2e-7; the gradient it scales is judged
+// against max(|ref|, 1), and half * d/d(angle) is O(1))
+DHFK_DI float sech2_from_tanh(float t) { return fmaf(-t, t, 1.0f); }
 // per-slot affine map of the generator epilogue (host-filled: half = (hi-lo)/2, mid = (hi+lo)/2, or
 // 180 / 0 when GAN_whether_use_preAngle is off) and the root scale (10)
 struct GenScale {
@@ -394,15 +400,16 @@ template <int TRIG, int J, class Ctx> DHFK_DI Wrench bwd_walk(Frame F, Ctx& ctx)
 static __constant__ LimbDesc c_limbs[NLIMB] = {make_limb(0), make_limb(1), make_limb(2), make_limb(3)};
 
 // One 5-joint limb, forward then reverse.  B = parent frame with the limb's alpha0 twist folded in.
-// Extra Ctx members used:  V3 upstream_rt(int k, V3 origin)
+// Extra Ctx members used:  void load_limb(const LimbDesc&),  template<int I> V3 upstream_limb(V3 origin)
 template <int TRIG, class Ctx>
 DHFK_DI Wrench bwd_limb(const Frame& B, const LimbDesc& L, Ctx& ctx) {
     const int j0 = L.ang0;
     const float sg = L.sigma;
     float s, c;
+    ctx.load_limb(L);     // the limb's 3 upstream-gradient rows: 128-bit shared loads, no bank conflicts
     // joint 0: hip / shoulder offset along parent x, rotation about B.Z
     const V3 o0 = axpy(L.sgn0 * ctx.bone[L.b0], B.X, B.O);
-    const V3 g0 = ctx.upstream_rt(L.k0, o0);
+    const V3 g0 = ctx.template upstream_limb<0>(o0);
     sincos_deg_rt<TRIG>(ctx.angle_rt(j0), L.q0, s, c);
     const V3 X1 = axpy(s, B.Y, scale(c, B.X));
     const V3 Y1 = axpy(c, B.Y, scale(-s, B.X));
@@ -418,12 +425,12 @@ DHFK_DI Wrench bwd_limb(const Frame& B, const LimbDesc& L, Ctx& ctx) {
     const V3 Y3 = axpy(c * sg, zj1, scale(-s, X2));
     // joint 3: knee / elbow, alpha 0, axis zj2
     const V3 o3 = axpy(ctx.bone[L.b3], X3, o0);
-    const V3 g3 = ctx.upstream_rt(L.k0 + 1, o3);
+    const V3 g3 = ctx.template upstream_limb<1>(o3);
     sincos_deg_rt<TRIG>(ctx.angle_rt(j0 + 3), 0, s, c);
     const V3 X4 = axpy(s, Y3, scale(c, X3));
     // joint 4: foot / wrist, leaf
     const V3 o4 = axpy(ctx.bone[L.b4], X4, o3);
-    const V3 g4 = ctx.upstream_rt(L.k0 + 2, o4);
+    const V3 g4 = ctx.template upstream_limb<2>(o4);
     // reverse sweep
     Wrench w;
     w.F = g4;

@@ -15,7 +15,7 @@ namespace dhfk {
 int DHFK_CAT(launch_fwd_t, DHFK_TRIG, _g, DHFK_GEN)(const FwdParams& p, bool cam, bool uv, cudaStream_t st,
                                                     const char** where) {
     constexpr bool G = DHFK_GEN != 0;
-    const size_t smem = fwd_smem_bytes(cam, uv, G);
+    const size_t smem = fwd_smem_bytes(cam, uv, G, p.w);
     if (cam && uv) return launch_tiles(dhfk_fwd_kernel<true, true, DHFK_TRIG, G>, smem, p, st, where);
     if (uv) return launch_tiles(dhfk_fwd_kernel<false, true, DHFK_TRIG, G>, smem, p, st, where);
     if (cam) return launch_tiles(dhfk_fwd_kernel<true, false, DHFK_TRIG, G>, smem, p, st, where);

@@ -51,8 +51,18 @@ struct RowDst {
     int vec;
 };
 
+// "Wide" rows (raw mode only): the generator hands the angles and the global rotation over as column slices of ONE
+// [N,S] tensor (S = 37: angles in columns 0..32, global rotation in 34..36, Fk_generator.py:136-184).  When that tensor
+// is 16-byte aligned a tile of it is one contiguous slab like any other input: `wide` = S makes the kernels stage the
+// [32,S] slab as it is (row stride S in shared memory too, odd => conflict-free) and read the global rotation at
+// column `goff` of the same rows; 0 = separate packed arrays.  `grot_slab` = 0 drops the separate [32,3] slab from
+// the shared-memory layout (possible when no ragged last tile needs it), which keeps 12 CTAs per SM.
+struct WideRows {
+    int wide, goff, grot_slab;
+};
 struct FwdParams {
     RowSrc ang, grot, bone, root;   // GEN mode: `ang` is the raw network output [N,35]; grot/root unused
+    WideRows w;
     float* out_world;
     float* out_cam;
     float* out_uv;
@@ -62,6 +72,8 @@ struct FwdParams {
 };
 struct BwdParams {
     RowSrc ang, grot, bone, root;
+    WideRows w;
+    int g_wide;                     // the gradient of the wide tensor is wanted as ONE [N,S] tensor (same S, goff)
     const float* g_world;
     const float* g_cam;
     const float* g_uv;
@@ -183,6 +195,11 @@ DHFK_DI void ldgsts_slab(float* s, const float* g) {
             ldgsts16(reinterpret_cast<float4*>(s) + i, reinterpret_cast<const float4*>(g) + i);
     }
 }
+// same for a slab whose size is only known at run time (wide rows)
+DHFK_DI void ldgsts_slab_rt(float* s, const float* g, int nv /* 16-byte chunks */) {
+    for (int i = threadIdx.x; i < nv; i += kTile)
+        ldgsts16(reinterpret_cast<float4*>(s) + i, reinterpret_cast<const float4*>(g) + i);
+}
 // block until every cp.async (LDGSTS) this thread issued has landed: a scoreboard wait, no polling
 DHFK_DI void ldgsts_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -215,12 +232,18 @@ DHFK_DI void stage_rows_in(float* s, const RowSrc& src, long long row0, int rows
         }
     }
 }
+// `ss` = row stride of the shared image (NCOLS unless the tile was staged as a wide slab)
 template <int NCOLS>
-DHFK_DI void stage_rows_out(const float* s, const RowDst& dst, long long row0, int rows) {
+DHFK_DI void stage_rows_out(const float* s, const RowDst& dst, long long row0, int rows, int ss = NCOLS) {
     const int lane = threadIdx.x;
     float* g = dst.p + row0 * dst.stride;
     const int nfl = rows * NCOLS;
-    if (dst.vec) {
+    if (ss != NCOLS) {
+        for (int i = lane; i < nfl; i += kTile) {
+            int r = i / NCOLS, c = i - r * NCOLS;
+            g[(long long)r * dst.stride + c] = s[r * ss + c];
+        }
+    } else if (dst.vec) {
         const int nv = nfl >> 2;
         float4* g4 = reinterpret_cast<float4*>(g);
         const float4* s4 = reinterpret_cast<const float4*>(s);
@@ -250,6 +273,27 @@ DHFK_DI void stage_padded_out(const float4* s4, float* gbase, long long row0, in
     }
 }
 
+// GEN mode: the raw network output slab becomes tanh(slab) in place, ONCE per column, by the whole warp: 128-bit
+// shared loads / stores over the contiguous slab (conflict-free), packed arithmetic, 2 MUFU per element.  The tree
+// walk then reads t and forms angle = t * half + mid with one FFMA; the backward gets sech^2 = 1 - t^2 from the same
+// cell.  (r1 decoded each column where the walk consumed it with scalar code: ~11 instructions per column and pass;
+// generator mode measured 0.2262 ms per fwd+bwd step against 0.2027 ms for the plain step.)
+DHFK_DI void tanh_slab_inplace(float* s) {
+    constexpr int NV = kTile * GEN_NCOL / 4;
+    static_assert(kTile * GEN_NCOL % 4 == 0, "slab must be a whole number of 16-byte chunks");
+    float4* s4 = reinterpret_cast<float4*>(s);
+    const int lane = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < (NV + 31) / 32; ++k) {
+        const int i = lane + 32 * k;
+        if (NV % 32 == 0 || i < NV) {
+            const float4 v = s4[i];
+            const float2 lo = tanh2(make_float2(v.x, v.y)), hi = tanh2(make_float2(v.z, v.w));
+            s4[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+    }
+}
+
 // global rotation R = Rx(gx) Ry(gy) Rz(gz), forward_kinematics_DH_model.py:141-191 (row-major)
 template <int TRIG>
 DHFK_DI void global_rotation(const float* g, float* R, float& sx, float& cx, float& sy, float& cy) {
@@ -265,7 +309,7 @@ DHFK_DI void global_rotation(const float* g, float* R, float& sx, float& cx, flo
 // ---- forward -------------------------------------------------------------------------------------
 template <bool CAM, bool UV, bool GEN>
 struct FwdCtx {
-    const float* ang;     // this pose's 33 angles, or (GEN) its 35 raw network outputs
+    const float* ang;     // this pose's 33 angles, or (GEN) tanh of its 35 raw network outputs (tanh_slab_inplace)
     const float* bone;
     const CamConst* cc;
     const GenScale* gs;
@@ -276,11 +320,7 @@ struct FwdCtx {
         else {
             constexpr int SRC = gen_src_col(J);
             if constexpr (SRC < 0) return gs->mid[J];
-            else {
-                float t, s2;
-                tanh_sech2(ang[SRC], t, s2);
-                return fmaf(t, gs->half[J], gs->mid[J]);
-            }
+            else return fmaf(ang[SRC], gs->half[J], gs->mid[J]);
         }
     }
     float R[9];
@@ -316,10 +356,11 @@ DHFK_DI void flush_chunks(float4* row4, const float* v) {
 template <bool CAM, bool UV, int TRIG, bool GEN>
 __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__ FwdParams p) {
     constexpr int NANG = GEN ? GEN_NCOL : 33;      // floats per pose in the first slab
+    const int wide = GEN ? 0 : p.w.wide;           // launch-uniform
     extern __shared__ __align__(16) float smem[];
     float* s_ang = smem;
-    float* s_grot = s_ang + kTile * NANG;
-    float* s_bone = s_grot + (GEN ? 0 : kTile * 3);
+    float* s_grot = s_ang + kTile * (wide ? wide : NANG);
+    float* s_bone = s_grot + ((GEN || !p.w.grot_slab) ? 0 : kTile * 3);
     float* s_root = s_bone + kTile * 15;
     float4* s_world = reinterpret_cast<float4*>(s_root + (GEN ? 0 : kTile * 3));
     float4* s_cam = s_world + kTile * kWorldRow4;
@@ -330,23 +371,26 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
     // full tile of packed, aligned rows: async slab path; ragged last tile / strided views: gather path
-    const bool bulk = rows == kTile && p.ang.vec && p.bone.vec && (GEN || (p.grot.vec && p.root.vec));
+    const bool wtile = wide != 0 && rows == kTile && p.bone.vec && p.root.vec;     // this tile is staged as a wide slab
+    const bool bulk = wtile || (rows == kTile && p.ang.vec && p.bone.vec && (GEN || (p.grot.vec && p.root.vec)));
+    const int sa = wtile ? wide : NANG;            // row stride of the first slab, in global and in shared memory
 
     if (bulk) {
-        ldgsts_slab<NANG>(s_ang, p.ang.p + row0 * NANG);
+        if (wtile) ldgsts_slab_rt(s_ang, p.ang.p + row0 * sa, kTile / 4 * sa);
+        else ldgsts_slab<NANG>(s_ang, p.ang.p + row0 * NANG);
         ldgsts_slab<15>(s_bone, p.bone.p + row0 * 15);
         if (!GEN) {
-            ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
+            if (!wtile) ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
             ldgsts_slab<3>(s_root, p.root.p + row0 * 3);
         }
 #if DHFK_PREFETCH_TILES_FWD > 0
         if (lane == 0) {
             const long long rowp = row0 + (long long)DHFK_PREFETCH_TILES_FWD * kTile;
             if (rowp + kTile <= p.n) {   // the warp one resident wave later finds its slabs in L2
-                bulk_prefetch_l2(p.ang.p + rowp * NANG, kTile * NANG * 4);
+                bulk_prefetch_l2(p.ang.p + rowp * sa, kTile * sa * 4);
                 bulk_prefetch_l2(p.bone.p + rowp * 15, kTile * 15 * 4);
                 if (!GEN) {
-                    bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
+                    if (!wtile) bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
                     bulk_prefetch_l2(p.root.p + rowp * 3, kTile * 3 * 4);
                 }
             }
@@ -363,32 +407,30 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
         ldgsts_wait_all();
     }
     __syncwarp();
+    if (GEN) {
+        tanh_slab_inplace(s_ang);
+        __syncwarp();
+    }
 
     if (lane < rows) {
         FwdCtx<CAM, UV, GEN> ctx;
         ctx.gs = &p.gs;
-        ctx.ang = s_ang + lane * NANG;
+        ctx.ang = s_ang + lane * sa;
         ctx.bone = s_bone + lane * 15;
         ctx.cc = &p.cam;
         float sx, cx, sy, cy;
         if (GEN) {
             // global rotation = slots 34..36 (columns 28..30), root = tanh(columns 32..34) * 10
-            float g[3], t, s2;
+            float g[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                tanh_sech2(ctx.ang[gen_src_col(GEN_GROT_SLOT) + i], t, s2);
-                g[i] = fmaf(t, p.gs.half[GEN_GROT_SLOT + i], p.gs.mid[GEN_GROT_SLOT + i]);
-            }
+            for (int i = 0; i < 3; ++i)
+                g[i] = fmaf(ctx.ang[gen_src_col(GEN_GROT_SLOT) + i], p.gs.half[GEN_GROT_SLOT + i],
+                            p.gs.mid[GEN_GROT_SLOT + i]);
             global_rotation<TRIG>(g, ctx.R, sx, cx, sy, cy);
-            float r[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                tanh_sech2(ctx.ang[GEN_ROOT_COL + i], t, s2);
-                r[i] = t * p.gs.root_scale;
-            }
-            ctx.root = v3(r[0], r[1], r[2]);
+            ctx.root = v3(ctx.ang[GEN_ROOT_COL] * p.gs.root_scale, ctx.ang[GEN_ROOT_COL + 1] * p.gs.root_scale,
+                          ctx.ang[GEN_ROOT_COL + 2] * p.gs.root_scale);
         } else {
-            global_rotation<TRIG>(s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
+            global_rotation<TRIG>(wtile ? ctx.ang + p.w.goff : s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
             ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
         }
         float4* wrow = s_world + lane * kWorldRow4;
@@ -432,51 +474,42 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
 template <bool GW, bool GCAM, bool GUV, bool GBONE, bool GEN>
 struct BwdCtx {
     static constexpr bool kBoneGrad = GBONE;
-    const float* ang;   // this pose's 33 angles, or (GEN) its 35 raw network outputs
+    const float* ang;   // this pose's 33 angles, or (GEN) tanh of its 35 raw network outputs
     const float* bone;
     float* g_ang;   // same shared row as ang (in place)
     float* g_bone;  // same shared row as bone (in place)
     const CamConst* cc;
     const GenScale* gs;
 
-    // Joint angle in degrees.  GEN: tanh + affine slot map on the fly; the slot's chain factor
-    // d(angle)/d(network output) = half * sech^2 is parked in the (now consumed) input cell so that
-    // grad_angle can turn d/d(angle) into d/d(network output) in place.
+    // Joint angle in degrees.  GEN: the cell holds t = tanh(network output) (tanh_slab_inplace); the angle is the affine
+    // slot map of t, and grad_angle turns d/d(angle) into d/d(network output) = g * half * (1 - t^2) in place.
     template <int J>
     DHFK_DI float angle() {
         if constexpr (!GEN) return ang[J];
         else {
             constexpr int SRC = gen_src_col(J);
             if constexpr (SRC < 0) return gs->mid[J];
-            else {
-                float t, s2;
-                tanh_sech2(ang[SRC], t, s2);
-                g_ang[SRC] = s2 * gs->half[J];
-                return fmaf(t, gs->half[J], gs->mid[J]);
-            }
+            else return fmaf(ang[SRC], gs->half[J], gs->mid[J]);
         }
     }
     DHFK_DI float angle_rt(int j) {
         if (!GEN) return ang[j];
         const int src = c_gen_src[j];       // warp-uniform
         if (src < 0) return gs->mid[j];
-        float t, s2;
-        tanh_sech2(ang[src], t, s2);
-        g_ang[src] = s2 * gs->half[j];
-        return fmaf(t, gs->half[j], gs->mid[j]);
+        return fmaf(ang[src], gs->half[j], gs->mid[j]);
     }
     template <int J>
     DHFK_DI void grad_angle(float g) {
         if constexpr (!GEN) g_ang[J] = g;
         else {
             constexpr int SRC = gen_src_col(J);
-            if constexpr (SRC >= 0) g_ang[SRC] = g * g_ang[SRC];
+            if constexpr (SRC >= 0) g_ang[SRC] = g * gs->half[J] * sech2_from_tanh(g_ang[SRC]);
         }
     }
     DHFK_DI void grad_angle_rt(int j, float g) {
         if (!GEN) { g_ang[j] = g; return; }
         const int src = c_gen_src[j];
-        if (src >= 0) g_ang[src] = g * g_ang[src];
+        if (src >= 0) g_ang[src] = g * gs->half[j] * sech2_from_tanh(g_ang[src]);
     }
     template <int J>
     DHFK_DI void zero_grad_angle() {
@@ -576,25 +609,51 @@ struct BwdCtx {
         }
         return to_frame(g, gc);
     }
-    // same for a runtime output index (shared limb routine): scalar shared loads at runtime offsets
-    DHFK_DI V3 upstream_rt(int k, V3 o) {
+    // The shared limb routine (runtime limb index, warp-uniform): the limb's three outputs are 9 consecutive floats of
+    // the [16,3] rows and 6 of the [16,2] row.  Rows are padded for 128-bit access (odd stride in 16-byte chunks), so a
+    // 32- or 64-bit load at a runtime offset is a 4- / 2-way bank conflict whatever the padding (every lane's address
+    // is congruent mod 16 bytes): r1 measured 46 % of the shared wavefronts as conflicts.  Instead the 3 (2) chunks
+    // that hold them are read with LDS.128 and the floats picked with a warp-uniform offset.
+    float lw[GW ? 9 : 1], lc[GCAM ? 9 : 1], lu[GUV ? 6 : 1];
+    // ld.shared.v4 spelled out: left to itself the compiler narrows the first chunk to a 64-bit + conditional 32-bit
+    // loads (only part of it is used for two of the three offsets), which brings the conflicts back
+    DHFK_DI static float4 lds128(const float4* p) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+        return v;
+    }
+    DHFK_DI static void pick9(const float4* row, int c0, int off, float* o) {
+        const float4 a = lds128(row + c0), b = lds128(row + c0 + 1), c = lds128(row + c0 + 2);
+        if (off == 0) {
+            o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w; o[8] = c.x;
+        } else if (off == 2) {
+            o[0] = a.z; o[1] = a.w; o[2] = b.x; o[3] = b.y; o[4] = b.z; o[5] = b.w; o[6] = c.x; o[7] = c.y; o[8] = c.z;
+        } else {   // off == 3
+            o[0] = a.w; o[1] = b.x; o[2] = b.y; o[3] = b.z; o[4] = b.w; o[5] = c.x; o[6] = c.y; o[7] = c.z; o[8] = c.w;
+        }
+    }
+    DHFK_DI void load_limb(const LimbDesc& L) {
+        if constexpr (GW) pick9(gw4, L.wc0, L.woff, lw);
+        if constexpr (GCAM) pick9(gc4, L.wc0, L.woff, lc);
+        if constexpr (GUV) {
+            const float4 a = lds128(gu4 + L.uc0), b = lds128(gu4 + L.uc0 + 1);
+            if (L.uoff == 0) { lu[0] = a.x; lu[1] = a.y; lu[2] = a.z; lu[3] = a.w; lu[4] = b.x; lu[5] = b.y; }
+            else { lu[0] = a.z; lu[1] = a.w; lu[2] = b.x; lu[3] = b.y; lu[4] = b.z; lu[5] = b.w; }
+        }
+    }
+    // total dL/d(origin of the limb's I-th output) in the working frame
+    template <int I>
+    DHFK_DI V3 upstream_limb(V3 o) {
         V3 g = v3(0.f, 0.f, 0.f);
-        if constexpr (GW) {
-            const float* r = reinterpret_cast<const float*>(gw4) + 3 * k;
-            g = v3(r[0], r[1], r[2]);
-        }
+        if constexpr (GW) g = v3(lw[3 * I], lw[3 * I + 1], lw[3 * I + 2]);
         V3 gc = v3(0.f, 0.f, 0.f);
-        if constexpr (GCAM) {
-            const float* r = reinterpret_cast<const float*>(gc4) + 3 * k;
-            gc = v3(r[0], r[1], r[2]);
-        }
+        if constexpr (GCAM) gc = v3(lc[3 * I], lc[3 * I + 1], lc[3 * I + 2]);
         if (GUV) {
             V3 X = o + v0;
             float u, v;
             ProjAux a;
             project_point(*cc, X, u, v, a);
-            const float2 q = reinterpret_cast<const float2*>(gu4)[k];
-            gc = gc + project_point_bwd(*cc, a, q.x, q.y);
+            gc = gc + project_point_bwd(*cc, a, lu[2 * I], lu[2 * I + 1]);
         }
         return to_frame(g, gc);
     }
@@ -606,10 +665,11 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
     static_assert(GW || GCAM || GUV, "at least one upstream gradient");
     static_assert(!(GEN && GBONE), "bone-length gradients are not produced in generator mode");
     constexpr int NANG = GEN ? GEN_NCOL : 33;
+    const int wide = GEN ? 0 : p.w.wide;           // launch-uniform (see WideRows)
     extern __shared__ __align__(16) float smem[];
     float* s_ang = smem;
-    float* s_grot = s_ang + kTile * NANG;
-    float* s_bone = s_grot + (GEN ? 0 : kTile * 3);
+    float* s_grot = s_ang + kTile * (wide ? wide : NANG);
+    float* s_bone = s_grot + ((GEN || !p.w.grot_slab) ? 0 : kTile * 3);
     float* s_root = s_bone + kTile * 15;
     float4* s_gw = reinterpret_cast<float4*>(s_root + (GEN ? 0 : kTile * 3));
     float4* s_gc = s_gw + (GW ? kTile * kWorldRow4 : 0);
@@ -619,14 +679,17 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
     const long long row0 = (long long)blockIdx.x * kTile;
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
-    const bool bulk = rows == kTile && p.ang.vec && p.bone.vec && (GEN || (p.grot.vec && p.root.vec));
+    const bool wtile = wide != 0 && rows == kTile && p.bone.vec && p.root.vec;
+    const bool bulk = wtile || (rows == kTile && p.ang.vec && p.bone.vec && (GEN || (p.grot.vec && p.root.vec)));
+    const int sa = wtile ? wide : NANG;
 
     if (bulk) {
         // one round trip: every byte of the tile is requested before anything is waited for
-        ldgsts_slab<NANG>(s_ang, p.ang.p + row0 * NANG);
+        if (wtile) ldgsts_slab_rt(s_ang, p.ang.p + row0 * sa, kTile / 4 * sa);
+        else ldgsts_slab<NANG>(s_ang, p.ang.p + row0 * NANG);
         ldgsts_slab<15>(s_bone, p.bone.p + row0 * 15);
         if (!GEN) {
-            ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
+            if (!wtile) ldgsts_slab<3>(s_grot, p.grot.p + row0 * 3);
             ldgsts_slab<3>(s_root, p.root.p + row0 * 3);
         }
         if (GW) ldgsts_padded_tile<kWorldChunks>(s_gw, p.g_world, row0);
@@ -636,10 +699,10 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         if (lane == 0) {
             const long long rowp = row0 + (long long)DHFK_PREFETCH_TILES_BWD * kTile;
             if (rowp + kTile <= p.n) {
-                bulk_prefetch_l2(p.ang.p + rowp * NANG, kTile * NANG * 4);
+                bulk_prefetch_l2(p.ang.p + rowp * sa, kTile * sa * 4);
                 bulk_prefetch_l2(p.bone.p + rowp * 15, kTile * 15 * 4);
                 if (!GEN) {
-                    bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
+                    if (!wtile) bulk_prefetch_l2(p.grot.p + rowp * 3, kTile * 3 * 4);
                     bulk_prefetch_l2(p.root.p + rowp * 3, kTile * 3 * 4);
                 }
                 if (GW) bulk_prefetch_l2(p.g_world + rowp * 48, kTile * 48 * 4);
@@ -662,12 +725,16 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         ldgsts_wait_all();
     }
     __syncwarp();
+    if (GEN) {
+        tanh_slab_inplace(s_ang);
+        __syncwarp();
+    }
 
     if (lane < rows) {
         BwdCtx<GW, GCAM, GUV, GBONE, GEN> ctx;
         ctx.gs = &p.gs;
-        ctx.ang = s_ang + lane * NANG;
-        ctx.g_ang = s_ang + lane * NANG;
+        ctx.ang = s_ang + lane * sa;
+        ctx.g_ang = s_ang + lane * sa;
         ctx.bone = s_bone + lane * 15;
         ctx.g_bone = s_bone + lane * 15;
         ctx.cc = &p.cam;
@@ -677,20 +744,19 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         float sx, cx, sy, cy;
         float chain_g[3], chain_r[3];   // GEN: d(grot_i)/d(col), d(root_i)/d(col)
         if (GEN) {
-            float g[3], r[3], t, s2;
+            float g[3], r[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                tanh_sech2(ctx.ang[gen_src_col(GEN_GROT_SLOT) + i], t, s2);
-                g[i] = fmaf(t, p.gs.half[GEN_GROT_SLOT + i], p.gs.mid[GEN_GROT_SLOT + i]);
-                chain_g[i] = s2 * p.gs.half[GEN_GROT_SLOT + i];
-                tanh_sech2(ctx.ang[GEN_ROOT_COL + i], t, s2);
-                r[i] = t * p.gs.root_scale;
-                chain_r[i] = s2 * p.gs.root_scale;
+                const float tg = ctx.ang[gen_src_col(GEN_GROT_SLOT) + i], tr = ctx.ang[GEN_ROOT_COL + i];
+                g[i] = fmaf(tg, p.gs.half[GEN_GROT_SLOT + i], p.gs.mid[GEN_GROT_SLOT + i]);
+                chain_g[i] = sech2_from_tanh(tg) * p.gs.half[GEN_GROT_SLOT + i];
+                r[i] = tr * p.gs.root_scale;
+                chain_r[i] = sech2_from_tanh(tr) * p.gs.root_scale;
             }
             global_rotation<TRIG>(g, ctx.R, sx, cx, sy, cy);
             ctx.root = v3(r[0], r[1], r[2]);
         } else {
-            global_rotation<TRIG>(s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
+            global_rotation<TRIG>(wtile ? ctx.ang + p.w.goff : s_grot + lane * 3, ctx.R, sx, cx, sy, cy);
             ctx.root = v3(s_root[lane * 3], s_root[lane * 3 + 1], s_root[lane * 3 + 2]);
         }
         ctx.setup_camera();
@@ -714,19 +780,28 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
             o[GEN_ROOT_COL + 2] = gr.z * chain_r[2];
         } else {
             s_root[lane * 3] = gr.x; s_root[lane * 3 + 1] = gr.y; s_root[lane * 3 + 2] = gr.z;
-            s_grot[lane * 3] = gg0; s_grot[lane * 3 + 1] = gg1; s_grot[lane * 3 + 2] = gg2;
+            if (wtile) {
+                // the row image becomes the gradient of the whole wide row: angles, global rotation at `goff`, and
+                // zeros in the columns that feed nothing
+                float* row = s_ang + lane * sa;
+                for (int c = 33; c < sa; ++c) row[c] = 0.f;
+                row[p.w.goff] = gg0; row[p.w.goff + 1] = gg1; row[p.w.goff + 2] = gg2;
+            } else {
+                s_grot[lane * 3] = gg0; s_grot[lane * 3 + 1] = gg1; s_grot[lane * 3 + 2] = gg2;
+            }
         }
     }
-    const bool bulk_out = rows == kTile && p.g_ang.vec &&
-                          (GEN || (p.g_grot.vec && p.g_root.vec && (!GBONE || p.g_bone.vec)));
-    if (bulk_out) {
+    const bool wide_out = wtile && p.g_wide;       // one slab store carries d(angles) and d(global rotation)
+    const bool bulk_out = wide_out || (!wtile && rows == kTile && p.g_ang.vec &&
+                                       (GEN || (p.g_grot.vec && p.g_root.vec && (!GBONE || p.g_bone.vec))));
+    if (bulk_out && (!wide_out || (p.g_root.vec && (!GBONE || p.g_bone.vec)))) {
         // results overwrote the input slabs in place; lane 0 ships the slabs
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            bulk_s2g(p.g_ang.p + row0 * NANG, s_ang, kTile * NANG * 4);
+            bulk_s2g(p.g_ang.p + row0 * sa, s_ang, kTile * sa * 4);
             if (!GEN) {
-                bulk_s2g(p.g_grot.p + row0 * 3, s_grot, kTile * 3 * 4);
+                if (!wide_out) bulk_s2g(p.g_grot.p + row0 * 3, s_grot, kTile * 3 * 4);
                 bulk_s2g(p.g_root.p + row0 * 3, s_root, kTile * 3 * 4);
                 if (GBONE) bulk_s2g(p.g_bone.p + row0 * 15, s_bone, kTile * 15 * 4);
             }
@@ -736,9 +811,10 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
         return;
     }
     __syncwarp();
-    stage_rows_out<NANG>(s_ang, p.g_ang, row0, rows);
+    stage_rows_out<NANG>(s_ang, p.g_ang, row0, rows, sa);
     if (!GEN) {
-        stage_rows_out<3>(s_grot, p.g_grot, row0, rows);
+        if (wtile) stage_rows_out<3>(s_ang + p.w.goff, p.g_grot, row0, rows, sa);
+        else stage_rows_out<3>(s_grot, p.g_grot, row0, rows);
         stage_rows_out<3>(s_root, p.g_root, row0, rows);
         if (GBONE) stage_rows_out<15>(s_bone, p.g_bone, row0, rows);
     }

@@ -123,12 +123,26 @@ struct LimbDesc {
     int q0, q2;        // theta0 quadrants of joints 0 and 2
     float sgn0;        // sign of the first length
     float sigma;       // alpha of joints 1 and 2 is sigma * 90 deg
+    // where the limb's three upstream-gradient rows start inside a [16,3] / [16,2] pose row: first 16-byte chunk
+    // and float offset inside it (the 9 / 6 floats are then read with 3 / 2 conflict-free 128-bit loads)
+    int wc0, woff;     // [16,3] rows: floats 3*k0 .. 3*k0+8
+    int uc0, uoff;     // [16,2] rows: floats 2*k0 .. 2*k0+5
 };
 constexpr LimbDesc make_limb(int l) {
     const int j = LIMB_ROOT[l];
     return LimbDesc{j, out_index_of_joint(j), LEN_BONE[j], LEN_BONE[j + 3], LEN_BONE[j + 4],
-                    THETA0_Q[j], THETA0_Q[j + 2], (float)LEN_SIGN[j], (float)ALPHA_Q[j + 1]};
+                    THETA0_Q[j], THETA0_Q[j + 2], (float)LEN_SIGN[j], (float)ALPHA_Q[j + 1],
+                    (3 * out_index_of_joint(j)) / 4, (3 * out_index_of_joint(j)) % 4,
+                    (2 * out_index_of_joint(j)) / 4, (2 * out_index_of_joint(j)) % 4};
 }
+// the 128-bit limb loads stay inside the 12- / 8-chunk rows and only the offsets handled below occur
+constexpr bool limb_chunks_ok(int l) {
+    const LimbDesc d = make_limb(l);
+    return d.wc0 + 2 <= 11 && d.uc0 + 1 <= 7 && (d.woff == 0 || d.woff == 2 || d.woff == 3) &&
+           (d.uoff == 0 || d.uoff == 2);
+}
+static_assert(limb_chunks_ok(0) && limb_chunks_ok(1) && limb_chunks_ok(2) && limb_chunks_ok(3),
+              "limb upstream rows do not fit the 3-chunk / 2-chunk 128-bit load pattern");
 constexpr bool limb_pattern_ok(int l) {
     const int j = LIMB_ROOT[l];
     const int k = out_index_of_joint(j);

@@ -24,7 +24,9 @@ def install(verbose: bool = False, generators: bool = False, loader_refresh: boo
     """Patch the reference modules that are currently imported.  Idempotent.  Returns the names patched.
     loader_refresh=True also swaps random_bl_aug / video_mode_random_bl_aug / dataloader_update for the fused
     retarget+project versions (same np.random stream, same data_dict contract).
-    critics=True rebinds special_KCS_Input_transform / video_mode_special_KCS_Input_transform.
+    critics=True rebinds special_KCS_Input_transform / video_mode_special_KCS_Input_transform and gives the reference's
+    two motion critics (Video_motion_Fk_3D_Discriminator / Video_motion_Fk_2D_Discriminator, Fk_discriminator.py:381-587)
+    the fused `forward` -- same classes, same sub-modules and state dicts, only the method is swapped.
     generators=True also swaps Fk_Generator / Video_Fk_Generator for the fused-epilogue versions (SURVEY 8 f1;
     same constructor and state dict) wherever `my_get_poseFk_model` (model_fk_gan_train.py:97-173) finds them."""
     patched = []
@@ -35,6 +37,11 @@ def install(verbose: bool = False, generators: bool = False, loader_refresh: boo
             for sym in ("special_KCS_Input_transform", "video_mode_special_KCS_Input_transform"):
                 setattr(mod, sym, getattr(_dis, sym))
                 patched.append("models_Fk_GAN.Fk_discriminator.%s" % sym)
+            for cls, fwd in (("Video_motion_Fk_3D_Discriminator", _dis.video_motion_3d_forward),
+                             ("Video_motion_Fk_2D_Discriminator", _dis.video_motion_2d_forward)):
+                if hasattr(mod, cls):
+                    getattr(mod, cls).forward = fwd
+                    patched.append("models_Fk_GAN.Fk_discriminator.%s.forward" % cls)
     if loader_refresh:
         from . import dataloader_update as _du
         for name, syms in (("function_aug.dataloader_update", ("random_bl_aug", "dataloader_update")),

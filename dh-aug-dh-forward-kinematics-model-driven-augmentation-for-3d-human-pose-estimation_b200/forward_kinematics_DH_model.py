@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import tables
-from .functional import fk_world16
+from .functional import fk_world16, fk_world16_wide, wide_rows_ok
 from .functional import scatter_16_to_32 as _scatter32
 from .tables import used_16key_15bone_len_table  # noqa: F401  (re-exported like the reference module)
 
@@ -88,6 +88,121 @@ def _shared_angle_view(rleg, lleg, body, rhand, lhand):
                 or t.storage_offset() - base.storage_offset() != col0 + off):
             return None
     return base[:, col0:col0 + 33]
+
+
+def _wide_layout(ang_view, grot):
+    """(base, goff) when the angle view starts at column 0 of a base tensor that also holds the global rotation (the
+    generator's [N,37] slot tensor, Fk_generator.py:136-184) and that tensor can go to the kernels as it is; else None."""
+    base = ang_view._base
+    if base is None or grot._base is not base or ang_view.storage_offset() != base.storage_offset():
+        return None
+    goff = grot.storage_offset() - base.storage_offset()
+    if grot.dim() != 2 or grot.shape != (base.shape[0], 3) or grot.stride(1) != 1 or \
+            (base.shape[0] > 1 and grot.stride(0) != base.stride(0)):
+        return None
+    return (base, goff) if wide_rows_ok(base, goff) else None
+
+
+class LazyWorld32:
+    """The [N,32,3] tensor `change_3d_joint_angle` returns, not yet materialised ("lazy 32-slot scatter only
+    when a caller really indexes it").
+
+    Every tensor-branch caller of the reference immediately gathers the 16 used joints back out,
+    ``x[:, H36M_32_To_16_Table]`` (Fk_generator.py:259, :453) -- with the 32-slot layout materialised that is the FK
+    kernel, a scatter kernel, a torch index gather and, in the backward, an index_put into zeros plus the scatter's
+    transpose: 5 launches and ~2.4 kB per pose where the FK kernel alone moves 408 B.  This object answers exactly that
+    index with the kernel's own [N,16,3] output (autograd history intact) and turns into the real [N,32,3] tensor --
+    one `dhfk_scatter32_forward` launch -- on any other use: any other index, any attribute or method of
+    torch.Tensor, any torch.* function it is passed to (`__torch_function__`).  It is not a torch.Tensor instance;
+    `.tensor()` returns one."""
+
+    __slots__ = ("_w16", "_root", "_t32")
+
+    def __init__(self, world16, root):
+        self._w16, self._root, self._t32 = world16, root, None
+
+    # ---- the cheap answers ------------------------------------------------------------------------------
+    @property
+    def shape(self):
+        return torch.Size((self._w16.shape[0], 32, 3))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def dim(self):
+        return 3
+
+    @property
+    def device(self):
+        return self._w16.device
+
+    @property
+    def dtype(self):
+        return self._w16.dtype
+
+    @property
+    def is_cuda(self):
+        return self._w16.is_cuda
+
+    @property
+    def requires_grad(self):
+        return self._w16.requires_grad or self._root.requires_grad
+
+    def __len__(self):
+        return self._w16.shape[0]
+
+    @staticmethod
+    def _is_joint_table(idx):
+        if isinstance(idx, torch.Tensor):
+            return idx.dim() == 1 and idx.numel() == 16 and not idx.is_cuda and idx.tolist() == tables.H36M_32_To_16_Table
+        if isinstance(idx, np.ndarray):
+            return idx.shape == (16,) and idx.tolist() == tables.H36M_32_To_16_Table
+        return isinstance(idx, (list, tuple)) and list(idx) == tables.H36M_32_To_16_Table
+
+    def __getitem__(self, index):
+        if (isinstance(index, tuple) and len(index) == 2 and isinstance(index[0], slice) and index[0] == slice(None)
+                and self._is_joint_table(index[1])):
+            return self._w16                       # x[:, H36M_32_To_16_Table]: the kernel's own output, no scatter
+        return self.tensor()[index]
+
+    # ---- everything else: the real tensor ----------------------------------------------------------------
+    def tensor(self):
+        if self._t32 is None:
+            self._t32 = _scatter32(self._w16, self._root.reshape(self._w16.shape[0], 3))
+        return self._t32
+
+    def __getattr__(self, name):                   # only reached for names not defined above
+        return getattr(self.tensor(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        unwrap = lambda a: a.tensor() if isinstance(a, LazyWorld32) else a
+        args = tuple(unwrap(a) if not isinstance(a, (list, tuple)) else type(a)(unwrap(b) for b in a) for a in args)
+        kwargs = {k: unwrap(v) for k, v in (kwargs or {}).items()}
+        return func(*args, **kwargs)
+
+    def __array__(self, dtype=None):
+        a = self.tensor().detach().cpu().numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __repr__(self):
+        return "LazyWorld32(n=%d, materialised=%s)" % (self._w16.shape[0], self._t32 is not None)
+
+
+def _binop(name):
+    def op(self, other):
+        return getattr(self.tensor(), name)(other.tensor() if isinstance(other, LazyWorld32) else other)
+    op.__name__ = name
+    return op
+
+
+for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__", "__neg__",
+           "__matmul__", "__pow__", "__eq__", "__ne__", "__lt__", "__le__", "__gt__", "__ge__"):
+    if _n == "__neg__":
+        LazyWorld32.__neg__ = lambda self: -self.tensor()
+    else:
+        setattr(LazyWorld32, _n, _binop(_n))
+LazyWorld32.__hash__ = object.__hash__
 
 
 def scatter_16_to_32(world16: torch.Tensor, root: torch.Tensor) -> torch.Tensor:
@@ -177,8 +292,12 @@ class Forward_Kinematics_DH_Model:
         bone = torch.stack(cols, dim=1)
         root = to(root_3d_pos).reshape(-1, 3)
         self.global_rot_angle = generator_global_rot_3d_pos_angle
-        world16 = fk_world16(ang, grot, bone, root)
-        self.single_generator_3d_world_32keyPoint = scatter_16_to_32(world16, root)
+        wide = _wide_layout(ang, grot) if ang._base is not None else None
+        if wide is not None:      # the generator's own [N,37] tensor goes to the kernels as one slab per tile
+            world16 = fk_world16_wide(wide[0], wide[1], bone, root)
+        else:
+            world16 = fk_world16(ang, grot, bone, root)
+        self.single_generator_3d_world_32keyPoint = LazyWorld32(world16, root)
         return self.single_generator_3d_world_32keyPoint
 
     def _single_pose_numpy(self, ll, rl, body, lh, rh, grot, lens, root):

@@ -187,6 +187,97 @@ class _FKProject(torch.autograd.Function):
                 None, None, None, None)
 
 
+class _FKProjectWide(torch.autograd.Function):
+    """The same kernels fed with the generator's own [N,S] tensor (S = 37: angles in columns 0..32, global rotation in
+    columns goff..goff+2, Fk_generator.py:136-184) instead of column slices of it: a tile of that tensor is one
+    contiguous slab, and the backward returns the gradient of the WHOLE tensor from one slab store -- autograd sees a
+    single edge into `wide` instead of six slice views whose backward would each allocate and add a zero [N,S] tensor."""
+
+    @staticmethod
+    def forward(ctx, wide, goff, bone, root, cam, want_cam, want_uv, flags):
+        _require_cuda()
+        lib = _cabi.load()
+        device = wide.device
+        n, S = wide.shape
+        bone2 = _rows(bone, 15, device)
+        root2 = _rows(root, 3, device)
+        if not (bone2.shape[0] == n and root2.shape[0] == n):
+            raise ValueError("row counts differ: angles %d, bone %d, root %d" % (n, bone2.shape[0], root2.shape[0]))
+        cam_arr = cam_block_array(cam) if (want_cam or want_uv) else None
+        world = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
+        camo = torch.empty((n, 16, 3), dtype=torch.float32, device=device) if want_cam else None
+        uv = torch.empty((n, 16, 2), dtype=torch.float32, device=device) if want_uv else None
+        base = wide.data_ptr()
+        if n > 0:
+            with _on_device(device):
+                rc = lib.dhfk_forward(
+                    base, S, base + 4 * goff, S, bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
+                    cam_arr.ctypes.data if cam_arr is not None else None, None, 0,
+                    world.data_ptr(), camo.data_ptr() if want_cam else None, uv.data_ptr() if want_uv else None,
+                    n, flags, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_forward")
+        ctx.save_for_backward(wide, bone2, root2)
+        ctx.cfg = (goff, cam_arr, flags, want_cam, want_uv, bone.shape, root.shape, (bone.device, bone.dtype),
+                   (root.device, root.dtype))
+        return (world,) + ((camo,) if want_cam else ()) + ((uv,) if want_uv else ())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        lib = _cabi.load()
+        wide, bone2, root2 = ctx.saved_tensors
+        goff, cam_arr, flags, want_cam, want_uv, bone_shape, root_shape, bone_meta, root_meta = ctx.cfg
+        device = wide.device
+        n, S = wide.shape
+        it = iter(grads)
+        g_world = _packed(next(it), (n, 16, 3), device)
+        g_cam = _packed(next(it), (n, 16, 3), device) if want_cam else None
+        g_uv = _packed(next(it), (n, 16, 2), device) if want_uv else None
+        need_bone = ctx.needs_input_grad[2]
+        # full tiles leave as one slab per tile (every column written); a ragged last tile writes only the columns
+        # that carry a gradient
+        g_wide = (torch.empty if n % 32 == 0 and n > 0 else torch.zeros)((n, S), dtype=torch.float32, device=device)
+        g_root = torch.empty((n, 3), dtype=torch.float32, device=device)
+        g_bone = torch.empty((n, 15), dtype=torch.float32, device=device) if need_bone else None
+        if g_world is None and g_cam is None and g_uv is None:
+            g_wide.zero_(); g_root.zero_()
+            if g_bone is not None:
+                g_bone.zero_()
+        elif n > 0:
+            base, gbase = wide.data_ptr(), g_wide.data_ptr()
+            with _on_device(device):
+                rc = lib.dhfk_backward(
+                    base, S, base + 4 * goff, S, bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
+                    cam_arr.ctypes.data if cam_arr is not None else None, None, 0,
+                    g_world.data_ptr() if g_world is not None else None,
+                    g_cam.data_ptr() if g_cam is not None else None, g_uv.data_ptr() if g_uv is not None else None,
+                    gbase, S, gbase + 4 * goff, S, g_root.data_ptr(), 3,
+                    g_bone.data_ptr() if g_bone is not None else None, 15, n, flags, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_backward")
+
+        def back(g, shape, meta):
+            if g is None:
+                return None
+            g = g.reshape(shape)
+            return g if (g.device, g.dtype) == meta else g.to(device=meta[0], dtype=meta[1])
+
+        return (g_wide if ctx.needs_input_grad[0] else None, None, back(g_bone, bone_shape, bone_meta),
+                back(g_root if ctx.needs_input_grad[3] else None, root_shape, root_meta), None, None, None, None)
+
+
+def wide_rows_ok(wide, goff):
+    """True when `wide` [N,S] can be handed to the kernels as it is (see _FKProjectWide)."""
+    return (wide.is_cuda and wide.dtype == torch.float32 and wide.dim() == 2 and wide.is_contiguous()
+            and 36 <= wide.shape[1] <= 64 and 33 <= goff <= wide.shape[1] - 3 and wide.data_ptr() % 16 == 0)
+
+
+def fk_world16_wide(wide, goff, bone_len, root, *, fast_trig=False, accurate_grad=False):
+    """DH-FK from the generator's [N,S] slot tensor: angles = wide[:, 0:33], global rotation = wide[:, goff:goff+3].
+    Returns world16 [N,16,3]; the gradient flows to `wide` as one [N,S] tensor."""
+    flags = _trig_flags(fast_trig, accurate_grad)
+    return _FKProjectWide.apply(wide, int(goff), bone_len, root, None, False, False, flags)[0]
+
+
 def fk_project(angles, global_rot, bone_len, root, cam, *, return_cam=True, fast_trig=False, accurate_grad=False):
     """Fused DH-FK -> global rotation/translation -> world->camera -> pinhole projection.
 
@@ -512,13 +603,192 @@ def critic_input(pose16, *, centre=False, flip=False, kcs_cols=30, return_pos=Tr
     """Fused critic input transform.  pose16 [...,16,3] (or [...,48]) -> (pos' [N,16,3], kcs [N,kcs_cols]):
     pos' = root-centred (model_fk_gan_train.py:312) and/or left-right flipped (:320-327) pose, kcs = the 15 bone-pair
     cosines (+ 15 bone lengths when kcs_cols = 30) of Fk_discriminator.py:36-146 / :269-377 computed on pos'.
-    kcs_cols = 0 returns pos' only; return_pos=False returns kcs only."""
+    kcs_cols = 0 returns pos' only; return_pos=False returns kcs only.
+    Differentiable once w.r.t. the pose and twice w.r.t. the upstream gradients (what WGAN-GP's create_graph=True pass
+    needs).  The second derivative w.r.t. the POSE is treated as zero: a gradient penalty differentiated through this
+    transform with respect to something upstream of the pose (e.g. generator weights) would be incomplete -- the
+    reference never does that (calc_gradient_penalty works on `.data`, model_fk_gan_train.py:213-214)."""
     if kcs_cols not in (0, 15, 30):
         raise ValueError("kcs_cols must be 0, 15 or 30")
     if not return_pos and not kcs_cols:
         raise ValueError("nothing to compute")
     outs = _CriticInput.apply(pose16, _critic_flags(centre, flip), int(kcs_cols), bool(return_pos))
     return outs[0] if len(outs) == 1 else outs
+
+
+# ---- SURVEY 8 f2, video part: inputs of the motion critics ------------------------------------------------------
+def _video_outs(n, frames, device, want_dpos, want_pos):
+    b = n // frames
+    kcs = torch.empty((b, frames, 15), dtype=torch.float32, device=device)
+    dk = torch.empty((b, frames - 1, 15), dtype=torch.float32, device=device)
+    dp = torch.empty((b, frames - 1, 48), dtype=torch.float32, device=device) if want_dpos else None
+    ps = torch.empty((b, frames, 48), dtype=torch.float32, device=device) if want_pos else None
+    return kcs, dk, dp, ps
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() else None
+
+
+class _VideoCritic(torch.autograd.Function):
+    """pose [B*F,16,3] -> (kcs [B,F,15], dkcs [B,F-1,15][, dpos [B,F-1,48]][, pos [B,F,48]]) in one launch.
+    Differentiable twice w.r.t. the upstream gradients (WGAN-GP), once w.r.t. the pose (see _CriticInputVJP)."""
+
+    @staticmethod
+    def forward(ctx, pose, frames, flags, want_dpos, want_pos):
+        _require_cuda()
+        lib = _cabi.load()
+        device = pose.device if pose.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        x = _packed(pose, (-1, 16, 3), device)
+        n = x.shape[0]
+        if frames < 1 or n % frames:
+            raise ValueError("%d poses are not a whole number of %d-frame clips" % (n, frames))
+        kcs, dk, dp, ps = _video_outs(n, frames, device, want_dpos, want_pos)
+        if n > 0:
+            with _on_device(device):
+                rc = lib.dhfk_video_critic_forward(x.data_ptr(), frames, flags, _ptr(kcs), _ptr(dk), _ptr(dp), _ptr(ps), n,
+                                                   _stream_ptr(device))
+            _cabi.check(rc, "dhfk_video_critic_forward")
+        ctx.save_for_backward(x)
+        ctx.cfg = (frames, flags, want_dpos, want_pos, pose.shape, pose.device, pose.dtype)
+        return tuple(o for o in (kcs, dk, dp, ps) if o is not None)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (x,) = ctx.saved_tensors
+        frames, flags, want_dpos, want_pos, shape, dev, dtype = ctx.cfg
+        it = iter(grads)
+        g_kcs, g_dk = next(it), next(it)
+        g_dp = next(it) if want_dpos else None
+        g_ps = next(it) if want_pos else None
+        if g_kcs is None and g_dk is None and g_dp is None and g_ps is None:
+            return None, None, None, None, None
+        gx = _VideoCriticVJP.apply(x, g_kcs, g_dk, g_dp, g_ps, frames, flags).reshape(shape)
+        if (gx.device, gx.dtype) != (dev, dtype):
+            gx = gx.to(device=dev, dtype=dtype)
+        return gx, None, None, None, None
+
+
+class _VideoCriticVJP(torch.autograd.Function):
+    """g_pose = J(pose)^T (g_kcs, g_dkcs, g_dpos, g_pos): linear in the upstream gradients, so its derivative w.r.t.
+    them is the JVP kernel.  The second derivative w.r.t. the pose is not propagated (WGAN-GP's `interpolates` is a
+    throw-away leaf, Fk_discriminator.py:221-231): d/d(pose) of a gradient penalty is treated as ZERO.  It cannot be
+    refused instead: in the reference's own penalty the pose that reaches this Function is a clone of a view of the
+    `interpolates` leaf, so autograd does ask for that gradient there -- only to drop it."""
+
+    @staticmethod
+    def forward(ctx, x, g_kcs, g_dk, g_dp, g_ps, frames, flags):
+        lib = _cabi.load()
+        device, n = x.device, x.shape[0]
+        b = n // frames
+        gk = _packed(g_kcs, (b, frames, 15), device)
+        gdk = _packed(g_dk, (b, frames - 1, 15), device) if frames > 1 else None
+        gdp = _packed(g_dp, (b, frames - 1, 48), device) if frames > 1 else None
+        gps = _packed(g_ps, (b, frames, 48), device)
+        gx = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
+        if n > 0:
+            with _on_device(device):
+                rc = lib.dhfk_video_critic_backward(x.data_ptr(), frames, flags, _ptr(gk), _ptr(gdk), _ptr(gdp), _ptr(gps),
+                                                    gx.data_ptr(), n, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_video_critic_backward")
+        ctx.save_for_backward(x)
+        ctx.cfg = (frames, flags, g_kcs is not None, g_dk is not None, g_dp is not None, g_ps is not None)
+        return gx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, v):
+        lib = _cabi.load()
+        (x,) = ctx.saved_tensors
+        frames, flags, has_k, has_dk, has_dp, has_ps = ctx.cfg
+        device, n = x.device, x.shape[0]
+        v = _packed(v, (n, 16, 3), device)
+        t_k, t_dk, t_dp, t_ps = _video_outs(n, frames, device, has_dp, has_ps)
+        if n > 0:
+            with _on_device(device):
+                rc = lib.dhfk_video_critic_jvp(x.data_ptr(), v.data_ptr(), frames, flags, _ptr(t_k), _ptr(t_dk), _ptr(t_dp),
+                                               _ptr(t_ps), n, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_video_critic_jvp")
+        return (None, t_k if has_k else None, t_dk if has_dk else None, t_dp if has_dp else None,
+                t_ps if has_ps else None, None, None)
+
+
+def video_critic_input(pose16, frames, *, reverse=False, want_dpos=True, want_pos=False):
+    """Inputs of Video_motion_Fk_3D_Discriminator (Fk_discriminator.py:436-512) from [B*F,16,3] (or [B,F,48]) poses:
+    kcs [B,F,15], dkcs [B,F-1,15], then (want_dpos) dpos [B,F-1,48], then (want_pos) pos [B,F,48] -- the clip itself in
+    playback order, only worth asking for with reverse=True.  reverse=True yields what the reference computes from
+    torch.flip(x.view(B,F,-1), dims=[1]) (video_GAN_fun.py:222-223) without materialising the flipped clip."""
+    outs = _VideoCritic.apply(pose16, int(frames), _cabi.VIDEO_REVERSE if reverse else 0, bool(want_dpos), bool(want_pos))
+    return outs
+
+
+class _VideoRootDiff(torch.autograd.Function):
+    """uv [B*F,16,2] -> root-joint differences [B,F-1,2] (and the clip in playback order).  Linear: the backward is the
+    transpose kernel, and differentiating that (WGAN-GP) is this Function again on the tangent."""
+
+    @staticmethod
+    def forward(ctx, uv, frames, flags, want_pb):
+        _require_cuda()
+        lib = _cabi.load()
+        device = uv.device if uv.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        x = _packed(uv, (-1, 16, 2), device)
+        n = x.shape[0]
+        if frames < 1 or n % frames:
+            raise ValueError("%d poses are not a whole number of %d-frame clips" % (n, frames))
+        b = n // frames
+        diff = torch.empty((b, frames - 1, 2), dtype=torch.float32, device=device)
+        pb = torch.empty((b, frames, 32), dtype=torch.float32, device=device) if want_pb else None
+        if n > 0:
+            with _on_device(device):
+                rc = lib.dhfk_video_root_diff_forward(x.data_ptr(), frames, flags, _ptr(diff), _ptr(pb), n, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_video_root_diff_forward")
+        ctx.cfg = (frames, flags, want_pb, n, uv.shape, uv.device, uv.dtype)
+        return (diff, pb) if want_pb else (diff,)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        frames, flags, want_pb, n, shape, dev, dtype = ctx.cfg
+        g_diff = grads[0]
+        g_pb = grads[1] if want_pb else None
+        if g_diff is None and g_pb is None:
+            return None, None, None, None
+        gx = _VideoRootDiffT.apply(g_diff, g_pb, frames, flags, n).reshape(shape)
+        if (gx.device, gx.dtype) != (dev, dtype):
+            gx = gx.to(device=dev, dtype=dtype)
+        return gx, None, None, None
+
+
+class _VideoRootDiffT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g_diff, g_pb, frames, flags, n):
+        lib = _cabi.load()
+        ref = g_diff if g_diff is not None else g_pb
+        device = ref.device
+        b = n // frames
+        gd = _packed(g_diff, (b, frames - 1, 2), device) if frames > 1 else None
+        gp = _packed(g_pb, (b, frames, 32), device)
+        gx = torch.empty((n, 16, 2), dtype=torch.float32, device=device)
+        if gd is None and gp is None:
+            gx.zero_()
+        elif n > 0:
+            with _on_device(device):
+                rc = lib.dhfk_video_root_diff_backward(_ptr(gd), _ptr(gp), frames, flags, gx.data_ptr(), n, _stream_ptr(device))
+            _cabi.check(rc, "dhfk_video_root_diff_backward")
+        ctx.cfg = (frames, flags, g_diff is not None, g_pb is not None)
+        return gx
+
+    @staticmethod
+    def backward(ctx, v):
+        frames, flags, has_d, has_pb = ctx.cfg
+        outs = _VideoRootDiff.apply(v, frames, flags, has_pb)
+        return (outs[0] if has_d else None, outs[1] if has_pb else None, None, None, None)
+
+
+def video_root_diff(uv16, frames, *, reverse=False, want_playback=False):
+    """Root-joint 2-D differences of Video_motion_Fk_2D_Discriminator (Fk_discriminator.py:566-579): uv16 [B*F,16,2]
+    (or [B,F,32]) -> [B,F-1,2]; want_playback=True also returns the clip in playback order [B,F,32]."""
+    outs = _VideoRootDiff.apply(uv16, int(frames), _cabi.VIDEO_REVERSE if reverse else 0, bool(want_playback))
+    return outs if want_playback else outs[0]
 
 
 class _FlipPose(torch.autograd.Function):

@@ -26,6 +26,8 @@
  *       (function_aug/dataloader_update.py:18-41,69; models_Fk_GAN/video_mode_operate.py:879-928)
  *   dhfk_critic_input_* / dhfk_flip_pose   flip, root-centring and KCS features of the critics' inputs
  *       (models_Fk_GAN/Fk_discriminator.py:36-146,269-377; model_fk_gan_train.py:311-331,393-405)
+ *   dhfk_video_critic_* / dhfk_video_root_diff_*   per-frame KCS, adjacent-frame differences and playback reverse of
+ *       the motion critics' inputs (Fk_discriminator.py:436-512,554-587; video_GAN_fun.py:222-223,269-270)
  *   dhfk_bank_gather            mini-batch out of the device-resident fake-pair bank
  *       (model_fk_gan_train.py:486-510; common/data_loader.py:9-36)
  *   dhfk_scatter32_*            the [N,32,3] H36M slot layout change_3d_joint_angle returns (...:745-820), both ways
@@ -219,6 +221,43 @@ int dhfk_critic_input_jvp(const float* pose_dev, const float* v_pose_dev, float*
 /* The flip alone for [N,16,dims] keypoints, dims = 2 (the 2D critic's inputs, model_fk_gan_train.py:393-405) or 3.
  * out_dev may alias x_dev.  The flip is its own transpose: the backward is the same call on the upstream gradient. */
 int dhfk_flip_pose(const float* x_dev, float* out_dev, int64_t n, int32_t dims, void* stream);
+
+/*
+ * SURVEY 8 f2, video part -- the inputs of the motion critics, fused (one thread per frame, one pass over the poses):
+ *   Video_motion_Fk_3D_Discriminator.forward     models_Fk_GAN/Fk_discriminator.py:436-512
+ *       per-frame KCS-15 (video_mode_special_KCS_Input_transform, :269-377)                  kcs  [B,F,15]
+ *       adjacent-frame KCS differences (a Python loop of F-1 slice writes + clones, :450-461) dkcs [B,F-1,15]
+ *       adjacent-frame 3-D differences (the same loop on the poses, :478-492)                 dpos [B,F-1,48]
+ *   Video_motion_Fk_2D_Discriminator.forward     :554-587   root-joint 2-D differences      [B,F-1,2]
+ *   temporal playback reverse                    models_Fk_GAN/video_GAN_fun.py:222-223,269-270 (torch.flip(dims=[1]))
+ * pose_dev [n_rows,16,3] packed with n_rows = B * frames (clip-major, frame-minor, as the generator emits them).
+ * DHFK_VIDEO_REVERSE: every output is what the reference computes from torch.flip(x.view(B,F,-1), dims=[1]); the
+ * reversal is index math on the outputs (features of the reversed clip = reversed features, differences negated).
+ * forward : out_kcs_dev [B,F,15] and out_dkcs_dev [B,F-1,15] required; out_dpos_dev [B,F-1,48] and out_pos_dev
+ *           [B,F,48] (the clip in playback order: the 3-D position branch's input) optional.
+ * backward: g_pose_dev [n_rows,16,3] = d( <g_kcs,kcs> + <g_dkcs,dkcs> + <g_dpos,dpos> + <g_pos,pos> ) / d pose; any
+ *           upstream gradient may be NULL (= zero), at least one must be given.
+ * jvp     : the forward's outputs along the tangent v_pose_dev -- the derivative of `backward` w.r.t. its upstream
+ *           gradients (WGAN-GP's create_graph=True pass, Fk_discriminator.py:208-233).
+ * frames >= 1 (frames == 1: the difference tensors are empty and their pointers may be NULL).
+ */
+#define DHFK_VIDEO_REVERSE 0x1u
+int dhfk_video_critic_forward(const float* pose_dev, int32_t frames, uint32_t flags, float* out_kcs_dev,
+                              float* out_dkcs_dev, float* out_dpos_dev, float* out_pos_dev, int64_t n_rows, void* stream);
+int dhfk_video_critic_backward(const float* pose_dev, int32_t frames, uint32_t flags, const float* g_kcs_dev,
+                               const float* g_dkcs_dev, const float* g_dpos_dev, const float* g_pos_dev,
+                               float* g_pose_dev, int64_t n_rows, void* stream);
+int dhfk_video_critic_jvp(const float* pose_dev, const float* v_pose_dev, int32_t frames, uint32_t flags,
+                          float* t_kcs_dev, float* t_dkcs_dev, float* t_dpos_dev, float* t_pos_dev, int64_t n_rows,
+                          void* stream);
+/* 2-D motion critic: uv_dev [n_rows,16,2] -> out_diff_dev [B,F-1,2] = uv[b,f+1,0,:] - uv[b,f,0,:] and, optionally,
+ * out_uv_dev [B,F,32] = the clip in playback order (the 2-D position branch's input).  The map is linear: `backward`
+ * is its transpose (g_uv_dev [n_rows,16,2] from g_diff_dev / g_uv_playback_dev, either may be NULL, not both) and the
+ * forward applied to a tangent is its own JVP. */
+int dhfk_video_root_diff_forward(const float* uv_dev, int32_t frames, uint32_t flags, float* out_diff_dev,
+                                 float* out_uv_dev, int64_t n_rows, void* stream);
+int dhfk_video_root_diff_backward(const float* g_diff_dev, const float* g_uv_playback_dev, int32_t frames,
+                                  uint32_t flags, float* g_uv_dev, int64_t n_rows, void* stream);
 
 /*
  * SURVEY 8 f4 -- device-resident fake-pair bank.  The reference copies every iteration's pos_3d_cam / uv / cam to

@@ -245,3 +245,103 @@ def flip(x):
                                 _ptr(out, ctypes.c_double))
     assert rc == 0, rc
     return out
+
+
+# ---- SURVEY 8 f2, video part: inputs of the motion critics (numpy float64 on top of the complex-step KCS oracle) ----
+def _clips(x, frames, width):
+    x = np.asarray(x, dtype=np.float64).reshape(-1, frames, width)
+    return x
+
+
+def _adjacent_diff(x):
+    """The reference's loop, restated: out[:, f] = x[:, f+1] - x[:, f] for f in 0..F-2
+    (Fk_discriminator.py:457-459, :486-489, :573-576)."""
+    b, f, w = x.shape
+    out = np.zeros((b, f - 1, w), np.float64)
+    for first, second in zip(range(0, f - 1), range(1, f)):
+        out[:, first, :] = x[:, second, :] - x[:, first, :]
+    return out
+
+
+def _adjacent_diff_T(g, frames):
+    """Transpose of _adjacent_diff: [B,F-1,W] -> [B,F,W]."""
+    b, _, w = g.shape
+    out = np.zeros((b, frames, w), np.float64)
+    for first, second in zip(range(0, frames - 1), range(1, frames)):
+        out[:, second, :] += g[:, first, :]
+        out[:, first, :] -= g[:, first, :]
+    return out
+
+
+def video_critic_forward(pose16, frames, reverse=False):
+    """Video_motion_Fk_3D_Discriminator's branch inputs (Fk_discriminator.py:436-492): dict(kcs [B,F,15],
+    dkcs [B,F-1,15], pos [B,F,48], dpos [B,F-1,48]).  reverse: on torch.flip(x, dims=[1]) (video_GAN_fun.py:222-223)."""
+    x = np.asarray(pose16, dtype=np.float32).reshape(-1, frames, 48)
+    if reverse:
+        x = x[:, ::-1]
+    x = np.ascontiguousarray(x)
+    kcs = critic_forward(x.reshape(-1, 16, 3), 0, 15)["kcs"].reshape(-1, frames, 15)
+    xd = x.astype(np.float64)
+    return dict(kcs=kcs, dkcs=_adjacent_diff(kcs), pos=xd, dpos=_adjacent_diff(xd))
+
+
+def video_critic_jvp(pose16, v, frames, reverse=False):
+    x = np.asarray(pose16, dtype=np.float32).reshape(-1, frames, 48)
+    v = np.asarray(v, dtype=np.float32).reshape(-1, frames, 48)
+    if reverse:
+        x, v = x[:, ::-1], v[:, ::-1]
+    x, v = np.ascontiguousarray(x), np.ascontiguousarray(v)
+    tk = critic_jvp(x.reshape(-1, 16, 3), v.reshape(-1, 16, 3), 0, 15)["kcs"].reshape(-1, frames, 15)
+    vd = v.astype(np.float64)
+    return dict(kcs=tk, dkcs=_adjacent_diff(tk), pos=vd, dpos=_adjacent_diff(vd))
+
+
+def video_critic_backward(pose16, frames, g_kcs=None, g_dkcs=None, g_dpos=None, g_pos=None, reverse=False):
+    """d( <g_kcs,kcs> + <g_dkcs,dkcs> + <g_dpos,dpos> + <g_pos,pos> ) / d pose -> [B*F,16,3] float64 (storage order)."""
+    x = np.asarray(pose16, dtype=np.float32).reshape(-1, frames, 48)
+    b = x.shape[0]
+    if reverse:
+        x = x[:, ::-1]
+    x = np.ascontiguousarray(x)
+    gk = np.zeros((b, frames, 15), np.float64)
+    gp = np.zeros((b, frames, 48), np.float64)
+    if g_kcs is not None:
+        gk += _clips(g_kcs, frames, 15)
+    if g_dkcs is not None and frames > 1:
+        gk += _adjacent_diff_T(_clips(g_dkcs, frames - 1, 15), frames)
+    if g_pos is not None:
+        gp += _clips(g_pos, frames, 48)
+    if g_dpos is not None and frames > 1:
+        gp += _adjacent_diff_T(_clips(g_dpos, frames - 1, 48), frames)
+    # the complex-step oracle takes float32 upstream gradients; split the float64 sums into hi + lo parts (linear map)
+    def apply(gk_, gp_):
+        return critic_backward(x.reshape(-1, 16, 3), g_pos=gp_.reshape(-1, 16, 3), g_kcs=gk_.reshape(-1, 15), flags=0)
+    gk_hi, gp_hi = gk.astype(np.float32), gp.astype(np.float32)
+    g = apply(gk_hi, gp_hi) + apply((gk - gk_hi).astype(np.float32), (gp - gp_hi).astype(np.float32))
+    g = g.reshape(b, frames, 48)
+    if reverse:
+        g = g[:, ::-1]
+    return np.ascontiguousarray(g).reshape(-1, 16, 3)
+
+
+def video_root_diff(uv16, frames, reverse=False):
+    """Video_motion_Fk_2D_Discriminator's branch inputs (Fk_discriminator.py:556-579): dict(pos [B,F,32], rdiff [B,F-1,2])."""
+    x = np.asarray(uv16, dtype=np.float64).reshape(-1, frames, 16, 2)
+    if reverse:
+        x = x[:, ::-1]
+    root = np.ascontiguousarray(x[:, :, 0, :])
+    return dict(pos=np.ascontiguousarray(x).reshape(-1, frames, 32), rdiff=_adjacent_diff(root))
+
+
+def video_root_diff_backward(frames, g_rdiff=None, g_pos=None, reverse=False):
+    g = None
+    if g_pos is not None:
+        g = _clips(g_pos, frames, 32).copy()
+    if g_rdiff is not None and frames > 1:
+        gr = _adjacent_diff_T(_clips(g_rdiff, frames - 1, 2), frames)
+        if g is None:
+            g = np.zeros((gr.shape[0], frames, 32), np.float64)
+        g[:, :, 0:2] += gr
+    if reverse:
+        g = g[:, ::-1]
+    return np.ascontiguousarray(g).reshape(-1, 16, 2)

@@ -16,10 +16,20 @@ Fixtures
   generator.npz    Fk_Generator / Video_Fk_Generator epilogue (tanh, slot scatter, range map, scaler) + FK,
                    outputs and d/d(raw network output), for a known raw last-layer output
   retarget.npz     random_bl_aug / video_mode_random_bl_aug + per-row project_to_2d, seeded
-                   np.random so the drawn template rows are part of the fixture  critic.npz       critic input transforms: special_KCS_Input_transform (30 cols) and its video variant
+                   np.random so the drawn template rows are part of the fixture
+  critic.npz       critic input transforms: special_KCS_Input_transform (30 cols) and its video variant
                    (15 cols), the train loop's root-centring and left/right flip, autograd gradients, and the
                    reference Fk_3D_Discriminator's WGAN-GP gradient penalty + parameter gradients (double backward
                    through the KCS transform) for a seeded state dict
+  video_critic.npz the motion critics of the multi-frame mode (video part): the unmodified
+                   Video_motion_Fk_3D_Discriminator / Video_motion_Fk_2D_Discriminator (F = 9, seeded state dicts) on
+                   a clip batch and on its torch.flip(dims=[1]) playback reverse -- the feature tensors each branch
+                   receives (captured with forward pre-hooks), outputs, input gradients, WGAN-GP penalty and its
+                   parameter gradients
+  gan_loop.npz     the reference's own training loops, unpatched, on CPU (oracle/ref_loop.py): 6 iterations of
+                   GAN_solutions_FK_generator (batch 32) and of video_mode_GAN_solutions_FK_generator (8 clips x 9
+                   frames) on seeded synthetic loaders -- every scalar the loop reports (per critic step), the generator
+                   gradients at the generator step, the fake-pair buffer it leaves behind
 
     python oracle/make_golden.py retarget      # regenerate only the named fixtures
 """
@@ -378,6 +388,100 @@ def critic_fixture():
     return out
 
 
+def video_critic_fixture():
+    """Fk_discriminator.py:381-587 and video_GAN_fun.py:222-223,269-270 on B=12 clips of F=9 frames."""
+    import argparse
+    rh.import_reference()
+    for name in ("progress", "progress.bar"):
+        if name not in sys.modules:
+            rh._stub_module(name)
+    from models_Fk_GAN import Fk_discriminator as fd
+    cpu = torch.device("cpu")
+    F, B = 9, 12
+    g = np.load(os.path.join(OUT, "gan133.npz"))
+    world = g["world16"].astype(np.float32)[:B * F]
+    world = world - world[:, :1]                                     # root-centred, as the loop feeds them (:206)
+    # make the clips temporally coherent enough to be meaningful: frame f = blend towards the clip's first pose
+    clips = world.reshape(B, F, 16, 3).copy()
+    w = np.linspace(0.0, 0.6, F, dtype=np.float32).reshape(1, F, 1, 1)
+    clips = (1 - w) * clips + w * clips[:, :1]
+    uv = g["uv"].astype(np.float32)[:B * F].reshape(B, F, 16, 2)
+    uv = (1 - w) * uv + w * uv[:, :1]
+    out = dict(pose=clips.reshape(B * F, 16, 3), uv=uv.reshape(B * F, 16, 2), frames=np.array([F]))
+    args = argparse.Namespace(video_Dis_DenseDim_3D=8, video_Dis_DenseDim_2D=8,
+                              motion_Dis_whether_use_3dPos_branch=True, motion_Dis_whether_use_3dDiff_branch=True)
+
+    def run(tag, D, x_np, width, branch_inputs, real_np, fake_np):
+        feats = {}
+        hooks = [getattr(D, name).register_forward_pre_hook(
+            lambda m, inp, key=key: feats.__setitem__(key, inp[0].detach().numpy().copy()))
+            for key, name in branch_inputs.items()]
+        x = t(x_np, True)
+        d = D(x)
+        for h in hooks:
+            h.remove()
+        for key, v in feats.items():
+            if key != "pos":                                         # the position branches receive x itself
+                out["%s_feat_%s" % (tag, key)] = v
+            else:
+                assert np.array_equal(v.reshape(x_np.shape), x_np)
+        rng = np.random.RandomState(7)
+        gd = rng.randn(*d.shape).astype(np.float32)
+        (gx,) = torch.autograd.grad((d * t(gd)).sum(), x)
+        out[tag + "_out"] = d.detach().numpy()
+        out[tag + "_g_out"] = gd
+        out[tag + "_g_x"] = gx.numpy()
+        D.zero_grad()
+        torch.manual_seed(3)
+        gp = fd.calc_gradient_penalty(D, t(real_np).data, t(fake_np).data, real_np.shape[0], 10, cpu)
+        gp.backward()
+        out[tag + "_gp"] = np.array([gp.item()], np.float64)
+        for k, v in D.named_parameters():
+            out["%s_gpgrad_%s" % (tag, k)] = v.grad.numpy().copy() if v.grad is not None else \
+                np.zeros(tuple(v.shape), np.float32)
+
+    torch.manual_seed(21)
+    D3 = fd.Video_motion_Fk_3D_Discriminator(cpu, args, F)
+    for k, v in D3.state_dict().items():
+        out["d3_w_" + k] = v.numpy().copy()
+    x3 = clips.reshape(B, F, 48)
+    half = B // 2
+    b3 = dict(kcs="special_KCS_previous", dkcs="diff_special_KCS_previous", pos="pos_3d_previous",
+              dpos="diff_pos_3d_previous")
+    run("d3_fwd", D3, x3, 48, b3, x3[:half], x3[half:])
+    x3r = torch.clone(torch.flip(t(x3), dims=[1])).numpy()               # video_GAN_fun.py:222-223
+    run("d3_rev", D3, x3r, 48, b3, x3r[:half], x3r[half:])
+    torch.manual_seed(22)
+    D2 = fd.Video_motion_Fk_2D_Discriminator(cpu, args, F)
+    for k, v in D2.state_dict().items():
+        out["d2_w_" + k] = v.numpy().copy()
+    x2 = uv.reshape(B, F, 32)
+    b2 = dict(pos="pos_2d_previous", rdiff="root_diff_2d_previous")
+    run("d2_fwd", D2, x2, 32, b2, x2[:half], x2[half:])
+    x2r = torch.clone(torch.flip(t(x2), dims=[1])).numpy()               # video_GAN_fun.py:269-270
+    run("d2_rev", D2, x2r, 32, b2, x2r[:half], x2r[half:])
+    torch.manual_seed(3)
+    out["gp_alpha"] = torch.rand(half, 1).numpy()
+    return out
+
+
+def gan_loop_fixture():
+    """model_fk_gan_train.py:236-512 and video_GAN_fun.py:79-602, unmodified, with torch.device("cuda") -> CPU."""
+    import ref_loop
+    out = {}
+    for mode, batch in (("single", 32), ("video", 8)):
+        r = ref_loop.run_loop(mode, device="cpu", iters=6, batch=batch, dense=16, seed=11)
+        names, vals = ref_loop.scalars_matrix(r["scalars"])
+        out[mode + "_scalar_names"] = np.array(names)
+        out[mode + "_scalars"] = vals
+        out[mode + "_g_grads"] = np.stack(r["g_grads"]).astype(np.float32)
+        out[mode + "_buffer_3d"] = np.asarray(r["buffer_3d"], np.float32)
+        out[mode + "_buffer_2d"] = np.asarray(r["buffer_2d"], np.float32)
+        out[mode + "_model_G"] = r["params"]["model_G"].astype(np.float32)
+        out[mode + "_cfg"] = np.array([6, batch, 16, 11])
+    return out
+
+
 def fixtures_table():
     from dhfk import synthetic
     return {
@@ -395,6 +499,8 @@ def fixtures_table():
         "generator": generator_fixture,
         "retarget": retarget_fixture,
         "critic": critic_fixture,
+        "video_critic": video_critic_fixture,
+        "gan_loop": gan_loop_fixture,
     }
 
 

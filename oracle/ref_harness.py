@@ -28,10 +28,27 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("DHFK_REFERENCE_ROOT", "/root/reference/DH-AUG_master")
+# the same tree staged as one archive by oracle/stage_ref.py (git-ignored, travels to the GPU box via gpurun)
+REF_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "dh_aug_ref.zip")
 
 
 def reference_available() -> bool:
+    """The mounted reference tree (build container)."""
     return os.path.isdir(os.path.join(REF_ROOT, "models_Fk_GAN"))
+
+
+def staged_reference_available() -> bool:
+    return os.path.isfile(REF_ZIP)
+
+
+def reference_source(prefer_staged: bool = False):
+    """sys.path entry the reference is imported from: the mounted tree when present (unless prefer_staged), else the
+    staged archive (zipimport), else None."""
+    if staged_reference_available() and (prefer_staged or not reference_available()):
+        return REF_ZIP
+    if reference_available():
+        return REF_ROOT
+    return None
 
 
 class _Anything:
@@ -50,7 +67,11 @@ class _Anything:
 def _stub_module(name: str, **attrs) -> types.ModuleType:
     mod = types.ModuleType(name)
     mod.__dict__.update(attrs)
-    mod.__getattr__ = lambda attr: _Anything()  # type: ignore[attr-defined]
+    def _attr(attr):
+        if attr.startswith("__"):          # inspect.getmodule() walks sys.modules and reads __file__ etc.
+            raise AttributeError(attr)
+        return _Anything()
+    mod.__getattr__ = _attr  # type: ignore[attr-defined]
     sys.modules[name] = mod
     return mod
 
@@ -58,13 +79,17 @@ def _stub_module(name: str, **attrs) -> types.ModuleType:
 _IMPORTED = None
 
 
-def import_reference():
-    """Return a namespace with the reference's hot-path symbols (CPU branch forced)."""
+def import_reference(force_cpu: bool = True, prefer_staged: bool = False):
+    """Return a namespace with the reference's hot-path symbols.  force_cpu=True (default) makes the reference take
+    its pure-CPU branch even on a GPU host; force_cpu=False leaves torch.cuda alone (the GPU tests that run the
+    reference's own training loops with the drop-in installed)."""
     global _IMPORTED
     if _IMPORTED is not None:
         return _IMPORTED
-    if not reference_available():
-        raise RuntimeError("reference tree not found at %s" % REF_ROOT)
+    src = reference_source(prefer_staged)
+    if src is None:
+        raise RuntimeError("reference not found: neither %s nor the staged archive %s (python oracle/stage_ref.py)"
+                           % (REF_ROOT, REF_ZIP))
 
     import numpy as np
     import torch
@@ -93,10 +118,11 @@ def import_reference():
 
     # Force the pure-CPU branch of the reference even on a GPU host
     # (the CUDA branch mixes devices inside autograd).
-    torch.cuda.is_available = lambda: False  # type: ignore[assignment]
+    if force_cpu:
+        torch.cuda.is_available = lambda: False  # type: ignore[assignment]
 
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    if src not in sys.path:
+        sys.path.insert(0, src)
 
     from models_Fk_GAN import forward_kinematics_DH_model as fkmod  # noqa: E402
     from common import camera as cammod  # noqa: E402
@@ -104,7 +130,7 @@ def import_reference():
     from common import quaternion as quatmod  # noqa: E402
     from models_Fk_GAN import Fk_generator as genmod  # noqa: E402
 
-    ns = types.SimpleNamespace(fk=fkmod, camera=cammod, h36m=h36m, quaternion=quatmod, generator=genmod)
+    ns = types.SimpleNamespace(fk=fkmod, camera=cammod, h36m=h36m, quaternion=quatmod, generator=genmod, source=src)
     _IMPORTED = ns
     return ns
 

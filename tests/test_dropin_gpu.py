@@ -66,6 +66,34 @@ def test_change_3d_joint_angle_like_the_generator_calls_it(golden, case, root_sh
     assert not torch.allclose(w32b, w32.detach())
 
 
+@pytest.mark.parametrize("n", [128, 96, 133, 31])
+def test_wide_slot_tensor_path_full_and_ragged_tiles(golden, n):
+    """The generator's [N,37] slot tensor goes to the kernels as one slab per tile and its gradient comes back as one
+    [N,37] tensor (full tiles: slab store incl. the zero column 33; ragged tile: per-column stores into zeros).  The
+    [N,32,3] result stays lazy: the generator's `[:, H36M_32_To_16_Table]` is the kernel's own output."""
+    from dhfk import forward_kinematics_DH_model as fkm
+    g = golden("gan133")
+    gen = torch.full((n, 37), 7.0, device="cuda")          # column 33 holds junk the kernels must ignore
+    gen[:, :33] = T(g["ang"][:n]); gen[:, 34:] = T(g["grot"][:n])
+    gen.requires_grad_(True)
+    slots = gen * 1.0                                      # a non-leaf, like the generator's range-mapped tensor
+    root = T(g["root"][:n], True)
+    kw = _kwargs(slots, T(g["bone"][:n]), root)
+    kw["generator_global_rot_3d_pos_angle"] = slots[:, 34:37]
+    w32 = _model(batch=n).change_3d_joint_angle(**kw)
+    assert isinstance(w32, fkm.LazyWorld32) and w32._t32 is None
+    fake = w32[:, [0, 1, 2, 3, 6, 7, 8, 12, 13, 15, 17, 18, 19, 25, 26, 27]]
+    assert w32._t32 is None and fake.shape == (n, 16, 3)
+    assert_parity(fake.detach().cpu().numpy(), g["world16"][:n], "world16")
+    (fake * T(g["g_world"][:n])).sum().backward()
+    gg = gen.grad.cpu().numpy()
+    assert_parity(gg[:, :33], g["g_ang_w"][:n], "g_ang")
+    assert_parity(gg[:, 34:], g["g_grot_w"][:n], "g_grot")
+    assert np.all(gg[:, 33] == 0.0)
+    assert_parity(root.grad.cpu().numpy(), g["g_root_w"][:n], "g_root")
+    assert_parity(w32.tensor().detach().cpu().numpy(), g["world32"][:n], "world32 (materialised on demand)")
+
+
 def test_init_fk_dh_angle_numpy_branch(golden):
     g = golden("kat")
     m = _model()

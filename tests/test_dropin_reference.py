@@ -26,10 +26,14 @@ def reference_modules():
             rh._stub_module(name)
     mods = {m: importlib.import_module(m) for m in REF_MODULES}
     saved = {m: dict(vars(mod)) for m, mod in mods.items()}
+    dis = mods["models_Fk_GAN.Fk_discriminator"]
+    forwards = {c: getattr(dis, c).forward for c in ("Video_motion_Fk_3D_Discriminator", "Video_motion_Fk_2D_Discriminator")}
     yield mods
     for m, mod in mods.items():          # undo the patching: other tests use the unmodified reference
         for k, v in saved[m].items():
             setattr(mod, k, v)
+    for c, f in forwards.items():        # install(critics=True) swaps these two methods on the reference's own classes
+        getattr(dis, c).forward = f
 
 
 def test_install_rebinds_the_real_reference_symbols(reference_modules):
@@ -57,7 +61,25 @@ def test_install_rebinds_the_real_reference_symbols(reference_modules):
     d = m["models_Fk_GAN.Fk_discriminator"]
     assert d.special_KCS_Input_transform is Fk_discriminator.special_KCS_Input_transform is not before
     assert d.video_mode_special_KCS_Input_transform is Fk_discriminator.video_mode_special_KCS_Input_transform
-    assert len(patched) >= 20
+    # the two motion critics keep their class (constructor, sub-modules, state dict) and get the fused forward
+    assert d.Video_motion_Fk_3D_Discriminator.forward is Fk_discriminator.video_motion_3d_forward
+    assert d.Video_motion_Fk_2D_Discriminator.forward is Fk_discriminator.video_motion_2d_forward
+    ref3 = d.Video_motion_Fk_3D_Discriminator("cpu", argparse.Namespace(
+        video_Dis_DenseDim_3D=8, motion_Dis_whether_use_3dPos_branch=True, motion_Dis_whether_use_3dDiff_branch=True), 9)
+    ours3 = Fk_discriminator.Video_motion_Fk_3D_Discriminator("cpu", ref3.args, 9)
+    assert {k: tuple(v.shape) for k, v in ref3.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in ours3.state_dict().items()}
+    ref2 = d.Video_motion_Fk_2D_Discriminator("cpu", argparse.Namespace(video_Dis_DenseDim_2D=8), 9)
+    ours2 = Fk_discriminator.Video_motion_Fk_2D_Discriminator("cpu", ref2.args, 9)
+    assert {k: tuple(v.shape) for k, v in ref2.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in ours2.state_dict().items()}
+    refd = d.Fk_3D_Discriminator("cpu", argparse.Namespace(Dis_DenseDim_3D=8))
+    assert {k: tuple(v.shape) for k, v in refd.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in Fk_discriminator.Fk_3D_Discriminator("cpu", refd.args).state_dict().items()}
+    ref2d = d.Fk_2D_Discriminator(argparse.Namespace(Dis_DenseDim_2D=8))
+    assert {k: tuple(v.shape) for k, v in ref2d.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in Fk_discriminator.Fk_2D_Discriminator(ref2d.args).state_dict().items()}
+    assert len(patched) >= 22
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -10,7 +10,8 @@ import ref_harness as rh
 
 pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not mounted")
 
-NAMES = ["tables", "kat", "gan133", "stress200", "video36", "camera_ops", "sampler40", "generator", "retarget", "critic"]
+NAMES = ["tables", "kat", "gan133", "stress200", "video36", "camera_ops", "sampler40", "generator", "retarget", "critic",
+         "video_critic", "gan_loop"]
 
 
 @pytest.mark.parametrize("name", NAMES)

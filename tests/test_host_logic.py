@@ -201,3 +201,39 @@ def test_shared_angle_view_detection():
     assert view(g2[:4, 0:5], sl(5, 10), sl(10, 23), sl(23, 28), sl(28, 33)) is None       # different bases
     assert view(*(torch.randn(7, w) for w in (5, 5, 13, 5, 5))) is None                   # independent tensors
     assert view(sl(0, 5), sl(5, 10), sl(10, 23), sl(23, 28), g[:, 28:33][::2]) is None    # a row-strided slice
+
+
+def test_lazy_world32_answers_the_joint_gather_without_materialising(monkeypatch):
+    """change_3d_joint_angle's [N,32,3] result (lazy 32-slot scatter): `x[:, H36M_32_To_16_Table]`
+    (Fk_generator.py:259) must hand back the kernel's [N,16,3] output itself; anything else gets the real tensor."""
+    from dhfk import forward_kinematics_DH_model as fkm
+    calls = []
+
+    def fake_scatter(w16, root):                      # the layout dhfk_scatter32_forward produces, in plain torch
+        calls.append(1)
+        out = root.reshape(-1, 1, 3).expand(-1, 32, 3).clone()
+        out[:, tables.H36M_32_To_16_Table] = w16
+        out[:, 14] = w16[:, 9]
+        return out
+
+    monkeypatch.setattr(fkm, "_scatter32", fake_scatter)
+    w16 = torch.randn(5, 16, 3, requires_grad=True)
+    root = torch.randn(5, 3)
+    x = fkm.LazyWorld32(w16 * 1.0, root)
+    assert x.shape == (5, 32, 3) and x.size(1) == 32 and x.dim() == 3 and len(x) == 5 and x.requires_grad
+    got = x[:, tables.H36M_32_To_16_Table]
+    assert got is x._w16 and not calls                # the generator's index: no scatter, autograd history intact
+    assert x[:, np.array(tables.H36M_32_To_16_Table)] is x._w16 and x[:, torch.tensor(tables.H36M_32_To_16_Table)] is x._w16
+    got.view(-1, 48).sum().backward()
+    assert torch.equal(w16.grad, torch.ones_like(w16))
+    # every other use sees the real [N,32,3] tensor, built once
+    assert torch.equal(x[:, 14], x._w16[:, 9]) and len(calls) == 1
+    assert torch.equal(x[:, [0, 1, 2]], x.tensor()[:, [0, 1, 2]])
+    assert torch.equal(x[2], x.tensor()[2])
+    assert torch.equal(torch.sum(x, dim=1), x.tensor().sum(dim=1))            # __torch_function__
+    assert torch.equal(torch.cat([x, x], dim=0), torch.cat([x.tensor(), x.tensor()], dim=0))
+    assert torch.equal(x.detach().view(5, 96), x.tensor().detach().view(5, 96))   # attribute / method fall-through
+    assert torch.equal(x * 2.0 - x, x.tensor()) and torch.equal(-x, -x.tensor())
+    assert np.array_equal(np.asarray(x), x.tensor().detach().numpy())
+    assert len(calls) == 1
+    assert torch.equal(x[:, 4], root) and torch.equal(x[:, 31], root)          # free slots hold the root
