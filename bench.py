@@ -6,9 +6,15 @@
 
 A *step* is one pass of the hot path over one batch of synthetic poses: dhfk_forward
 (world16 + uv16) followed by dhfk_backward (d angles, d global rotation, d root from upstream
-gradients on world16 and uv16).  Workload = BASELINE.json configs[1]: 1,048,576 poses per GPU,
-S1/cam0, generator-range angles, template bone lengths x (1 +- 0.2), in-volume roots.
-Rows shard across ranks with no data-path collective (weak scaling: per-GPU batch fixed).
+gradients on world16 and uv16).
+
+  --gpus 1   BASELINE.json configs[1]: 1,048,576 poses on one B200, S1/cam0, generator-range angles, template bone
+             lengths x (1 +- 0.2), in-volume roots.
+  --gpus N   BASELINE.json configs[4]: 16,777,216 poses per step sharded over the N ranks (strong scaling), and the
+             GAN's gradient all-reduce -- generator + 3-D critic + 2-D critic (dense 256: 0.44 M + 0.88 M + 0.27 M
+             parameters), ONE NCCL all-reduce on a persistent flat buffer (dhfk.parallel.FlatGradBuffer) -- INSIDE the
+             timed step, issued on a side stream so that it overlaps the rank's FK kernels.  The same step at 1 M poses
+             per rank (weak scaling) is reported next to it.  (--mode configs1 forces the N = 1 workload per rank.)
 
 Rank 0 prints ONE JSON line (keys: see the task contract).  `value` is device-resident
 throughput; `e2e` goes through the host-buffer C-ABI entry (pinned host memory in and out, copies
@@ -95,17 +101,33 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-chunk", type=int, default=1024, help="reference arm: poses per torch call")
     ap.add_argument("--ref-chunks", type=int, default=4, help="reference arm: chunks per step")
+    ap.add_argument("--mode", default="auto", choices=["auto", "configs1", "configs4"],
+                    help="auto: configs[1] at --gpus 1, configs[4] (16M poses sharded + in-step gradient all-reduce) otherwise")
+    ap.add_argument("--total-poses", type=int, default=1 << 24, help="configs[4]: poses per step over all ranks")
+    ap.add_argument("--no-extras", action="store_true", help="skip side-kernel / drop-in path / GAN-step extras")
     return ap.parse_args()
 
 
+def resolve_mode(args):
+    if args.mode == "auto":
+        return "configs1" if args.gpus <= 1 else "configs4"
+    return args.mode
+
+
 def workload_config(args, extra=None):
+    strong = resolve_mode(args) == "configs4"
     cfg = {
-        "workload": "BASELINE configs[1]: fused DH-FK + projection forward+backward, 1M poses per B200, "
-                    "16-joint H36M skeleton, synthetic generator-range angles + template bone lengths, S1/cam0",
-        "poses_per_gpu": args.poses,
+        "workload": ("BASELINE configs[4]: data-parallel GAN augmentation sweep, %d poses per step sharded over %d B200 "
+                     "(fused DH-FK + projection forward+backward per shard) with the NCCL gradient all-reduce of generator + "
+                     "3-D critic + 2-D critic (dense 256) inside the step" % (args.total_poses, args.gpus)) if strong else
+                    ("BASELINE configs[1]: fused DH-FK + projection forward+backward, 1M poses per B200, "
+                     "16-joint H36M skeleton, synthetic generator-range angles + template bone lengths, S1/cam0"),
+        "poses_per_gpu": (args.total_poses // max(args.gpus, 1)) if strong else args.poses,
         "outputs": "world16[N,16,3]+uv16[N,16,2]; grads d_ang[N,33]+d_grot[N,3]+d_root[N,3]",
         "bytes_per_pose": {"forward": FWD_BYTES, "backward": BWD_BYTES},
-        "parallelism": "dp%d (rows sharded, no data-path collective)" % args.gpus,
+        "parallelism": ("dp%d (rows sharded with dhfk.parallel.shard_rows; one NCCL all-reduce of the flat gradient buffer "
+                        "per step, overlapped with the FK kernels on a side stream)" % args.gpus) if strong else
+                       ("dp%d (rows sharded, no data-path collective)" % args.gpus),
         "trig": ("fwd+bwd MUFU.SIN/COS (DHFK_FLAG_FAST_TRIG)" if args.fast_trig else
                  "fwd polynomial + bwd table sincos, <=1e-7 (DHFK_FLAG_ACCURATE_TRIG)" if getattr(args, "accurate_trig", False) else
                  "library default: fwd polynomial (abs err 7.7e-8), bwd MUFU.SIN/COS after exact degree reduction "
@@ -272,21 +294,74 @@ def time_c_oracle(n=131072):
     return n / dt, c_oracle.num_threads()
 
 
+def time_reference_pipeline(chunk, chunks, steps, warmup, threads=None):
+    """The reference's OWN code -- Forward_Kinematics_DH_Model.change_3d_joint_angle -> [:, H36M_32_To_16_Table] ->
+    GAN_torch_world_to_camera -> project_to_2d and autograd through them -- imported unmodified from the archive
+    oracle/stage_ref.py staged (oracle/_ref/dh_aug_ref.zip), on the host cores.  The model object is built once, as
+    run_Fk_GAN.py does.  Returns (poses_per_s, seconds_per_step, threads) or None when the archive is absent."""
+    import torch
+    import ref_harness as rh
+    if rh.reference_source(prefer_staged=True) is None:
+        return None
+    from dhfk import synthetic, tables
+    torch.set_num_threads(threads or host_threads())
+    threads = torch.get_num_threads()
+    ref = rh.import_reference(force_cpu=True, prefer_staged=True)
+    blk = tables.camera_block("S1", 0)
+    inp = synthetic.gan_like(chunk, seed=1234)
+    up = synthetic.upstream_grads(chunk, seed=4321)
+    ang, grot, bone, root = (torch.tensor(inp[k]) for k in ("ang", "grot", "bone", "root"))
+    gw, gu = torch.tensor(up["g_world"]), torch.tensor(up["g_uv"])
+    model = ref.fk.Forward_Kinematics_DH_Model(rh.make_args(chunk), ["S1"], None)
+    q, t = torch.tensor(blk[0:4]).view(1, 4), torch.tensor(blk[4:7]).view(1, 3)
+    rows = torch.tensor(blk[7:16]).view(1, 9).repeat(chunk, 1)
+    idx = ref.h36m.H36M_32_To_16_Table
+
+    def one_step():
+        for _ in range(chunks):
+            a = ang.clone().requires_grad_(True); g = grot.clone().requires_grad_(True)
+            r = root.clone().requires_grad_(True)
+            kw = dict(right_leg_joints_angle=a[:, 0:5], left_leg_joints_angle=a[:, 5:10], body_joints_angle=a[:, 10:23],
+                      right_hand_joints_angle=a[:, 23:28], left_hand_joints_angle=a[:, 28:33],
+                      generator_global_rot_3d_pos_angle=g, root_3d_pos=r)
+            for i, name in enumerate(rh.BONE_KWARGS):
+                kw[name] = bone[:, i]
+            w16 = model.change_3d_joint_angle(**kw)[:, idx]
+            uv = ref.camera.project_to_2d(ref.camera.GAN_torch_world_to_camera(w16, R=q, t=t), rows)
+            ((w16 * gw).sum() + (uv * gu).sum()).backward()
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return chunk * chunks / dt, dt, threads
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warmup = max(args.steps, 1), max(args.warmup, 0)
     # bound the run: a step is ref_chunks x ref_chunk poses (~0.1 s per 1024-pose call on 8 cores)
-    pps, dt, threads = time_torch_port(args.ref_chunk, args.ref_chunks, steps, warmup)
+    kind, what = "reference", ("the UNMODIFIED reference (oracle/_ref/dh_aug_ref.zip: Forward_Kinematics_DH_Model."
+                               "change_3d_joint_angle -> 32->16 gather -> GAN_torch_world_to_camera -> project_to_2d, "
+                               "torch autograd), host cores only")
+    res = time_reference_pipeline(args.ref_chunk, args.ref_chunks, steps, warmup)
+    if res is None:
+        kind, what = "port", ("oracle/torch_port.py: the reference's own torch op sequence (bit-identical to /root/reference "
+                              "on the build host; the staged archive is absent), host cores only")
+        res = time_torch_port(args.ref_chunk, args.ref_chunks, steps, warmup)
+    pps, dt, threads = res
     sample = "%d x %d-pose torch calls per step (reference batch size), fwd+bwd, CPU" % (args.ref_chunks, args.ref_chunk)
     line = {
         "impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong" if resolve_mode(args) == "configs4" else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, {"reference_arm": "oracle/torch_port.py: the reference's own torch op sequence "
-                                                           "(bit-identical to /root/reference on the build host), host cores only"}),
-        "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args, {"reference_arm": what}),
+        "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -294,12 +369,159 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+class HotPath:
+    """Device buffers + the two C-ABI calls of one step over `n` poses (rotating over `nbuf` input sets)."""
+
+    def __init__(self, lib, n, dev, nbuf, seed, flags, cam_ptr, stream_ptr):
+        import torch
+        from dhfk import synthetic
+        self.lib, self.n, self.flags, self.cam_ptr, self.sp, self.nbuf = lib, n, flags, cam_ptr, stream_ptr, nbuf
+        self.sets = []
+        for b in range(nbuf):
+            d = synthetic.gan_like_torch(n, dev, seed=seed + b)
+            g = torch.Generator(device=dev).manual_seed(seed + 3087 + b)
+            d["g_world"] = torch.randn((n, 16, 3), generator=g, device=dev)
+            d["g_uv"] = torch.randn((n, 16, 2), generator=g, device=dev)
+            self.sets.append(d)
+        self.world = torch.empty((n, 16, 3), device=dev); self.uv = torch.empty((n, 16, 2), device=dev)
+        self.g_ang = torch.empty((n, 33), device=dev); self.g_grot = torch.empty((n, 3), device=dev)
+        self.g_root = torch.empty((n, 3), device=dev)
+
+    def fwd(self, i, flags=None):
+        from dhfk import _cabi
+        d = self.sets[i % self.nbuf]
+        rc = self.lib.dhfk_forward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
+                                   d["root"].data_ptr(), 3, self.cam_ptr, None, 0, self.world.data_ptr(), None,
+                                   self.uv.data_ptr(), self.n, self.flags if flags is None else flags, self.sp)
+        _cabi.check(rc, "dhfk_forward")
+
+    def bwd(self, i, flags=None):
+        from dhfk import _cabi
+        d = self.sets[i % self.nbuf]
+        rc = self.lib.dhfk_backward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
+                                    d["root"].data_ptr(), 3, self.cam_ptr, None, 0, d["g_world"].data_ptr(), None,
+                                    d["g_uv"].data_ptr(), self.g_ang.data_ptr(), 33, self.g_grot.data_ptr(), 3,
+                                    self.g_root.data_ptr(), 3, None, 15, self.n, self.flags if flags is None else flags, self.sp)
+        _cabi.check(rc, "dhfk_backward")
+
+    def step(self, i, flags=None):
+        self.fwd(i, flags); self.bwd(i, flags)
+
+
+def gan_models(dev):
+    """Generator + 3-D critic + 2-D critic at the sizes of SURVEY 5 (dense 256): what a data-parallel GAN step all-reduces."""
+    import argparse
+    import torch
+    from dhfk import Fk_discriminator, Fk_generator
+    a = argparse.Namespace(batch_size=1024, GAN_OUTPUT_DIM=35, Gen_DenseDim=256, Dis_DenseDim_3D=256, Dis_DenseDim_2D=256,
+                           GAN_whether_use_preAngle=True, whether_use_RT=True, bone_len_scaler="different")
+    torch.manual_seed(0)
+    G = Fk_generator.Fk_Generator(None, a, dev).to(dev)
+    D3 = Fk_discriminator.Fk_3D_Discriminator(dev, a).to(dev)
+    D2 = Fk_discriminator.Fk_2D_Discriminator(a).to(dev)
+    return G, D3, D2
+
+
+def timed_steps(path, steps, stream, dev, barrier, allreduce=None, probe_every=0):
+    """K steps bracketed by CUDA events on the launching stream.  allreduce: (FlatGradBuffer, side stream) -> one
+    collective per step on the side stream, started when the step starts and joined before the step ends."""
+    import torch
+    probes = {}
+    if probe_every:
+        probes = {i: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for i in range(0, steps, probe_every)}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    go = torch.cuda.Event()
+    barrier()
+    ev0.record(stream)
+    for i in range(steps):
+        if allreduce is not None:
+            buf, side = allreduce
+            go.record(stream)
+            side.wait_event(go)
+            with torch.cuda.stream(side):
+                buf.allreduce()
+        pr = probes.get(i)
+        if pr is None:
+            path.step(i)
+        else:
+            pr[0].record(stream); path.fwd(i)
+            pr[1].record(stream); path.bwd(i)
+            pr[2].record(stream)
+        if allreduce is not None:
+            stream.wait_stream(allreduce[1])
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    total_ms = ev0.elapsed_time(ev1)
+    fwd_ms = bwd_ms = None
+    if probes:
+        fwd_ms = sum(e[0].elapsed_time(e[1]) for e in probes.values()) / len(probes)
+        bwd_ms = sum(e[1].elapsed_time(e[2]) for e in probes.values()) / len(probes)
+    return total_ms, fwd_ms, bwd_ms
+
+
+def max_over_ranks(vals, dev, distributed):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([v if v is not None else -1.0 for v in vals], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) if x >= 0 else None for x in t.tolist()]
+
+
+def copy_ceiling(n, dev, chunk, reps=5):
+    """A bare pinned-memory H2D + D2H of the bytes the e2e step moves (536 B/row up, 476 B/row down), in the same chunk
+    sizes, on two streams with no kernel and no dependency between them: the PCIe / host-memory floor of `e2e`."""
+    import torch
+    up_b, down_b = 536, 476
+    h_up = torch.empty(n * up_b // 4, dtype=torch.float32).pin_memory()
+    h_dn = torch.empty(n * down_b // 4, dtype=torch.float32).pin_memory()
+    d_up = torch.empty(chunk * up_b // 4, dtype=torch.float32, device=dev)
+    d_dn = torch.empty(chunk * down_b // 4, dtype=torch.float32, device=dev)
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def once():
+        for r0 in range(0, n, chunk):
+            rows = min(chunk, n - r0)
+            with torch.cuda.stream(s_up):
+                d_up[:rows * up_b // 4].copy_(h_up[r0 * up_b // 4:(r0 + rows) * up_b // 4], non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_dn[r0 * down_b // 4:(r0 + rows) * down_b // 4].copy_(d_dn[:rows * down_b // 4], non_blocking=True)
+        s_up.synchronize(); s_dn.synchronize()
+
+    once()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    return (time.perf_counter() - t0) / reps
+
+
+def reference_loop_timings(timeout=420):
+    """BASELINE configs[2] / configs[3] through the reference's OWN loops (oracle/ref_loop.py, test infrastructure, run in
+    child processes): unpatched on this GPU where its CUDA branch runs at all, then with dhfk.dropin.install(all)."""
+    import subprocess
+    out = {}
+    script = os.path.join(ROOT, "oracle", "ref_loop.py")
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    for key, inst in (("reference_unpatched_same_gpu", "none"), ("reference_loop_with_dropin", "all")):
+        try:
+            r = subprocess.run([sys.executable, script, "--device", "cuda", "--install", inst, "--iters", "10"],
+                               capture_output=True, text=True, timeout=timeout, env=env)
+            lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+            out[key] = json.loads(lines[-1]) if lines else {"error": "rc=%d %s" % (r.returncode, r.stderr[-300:])}
+        except Exception as e:
+            out[key] = {"error": repr(e)[:300]}
+    return out
+
+
 def run_native(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     import dhfk
-    from dhfk import _cabi, synthetic, tables
+    from dhfk import _cabi, parallel, synthetic, tables
 
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -313,43 +535,26 @@ def run_native(args):
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    strong = resolve_mode(args) == "configs4"
 
     lib = _cabi.load()
-    n = args.poses
     flags = (_cabi.FLAG_FAST_TRIG if args.fast_trig else 0) | (_cabi.FLAG_ACCURATE_TRIG if args.accurate_trig else 0)
     blk = tables.camera_block("S1", 0)
     cam_ptr = blk.ctypes.data
-    nbuf = max(1, args.buffers)
-    sets = []
-    for b in range(nbuf):
-        d = synthetic.gan_like_torch(n, dev, seed=1234 + 97 * rank + b)
-        g = torch.Generator(device=dev).manual_seed(4321 + 97 * rank + b)
-        d["g_world"] = torch.randn((n, 16, 3), generator=g, device=dev)
-        d["g_uv"] = torch.randn((n, 16, 2), generator=g, device=dev)
-        sets.append(d)
-    world = torch.empty((n, 16, 3), device=dev); uv = torch.empty((n, 16, 2), device=dev)
-    g_ang = torch.empty((n, 33), device=dev); g_grot = torch.empty((n, 3), device=dev)
-    g_root = torch.empty((n, 3), device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
-
-    def fwd(d):
-        rc = lib.dhfk_forward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
-                              d["root"].data_ptr(), 3, cam_ptr, None, 0, world.data_ptr(), None, uv.data_ptr(),
-                              n, flags, sp)
-        _cabi.check(rc, "dhfk_forward")
-
-    def bwd(d):
-        rc = lib.dhfk_backward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
-                               d["root"].data_ptr(), 3, cam_ptr, None, 0, d["g_world"].data_ptr(), None,
-                               d["g_uv"].data_ptr(), g_ang.data_ptr(), 33, g_grot.data_ptr(), 3, g_root.data_ptr(), 3,
-                               None, 15, n, flags, sp)
-        _cabi.check(rc, "dhfk_backward")
+    nbuf = max(1, args.buffers)
 
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    # the 1M-poses-per-GPU workload (configs[1]; the weak-scaling companion of configs[4])
+    n = args.poses
+    path1 = HotPath(lib, n, dev, nbuf, 1234 + 97 * rank, flags, cam_ptr, sp)
+    fwd, bwd = path1.fwd, path1.bwd
+    sets, world, uv, g_ang, g_grot, g_root = path1.sets, path1.world, path1.uv, path1.g_ang, path1.g_grot, path1.g_root
 
     # parity before any timing is reported: the first rows of buffer set 0 against the float64 C oracle,
     # as the checker only (part of the cpu_baseline leg: skipped with --no-cpu-baseline)
@@ -358,7 +563,7 @@ def run_native(args):
         import c_oracle
         m = min(n, 4096)
         d = sets[0]
-        fwd(d); bwd(d)
+        fwd(0); bwd(0)
         torch.cuda.synchronize(dev)
         host = {k: d[k][:m].cpu().numpy() for k in ("ang", "grot", "bone", "root", "g_world", "g_uv")}
         o = c_oracle.forward(host["ang"], host["grot"], host["bone"], host["root"], blk)
@@ -372,56 +577,99 @@ def run_native(args):
         parity = {"checked_poses": m, "tolerance": 1e-5, "max_rel_err": errs, "oracle": "oracle/dhfk_oracle.c (float64)"}
 
     steps, warmup = max(args.steps, 1), max(args.warmup, 3)
-    for i in range(warmup):
-        fwd(sets[i % nbuf]); bwd(sets[i % nbuf])
-    barrier()
+
+    # the gradient exchange of the data-parallel GAN step (N > 1): generator + both critics in ONE flat buffer
+    gbuf = side = None
+    allreduce_extra = None
+    if distributed:
+        G, D3, D2 = gan_models(dev)
+        gbuf = parallel.FlatGradBuffer([*G.parameters(), *D3.parameters(), *D2.parameters()])
+        gbuf.flat.fill_(1.0)
+        side = torch.cuda.Stream(dev)
+        for _ in range(5):
+            gbuf.allreduce()
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record(stream)
+        for _ in range(50):
+            nel = gbuf.allreduce()
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        (alone_ms,) = max_over_ranks([a0.elapsed_time(a1) / 50], dev, True)
+        allreduce_extra = {"bytes": int(nel) * 4, "ms_alone": alone_ms, "backend": "nccl", "collectives_per_step": 1,
+                           "what": "dhfk.parallel.FlatGradBuffer.allreduce: generator + 3-D critic + 2-D critic gradients "
+                                   "(dense 256) live in one persistent buffer (the slices are the .grad tensors), one "
+                                   "ncclAllReduce(AVG), no pack / unpack kernels; ms_alone = back to back on an idle GPU"}
 
     sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    # One event pair brackets the K timed steps; every `probe_every`-th step additionally carries three events around its
-    # two launches for the live per-kernel durations (an event record is a ~2 us bubble on the stream, so probing every
-    # launch would cost the headline ~3 %).
     probe_every = 8 if steps >= 16 else 1
-    probes = {i: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for i in range(0, steps, probe_every)}
-    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev_start.record(stream)
-    for i in range(steps):
-        d = sets[i % nbuf]
-        pr = probes.get(i)
-        if pr is None:
-            fwd(d); bwd(d)
-        else:
-            pr[0].record(stream); fwd(d)
-            pr[1].record(stream); bwd(d)
-            pr[2].record(stream)
-    ev_end.record(stream)
-    torch.cuda.synchronize(dev)
-    total_ms = ev_start.elapsed_time(ev_end)
-    barrier()
-    # keep the sampler fed if the timed region was shorter than a few polling periods
     extension = False
-    if sampler and len(sampler.samples) < 10:
-        extension = True
-        t_end = time.time() + 1.0
-        i = 0
-        while time.time() < t_end:
-            fwd(sets[i % nbuf]); bwd(sets[i % nbuf]); i += 1
-            if i % 32 == 0:
-                torch.cuda.synchronize(dev)
-        torch.cuda.synchronize(dev)
-    if sampler:
-        sampler.stop()
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in probes.values()) / len(probes)
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in probes.values()) / len(probes)
-
-    t = torch.tensor([total_ms, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, fwd_ms, bwd_ms = (float(x) for x in t.tolist())
+    weak_extra = None
+    if strong:
+        lo, hi = parallel.shard_rows(args.total_poses, rank, world_size)
+        n_big = hi - lo
+        path = HotPath(lib, n_big, dev, 1 if n_big >= (1 << 21) else 2, 777 + 97 * rank, flags, cam_ptr, sp)
+        ar = (gbuf, side) if distributed else None
+        # weak companion first (1M poses per rank, same in-step all-reduce), then the headline
+        for i in range(warmup):
+            path1.step(i)
+        w_ms, _, _ = timed_steps(path1, steps, stream, dev, barrier, allreduce=ar)
+        w_plain, _, _ = timed_steps(path1, steps, stream, dev, barrier)
+        w_ms, w_plain = max_over_ranks([w_ms, w_plain], dev, distributed)
+        weak_extra = {"poses_per_gpu": n, "value": n * world_size / (w_ms / steps * 1e-3), "unit": UNIT,
+                      "ms_per_step": w_ms / steps, "ms_per_step_without_allreduce": w_plain / steps,
+                      "what": "weak scaling: 1,048,576 poses per rank + the same in-step gradient all-reduce"}
+        for i in range(warmup):
+            path.step(i)
+        if sampler:
+            sampler.start()
+        total_ms, fwd_ms, bwd_ms = timed_steps(path, steps, stream, dev, barrier, allreduce=ar, probe_every=probe_every)
+        barrier()
+        if sampler:
+            sampler.stop()
+        plain_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)
+        total_ms, fwd_ms, bwd_ms, plain_ms = max_over_ranks([total_ms, fwd_ms, bwd_ms, plain_ms], dev, distributed)
+        n_step = n_big
+        value = args.total_poses / (total_ms / steps * 1e-3)
+        if allreduce_extra is not None:
+            allreduce_extra["ms_exposed_per_step"] = (total_ms - plain_ms) / steps
+            allreduce_extra["ms_per_step_without_allreduce"] = plain_ms / steps
+    else:
+        path = path1
+        for i in range(warmup):
+            path.step(i)
+        barrier()
+        if sampler:
+            sampler.start()
+        # One event pair brackets the K timed steps; every `probe_every`-th step additionally carries three events around
+        # its two launches for the live per-kernel durations (an event record is a ~2 us bubble on the stream, so probing
+        # every launch would cost the headline ~3 %).
+        total_ms, fwd_ms, bwd_ms = timed_steps(path, steps, stream, dev, barrier, probe_every=probe_every)
+        barrier()
+        # keep the sampler fed if the timed region was shorter than a few polling periods
+        if sampler and len(sampler.samples) < 10:
+            extension = True
+            t_end = time.time() + 1.0
+            i = 0
+            while time.time() < t_end:
+                path.step(i); i += 1
+                if i % 32 == 0:
+                    torch.cuda.synchronize(dev)
+            torch.cuda.synchronize(dev)
+        if sampler:
+            sampler.stop()
+        total_ms, fwd_ms, bwd_ms = max_over_ranks([total_ms, fwd_ms, bwd_ms], dev, distributed)
+        n_step = n
+        value = n * world_size / (total_ms / steps * 1e-3)
+        if distributed:      # forced configs1 at N > 1: report the collective next to the collective-free step
+            ar_ms, _, _ = timed_steps(path, steps, stream, dev, barrier, allreduce=(gbuf, side))
+            (ar_ms,) = max_over_ranks([ar_ms], dev, True)
+            allreduce_extra["ms_exposed_per_step"] = (ar_ms - total_ms) / steps
     ms_per_step = total_ms / steps
-    value = n * world_size / (ms_per_step * 1e-3)
+    del path
+    if strong:
+        torch.cuda.empty_cache()
 
     # ---- e2e through the host-buffer C-ABI entry (pinned host in/out, copies inside the timed region) ----
     e2e = None
@@ -435,33 +683,65 @@ def run_native(args):
         out = {}
         e2e_steps = max(3, min(steps, 10))
         chunk, slots = 1 << 17, 3
+        call = lambda o, gw_, gu_: dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, gw_, gu_, chunk_rows=chunk,
+                                                        num_streams=slots, workspace=o.get("_workspace"), out=o,
+                                                        fast_trig=args.fast_trig, accurate_grad=args.accurate_trig)
         for _ in range(2):
-            out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=slots,
-                                       workspace=out.get("_workspace"), out=out, fast_trig=args.fast_trig,
-                                       accurate_grad=args.accurate_trig)
+            out = call(out, h_gw, h_gu)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            out = dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, h_gw, h_gu, chunk_rows=chunk, num_streams=slots,
-                                       workspace=out["_workspace"], out=out, fast_trig=args.fast_trig,
-                                       accurate_grad=args.accurate_trig)
+            out = call(out, h_gw, h_gu)
         torch.cuda.synchronize(dev)
         e2e_s = (time.perf_counter() - t0) / e2e_steps
-        te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        if distributed:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-        e2e = {"value": n * world_size / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * (FWD_BYTES - 320 + 320),
-               "d2h_bytes_per_step": n * (320 + 156), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+        # forward only (what the reference itself moves: only the fake pairs ever leave the GPU, model_fk_gan_train.py:486-488)
+        fo = {}
+        for _ in range(2):
+            fo = call(fo, None, None)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fo = call(fo, None, None)
+        torch.cuda.synchronize(dev)
+        fo_s = (time.perf_counter() - t0) / e2e_steps
+        barrier()
+        ceil_s = copy_ceiling(n, dev, chunk)
+        e2e_s, fo_s, ceil_s = max_over_ranks([e2e_s, fo_s, ceil_s], dev, distributed)
+        h2d, d2h = n * 536, n * 476
+        e2e = {"value": n * world_size / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "poses_per_rank": n,
+               "copy_ceiling_ms": ceil_s * 1e3, "frac_of_ceiling": ceil_s / e2e_s,
+               "per_rank_gbs": {"h2d": h2d / e2e_s / 1e9, "d2h": d2h / e2e_s / 1e9,
+                                "ceiling_h2d": h2d / ceil_s / 1e9, "ceiling_d2h": d2h / ceil_s / 1e9},
+               "copy_ceiling": "bare pinned H2D (536 B/row) + D2H (476 B/row) of the same bytes in the same %d-row chunks on "
+                               "two streams, no kernels, same ranks active: the PCIe / host-memory floor" % chunk,
+               "forward_only": {"value": n * world_size / fo_s, "unit": UNIT, "ms_per_step": fo_s * 1e3,
+                                "h2d_bytes_per_step": n * 216, "d2h_bytes_per_step": n * 320,
+                                "what": "same entry with no upstream gradients: inputs up, world16 + uv16 down"},
                "api": "dhfk.fk_project_host -> dhfk_forward_backward_host (pinned host buffers, %d-row chunks through an "
                       "upload / compute / download stream pipeline over %d device slots)" % (chunk, slots)}
+        if strong:
+            e2e["workload_note"] = "measured on 1,048,576 poses per rank (the configs[1] batch), not on the 16M-pose step"
         if numa:
             e2e["host_affinity"] = numa
+        del h_ang, h_grot, h_bone, h_root, h_gw, h_gu, out, fo
 
-    # ---- extra: generator-epilogue mode, same batch, device-resident, rank 0 only ----
-    gen_extra = None
-    if rank == 0:
-        try:
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = HBM_FALLBACK_GBS; peak_src = "fallback (B200_PROFILING.md)"
+
+    # ---- extras, rank 0 only, never allowed to break the headline line ----
+    extras = {}
+    if rank == 0 and not strong:
+        def guarded(key, fn):
+            try:
+                extras[key] = fn()
+            except Exception as e:
+                extras[key] = {"error": repr(e)[:300]}
+
+        def generator_mode():
             half, mid = tables.generator_slot_scale(True)
             g = torch.Generator(device=dev).manual_seed(99)
             raws = [torch.randn((n, 35), generator=g, device=dev) for _ in range(2)]
@@ -490,70 +770,63 @@ def run_native(args):
             torch.cuda.synchronize(dev)
             gms = e0.elapsed_time(e1) / gsteps
             gbytes = (200 + 320) + (200 + 320 + 140)     # fwd: 50 floats in, 80 out; bwd: 50 + 80 in, 35 out
-            gen_extra = {"poses_per_s": n / (gms * 1e-3), "ms_per_step": gms, "bytes_per_pose": gbytes,
-                         "hbm_gbs": gbytes * n / (gms * 1e-3) / 1e9,
-                         "what": "dhfk_generator_forward + dhfk_generator_backward: raw network output [N,35] in, "
-                                 "d(raw) out; tanh / slot scatter / range map fused (SURVEY 8 f1)"}
-        except Exception as e:      # never let the extra break the headline line
-            gen_extra = {"error": repr(e)}
+            gbs = gbytes * n / (gms * 1e-3) / 1e9
+            return {"poses_per_s": n / (gms * 1e-3), "ms_per_step": gms, "bytes_per_pose": gbytes, "hbm_gbs": gbs,
+                    "frac_of_copy_peak": gbs / peak,
+                    "what": "dhfk_generator_forward + dhfk_generator_backward: raw network output [N,35] in, "
+                            "d(raw) out; tanh / slot scatter / range map fused (SURVEY 8 f1)"}
 
-    # ---- extra: the same step under the two other trig policies of include/dhfk.h (rank 0 only, not the headline;
-    # distances to exact arithmetic and to the reference: tools/trig_parity.py) ----
-    trig_extra = None
-    if rank == 0 and not args.fast_trig and not args.accurate_trig:
-        trig_extra = {}
-        for key, ff, what in (("fast_trig_variant", _cabi.FLAG_FAST_TRIG, "DHFK_FLAG_FAST_TRIG: MUFU.SIN/COS in the forward too"),
-                              ("accurate_trig_variant", _cabi.FLAG_ACCURATE_TRIG,
-                               "DHFK_FLAG_ACCURATE_TRIG: table sincos (abs err 1e-7) in the backward too")):
-            try:
-                def var_step(i, ff=ff):
-                    d = sets[i % nbuf]
-                    _cabi.check(lib.dhfk_forward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
-                                                 d["root"].data_ptr(), 3, cam_ptr, None, 0, world.data_ptr(), None,
-                                                 uv.data_ptr(), n, ff, sp), "fwd")
-                    _cabi.check(lib.dhfk_backward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
-                                                  d["root"].data_ptr(), 3, cam_ptr, None, 0, d["g_world"].data_ptr(), None,
-                                                  d["g_uv"].data_ptr(), g_ang.data_ptr(), 33, g_grot.data_ptr(), 3,
-                                                  g_root.data_ptr(), 3, None, 15, n, ff, sp), "bwd")
+        def trig_variant(ff, what):
+            def run():
                 for i in range(5):
-                    var_step(i)
+                    path1.step(i, ff)
                 torch.cuda.synchronize(dev)
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 fsteps = min(steps, 50)
                 f0.record(stream)
                 for i in range(fsteps):
-                    var_step(i)
+                    path1.step(i, ff)
                 f1.record(stream)
                 torch.cuda.synchronize(dev)
                 fms = f0.elapsed_time(f1) / fsteps
-                trig_extra[key] = {"poses_per_s": n / (fms * 1e-3), "ms_per_step": fms,
-                                   "hbm_gbs": (FWD_BYTES + BWD_BYTES) * n / (fms * 1e-3) / 1e9, "what": "same step, " + what}
-            except Exception as e:
-                trig_extra[key] = {"error": repr(e)}
+                return {"poses_per_s": n / (fms * 1e-3), "ms_per_step": fms,
+                        "hbm_gbs": (FWD_BYTES + BWD_BYTES) * n / (fms * 1e-3) / 1e9, "what": "same step, " + what}
+            return run
 
-    # ---- extra (N > 1): the only exchange of the data-parallel GAN step, the flat gradient all-reduce of a
-    # generator/critic-sized model (1-4 MB, latency-bound), outside the timed region ----
-    allreduce_extra = None
-    if distributed:
-        from dhfk import parallel
-        net = torch.nn.Sequential(torch.nn.Linear(128, 256), *[torch.nn.Linear(256, 256) for _ in range(7)],
-                                  torch.nn.Linear(256, 35)).to(dev)           # Fk_Generator-sized (dense 256)
-        for p_ in net.parameters():
-            p_.grad = torch.ones_like(p_)
-        for _ in range(3):
-            parallel.allreduce_grads_flat(list(net.parameters()))
-        torch.cuda.synchronize(dev)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        for _ in range(20):
-            nel = parallel.allreduce_grads_flat(list(net.parameters()))
-        a1.record(stream)
-        torch.cuda.synchronize(dev)
-        ta = torch.tensor([a0.elapsed_time(a1) / 20], device=dev, dtype=torch.float64)
-        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
-        allreduce_extra = {"bytes": int(nel) * 4, "ms": float(ta.item()), "backend": "nccl",
-                           "what": "dhfk.parallel.allreduce_grads_flat of a dense-256 generator's gradients "
-                                   "(cat + one all-reduce + scatter back); not part of the timed FK region"}
+        guarded("generator_mode", generator_mode)
+        if not args.fast_trig and not args.accurate_trig:
+            guarded("fast_trig_variant", trig_variant(_cabi.FLAG_FAST_TRIG, "DHFK_FLAG_FAST_TRIG: MUFU.SIN/COS in the forward too"))
+            guarded("accurate_trig_variant", trig_variant(_cabi.FLAG_ACCURATE_TRIG,
+                                                          "DHFK_FLAG_ACCURATE_TRIG: table sincos (abs err 1e-7) in the backward too"))
+        if not args.no_extras:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            del path1, sets
+            torch.cuda.empty_cache()
+
+            def side_kernels():
+                import aux_bench
+                r = aux_bench.measure(dev, n, peak, steps=30)
+                return {"poses": n, "what": "the kernels either side of the path (SURVEY 8 f2-f4, standalone camera ops, 32-slot "
+                                            "layout), device-resident, CUDA events, 4 rotating buffer sets; frac = algorithmic "
+                                            "bytes / time / measured copy peak",
+                        "kernels": {k: {"ms": v["ms"], "bytes_per_pose": v["bytes_per_pose"], "frac": v["frac"]}
+                                    for k, v in r["kernels"].items()}}
+
+            def dropin_path():
+                import dropin_path_bench
+                return dropin_path_bench.measure(dev, peak_gbs=peak)
+
+            guarded("side_kernels", side_kernels)
+            torch.cuda.empty_cache()
+            guarded("dropin_path", dropin_path)
+            torch.cuda.empty_cache()
+            guarded("gan_step", lambda: dict(reference_loop_timings(),
+                                             what="BASELINE configs[2] (single-frame, batch 1024, dense 256) and configs[3] "
+                                                  "(multi-frame, 512 clips x 9 frames, architecture 3,3): ms per iteration of "
+                                                  "the reference's own loop functions (GAN_solutions_FK_generator / "
+                                                  "video_mode_GAN_solutions_FK_generator, unmodified, from oracle/_ref) on this "
+                                                  "GPU -- as they are, and with dhfk.dropin.install(generators, critics, "
+                                                  "loader_refresh); wall clock incl. their host RNG and .cpu() copies"))
 
     if distributed:
         dist.barrier()
@@ -562,35 +835,37 @@ def run_native(args):
             dist.destroy_process_group()
         return
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak = HBM_FALLBACK_GBS; peak_src = "fallback (B200_PROFILING.md)"
-    bwd_gbs = BWD_BYTES * n / (bwd_ms * 1e-3) / 1e9
-    fwd_gbs = FWD_BYTES * n / (fwd_ms * 1e-3) / 1e9
-    traffic = None
+    bwd_gbs = BWD_BYTES * n_step / (bwd_ms * 1e-3) / 1e9
+    fwd_gbs = FWD_BYTES * n_step / (fwd_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")     # written from an `ncu --set full` capture (per launch)
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dhfk_bwd_kernel_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dhfk_bwd_kernel_bytes_per_launch")
+            traffic_src = tj.get("source", "profiles/traffic.json")
+            if traffic is not None and n_step != tj.get("poses_per_launch", 1 << 20):
+                traffic = traffic * n_step / tj.get("poses_per_launch", 1 << 20)
+                traffic_src += " (scaled from the captured launch size to this one)"
         except Exception:
             traffic = None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": workload_config(args, {"l2": "inputs rotate over %d buffer sets (%.1f GB per set) > 126 MB L2"
-                                                % (nbuf, n * (216 + 320) / 1e9)}),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, {"l2": ("one input set of %.1f GB per rank, far larger than the 126 MB L2"
+                                                % (n_step * (216 + 320) / 1e9)) if strong else
+                                               ("inputs rotate over %d buffer sets (%.1f GB per set) > 126 MB L2"
+                                                % (nbuf, n * (216 + 320) / 1e9))}),
         "roofline": {"bound": "hbm", "kernel": "dhfk_bwd_kernel<GUV=1,GBONE=0>", "achieved": bwd_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "peak_source": peak_src,
-                     "ms_per_launch": bwd_ms, "algorithmic_bytes_per_launch": BWD_BYTES * n},
+                     "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "ms_per_launch": bwd_ms, "algorithmic_bytes_per_launch": BWD_BYTES * n_step},
         "roofline_fwd": {"bound": "hbm", "kernel": "dhfk_fwd_kernel<CAM=0,UV=1>", "achieved": fwd_gbs, "peak": peak,
                          "unit": "GB/s", "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
-                         "algorithmic_bytes_per_launch": FWD_BYTES * n},
-        "roofline_step": {"achieved": (FWD_BYTES + BWD_BYTES) * n / (ms_per_step * 1e-3) / 1e9, "peak": peak,
-                          "frac": (FWD_BYTES + BWD_BYTES) * n / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"},
+                         "algorithmic_bytes_per_launch": FWD_BYTES * n_step},
+        "roofline_step": {"achieved": (FWD_BYTES + BWD_BYTES) * n_step / (ms_per_step * 1e-3) / 1e9, "peak": peak,
+                          "frac": (FWD_BYTES + BWD_BYTES) * n_step / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"},
         "clocks": dict(sampler.summary(), window="timed region" + (" + 1 s extension of the same loop" if extension else "")),
         "gpu_launches": 2 * steps,
     }
@@ -598,16 +873,22 @@ def run_native(args):
         line["parity"] = parity
     if e2e:
         line["e2e"] = e2e
-    if gen_extra:
-        line["generator_mode"] = gen_extra
-    if trig_extra:
-        line.update(trig_extra)
+    if weak_extra:
+        line["weak"] = weak_extra
+    line.update(extras)
     if allreduce_extra:
         line["grad_allreduce"] = allreduce_extra
     if not args.no_cpu_baseline:
+        res = time_reference_pipeline(args.ref_chunk, 1, steps=10, warmup=2)
+        if res is not None:
+            pps, dt, threads = res
+            line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": "reference",
+                                    "sample": "10 x %d-pose calls (reference batch size), fwd+bwd, the unmodified reference "
+                                              "from oracle/_ref/dh_aug_ref.zip" % args.ref_chunk}
         pps, dt, threads = time_torch_port(args.ref_chunk, 1, steps=10, warmup=2)
-        line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "10 x %d-pose torch calls (reference batch size), fwd+bwd, oracle/torch_port.py" % args.ref_chunk}
+        port = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "10 x %d-pose torch calls (reference batch size), fwd+bwd, oracle/torch_port.py" % args.ref_chunk}
+        line["cpu_baseline_port" if "cpu_baseline" in line else "cpu_baseline"] = port
         try:
             fps, fthreads = time_torch_port_forward_only(args.ref_chunk)
             line["cpu_baseline_forward_only"] = {"value": fps, "unit": UNIT, "cores": fthreads, "kind": "port",

@@ -19,7 +19,10 @@ constexpr int kRec2d = kWorldChunks + kUvChunks;  // chunks 12..19 : pose2d;  ch
 // so throughput is bytes in flight.  (r1: one chunk per thread = 32 KB in flight per SM = 64 % of the streaming peak.)
 // rec_chunks = record stride in 16-byte chunks (>= 20 + ceil(cam_cols/4)).
 constexpr int kBankThreads = 256;
-constexpr int kBankUnroll = 4;
+#ifndef DHFK_BANK_UNROLL
+#define DHFK_BANK_UNROLL 4
+#endif
+constexpr int kBankUnroll = DHFK_BANK_UNROLL;
 
 __global__ void __launch_bounds__(kBankThreads)
 dhfk_bank_gather_kernel(const float4* __restrict__ bank, int rec_chunks, int cam_cols, const long long* __restrict__ idx,

@@ -609,7 +609,7 @@ static int video_common(int32_t frames, uint32_t flags, int64_t n) {
     if (frames < 1) return fail(DHFK_E_INVAL, "frames must be >= 1");
     if (n % frames != 0) return fail(DHFK_E_INVAL, "n_rows must be a multiple of frames");
     if (flags & ~DHFK_VIDEO_REVERSE) return fail(DHFK_E_INVAL, "unknown video flag");
-    if ((n + dhfk::kTile - 2) / (dhfk::kTile - 1) > 2147483647LL) return fail(DHFK_E_INVAL, "n_rows too large for one launch");
+    if (n > 2147483647LL) return fail(DHFK_E_INVAL, "n_rows too large for one launch (< 2^31)");
     return DHFK_OK;
 }
 int dhfk_video_critic_forward(const float* pose, int32_t frames, uint32_t flags, float* out_kcs, float* out_dkcs,

@@ -262,14 +262,21 @@ DHFK_DI float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.RCP, <= 1 ulp; 1/0 = inf like the reference's x / 0
     return r;
 }
+// torch.clamp(x, -1, 1) (common/camera.py:85) propagates NaN (0/0 at x = z = 0, or NaN inputs); fminf / fmaxf would
+// return the non-NaN operand.  min.NaN / max.NaN are the same single FMNMX instruction with NaN propagation.
+DHFK_DI float clamp_unit_nan(float x) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0fBF800000;\n\tmin.NaN.f32 %0, %0, 0f3F800000;" : "=f"(r) : "f"(x));
+    return r;
+}
 DHFK_DI void project_point(const CamConst& cc, V3 X, float& u, float& v, ProjAux& a) {
     float iz = rcp_approx(X.z);
     a.iz = iz;
 #if DHFK_PACKED_PROJ
     const float2 r = __fmul2_rn(make_float2(X.x, X.y), bc2(iz));
     a.rx = r.x; a.ry = r.y;
-    a.x = fminf(fmaxf(r.x, -1.f), 1.f);
-    a.y = fminf(fmaxf(r.y, -1.f), 1.f);
+    a.x = clamp_unit_nan(r.x);
+    a.y = clamp_unit_nan(r.y);
     a.r2 = fmaf(a.x, a.x, a.y * a.y);
     float radial = fmaf(a.r2, fmaf(a.r2, fmaf(a.r2, cc.k[2], cc.k[1]), cc.k[0]), 1.f);
     float tan = fmaf(cc.p.x, a.x, cc.p.y * a.y);
@@ -280,8 +287,8 @@ DHFK_DI void project_point(const CamConst& cc, V3 X, float& u, float& v, ProjAux
 #else
     a.rx = X.x * iz;
     a.ry = X.y * iz;
-    a.x = fminf(fmaxf(a.rx, -1.f), 1.f);
-    a.y = fminf(fmaxf(a.ry, -1.f), 1.f);
+    a.x = clamp_unit_nan(a.rx);
+    a.y = clamp_unit_nan(a.ry);
     a.r2 = fmaf(a.x, a.x, a.y * a.y);
     float radial = fmaf(a.r2, fmaf(a.r2, fmaf(a.r2, cc.k[2], cc.k[1]), cc.k[0]), 1.f);
     float tan = fmaf(cc.p.x, a.x, cc.p.y * a.y);

@@ -69,6 +69,10 @@ inline size_t bwd_smem_bytes(bool gw, bool gcam, bool guv, bool gen, const WideR
 // cudaFuncSetAttribute is needed once per (kernel, device), not once per launch: at the reference's real batch sizes
 // (1 024 / 4 608 poses) the kernels take ~7 us and two attribute calls per launch were a measurable part of the
 // 13 us a C-ABI forward+backward pair cost in round 1.  Lock-free set keyed by (kernel address, device).
+// MaxDynamicSharedMemorySize is set ONCE to a bound that covers every launch of the library (it is a limit, not a
+// reservation: launches asking for more than the value last set fail with cudaErrorInvalidValue, and the same kernel
+// is launched with different sizes -- packed rows, wide rows, with / without the separate global-rotation slab).
+constexpr int kMaxDynSmem = 64 * 1024;
 bool func_attrs_done(const void* kernel, int device);     // true when already recorded; records it otherwise
 void func_attrs_forget(const void* kernel, int device);   // undo after a failed attribute call
 
@@ -77,8 +81,9 @@ int launch_tiles(K kernel, size_t smem, const P& p, cudaStream_t st, const char*
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { *where = "cudaGetDevice"; return (int)e; }
+    if ((int)smem > kMaxDynSmem) { *where = "dynamic shared memory request exceeds kMaxDynSmem"; return (int)cudaErrorInvalidValue; }
     if (!func_attrs_done((const void*)kernel, dev)) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) {

@@ -118,33 +118,35 @@ DHFK_DI void vkcs_vjp(const VBones& B, const float* gk, float* gx) {
 
 // Output rows of storage row r = (clip b, frame f): per-frame tensors [B,F,*] and difference tensors [B,F-1,*]
 // (difference f = frame f+1 minus frame f, defined for f < F-1; -1 otherwise).
-struct VideoRows { long long per_frame, diff; };
-DHFK_DI VideoRows video_rows(long long r, int F, bool rev) {
-    const long long b = r / F;
-    const int f = (int)(r - b * F);
+// (n_rows < 2^31 is checked at the C ABI: 32-bit arithmetic; a 64-bit division is ~60 emulated instructions)
+struct VideoRows { int per_frame, diff; };
+DHFK_DI VideoRows video_rows(unsigned r, unsigned F, bool rev) {
+    const unsigned b = r / F;
+    const unsigned f = r - b * F;
     VideoRows o;
-    o.per_frame = b * F + (rev ? F - 1 - f : f);
-    o.diff = f < F - 1 ? b * (F - 1) + (rev ? F - 2 - f : f) : -1;
+    o.per_frame = (int)(b * F + (rev ? F - 1 - f : f));
+    o.diff = f < F - 1 ? (int)(b * (F - 1) + (rev ? F - 2 - f : f)) : -1;
     return o;
 }
 
-// rows of `cols` floats from a compact shared image (slot * cols) to mapped global rows (-1 = skip): 4-byte stores,
-// consecutive lanes -> consecutive floats of a row
-template <int COLS>
-DHFK_DI void store_rows_mapped(const float* s, float* g, const long long* map, int slots) {
-    for (int i = threadIdx.x; i < slots * COLS; i += kTile) {
-        const int slot = i / COLS, c = i - slot * COLS;
-        const long long row = map[slot];
-        if (row >= 0) __stcs(g + row * COLS + c, s[i]);
+// rows of 15 floats from a compact shared image (slot * 15) to mapped global rows (-1 = skip): each half-warp ships
+// one row per pass (lanes 0..14 of the half: 60 contiguous bytes), so a pass costs one LDS, one broadcast LDS of the
+// row index and one STG -- no per-element division, no 64-bit multiply
+DHFK_DI void store_rows15_mapped(const float* s, float* g, const int* map, int slots) {
+    const int lane = threadIdx.x, half = lane >> 4, c = lane & 15;
+#pragma unroll 4
+    for (int slot = half; slot < slots; slot += 2) {
+        const int row = map[slot];
+        if (c < 15 && row >= 0) __stcs(g + (size_t)row * 15 + c, s[slot * 15 + c]);
     }
 }
-// 48-float rows from padded shared rows to mapped global rows: 16-byte stores, 12 consecutive lanes per row
-DHFK_DI void store_rows48_mapped(const float4* s4, float* g, const long long* map, int slots) {
+// 48-float rows from padded shared rows to mapped global rows: 16-byte stores; 8 rows of 12 chunks per 3 passes
+DHFK_DI void store_rows48_mapped(const float4* s4, float* g, const int* map, int slots) {
     float4* g4 = reinterpret_cast<float4*>(g);
     for (int i = threadIdx.x; i < slots * kWorldChunks; i += kTile) {
         const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
-        const long long row = map[slot];
-        if (row >= 0) __stcs(g4 + row * kWorldChunks + c, s4[slot * kWorldRow4 + c]);
+        const int row = map[slot];
+        if (row >= 0) __stcs(g4 + (size_t)row * kWorldChunks + c, s4[slot * kWorldRow4 + c]);
     }
 }
 
@@ -158,8 +160,8 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_kernel(const __grid_c
     float4* s_dp = s_v + (JVP ? kTile * kWorldRow4 : 0);                    // differences of the poses
     float* s_k = reinterpret_cast<float*>(s_dp + (DPOS ? kTile * kWorldRow4 : 0));
     float* s_dk = s_k + kTile * 15;
-    long long* s_map_f = reinterpret_cast<long long*>(s_dk + kTile * 15);  // per-frame output row of each slot
-    long long* s_map_d = s_map_f + kTile;                                   // difference output row (or -1)
+    int* s_map_f = reinterpret_cast<int*>(s_dk + kTile * 15);              // per-frame output row of each slot
+    int* s_map_d = s_map_f + kTile;                                         // difference output row (or -1)
 
     const int lane = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kOwn;
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_kernel(const __grid_c
     const bool rev = (p.flags & kVideoReverse) != 0;
     VideoRows o;
     o.per_frame = o.diff = -1;
-    if (lane < own) o = video_rows(row0 + lane, p.frames, rev);
+    if (lane < own) o = video_rows((unsigned)(row0 + lane), (unsigned)p.frames, rev);
     s_map_f[lane] = o.per_frame;
     s_map_d[lane] = o.diff;
     ldgsts_wait_all();
@@ -216,8 +218,8 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_kernel(const __grid_c
         }
     }
     __syncwarp();
-    store_rows_mapped<15>(s_k, p.out_kcs, s_map_f, own);
-    store_rows_mapped<15>(s_dk, p.out_dkcs, s_map_d, own);
+    store_rows15_mapped(s_k, p.out_kcs, s_map_f, own);
+    store_rows15_mapped(s_dk, p.out_dkcs, s_map_d, own);
     if (DPOS) store_rows48_mapped(s_dp, p.out_dpos, s_map_d, own);
     if (POS) store_rows48_mapped(JVP ? s_v : s_pose, p.out_pos, s_map_f, own);
 }
@@ -232,10 +234,10 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
     float4* s_pose = reinterpret_cast<float4*>(smem);                        // 32 padded rows; g_pose leaves from here
     float4* s_gp = s_pose + kTile * kWorldRow4;                              // g_pos, 32 padded rows
     float4* s_gdp = s_gp + (GP ? kTile * kWorldRow4 : 0);                    // g_dpos, 33 padded rows
-    float* s_gk = reinterpret_cast<float*>(s_gdp + (GDP ? (kTile + 1) * kWorldRow4 : 0));   // g_kcs, 32 x 15 (padded to 16)
-    float* s_gdk = s_gk + (GK ? kTile * 16 : 0);                             // g_dkcs, 33 x 15 (padded to 16)
-    long long* s_map_f = reinterpret_cast<long long*>(s_gdk + (GDK ? (kTile + 1) * 16 : 0) );
-    long long* s_map_d = s_map_f + kTile;                                    // 33 entries
+    float* s_gk = reinterpret_cast<float*>(s_gdp + (GDP ? (kTile + 1) * kWorldRow4 : 0));   // g_kcs, 32 x 15 (odd stride:
+    float* s_gdk = s_gk + (GK ? kTile * 15 : 0);                             // conflict-free); g_dkcs, 33 x 15
+    int* s_map_f = reinterpret_cast<int*>(s_gdk + (GDK ? (kTile + 1) * 15 : 0));
+    int* s_map_d = s_map_f + kTile;                                          // 33 entries
 
     const int lane = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kTile;
@@ -245,10 +247,10 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
     {
         VideoRows o;
         o.per_frame = o.diff = -1;
-        if (lane < rows) o = video_rows(row0 + lane, p.frames, rev);
+        if (lane < rows) o = video_rows((unsigned)(row0 + lane), (unsigned)p.frames, rev);
         s_map_f[lane] = o.per_frame;
         s_map_d[lane + 1] = o.diff;
-        if (lane == 0) s_map_d[0] = row0 > 0 ? video_rows(row0 - 1, p.frames, rev).diff : -1;
+        if (lane == 0) s_map_d[0] = row0 > 0 ? video_rows((unsigned)(row0 - 1), (unsigned)p.frames, rev).diff : -1;
     }
     if (rows == kTile) ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
     else stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
@@ -258,28 +260,27 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
         const float4* g4 = reinterpret_cast<const float4*>(p.g_pos);
         for (int i = lane; i < rows * kWorldChunks; i += kTile) {
             const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
-            ldgsts16(s_gp + slot * kWorldRow4 + c, g4 + s_map_f[slot] * kWorldChunks + c);
+            ldgsts16(s_gp + slot * kWorldRow4 + c, g4 + (size_t)s_map_f[slot] * kWorldChunks + c);
         }
     }
     if (GDP) {
         const float4* g4 = reinterpret_cast<const float4*>(p.g_dpos);
         for (int i = lane; i < (rows + 1) * kWorldChunks; i += kTile) {
             const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
-            const long long row = s_map_d[slot];
-            if (row >= 0) ldgsts16(s_gdp + slot * kWorldRow4 + c, g4 + row * kWorldChunks + c);
+            const int row = s_map_d[slot];
+            if (row >= 0) ldgsts16(s_gdp + slot * kWorldRow4 + c, g4 + (size_t)row * kWorldChunks + c);
         }
     }
     if (GK) {
-        for (int i = lane; i < rows * 15; i += kTile) {
-            const int slot = i / 15, c = i - slot * 15;
-            ldgsts4(s_gk + slot * 16 + c, p.g_kcs + s_map_f[slot] * 15 + c);
-        }
+        const int half = lane >> 4, c = lane & 15;
+        for (int slot = half; slot < rows; slot += 2)
+            if (c < 15) ldgsts4(s_gk + slot * 15 + c, p.g_kcs + (size_t)s_map_f[slot] * 15 + c);
     }
     if (GDK) {
-        for (int i = lane; i < (rows + 1) * 15; i += kTile) {
-            const int slot = i / 15, c = i - slot * 15;
-            const long long row = s_map_d[slot];
-            if (row >= 0) ldgsts4(s_gdk + slot * 16 + c, p.g_dkcs + row * 15 + c);
+        const int half = lane >> 4, c = lane & 15;
+        for (int slot = half; slot < rows + 1; slot += 2) {
+            const int row = s_map_d[slot];
+            if (c < 15 && row >= 0) ldgsts4(s_gdk + slot * 15 + c, p.g_dkcs + (size_t)row * 15 + c);
         }
     }
     ldgsts_wait_all();
@@ -308,10 +309,10 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
             float gk[15];
 #pragma unroll
             for (int q = 0; q < 15; ++q) {
-                float a = GK ? s_gk[lane * 16 + q] : 0.f;
+                float a = GK ? s_gk[lane * 15 + q] : 0.f;
                 if (GDK) {
-                    if (has_prev) a = fmaf(sgn, s_gdk[lane * 16 + q], a);
-                    if (has_next) a = fmaf(-sgn, s_gdk[(lane + 1) * 16 + q], a);
+                    if (has_prev) a = fmaf(sgn, s_gdk[lane * 15 + q], a);
+                    if (has_next) a = fmaf(-sgn, s_gdk[(lane + 1) * 15 + q], a);
                 }
                 gk[q] = a;
             }
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(256) dhfk_video_root_diff_fwd_kernel(const __g
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.n) return;
     const bool rev = (p.flags & kVideoReverse) != 0;
-    const VideoRows o = video_rows(r, p.frames, rev);
+    const VideoRows o = video_rows((unsigned)r, (unsigned)p.frames, rev);
     const float2* u2 = reinterpret_cast<const float2*>(p.uv);
     if (o.diff >= 0) {
         const float2 a = __ldg(u2 + r * 16), b = __ldg(u2 + (r + 1) * 16);
@@ -365,15 +366,15 @@ __global__ void __launch_bounds__(256) dhfk_video_root_diff_bwd_kernel(const __g
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.n) return;
     const bool rev = (p.flags & kVideoReverse) != 0;
-    const VideoRows o = video_rows(r, p.frames, rev);
-    const long long b = r / p.frames;
-    const int f = (int)(r - b * p.frames);
+    const VideoRows o = video_rows((unsigned)r, (unsigned)p.frames, rev);
+    const unsigned b = (unsigned)r / (unsigned)p.frames;
+    const int f = (int)((unsigned)r - b * (unsigned)p.frames);
     float gx = 0.f, gy = 0.f;
     if (p.g_diff) {
         const float2* g2 = reinterpret_cast<const float2*>(p.g_diff);
         const float s = rev ? -1.f : 1.f;
         if (f > 0) {                      // difference f-1 = frame f - frame f-1
-            const float2 g = __ldg(g2 + video_rows(r - 1, p.frames, rev).diff);
+            const float2 g = __ldg(g2 + video_rows((unsigned)(r - 1), (unsigned)p.frames, rev).diff);
             gx += s * g.x; gy += s * g.y;
         }
         if (o.diff >= 0) {
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(256) dhfk_video_root_diff_bwd_kernel(const __g
 
 static size_t video_fwd_smem(bool jvp, bool dpos) {
     return sizeof(float4) * kTile * kWorldRow4 * (1 + (jvp ? 1 : 0) + (dpos ? 1 : 0)) + sizeof(float) * kTile * 30 +
-           sizeof(long long) * kTile * 2;
+           sizeof(int) * kTile * 2;
 }
 
 // launch_tiles sizes the grid as ceil(p.n / 32); forward / jvp tiles advance 31 rows, so they get their own launcher
@@ -403,7 +404,7 @@ static int launch_video(K kernel, size_t smem, const VideoParams& p, long long b
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { *where = "cudaGetDevice"; return (int)e; }
     if (!func_attrs_done((const void*)kernel, dev)) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) {
@@ -444,8 +445,8 @@ int launch_video_critic_bwd(const float* pose, int frames, unsigned flags, const
     p.n = n; p.frames = frames; p.flags = flags;
     const bool gk = g_kcs != nullptr, gdk = g_dkcs != nullptr, gdp = g_dpos != nullptr, gp = g_pos != nullptr;
     const size_t smem = sizeof(float4) * (kTile * kWorldRow4 * (1 + (gp ? 1 : 0)) + (gdp ? (kTile + 1) * kWorldRow4 : 0)) +
-                        sizeof(float) * ((gk ? kTile * 16 : 0) + (gdk ? (kTile + 1) * 16 : 0)) +
-                        sizeof(long long) * (2 * kTile + 2);
+                        sizeof(float) * ((gk ? kTile * 15 : 0) + (gdk ? (kTile + 1) * 15 : 0)) +
+                        sizeof(int) * (2 * kTile + 2);
     const long long blocks = (n + kTile - 1) / kTile;
     // the combinations the critics produce: everything (3-D motion critic with both extra branches), features only,
     // and the two single-branch configurations (motion_Dis_whether_use_3dPos_branch / _3dDiff_branch)

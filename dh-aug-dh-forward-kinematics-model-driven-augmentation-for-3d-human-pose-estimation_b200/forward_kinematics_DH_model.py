@@ -46,13 +46,30 @@ def _index16(device):
     return _IDX16
 
 
+def _col(v, like):
+    """[N] float32 tensor on `like`'s device from a tensor, a Python number or a numpy value."""
+    if torch.is_tensor(v):
+        return v.to(device=like.device, dtype=torch.float32).reshape(-1).expand(like.shape[0]) if v.numel() == 1 \
+            else v.to(device=like.device, dtype=torch.float32).reshape(-1)
+    return torch.full((like.shape[0],), float(v), dtype=torch.float32, device=like.device)
+
+
 def dh_matrix(alpha, a, d, theta, args=None):
-    """One modified-DH 4x4 transform for SCALAR inputs in degrees (the reference's numpy branch,
-    forward_kinematics_DH_model.py:54-78; the GUI uses it).  Batched tensors are not built matrix by matrix
-    here -- that is the whole point of the fused kernel -- so tensor inputs are rejected."""
+    """One modified-DH 4x4 transform per row, degrees in (forward_kinematics_DH_model.py:53-116).
+    Scalar inputs: float64 numpy (4,4), the reference's numpy branch (:54-78; the GUI uses it).  Tensor `theta` [N]:
+    float32 [N,4,4] on theta's device, differentiable -- the same 16 entries the reference writes one column at a time
+    into a pre-sized buffer (:99-114), here N comes from theta, not from args.batch_size.  The fused kernels never
+    build these matrices (every alpha is 0 or +-90 deg, so a joint step is a signed axis permutation and one planar
+    rotation); this function exists for callers that want the matrices themselves."""
     if torch.is_tensor(theta):
-        raise NotImplementedError("dh_matrix on tensors is replaced by the fused kernel: use "
-                                  "Forward_Kinematics_DH_Model.change_3d_joint_angle / dhfk.fk_project")
+        th = theta.reshape(-1).to(torch.float32)
+        al = _col(alpha, th) / 180 * np.pi
+        th = th / 180 * torch.tensor(np.pi, dtype=torch.float32, device=th.device)     # as the reference rounds it (:91)
+        a_, d_ = _col(a, th), _col(d, th)
+        ct, st, ca, sa = torch.cos(th), torch.sin(th), torch.cos(al), torch.sin(al)
+        z, o = torch.zeros_like(th), torch.ones_like(th)
+        rows = [ct, -st, z, a_, st * ca, ct * ca, -sa, -sa * d_, st * sa, ct * sa, ca, ca * d_, z, z, z, o]
+        return torch.stack(rows, dim=1).view(-1, 4, 4)
     al, th = alpha / 180 * np.pi, theta / 180 * np.pi
     ca, sa, ct, st = np.cos(al), np.sin(al), np.cos(th), np.sin(th)
     return np.array([[ct, -st, 0.0, a], [st * ca, ct * ca, -sa, -sa * d], [st * sa, ct * sa, ca, ca * d],
@@ -60,9 +77,17 @@ def dh_matrix(alpha, a, d, theta, args=None):
 
 
 def rotationMatrix(angle_x, angle_y, angle_z, args=None):
-    """R = Rx(angle_x) Ry(angle_y) Rz(angle_z) for SCALAR degrees (forward_kinematics_DH_model.py:120-139)."""
+    """R = Rx(angle_x) Ry(angle_y) Rz(angle_z), degrees in (forward_kinematics_DH_model.py:118-191).  Scalars: numpy
+    (3,3); tensors [N]: float32 [N,3,3] on their device, differentiable (the closed form of the reference's
+    R1.bmm(R2).bmm(R3), the one the kernels' `global_rotation` evaluates)."""
     if torch.is_tensor(angle_x):
-        raise NotImplementedError("rotationMatrix on tensors is replaced by the fused kernel")
+        ax = angle_x.reshape(-1).to(torch.float32) / 180 * np.pi
+        ay, az = _col(angle_y, ax) / 180 * np.pi, _col(angle_z, ax) / 180 * np.pi
+        sx, cx, sy, cy, sz, cz = torch.sin(ax), torch.cos(ax), torch.sin(ay), torch.cos(ay), torch.sin(az), torch.cos(az)
+        rows = [cy * cz, -cy * sz, sy,
+                sx * sy * cz + cx * sz, -sx * sy * sz + cx * cz, -sx * cy,
+                -cx * sy * cz + sx * sz, cx * sy * sz + sx * cz, cx * cy]
+        return torch.stack(rows, dim=1).view(-1, 3, 3)
     ax, ay, az = (v / 180 * np.pi for v in (angle_x, angle_y, angle_z))
     r1 = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
     r2 = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
@@ -284,12 +309,15 @@ class Forward_Kinematics_DH_Model:
                              to(right_hand_joints_angle), to(left_hand_joints_angle)], dim=1)
         n = ang.shape[0]
         grot = to(generator_global_rot_3d_pos_angle)
-        cols = []
-        for v in lens:
-            if not torch.is_tensor(v):
-                v = torch.full((n,), float(v), dtype=torch.float32, device=dev)
-            cols.append(to(v).reshape(-1))
-        bone = torch.stack(cols, dim=1)
+        if all(type(v) is torch.Tensor and v.dim() == 1 and v.device == dev for v in lens):
+            bone = torch.stack(lens, dim=1)           # the generator's 15 length products: one launch, no per-column glue
+        else:
+            cols = []
+            for v in lens:
+                if not torch.is_tensor(v):
+                    v = torch.full((n,), float(v), dtype=torch.float32, device=dev)
+                cols.append(to(v).reshape(-1))
+            bone = torch.stack(cols, dim=1)
         root = to(root_3d_pos).reshape(-1, 3)
         self.global_rot_angle = generator_global_rot_3d_pos_angle
         wide = _wide_layout(ang, grot) if ang._base is not None else None

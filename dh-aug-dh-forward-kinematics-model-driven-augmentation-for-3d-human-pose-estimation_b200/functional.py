@@ -391,6 +391,8 @@ class _WorldToCamera(torch.autograd.Function):
         _cabi.check(rc, "dhfk_world_to_camera_forward")
         ctx.save_for_backward(q)
         ctx.meta = (x.device, x.dtype)
+        if (out.device, out.dtype) != ctx.meta:      # CPU / float64 callers (common/camera.py::wrap) get their own kind back
+            out = out.to(device=ctx.meta[0], dtype=ctx.meta[1])
         return out
 
     @staticmethod
@@ -438,6 +440,8 @@ class _Project(torch.autograd.Function):
         _cabi.check(rc, "dhfk_project_forward")
         ctx.save_for_backward(xs, cams)
         ctx.meta = (x.device, x.dtype)
+        if (uv.device, uv.dtype) != ctx.meta:        # wrap(project_to_2d, True, numpy, numpy) feeds CPU float64 tensors
+            uv = uv.to(device=ctx.meta[0], dtype=ctx.meta[1])  # and calls .numpy() on the result (model_fk_gan_train.py:74)
         return uv
 
     @staticmethod
@@ -831,7 +835,7 @@ class _Scatter32(torch.autograd.Function):
     def forward(ctx, world16, root):
         _require_cuda()
         lib = _cabi.load()
-        device = world16.device
+        device = world16.device if world16.is_cuda else torch.device("cuda", torch.cuda.current_device())
         w = _packed(world16, (-1, 16, 3), device)
         n = w.shape[0]
         r = _rows(root, 3, device)
@@ -842,13 +846,16 @@ class _Scatter32(torch.autograd.Function):
             rc = lib.dhfk_scatter32_forward(w.data_ptr(), r.data_ptr(), _row_stride(r), out.data_ptr(), n, _stream_ptr(device))
         _cabi.check(rc, "dhfk_scatter32_forward")
         ctx.meta = (root.shape, root.device, root.dtype)
+        ctx.w_meta = (world16.device, world16.dtype)
+        if (out.device, out.dtype) != ctx.w_meta:
+            out = out.to(device=ctx.w_meta[0], dtype=ctx.w_meta[1])
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g32):
         lib = _cabi.load()
-        device = g32.device
+        device = g32.device if g32.is_cuda else torch.device("cuda", torch.cuda.current_device())
         n = g32.shape[0]
         g = _packed(g32, (n, 32, 3), device)
         g16 = torch.empty((n, 16, 3), dtype=torch.float32, device=device)
@@ -861,6 +868,8 @@ class _Scatter32(torch.autograd.Function):
         g_root = g_root.reshape(shape)
         if (g_root.device, g_root.dtype) != (dev, dtype):
             g_root = g_root.to(device=dev, dtype=dtype)
+        if (g16.device, g16.dtype) != ctx.w_meta:
+            g16 = g16.to(device=ctx.w_meta[0], dtype=ctx.w_meta[1])
         return g16, g_root
 
 
@@ -885,6 +894,10 @@ def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chun
     do_bwd = g_world is not None or g_uv is not None
     if do_bwd and (g_world is None or g_uv is None):
         raise ValueError("backward needs both g_world and g_uv")
+    if do_bwd:
+        for name, t, shape in (("g_world", g_world, (n, 16, 3)), ("g_uv", g_uv, (n, 16, 2))):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise ValueError("%s must be a contiguous float32 host tensor of shape %r" % (name, shape))
     cam_arr = cam_block_array(cam)
     device = torch.device("cuda", torch.cuda.current_device())
     need = lib.dhfk_host_workspace_bytes(chunk_rows, num_streams)
@@ -894,7 +907,7 @@ def fk_project_host(ang, grot, bone, root, cam, g_world=None, g_uv=None, *, chun
         out = {}
     def host(name, shape):
         t = out.get(name)
-        if t is None or tuple(t.shape) != shape:
+        if (t is None or tuple(t.shape) != shape or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
             t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
             out[name] = t
         return t

@@ -50,7 +50,12 @@
  *     The caller selects the device (cudaSetDevice / torch.cuda.device).
  *   - Return value: 0 on success, negative DHFK_E_* on argument errors, positive cudaError_t
  *     on CUDA errors.  dhfk_last_error() returns a thread-local message for the last failure.
- *   - Entry points are re-entrant; the library holds no mutable global state.
+ *   - Entry points are re-entrant; the library holds no mutable global state (one process-wide, append-only table of
+ *     "cudaFuncSetAttribute done" marks aside).
+ *   - Non-finite inputs follow the reference's torch semantics: project_to_2d's torch.clamp (common/camera.py:85)
+ *     propagates NaN (0/0 at x = z = 0, NaN inputs) and x/0 = +-inf clamps to +-1; the kernels do the same
+ *     (FMNMX.NAN).  One documented divergence: 1/z is MUFU.RCP with flush-to-zero, so a DENORMAL depth
+ *     (|z| < 1.18e-38) behaves like z = 0 -- (x = 0, z denormal) yields NaN where torch yields 0.
  */
 #ifndef DHFK_H_
 #define DHFK_H_

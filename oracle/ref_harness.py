@@ -29,7 +29,8 @@ import types
 
 REF_ROOT = os.environ.get("DHFK_REFERENCE_ROOT", "/root/reference/DH-AUG_master")
 # the same tree staged as one archive by oracle/stage_ref.py (git-ignored, travels to the GPU box via gpurun)
-REF_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "dh_aug_ref.zip")
+REF_ZIP = os.environ.get("DHFK_REFERENCE_ZIP") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref",
+                                                               "dh_aug_ref.zip")
 
 
 def reference_available() -> bool:

@@ -229,3 +229,48 @@ def run_loop(mode="single", *, device="cpu", iters=6, batch=32, dense=16, seed=1
 def scalars_matrix(scalars):
     """(names, values): the recorded scalars in call order as one float64 vector, with their tags."""
     return [s[0] for s in scalars], np.array([s[2] for s in scalars], np.float64)
+
+
+def time_loops(device, install, modes=("single", "video"), iters=10, batch=None, dense=256, prefer_staged=True):
+    """Wall-clock ms per iteration of the reference's own loops at BASELINE configs[2] / configs[3] sizes
+    (batch 1024 single-frame; 512 clips x 9 frames, architecture 3,3), after a short warm-up call of the same loop."""
+    import time
+    out = {}
+    for mode in modes:
+        b = batch or (1024 if mode == "single" else 512)
+        try:
+            run_loop(mode, device=device, iters=5, batch=b, dense=dense, seed=5, install=install, prefer_staged=prefer_staged)
+            if device != "cpu":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = run_loop(mode, device=device, iters=iters, batch=b, dense=dense, seed=6, install=install,
+                         prefer_staged=prefer_staged)
+            if device != "cpu":
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            poses = b * r["frames"]
+            out[mode] = {"ms_per_iteration": dt / iters * 1e3, "iterations": iters, "batch": b, "frames": r["frames"],
+                         "dense": dense, "poses_per_iteration": poses,
+                         "generator_steps": len(r["g_grads"]), "critic_steps": len(r["scalars"]) // 3}
+        except Exception as e:            # e.g. the unpatched reference's CUDA branch mixing devices
+            out[mode] = {"error": repr(e)[:400]}
+    return out
+
+
+if __name__ == "__main__":
+    import argparse
+    import json
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--install", default="all", choices=["none", "plain", "all"])
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--dense", type=int, default=256)
+    ap.add_argument("--modes", default="single,video")
+    a = ap.parse_args()
+    inst = {"none": None, "plain": {}, "all": dict(generators=True, critics=True, loader_refresh=True)}[a.install]
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    fd = os.dup(1)
+    os.dup2(2, 1)                       # the loops print progress bars: keep stdout for the JSON line
+    res = time_loops(a.device, inst, tuple(a.modes.split(",")), a.iters, None, a.dense)
+    os.write(fd, (json.dumps(res) + "\n").encode())

@@ -40,6 +40,30 @@ def assert_parity(x, ref, what="", rtol=RTOL, row_scale=None, floor=1.0):
     return e
 
 
+def assert_parity_vs_reference(x, ref32, exact64, what="", rtol=RTOL, c=4.0):
+    """Reference-relative bound (parity item): against the reference's own fp32 result `ref32`,
+        |x - ref32| <= rtol * max(|ref32|, 1)  +  c * E_ref(pose),    E_ref(pose) = max_elements |ref32 - exact64|,
+    where `exact64` is the float64 oracle on the same inputs.  For every normally placed pose the reference sits ~1e-7
+    from exact arithmetic, so the second term is nothing and the plain north-star bound applies; for poses the generator
+    drops onto the camera plane (clamp active, x/z ill-conditioned) the kernel is allowed c times the reference's OWN
+    distance from the exact value of that pose -- not an a-priori error model.  Returns (max scaled error, number of
+    poses that needed the second term)."""
+    x = np.asarray(x, dtype=np.float64)
+    ref32 = np.asarray(ref32, dtype=np.float64)
+    exact64 = np.asarray(exact64, dtype=np.float64)
+    assert x.shape == ref32.shape == exact64.shape, (x.shape, ref32.shape, exact64.shape)
+    n = x.shape[0]
+    e_ref = np.abs(ref32 - exact64).reshape(n, -1).max(axis=1).reshape((n,) + (1,) * (x.ndim - 1))
+    plain = rtol * np.maximum(np.abs(ref32), 1.0)
+    err = np.abs(x - ref32)
+    ok = err <= plain + c * e_ref
+    assert np.isfinite(err).all() and ok.all(), "%s: %d elements beyond rtol*max(|ref|,1) + %g*E_ref; worst %.3e (plain bound %.1e, E_ref %.3e)" % (
+        what, int((~ok).sum()), float((err / plain).max()), rtol,
+        float(e_ref.reshape(-1)[np.unravel_index(np.argmax(err / plain), err.shape)[0]]))
+    needed = int((~(err <= plain)).reshape(n, -1).any(axis=1).sum())
+    return float((err / (plain + c * e_ref)).max()), needed
+
+
 def projection_conditioning(cam_xyz, world=None, cam_block=None, g_uv=None, kind="grad"):
     """Per-pose tolerance multiplier (>= 1) for quantities that pass through x/z.  It is exactly 1 for
     every pose in front of the camera at a normal distance, so those are held to the plain 1e-5 bound.

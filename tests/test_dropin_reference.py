@@ -115,3 +115,28 @@ def test_reference_generator_class_is_state_dict_compatible(reference_modules):
     assert list(sd_ref) == list(sd_nat)
     assert all(sd_ref[k].shape == sd_nat[k].shape for k in sd_ref)
     G_nat.load_state_dict(sd_ref)
+
+
+def test_tensor_dh_matrix_and_rotation_matrix_match_the_reference():
+    """forward_kinematics_DH_model.py:80-116 / :141-191 on tensor inputs (SURVEY 8b lists both as module globals to
+    preserve): same matrices as the unmodified reference, and differentiable."""
+    ref = rh.import_reference()
+    from dhfk import forward_kinematics_DH_model as ours
+    n = 24
+    args = rh.make_args(n)
+    g = torch.Generator().manual_seed(2)
+    theta = (torch.rand(n, generator=g) * 720 - 360).requires_grad_(True)
+    a, d = torch.rand(n, generator=g), torch.rand(n, generator=g)
+    for alpha_deg in (0.0, 90.0, -90.0, 37.5):
+        alpha = torch.full((n,), alpha_deg)
+        want = ref.fk.dh_matrix(alpha, a, d, theta, args)
+        got = ours.dh_matrix(alpha, a, d, theta, args)
+        assert got.shape == (n, 4, 4) and torch.allclose(got, want, atol=1e-6, rtol=0)
+        (gw,) = torch.autograd.grad((want * torch.arange(16.0).view(4, 4)).sum(), theta)
+        (gg,) = torch.autograd.grad((got * torch.arange(16.0).view(4, 4)).sum(), theta)
+        assert torch.allclose(gg, gw, atol=1e-5, rtol=1e-5)
+    ax, ay, az = (torch.rand(n, generator=g) * 360 - 180 for _ in range(3))
+    assert torch.allclose(ours.rotationMatrix(ax, ay, az, args), ref.fk.rotationMatrix(ax, ay, az, args), atol=1e-6, rtol=0)
+    import numpy as np
+    assert np.allclose(ours.dh_matrix(-90.0, 0.3, 0.2, 33.0), ref.fk.dh_matrix(-90.0, 0.3, 0.2, 33.0, args), atol=1e-12)
+    assert np.allclose(ours.rotationMatrix(10.0, -20.0, 30.0), ref.fk.rotationMatrix(10.0, -20.0, 30.0, args), atol=1e-12)

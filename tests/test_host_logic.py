@@ -135,8 +135,11 @@ def test_scalar_dh_matrix_and_rotation_helpers(c_oracle):
     assert np.allclose(dh_matrix(-90.0, 0.3, 0.2, 37.0, None), T.reshape(4, 4), atol=1e-15)
     lib.dhfk_oracle_rotation_matrix(d(10.0), d(20.0), d(30.0), R.ctypes.data_as(ctypes.POINTER(d)))
     assert np.allclose(rotationMatrix(10.0, 20.0, 30.0, None), R.reshape(3, 3), atol=1e-15)
-    with pytest.raises(NotImplementedError):
-        dh_matrix(torch.zeros(2), torch.zeros(2), torch.zeros(2), torch.zeros(2), None)
+    # tensor inputs: one matrix per row, the same numbers (pinned to the reference itself in test_dropin_reference.py)
+    Tt = dh_matrix(torch.full((3,), -90.0), torch.full((3,), 0.3), torch.full((3,), 0.2), torch.full((3,), 37.0), None)
+    assert Tt.shape == (3, 4, 4) and np.allclose(Tt[1].numpy(), T.reshape(4, 4), atol=1e-6)
+    Rt = rotationMatrix(torch.full((3,), 10.0), torch.full((3,), 20.0), torch.full((3,), 30.0), None)
+    assert Rt.shape == (3, 3, 3) and np.allclose(Rt[2].numpy(), R.reshape(3, 3), atol=1e-6)
 
 
 def test_dropin_install_widening_flags(monkeypatch):

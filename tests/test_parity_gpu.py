@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import RTOL, assert_parity, projection_conditioning, rel_err
+from conftest import RTOL, assert_parity, assert_parity_vs_reference, projection_conditioning, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -56,13 +56,21 @@ def test_forward_matches_reference_golden(golden, case, trig):
 @pytest.mark.parametrize("trig", TRIG_IDS)
 @pytest.mark.parametrize("tag", ["w", "wu", "wcu"])
 @pytest.mark.parametrize("case", CASES)
-def test_backward_matches_reference_autograd(golden, case, tag, trig):
+def test_backward_matches_reference_autograd(golden, c_oracle, case, tag, trig):
+    """Against the reference's own autograd (goldens).  The bound is reference-relative (conftest.
+    assert_parity_vs_reference): the plain 1e-5 for every pose the reference itself computes accurately -- all of gan133 and
+    video36 -- plus, for the clamp-active / near-camera-plane poses of stress200, 4x the reference's OWN fp32-vs-float64
+    error on that pose."""
     g = golden(case)
     *_, g_ang, g_grot, g_root = run_fused(g, trig, tag)
-    cond = projection_conditioning(g["cam"], g["world16"], g["cam_block"], g["g_uv"]) if "u" in tag else None
-    assert_parity(g_ang, g["g_ang_" + tag], "g_ang", row_scale=cond)
-    assert_parity(g_grot, g["g_grot_" + tag], "g_grot", row_scale=cond)
-    assert_parity(g_root, g["g_root_" + tag], "g_root", row_scale=cond)
+    b = c_oracle.backward(g["ang"], g["grot"], g["bone"], g["root"], g["cam_block"], g_world=g["g_world"],
+                          g_cam=g["g_cam"] if "c" in tag else None, g_uv=g["g_uv"] if "u" in tag else None, want_bone=False)
+    needed = 0
+    for name, x in (("g_ang", g_ang), ("g_grot", g_grot), ("g_root", g_root)):
+        _, k = assert_parity_vs_reference(x, g["%s_%s" % (name, tag)], b[name], "%s %s %s" % (case, tag, name))
+        needed += k
+    if case != "stress200":
+        assert needed == 0, "a normally placed pose needed the reference-error allowance"
     assert np.all(g_ang[:, [4, 9, 22, 27, 32]] == 0)
 
 
@@ -333,3 +341,49 @@ def test_host_pipeline_shapes(n, chunk, slots, bwd):
     with pytest.raises(ValueError):
         dhfk.fk_project_host(pin(inp["ang"]), pin(inp["grot"]), pin(inp["bone"]), pin(inp["root"]), blk,
                              pin(up["g_world"]), None)
+
+
+def test_projection_nan_and_zero_depth_semantics_match_torch_clamp():
+    """common/camera.py:85: XX = torch.clamp(X[..., :2] / X[..., 2:], -1, 1).  torch.clamp propagates NaN (0/0 at
+    x = z = 0, NaN inputs) and x/0 = +-inf clamps to +-1; the kernels use FMNMX.NAN for the same result.  Checked against
+    the reference's op sequence in torch (oracle/torch_port.py::project_to_2d) on the CPU, forward and gradient:
+    identical NaN pattern, finite values within the north-star tolerance.  The one documented divergence
+    (include/dhfk.h): a DENORMAL z is flushed to zero by MUFU.RCP, so (x = 0, |z| < 1.2e-38) yields NaN instead of 0."""
+    import dhfk
+    import torch_port
+    nan, inf = float("nan"), float("inf")
+    pts = np.array([
+        [0.3, -0.2, 4.0], [1.0, 2.0, 0.0], [-1.0, 0.5, 0.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0], [nan, 0.1, 3.0],
+        [0.1, nan, 3.0], [0.1, 0.2, nan], [inf, 0.1, 2.0], [0.1, 0.2, inf], [5.0, -7.0, 1e-30], [0.2, 0.1, -3.0],
+        [3.0, 3.0, 3.0], [-3.0, 2.9999, 3.0], [1e-20, 1e-20, 1e-20], [0.5, 0.5, 0.5],
+    ], np.float32)
+    n = 37
+    x = np.tile(pts[None], (n, 1, 1)).copy()
+    x[1:] += np.where(np.isfinite(x[1:]) & (x[1:] != 0), np.random.RandomState(3).randn(n - 1, 16, 3).astype(np.float32) * 1e-3, 0)
+    rows = np.tile(tables_cam_rows(), (n, 1))
+    g_uv = np.random.RandomState(4).randn(n, 16, 2).astype(np.float32)
+    xt = torch.tensor(x, requires_grad=True)
+    ref = torch_port.project_to_2d(xt, torch.tensor(rows))
+    (ref * torch.tensor(g_uv)).sum().backward()
+    xd = T(x, True)
+    uv = dhfk.project_to_2d(xd, T(rows))
+    (uv * T(g_uv)).sum().backward()
+    got, want = uv.detach().cpu().numpy(), ref.detach().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want)), "uv: NaN pattern differs from torch.clamp semantics"
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin), "uv: inf pattern differs"
+    assert (np.abs(got[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1.0)).max() <= 1e-5
+    assert np.isnan(want[:, 3]).all() and (np.abs(want[:, 1, 0] - want[:, 12, 0]) < 1e-6).all()   # 0/0 -> NaN, x/0 -> clamp edge
+    # gradients: wherever torch's own backward stays finite the kernel agrees; a NaN the kernel produces is one torch
+    # produces too (torch additionally turns 0 * (x / z^2 = inf) into NaN where the kernel's mask has already zeroed it)
+    gg, gw = xd.grad.cpu().numpy(), xt.grad.numpy()
+    both = np.isfinite(gw) & np.isfinite(gg)
+    assert (np.abs(gg[both] - gw[both]) / np.maximum(np.abs(gw[both]), 1.0)).max() <= 1e-5
+    assert not (np.isnan(gg) & np.isfinite(gw)).any(), "the kernel produced a NaN gradient where torch has a finite one"
+    for row in (0, 11, 12, 13, 14, 15):
+        assert np.isfinite(gg[:, row]).all() and np.isfinite(gw[:, row]).all()
+
+
+def tables_cam_rows():
+    from dhfk import tables
+    return tables.camera_block("S1", 0)[7:16].reshape(1, 9).astype(np.float32)

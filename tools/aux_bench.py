@@ -27,12 +27,15 @@ def timeit(fn, sets, steps=50, warmup=5):
     return a.elapsed_time(b) / steps
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-    dev = torch.device("cuda:0")
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6528.7)
+def measure(dev=None, n=1 << 20, peak=None, steps=50):
+    """-> dict(poses, peak_gbs, kernels={name: ms, bytes_per_pose, gbs, frac, poses_per_s}).  bench.py imports this for
+    its `side_kernels` extra."""
+    dev = dev or torch.device("cuda:0")
+    if peak is None:
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = json.load(open(pk)).get("hbm_gbs", 6528.7) if os.path.exists(pk) else 6650.0
     lib = _cabi.load()
-    st = torch.cuda.current_stream().cuda_stream
+    st = torch.cuda.current_stream(dev).cuda_stream
     g = torch.Generator(device=dev).manual_seed(1)
     sets = []
     for _ in range(4):
@@ -119,14 +122,41 @@ def main():
         s_["o96"] = torch.empty(n, 96, device=dev)
     cases["context: torch.index_select of the same records (384 B in, 384 B out)"] = (
         lambda s: torch.index_select(rec, 0, s["perm"], out=s["o96"]), 8 + 2 * 384)
+    # f2, video part: inputs of the motion critics, F = 9 (architecture 3,3), per-frame KCS + adjacent-frame differences
+    F = 9
+    nv = n // F * F
+    bv = nv // F
+    for s_ in sets:
+        s_["vk"], s_["vdk"] = torch.empty(bv, F, 15, device=dev), torch.empty(bv, F - 1, 15, device=dev)
+        s_["vdp"], s_["vgx"] = torch.empty(bv, F - 1, 48, device=dev), torch.empty(nv, 16, 3, device=dev)
+        s_["gvk"], s_["gvdk"] = torch.randn(bv, F, 15, device=dev, generator=g), torch.randn(bv, F - 1, 15, device=dev, generator=g)
+        s_["gvdp"] = torch.randn(bv, F - 1, 48, device=dev, generator=g)
+        s_["vrd"] = torch.empty(bv, F - 1, 2, device=dev)
+    fr = (F - 1) / F
+    cases["video critic fwd: kcs + dkcs + dpos, F=9 (f2)"] = (
+        lambda s: lib.dhfk_video_critic_forward(P(s["pose"]), F, 0, P(s["vk"]), P(s["vdk"]), P(s["vdp"]), None, nv, st),
+        192 + 60 + fr * (60 + 192))
+    cases["video critic fwd, playback reverse (f2)"] = (
+        lambda s: lib.dhfk_video_critic_forward(P(s["pose"]), F, 1, P(s["vk"]), P(s["vdk"]), P(s["vdp"]), None, nv, st),
+        192 + 60 + fr * (60 + 192))
+    cases["video critic vjp (f2)"] = (
+        lambda s: lib.dhfk_video_critic_backward(P(s["pose"]), F, 0, P(s["gvk"]), P(s["gvdk"]), P(s["gvdp"]), None, P(s["vgx"]), nv, st),
+        192 + 60 + fr * (60 + 192) + 192)
+    cases["video critic jvp (f2)"] = (
+        lambda s: lib.dhfk_video_critic_jvp(P(s["pose"]), P(s["gp"]), F, 0, P(s["vk"]), P(s["vdk"]), P(s["vdp"]), None, nv, st),
+        192 + 192 + 60 + fr * (60 + 192))
+    cases["video 2-D root differences fwd (f2; reads 8 of every 128 bytes: sector-bound)"] = (
+        lambda s: lib.dhfk_video_root_diff_forward(P(s["gu"]), F, 0, P(s["vrd"]), None, nv, st), 32 + fr * 8)
+    cases["video 2-D root differences bwd (f2)"] = (
+        lambda s: lib.dhfk_video_root_diff_backward(P(s["vrd"]), None, F, 0, P(s["o32"]), nv, st), fr * 8 + 128)
     out = {"poses": n, "peak_gbs": peak, "kernels": {}}
     for name, (fn, bpp) in cases.items():
-        ms = timeit(fn, sets)
+        ms = timeit(fn, sets, steps=steps)
         gbs = n * bpp / ms / 1e6
         out["kernels"][name] = {"ms": round(ms, 5), "bytes_per_pose": bpp, "gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
                                 "poses_per_s": round(n / ms * 1e3)}
-    print(json.dumps(out, indent=1))
+    return out
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(measure(n=int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20), indent=1))
