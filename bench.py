@@ -391,7 +391,7 @@ class HotPath:
         from dhfk import _cabi
         d = self.sets[i % self.nbuf]
         rc = self.lib.dhfk_forward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
-                                   d["root"].data_ptr(), 3, self.cam_ptr, None, 0, self.world.data_ptr(), None,
+                                   d["root"].data_ptr(), 3, self.cam_ptr, self.world.data_ptr(), None,
                                    self.uv.data_ptr(), self.n, self.flags if flags is None else flags, self.sp)
         _cabi.check(rc, "dhfk_forward")
 
@@ -399,7 +399,7 @@ class HotPath:
         from dhfk import _cabi
         d = self.sets[i % self.nbuf]
         rc = self.lib.dhfk_backward(d["ang"].data_ptr(), 33, d["grot"].data_ptr(), 3, d["bone"].data_ptr(), 15,
-                                    d["root"].data_ptr(), 3, self.cam_ptr, None, 0, d["g_world"].data_ptr(), None,
+                                    d["root"].data_ptr(), 3, self.cam_ptr, d["g_world"].data_ptr(), None,
                                     d["g_uv"].data_ptr(), self.g_ang.data_ptr(), 33, self.g_grot.data_ptr(), 3,
                                     self.g_root.data_ptr(), 3, None, 15, self.n, self.flags if flags is None else flags, self.sp)
         _cabi.check(rc, "dhfk_backward")

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DHFK_LIB_PATH") or os.path.join(_HERE, "lib", "libdhfk.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FLAG_FAST_TRIG = 0x1
 FLAG_ACCURATE_TRIG = 0x2
 CRITIC_CENTRE, CRITIC_FLIP = 0x1, 0x2
@@ -31,9 +31,9 @@ SIGNATURES = {
     "dhfk_last_error": (ctypes.c_char_p, []),
     "dhfk_tile_rows": (ctypes.c_int, []),
     "dhfk_topology": (ctypes.c_int, [_vp] * 8),
-    "dhfk_forward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64,
+    "dhfk_forward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp,
                                     _vp, _vp, _vp, _i64, _u32, _vp]),
-    "dhfk_backward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64,
+    "dhfk_backward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp,
                                      _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
                                      _i64, _u32, _vp]),
     "dhfk_generator_forward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, ctypes.c_float, _vp,

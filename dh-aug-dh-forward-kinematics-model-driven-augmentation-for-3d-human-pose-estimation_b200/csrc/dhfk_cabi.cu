@@ -245,15 +245,12 @@ int dhfk_topology(int32_t* parent33, int32_t* out16, float* alpha33, float* thet
 }
 
 int dhfk_forward(const float* ang, int64_t ang_stride, const float* grot, int64_t grot_stride, const float* bone,
-                 int64_t bone_stride, const float* root, int64_t root_stride, const float* cam,
-                 const float* cam_rows, int64_t cam_rows_stride, float* out_world, float* out_cam, float* out_uv,
-                 int64_t n, uint32_t flags, void* stream) {
-    (void)cam_rows_stride;
+                 int64_t bone_stride, const float* root, int64_t root_stride, const float* cam, float* out_world,
+                 float* out_cam, float* out_uv, int64_t n, uint32_t flags, void* stream) {
     int rc = check_inputs(ang, ang_stride, grot, grot_stride, bone, bone_stride, root, root_stride, n);
     if (rc != DHFK_OK) return rc;
     if (n == 0) return DHFK_OK;
     if (bad_trig_flags(flags)) return fail(DHFK_E_INVAL, "DHFK_FLAG_FAST_TRIG and DHFK_FLAG_ACCURATE_TRIG are mutually exclusive");
-    if (cam_rows) return fail(DHFK_E_UNSUPPORTED, "per-row intrinsics are not supported in the fused path; use dhfk_project_*");
     if (!out_world) return fail(DHFK_E_INVAL, "out_world is required");
     if ((out_cam || out_uv) && !cam) return fail(DHFK_E_INVAL, "cam block required for out_cam / out_uv");
     if (!aligned16(out_world) || !aligned16(out_cam) || !aligned16(out_uv))
@@ -280,17 +277,14 @@ int dhfk_forward(const float* ang, int64_t ang_stride, const float* grot, int64_
 }
 
 int dhfk_backward(const float* ang, int64_t ang_stride, const float* grot, int64_t grot_stride, const float* bone,
-                  int64_t bone_stride, const float* root, int64_t root_stride, const float* cam,
-                  const float* cam_rows, int64_t cam_rows_stride, const float* g_world, const float* g_cam,
-                  const float* g_uv, float* g_ang, int64_t g_ang_stride, float* g_grot, int64_t g_grot_stride,
-                  float* g_root, int64_t g_root_stride, float* g_bone, int64_t g_bone_stride, int64_t n,
-                  uint32_t flags, void* stream) {
-    (void)cam_rows_stride;
+                  int64_t bone_stride, const float* root, int64_t root_stride, const float* cam, const float* g_world,
+                  const float* g_cam, const float* g_uv, float* g_ang, int64_t g_ang_stride, float* g_grot,
+                  int64_t g_grot_stride, float* g_root, int64_t g_root_stride, float* g_bone, int64_t g_bone_stride,
+                  int64_t n, uint32_t flags, void* stream) {
     int rc = check_inputs(ang, ang_stride, grot, grot_stride, bone, bone_stride, root, root_stride, n);
     if (rc != DHFK_OK) return rc;
     if (n == 0) return DHFK_OK;
     if (bad_trig_flags(flags)) return fail(DHFK_E_INVAL, "DHFK_FLAG_FAST_TRIG and DHFK_FLAG_ACCURATE_TRIG are mutually exclusive");
-    if (cam_rows) return fail(DHFK_E_UNSUPPORTED, "per-row intrinsics are not supported in the fused path; use dhfk_project_*");
     if (!g_world && !g_cam && !g_uv) return fail(DHFK_E_INVAL, "at least one upstream gradient is required");
     if ((g_cam || g_uv) && !cam) return fail(DHFK_E_INVAL, "cam block required for g_cam / g_uv");
     if (!g_ang || !g_grot || !g_root) return fail(DHFK_E_INVAL, "g_ang, g_grot and g_root are required");
@@ -790,13 +784,13 @@ int dhfk_forward_backward_host(const float* ang_h, const float* grot_h, const fl
         }
         DHFK_EV(cudaStreamWaitEvent(s_run, E[kUpIn], 0))
         if (rc == DHFK_OK)
-            rc = dhfk_forward(d_ang, 33, d_grot, 3, d_bone, 15, d_root, 3, cam, nullptr, 0, d_world, nullptr, d_uv,
+            rc = dhfk_forward(d_ang, 33, d_grot, 3, d_bone, 15, d_root, 3, cam, d_world, nullptr, d_uv,
                               rows, flags, s_run);
         DHFK_EV(cudaEventRecord(E[kFwd], s_run))
         if (do_bwd) {
             DHFK_EV(cudaStreamWaitEvent(s_run, E[kUpGrad], 0))
             if (rc == DHFK_OK)
-                rc = dhfk_backward(d_ang, 33, d_grot, 3, d_bone, 15, d_root, 3, cam, nullptr, 0, d_gw, nullptr, d_gu,
+                rc = dhfk_backward(d_ang, 33, d_grot, 3, d_bone, 15, d_root, 3, cam, d_gw, nullptr, d_gu,
                                    d_gang, 33, d_ggrot, 3, d_groot, 3, nullptr, 0, rows, flags, s_run);
             DHFK_EV(cudaEventRecord(E[kBwd], s_run))
         }

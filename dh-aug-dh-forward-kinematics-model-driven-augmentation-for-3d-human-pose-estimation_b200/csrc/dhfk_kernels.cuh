@@ -60,6 +60,9 @@ struct RowDst {
 struct WideRows {
     int wide, goff, grot_slab;
 };
+#ifndef DHFK_WIDE_ROWS        // A/B switch: 0 compiles the wide-row path out of the kernels (profiles/r2_ab.md)
+#define DHFK_WIDE_ROWS 1
+#endif
 struct FwdParams {
     RowSrc ang, grot, bone, root;   // GEN mode: `ang` is the raw network output [N,35]; grot/root unused
     WideRows w;
@@ -356,7 +359,7 @@ DHFK_DI void flush_chunks(float4* row4, const float* v) {
 template <bool CAM, bool UV, int TRIG, bool GEN>
 __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__ FwdParams p) {
     constexpr int NANG = GEN ? GEN_NCOL : 33;      // floats per pose in the first slab
-    const int wide = GEN ? 0 : p.w.wide;           // launch-uniform
+    const int wide = (GEN || !DHFK_WIDE_ROWS) ? 0 : p.w.wide;           // launch-uniform
     extern __shared__ __align__(16) float smem[];
     float* s_ang = smem;
     float* s_grot = s_ang + kTile * (wide ? wide : NANG);
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
     static_assert(GW || GCAM || GUV, "at least one upstream gradient");
     static_assert(!(GEN && GBONE), "bone-length gradients are not produced in generator mode");
     constexpr int NANG = GEN ? GEN_NCOL : 33;
-    const int wide = GEN ? 0 : p.w.wide;           // launch-uniform (see WideRows)
+    const int wide = (GEN || !DHFK_WIDE_ROWS) ? 0 : p.w.wide;           // launch-uniform (see WideRows)
     extern __shared__ __align__(16) float smem[];
     float* s_ang = smem;
     float* s_grot = s_ang + kTile * (wide ? wide : NANG);

@@ -119,7 +119,7 @@ class _FKProject(torch.autograd.Function):
             rc = lib.dhfk_forward(
                 ang2.data_ptr(), _row_stride(ang2), grot2.data_ptr(), _row_stride(grot2),
                 bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
-                cam_arr.ctypes.data if cam_arr is not None else None, None, 0,
+                cam_arr.ctypes.data if cam_arr is not None else None,
                 world.data_ptr(), camo.data_ptr() if want_cam else None, uv.data_ptr() if want_uv else None,
                 n, flags, _stream_ptr(device))
         _cabi.check(rc, "dhfk_forward")
@@ -158,7 +158,7 @@ class _FKProject(torch.autograd.Function):
                 rc = lib.dhfk_backward(
                     ang2.data_ptr(), _row_stride(ang2), grot2.data_ptr(), _row_stride(grot2),
                     bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
-                    ctx.cam_arr.ctypes.data if ctx.cam_arr is not None else None, None, 0,
+                    ctx.cam_arr.ctypes.data if ctx.cam_arr is not None else None,
                     g_world.data_ptr() if g_world is not None else None,
                     g_cam.data_ptr() if g_cam is not None else None,
                     g_uv.data_ptr() if g_uv is not None else None,
@@ -212,7 +212,7 @@ class _FKProjectWide(torch.autograd.Function):
             with _on_device(device):
                 rc = lib.dhfk_forward(
                     base, S, base + 4 * goff, S, bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
-                    cam_arr.ctypes.data if cam_arr is not None else None, None, 0,
+                    cam_arr.ctypes.data if cam_arr is not None else None,
                     world.data_ptr(), camo.data_ptr() if want_cam else None, uv.data_ptr() if want_uv else None,
                     n, flags, _stream_ptr(device))
             _cabi.check(rc, "dhfk_forward")
@@ -248,7 +248,7 @@ class _FKProjectWide(torch.autograd.Function):
             with _on_device(device):
                 rc = lib.dhfk_backward(
                     base, S, base + 4 * goff, S, bone2.data_ptr(), _row_stride(bone2), root2.data_ptr(), _row_stride(root2),
-                    cam_arr.ctypes.data if cam_arr is not None else None, None, 0,
+                    cam_arr.ctypes.data if cam_arr is not None else None,
                     g_world.data_ptr() if g_world is not None else None,
                     g_cam.data_ptr() if g_cam is not None else None, g_uv.data_ptr() if g_uv is not None else None,
                     gbase, S, gbase + 4 * goff, S, g_root.data_ptr(), 3,

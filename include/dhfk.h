@@ -66,7 +66,7 @@
 extern "C" {
 #endif
 
-#define DHFK_ABI_VERSION 1
+#define DHFK_ABI_VERSION 2
 
 #define DHFK_OK 0
 #define DHFK_E_INVAL (-1)       /* null / negative / inconsistent argument                     */
@@ -106,16 +106,16 @@ int dhfk_tile_rows(void);
  *   grot_dev  [N, >=3]  global rotation angles x,y,z (deg), row stride grot_stride
  *   bone_dev  [N, >=15] bone lengths (m), row stride bone_stride
  *   root_dev  [N, >=3]  root translation (m), row stride root_stride
- *   cam       host, 16 floats (DHFK_CAM_BLOCK); required iff out_cam_dev or out_uv_dev
- *   cam_rows_dev  reserved for per-row intrinsics in the fused path; must be NULL (use
- *                 dhfk_project_* for per-row cameras)
+ *   cam       host, 16 floats (DHFK_CAM_BLOCK); required iff out_cam_dev or out_uv_dev.  The camera of the fused path is
+ *             batch-uniform, as in the GAN step (one subject/camera draw per batch, model_fk_gan_train.py:344-363);
+ *             per-row intrinsics (the loader refresh, function_aug/dataloader_update.py:69) go through
+ *             dhfk_project_* / dhfk_retarget_project.  (ABI 1 carried a reserved cam_rows_dev pair here; ABI 2 drops it.)
  *   out_world_dev [N,16,3] required; out_cam_dev [N,16,3] / out_uv_dev [N,16,2] optional
  */
 int dhfk_forward(const float* ang_dev, int64_t ang_stride, const float* grot_dev, int64_t grot_stride,
                  const float* bone_dev, int64_t bone_stride, const float* root_dev, int64_t root_stride,
-                 const float* cam, const float* cam_rows_dev, int64_t cam_rows_stride,
-                 float* out_world_dev, float* out_cam_dev, float* out_uv_dev, int64_t n, uint32_t flags,
-                 void* stream);
+                 const float* cam, float* out_world_dev, float* out_cam_dev, float* out_uv_dev, int64_t n,
+                 uint32_t flags, void* stream);
 
 /*
  * Fused backward (recomputes the forward in registers):
@@ -127,8 +127,7 @@ int dhfk_forward(const float* ang_dev, int64_t ang_stride, const float* grot_dev
  */
 int dhfk_backward(const float* ang_dev, int64_t ang_stride, const float* grot_dev, int64_t grot_stride,
                   const float* bone_dev, int64_t bone_stride, const float* root_dev, int64_t root_stride,
-                  const float* cam, const float* cam_rows_dev, int64_t cam_rows_stride,
-                  const float* g_world_dev, const float* g_cam_dev, const float* g_uv_dev,
+                  const float* cam, const float* g_world_dev, const float* g_cam_dev, const float* g_uv_dev,
                   float* g_ang_dev, int64_t g_ang_stride, float* g_grot_dev, int64_t g_grot_stride,
                   float* g_root_dev, int64_t g_root_stride, float* g_bone_dev, int64_t g_bone_stride,
                   int64_t n, uint32_t flags, void* stream);

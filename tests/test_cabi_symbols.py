@@ -30,7 +30,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_abi_version_and_tile():
     lib = _cabi.load()
-    assert lib.dhfk_abi_version() == _cabi.ABI_VERSION == 1
+    assert lib.dhfk_abi_version() == _cabi.ABI_VERSION == 2
     assert lib.dhfk_tile_rows() == 32
 
 
@@ -38,26 +38,25 @@ def test_argument_validation_without_gpu():
     lib = _cabi.load()
     z = None
     # n == 0 is a no-op success for every entry point
-    assert lib.dhfk_forward(z, 33, z, 3, z, 15, z, 3, z, z, 0, z, z, z, 0, 0, z) == 0
-    assert lib.dhfk_backward(z, 33, z, 3, z, 15, z, 3, z, z, 0, z, z, z, z, 33, z, 3, z, 3, z, 15, 0, 0, z) == 0
+    assert lib.dhfk_forward(z, 33, z, 3, z, 15, z, 3, z, z, z, z, 0, 0, z) == 0
+    assert lib.dhfk_backward(z, 33, z, 3, z, 15, z, 3, z, z, z, z, z, 33, z, 3, z, 3, z, 15, 0, 0, z) == 0
     assert lib.dhfk_world_to_camera_forward(z, z, z, 0, z, 0, z) == 0
     assert lib.dhfk_project_forward(z, z, 9, z, 0, 16, z) == 0
     # negative n, null pointers, short strides -> DHFK_E_INVAL with a message
-    assert lib.dhfk_forward(z, 33, z, 3, z, 15, z, 3, z, z, 0, z, z, z, -1, 0, z) == _cabi.E_INVAL
+    assert lib.dhfk_forward(z, 33, z, 3, z, 15, z, 3, z, z, z, z, -1, 0, z) == _cabi.E_INVAL
     assert "n must be" in _cabi.last_error()
-    assert lib.dhfk_forward(z, 33, z, 3, z, 15, z, 3, z, z, 0, z, z, z, 5, 0, z) == _cabi.E_INVAL
+    assert lib.dhfk_forward(z, 33, z, 3, z, 15, z, 3, z, z, z, z, 5, 0, z) == _cabi.E_INVAL
     buf = np.zeros(64 * 48, np.float32)
     p = buf.ctypes.data
-    assert lib.dhfk_forward(p, 32, p, 3, p, 15, p, 3, z, z, 0, p, z, z, 4, 0, z) == _cabi.E_INVAL   # ang stride < 33
+    assert lib.dhfk_forward(p, 32, p, 3, p, 15, p, 3, z, p, z, z, 4, 0, z) == _cabi.E_INVAL   # ang stride < 33
     assert "stride" in _cabi.last_error()
-    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, z, z, z, 4, 0, z) == _cabi.E_INVAL   # out_world missing
-    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, p, z, p, 4, 0, z) == _cabi.E_INVAL   # uv without cam
-    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, p, p, 9, p, z, p, 4, 0, z) == _cabi.E_UNSUPPORTED  # cam_rows
-    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, p + 4, z, z, 4, 0, z) == _cabi.E_ALIGN
+    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, z, z, 4, 0, z) == _cabi.E_INVAL   # out_world missing
+    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, p, z, p, 4, 0, z) == _cabi.E_INVAL   # uv without cam
+    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, p + 4, z, z, 4, 0, z) == _cabi.E_ALIGN
     both = _cabi.FLAG_FAST_TRIG | _cabi.FLAG_ACCURATE_TRIG          # contradictory trig policies
-    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, z, 0, p, z, z, 4, both, z) == _cabi.E_INVAL
+    assert lib.dhfk_forward(p, 33, p, 3, p, 15, p, 3, z, p, z, z, 4, both, z) == _cabi.E_INVAL
     assert "mutually exclusive" in _cabi.last_error()
-    assert lib.dhfk_backward(p, 33, p, 3, p, 15, p, 3, z, z, 0, z, z, z, p, 33, p, 3, p, 3, z, 15, 4, 0, z) == _cabi.E_INVAL
+    assert lib.dhfk_backward(p, 33, p, 3, p, 15, p, 3, z, z, z, z, p, 33, p, 3, p, 3, z, 15, 4, 0, z) == _cabi.E_INVAL
     assert "upstream" in _cabi.last_error()
     assert lib.dhfk_project_forward(p, p, 8, p, 4, 16, z) == _cabi.E_INVAL
     assert lib.dhfk_host_workspace_bytes(0, 2) == 0

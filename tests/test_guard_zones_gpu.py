@@ -49,17 +49,17 @@ def test_no_kernel_writes_outside_its_outputs(n):
     world, cam, uv = A.out(n, 16, 3), A.out(n, 16, 3), A.out(n, 16, 2)
     for flags in (0, _cabi.FLAG_FAST_TRIG):
         _cabi.check(lib.dhfk_forward(P(d["ang"]), 33, P(d["grot"]), 3, P(d["bone"]), 15, P(d["root"]), 3, blk.ctypes.data,
-                                     None, 0, P(world), P(cam), P(uv), n, flags, st), "fwd")
+                                     P(world), P(cam), P(uv), n, flags, st), "fwd")
     g_ang, g_grot, g_root, g_bone = A.out(n, 33), A.out(n, 3), A.out(n, 3), A.out(n, 15)
     for flags in (0, _cabi.FLAG_ACCURATE_TRIG):
         _cabi.check(lib.dhfk_backward(P(d["ang"]), 33, P(d["grot"]), 3, P(d["bone"]), 15, P(d["root"]), 3, blk.ctypes.data,
-                                      None, 0, P(up["g_world"]), P(up["g_cam"]), P(up["g_uv"]), P(g_ang), 33, P(g_grot), 3,
+                                      P(up["g_world"]), P(up["g_cam"]), P(up["g_uv"]), P(g_ang), 33, P(g_grot), 3,
                                       P(g_root), 3, P(g_bone), 15, n, flags, st), "bwd")
     # strided gradient outputs (a [n,37] angle-gradient view): only columns 0..32 of each row may be written
     g37 = A.out(n, 37)
     g37.fill_(7.0)
     _cabi.check(lib.dhfk_backward(P(d["ang"]), 33, P(d["grot"]), 3, P(d["bone"]), 15, P(d["root"]), 3, blk.ctypes.data,
-                                  None, 0, P(up["g_world"]), None, P(up["g_uv"]), P(g37), 37, P(g_grot), 3, P(g_root), 3,
+                                  P(up["g_world"]), None, P(up["g_uv"]), P(g37), 37, P(g_grot), 3, P(g_root), 3,
                                   None, 15, n, 0, st), "bwd strided")
     torch.cuda.synchronize()
     assert (g37[:, 33:] == 7.0).all() and not (g37[:, :33] == 7.0).all()

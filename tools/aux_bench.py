@@ -68,17 +68,17 @@ def measure(dev=None, n=1 << 20, peak=None, steps=50):
         s_["o48b"] = torch.empty(n, 16, 3, device=dev)
         s_["g33"], s_["g3a"], s_["g3b"] = torch.empty(n, 33, device=dev), torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
     cases["FK forward: world + cam + uv"] = (
-        lambda s: lib.dhfk_forward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, blk.ctypes.data, None, 0,
+        lambda s: lib.dhfk_forward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, blk.ctypes.data,
                                    P(s["o48"]), P(s["o48b"]), P(s["o32"]), n, 0, st), 216 + 192 + 192 + 128)
     cases["FK forward: world only"] = (
-        lambda s: lib.dhfk_forward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, None, None, 0,
+        lambda s: lib.dhfk_forward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, None,
                                    P(s["o48"]), None, None, n, 0, st), 216 + 192)
     cases["FK backward: g_world only"] = (
-        lambda s: lib.dhfk_backward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, None, None, 0,
+        lambda s: lib.dhfk_backward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, None,
                                     P(s["gp"]), None, None, P(s["g33"]), 33, P(s["g3a"]), 3, P(s["g3b"]), 3, None, 15, n, 0, st),
         216 + 192 + 156)
     cases["FK backward: g_world + g_cam + g_uv"] = (
-        lambda s: lib.dhfk_backward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, blk.ctypes.data, None, 0,
+        lambda s: lib.dhfk_backward(P(s["ang"]), 33, P(s["grot"]), 3, P(s["bone"]), 15, P(s["root"]), 3, blk.ctypes.data,
                                     P(s["gp"]), P(s["pose"]), P(s["gu2"]), P(s["g33"]), 33, P(s["g3a"]), 3, P(s["g3b"]), 3, None, 15,
                                     n, 0, st), 216 + 192 + 192 + 128 + 156)
     for s_ in sets:
@@ -87,7 +87,7 @@ def measure(dev=None, n=1 << 20, peak=None, steps=50):
         s_["g37"] = torch.zeros(n, 37, device=dev)
         s_["g37"][:, :33] = s_["ang"]; s_["g37"][:, 34:] = s_["grot"]
     cases["FK forward world only, angles / global rotation as views of one [N,37] tensor"] = (
-        lambda s: lib.dhfk_forward(P(s["g37"]), 37, P(s["g37"]) + 34 * 4, 37, P(s["bone"]), 15, P(s["root"]), 3, None, None, 0,
+        lambda s: lib.dhfk_forward(P(s["g37"]), 37, P(s["g37"]) + 34 * 4, 37, P(s["bone"]), 15, P(s["root"]), 3, None,
                                    P(s["o48"]), None, None, n, 0, st), 148 + 60 + 12 + 192)
     for s_ in sets:
         s_["o96b"] = torch.empty(n, 32, 3, device=dev)

@@ -114,7 +114,8 @@ def measure(dev, big=1 << 20, small=(1024, 4608), peak_gbs=6528.7, profile=False
         torch.cuda.synchronize(dev)
         rec = {"us_per_step_wall": wall * 1e6, "us_per_step_gpu_events": e0.elapsed_time(e1) / 100 * 1e3,
                "note": "wall = host-bound: three torch.autograd.Function nodes each way + the caller's own slicing"}
-        try:    # the same step captured once and replayed: what the GPU itself needs (the C-ABI calls are plain stream work)
+        for attempt in range(2):    # the same step captured once and replayed: what the GPU itself needs (the C-ABI calls
+          try:                      # are plain stream work); a first capture in a process can trip over lazy initialisation
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
@@ -133,8 +134,10 @@ def measure(dev, big=1 << 20, small=(1024, 4608), peak_gbs=6528.7, profile=False
             e1.record()
             torch.cuda.synchronize(dev)
             rec["us_per_step_cuda_graph"] = e0.elapsed_time(e1) / 200 * 1e3
-        except Exception as e:
+            break
+          except Exception as e:
             rec["us_per_step_cuda_graph"] = {"error": repr(e)[:200]}
+            torch.cuda.synchronize(dev)
         out["at_%d" % n] = rec
         if profile and n == small[0]:
             import cProfile

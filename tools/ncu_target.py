@@ -63,9 +63,9 @@ elif which == "wide":
     gs = torch.empty((n, 37), device=dev)
     gr = torch.empty((n, 3), device=dev)
     for _ in range(reps):
-        _cabi.check(lib.dhfk_forward(P(slots), 37, P(slots) + 136, 37, P(d["bone"]), 15, P(d["root"]), 3, None, None, 0,
+        _cabi.check(lib.dhfk_forward(P(slots), 37, P(slots) + 136, 37, P(d["bone"]), 15, P(d["root"]), 3, None,
                                      P(world), None, None, n, 0, st), "wide fwd")
-        _cabi.check(lib.dhfk_backward(P(slots), 37, P(slots) + 136, 37, P(d["bone"]), 15, P(d["root"]), 3, None, None, 0,
+        _cabi.check(lib.dhfk_backward(P(slots), 37, P(slots) + 136, 37, P(d["bone"]), 15, P(d["root"]), 3, None,
                                       P(gw), None, None, P(gs), 37, P(gs) + 136, 37, P(gr), 3, None, 15, n, 0, st), "wide bwd")
 torch.cuda.synchronize()
 print("ok", which, n)

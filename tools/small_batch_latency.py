@@ -20,8 +20,8 @@ for n in (1024, 4608):
     w=torch.empty(n,16,3,device=dev); uv=torch.empty(n,16,2,device=dev); ga=torch.empty(n,33,device=dev); gg=torch.empty(n,3,device=dev); gr=torch.empty(n,3,device=dev)
     P=lambda t:t.data_ptr()
     def raw():
-        lib.dhfk_forward(P(d['ang']),33,P(d['grot']),3,P(d['bone']),15,P(d['root']),3,blk.ctypes.data,None,0,P(w),None,P(uv),n,0,st)
-        lib.dhfk_backward(P(d['ang']),33,P(d['grot']),3,P(d['bone']),15,P(d['root']),3,blk.ctypes.data,None,0,P(gw),None,P(gu),P(ga),33,P(gg),3,P(gr),3,None,15,n,0,st)
+        lib.dhfk_forward(P(d['ang']),33,P(d['grot']),3,P(d['bone']),15,P(d['root']),3,blk.ctypes.data,P(w),None,P(uv),n,0,st)
+        lib.dhfk_backward(P(d['ang']),33,P(d['grot']),3,P(d['bone']),15,P(d['root']),3,blk.ctypes.data,P(gw),None,P(gu),P(ga),33,P(gg),3,P(gr),3,None,15,n,0,st)
     for _ in range(50): raw()
     torch.cuda.synchronize(); t=time.perf_counter()
     for _ in range(2000): raw()
