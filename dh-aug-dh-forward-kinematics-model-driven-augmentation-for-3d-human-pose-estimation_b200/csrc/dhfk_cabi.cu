@@ -271,8 +271,11 @@ int dhfk_forward(const float* ang, int64_t ang_stride, const float* grot, int64_
     cudaStream_t st = (cudaStream_t)stream;
     const char* where = "";
     const bool oc = out_cam != nullptr, ou = out_uv != nullptr;
-    int e = (flags & DHFK_FLAG_FAST_TRIG) ? dhfk::launch_fwd_t1_g0(p, oc, ou, st, &where)
-                                          : dhfk::launch_fwd_t0_g0(p, oc, ou, st, &where);
+    int e;
+    if (p.w.wide) e = (flags & DHFK_FLAG_FAST_TRIG) ? dhfk::launch_fwd_t1_g2(p, oc, ou, st, &where)
+                                                    : dhfk::launch_fwd_t0_g2(p, oc, ou, st, &where);
+    else e = (flags & DHFK_FLAG_FAST_TRIG) ? dhfk::launch_fwd_t1_g0(p, oc, ou, st, &where)
+                                           : dhfk::launch_fwd_t0_g0(p, oc, ou, st, &where);
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }
 
@@ -317,8 +320,15 @@ int dhfk_backward(const float* ang, int64_t ang_stride, const float* grot, int64
     const bool fast = (flags & DHFK_FLAG_ACCURATE_TRIG) == 0;   // backward default: MUFU trig (see dhfk.h)
     const char* where = "";
     int e;
-    if (g_bone) e = fast ? dhfk::launch_bwd_t1_b1_g0(p, gu, st, &where) : dhfk::launch_bwd_t0_b1_g0(p, gu, st, &where);
-    else e = fast ? dhfk::launch_bwd_t1_b0_g0(p, gu, st, &where) : dhfk::launch_bwd_t0_b0_g0(p, gu, st, &where);
+    if (g_bone) {     // no wide-row instantiation with bone gradients: the strided views take the gather path
+        p.w = WideRows{0, 0, 1};
+        p.g_wide = 0;
+        e = fast ? dhfk::launch_bwd_t1_b1_g0(p, gu, st, &where) : dhfk::launch_bwd_t0_b1_g0(p, gu, st, &where);
+    } else if (p.w.wide) {
+        e = fast ? dhfk::launch_bwd_t1_b0_g2(p, gu, st, &where) : dhfk::launch_bwd_t0_b0_g2(p, gu, st, &where);
+    } else {
+        e = fast ? dhfk::launch_bwd_t1_b0_g0(p, gu, st, &where) : dhfk::launch_bwd_t0_b0_g0(p, gu, st, &where);
+    }
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }
 

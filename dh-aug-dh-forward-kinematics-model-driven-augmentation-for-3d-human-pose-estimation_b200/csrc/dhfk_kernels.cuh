@@ -60,9 +60,8 @@ struct RowDst {
 struct WideRows {
     int wide, goff, grot_slab;
 };
-#ifndef DHFK_WIDE_ROWS        // A/B switch: 0 compiles the wide-row path out of the kernels (profiles/r2_ab.md)
-#define DHFK_WIDE_ROWS 1
-#endif
+// WIDE is a template parameter of the kernels: carrying the run-time row stride in the packed-row instantiations cost
+// the headline backward 0.8 % (A/B on one box, profiles/r2_summary.md), so the packed kernels are compiled without it.
 struct FwdParams {
     RowSrc ang, grot, bone, root;   // GEN mode: `ang` is the raw network output [N,35]; grot/root unused
     WideRows w;
@@ -356,14 +355,15 @@ DHFK_DI void flush_chunks(float4* row4, const float* v) {
     for (int c = LO; c < HI; ++c) row4[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
-template <bool CAM, bool UV, int TRIG, bool GEN>
+template <bool CAM, bool UV, int TRIG, bool GEN, bool WIDE = false>
 __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__ FwdParams p) {
+    static_assert(!(GEN && WIDE), "wide rows are a raw-mode layout");
     constexpr int NANG = GEN ? GEN_NCOL : 33;      // floats per pose in the first slab
-    const int wide = (GEN || !DHFK_WIDE_ROWS) ? 0 : p.w.wide;           // launch-uniform
+    const int wide = WIDE ? p.w.wide : 0;          // launch-uniform
     extern __shared__ __align__(16) float smem[];
     float* s_ang = smem;
     float* s_grot = s_ang + kTile * (wide ? wide : NANG);
-    float* s_bone = s_grot + ((GEN || !p.w.grot_slab) ? 0 : kTile * 3);
+    float* s_bone = s_grot + ((GEN || (WIDE && !p.w.grot_slab)) ? 0 : kTile * 3);
     float* s_root = s_bone + kTile * 15;
     float4* s_world = reinterpret_cast<float4*>(s_root + (GEN ? 0 : kTile * 3));
     float4* s_cam = s_world + kTile * kWorldRow4;
@@ -663,16 +663,17 @@ struct BwdCtx {
     DHFK_DI void grad_bone(int b, float g) { g_bone[b] = g; }
 };
 
-template <bool GW, bool GCAM, bool GUV, bool GBONE, int TRIG, bool GEN>
+template <bool GW, bool GCAM, bool GUV, bool GBONE, int TRIG, bool GEN, bool WIDE = false>
 __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__ BwdParams p) {
+    static_assert(!(GEN && WIDE), "wide rows are a raw-mode layout");
     static_assert(GW || GCAM || GUV, "at least one upstream gradient");
     static_assert(!(GEN && GBONE), "bone-length gradients are not produced in generator mode");
     constexpr int NANG = GEN ? GEN_NCOL : 33;
-    const int wide = (GEN || !DHFK_WIDE_ROWS) ? 0 : p.w.wide;           // launch-uniform (see WideRows)
+    const int wide = WIDE ? p.w.wide : 0;          // launch-uniform (see WideRows)
     extern __shared__ __align__(16) float smem[];
     float* s_ang = smem;
     float* s_grot = s_ang + kTile * (wide ? wide : NANG);
-    float* s_bone = s_grot + ((GEN || !p.w.grot_slab) ? 0 : kTile * 3);
+    float* s_bone = s_grot + ((GEN || (WIDE && !p.w.grot_slab)) ? 0 : kTile * 3);
     float* s_root = s_bone + kTile * 15;
     float4* s_gw = reinterpret_cast<float4*>(s_root + (GEN ? 0 : kTile * 3));
     float4* s_gc = s_gw + (GW ? kTile * kWorldRow4 : 0);

@@ -10,6 +10,11 @@ int launch_fwd_t0_g0(const FwdParams& p, bool cam, bool uv, cudaStream_t st, con
 int launch_fwd_t1_g0(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
 int launch_fwd_t0_g1(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
 int launch_fwd_t1_g1(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
+// g2 = raw mode with wide rows (the generator's [N,37] slot tensor as one slab per tile); no bone-gradient variant
+int launch_fwd_t0_g2(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
+int launch_fwd_t1_g2(const FwdParams& p, bool cam, bool uv, cudaStream_t st, const char** where);
+int launch_bwd_t0_b0_g2(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
+int launch_bwd_t1_b0_g2(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
 int launch_bwd_t0_b0_g0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
 int launch_bwd_t0_b1_g0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
 int launch_bwd_t1_b0_g0(const BwdParams& p, bool guv, cudaStream_t st, const char** where);
