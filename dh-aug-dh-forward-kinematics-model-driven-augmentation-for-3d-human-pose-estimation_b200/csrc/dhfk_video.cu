@@ -150,6 +150,21 @@ DHFK_DI void store_rows48_mapped(const float4* s4, float* g, const int* map, int
     }
 }
 
+// adjacent-frame differences of 48-float rows, formed in the store loop straight from the staged rows (slot+1 minus slot,
+// times sgn): no difference buffer in shared memory, so more CTAs fit an SM
+DHFK_DI void store_rowdiff48_mapped(const float4* s4, float* g, const int* map, int slots, float sgn) {
+    float4* g4 = reinterpret_cast<float4*>(g);
+    for (int i = threadIdx.x; i < slots * kWorldChunks; i += kTile) {
+        const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
+        const int row = map[slot];
+        if (row >= 0) {
+            const float4 a = s4[slot * kWorldRow4 + c], b = s4[(slot + 1) * kWorldRow4 + c];
+            __stcs(g4 + (size_t)row * kWorldChunks + c,
+                   make_float4(sgn * (b.x - a.x), sgn * (b.y - a.y), sgn * (b.z - a.z), sgn * (b.w - a.w)));
+        }
+    }
+}
+
 // MODE 0: forward.  MODE 2: jvp (tangent p.v through the same maps).
 template <int MODE, bool DPOS, bool POS>
 __global__ void __launch_bounds__(kTile) dhfk_video_critic_kernel(const __grid_constant__ VideoParams p) {
@@ -157,8 +172,7 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_kernel(const __grid_c
     extern __shared__ __align__(16) float smem[];
     float4* s_pose = reinterpret_cast<float4*>(smem);                       // 32 padded rows
     float4* s_v = s_pose + kTile * kWorldRow4;                              // jvp: tangents
-    float4* s_dp = s_v + (JVP ? kTile * kWorldRow4 : 0);                    // differences of the poses
-    float* s_k = reinterpret_cast<float*>(s_dp + (DPOS ? kTile * kWorldRow4 : 0));
+    float* s_k = reinterpret_cast<float*>(s_v + (JVP ? kTile * kWorldRow4 : 0));
     float* s_dk = s_k + kTile * 15;
     int* s_map_f = reinterpret_cast<int*>(s_dk + kTile * 15);              // per-frame output row of each slot
     int* s_map_d = s_map_f + kTile;                                         // difference output row (or -1)
@@ -207,35 +221,26 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_kernel(const __grid_c
         s_k[lane * 15 + q] = k[q];
         s_dk[lane * 15 + q] = sgn * (kn - k[q]);
     }
-    if (DPOS && o.diff >= 0) {
-        const float4* nrow = (JVP ? s_v : s_pose) + (lane + 1) * kWorldRow4;
-        float4* drow = s_dp + lane * kWorldRow4;
-#pragma unroll
-        for (int c = 0; c < 12; ++c) {
-            const float4 a = nrow[c];
-            drow[c] = make_float4(sgn * (a.x - x[4 * c]), sgn * (a.y - x[4 * c + 1]), sgn * (a.z - x[4 * c + 2]),
-                                  sgn * (a.w - x[4 * c + 3]));
-        }
-    }
     __syncwarp();
     store_rows15_mapped(s_k, p.out_kcs, s_map_f, own);
     store_rows15_mapped(s_dk, p.out_dkcs, s_map_d, own);
-    if (DPOS) store_rows48_mapped(s_dp, p.out_dpos, s_map_d, own);
+    if (DPOS) store_rowdiff48_mapped(JVP ? s_v : s_pose, p.out_dpos, s_map_d, own, sgn);
     if (POS) store_rows48_mapped(JVP ? s_v : s_pose, p.out_pos, s_map_f, own);
 }
 
 // backward: g_pose[r] = J_kcs(x_r)^T ( g_kcs[pf(r)] + s g_dkcs[d(r-1)] - s g_dkcs[d(r)] )
 //                       + g_pos[pf(r)] + s g_dpos[d(r-1)] - s g_dpos[d(r)]
 // with pf / d the output rows of video_rows(), s = -1 in reverse mode, terms outside the clip dropped.
-// Shared slots: per-frame gradients slot = lane; difference gradients slot j <-> storage row row0 - 1 + j (33 slots).
+// The KCS part is per-lane work on the staged pose rows; the positional part is linear and independent of the pose, so
+// it is added in the cooperative store loop straight from global memory (coalesced 16-byte loads of the mapped rows):
+// no 48-float gradient rows in shared memory, 20 CTAs per SM instead of 9 - 12.
+// Shared slots of the 15-float gradients: per-frame slot = lane; differences slot j <-> storage row row0 - 1 + j (33).
 template <bool GK, bool GDK, bool GDP, bool GP>
 __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __grid_constant__ VideoParams p) {
     extern __shared__ __align__(16) float smem[];
-    float4* s_pose = reinterpret_cast<float4*>(smem);                        // 32 padded rows; g_pose leaves from here
-    float4* s_gp = s_pose + kTile * kWorldRow4;                              // g_pos, 32 padded rows
-    float4* s_gdp = s_gp + (GP ? kTile * kWorldRow4 : 0);                    // g_dpos, 33 padded rows
-    float* s_gk = reinterpret_cast<float*>(s_gdp + (GDP ? (kTile + 1) * kWorldRow4 : 0));   // g_kcs, 32 x 15 (odd stride:
-    float* s_gdk = s_gk + (GK ? kTile * 15 : 0);                             // conflict-free); g_dkcs, 33 x 15
+    float4* s_pose = reinterpret_cast<float4*>(smem);                        // 32 padded rows; the KCS part of g_pose
+    float* s_gk = reinterpret_cast<float*>(s_pose + kTile * kWorldRow4);     // g_kcs, 32 x 15 (odd stride: conflict-free)
+    float* s_gdk = s_gk + (GK ? kTile * 15 : 0);                             // g_dkcs, 33 x 15
     int* s_map_f = reinterpret_cast<int*>(s_gdk + (GDK ? (kTile + 1) * 15 : 0));
     int* s_map_d = s_map_f + kTile;                                          // 33 entries
 
@@ -244,6 +249,7 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
     const long long left = p.n - row0;
     const int rows = left < kTile ? (int)left : kTile;
     const bool rev = (p.flags & kVideoReverse) != 0;
+    constexpr bool KCS = GK || GDK;
     {
         VideoRows o;
         o.per_frame = o.diff = -1;
@@ -252,25 +258,12 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
         s_map_d[lane + 1] = o.diff;
         if (lane == 0) s_map_d[0] = row0 > 0 ? video_rows((unsigned)(row0 - 1), (unsigned)p.frames, rev).diff : -1;
     }
-    if (rows == kTile) ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
-    else stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
+    if (KCS) {
+        if (rows == kTile) ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
+        else stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
+    }
     __syncwarp();
-    // mapped gathers of the upstream gradients (cp.async, 16-byte chunks for the 48-float rows, 4-byte otherwise)
-    if (GP) {
-        const float4* g4 = reinterpret_cast<const float4*>(p.g_pos);
-        for (int i = lane; i < rows * kWorldChunks; i += kTile) {
-            const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
-            ldgsts16(s_gp + slot * kWorldRow4 + c, g4 + (size_t)s_map_f[slot] * kWorldChunks + c);
-        }
-    }
-    if (GDP) {
-        const float4* g4 = reinterpret_cast<const float4*>(p.g_dpos);
-        for (int i = lane; i < (rows + 1) * kWorldChunks; i += kTile) {
-            const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
-            const int row = s_map_d[slot];
-            if (row >= 0) ldgsts16(s_gdp + slot * kWorldRow4 + c, g4 + (size_t)row * kWorldChunks + c);
-        }
-    }
+    // mapped gathers of the 15-float upstream gradients (cp.async, one row per half-warp and pass)
     if (GK) {
         const int half = lane >> 4, c = lane & 15;
         for (int slot = half; slot < rows; slot += 2)
@@ -285,48 +278,54 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
     }
     ldgsts_wait_all();
     __syncwarp();
-    if (lane < rows) {
+    const float sgn = rev ? -1.f : 1.f;
+    if (KCS && lane < rows) {
         const bool has_prev = s_map_d[lane] >= 0, has_next = s_map_d[lane + 1] >= 0;
-        const float sgn = rev ? -1.f : 1.f;
-        float g[48];
+        float g[48], gk[15];
 #pragma unroll
         for (int i = 0; i < 48; ++i) g[i] = 0.f;
-        if (GP) vload48(s_gp + lane * kWorldRow4, g);
-        if (GDP) {
-            float t[48];
-            if (has_prev) {
-                vload48(s_gdp + lane * kWorldRow4, t);
 #pragma unroll
-                for (int i = 0; i < 48; ++i) g[i] = fmaf(sgn, t[i], g[i]);
+        for (int q = 0; q < 15; ++q) {
+            float a = GK ? s_gk[lane * 15 + q] : 0.f;
+            if (GDK) {
+                if (has_prev) a = fmaf(sgn, s_gdk[lane * 15 + q], a);
+                if (has_next) a = fmaf(-sgn, s_gdk[(lane + 1) * 15 + q], a);
             }
-            if (has_next) {
-                vload48(s_gdp + (lane + 1) * kWorldRow4, t);
-#pragma unroll
-                for (int i = 0; i < 48; ++i) g[i] = fmaf(-sgn, t[i], g[i]);
-            }
+            gk[q] = a;
         }
-        if (GK || GDK) {
-            float gk[15];
-#pragma unroll
-            for (int q = 0; q < 15; ++q) {
-                float a = GK ? s_gk[lane * 15 + q] : 0.f;
-                if (GDK) {
-                    if (has_prev) a = fmaf(sgn, s_gdk[lane * 15 + q], a);
-                    if (has_next) a = fmaf(-sgn, s_gdk[(lane + 1) * 15 + q], a);
-                }
-                gk[q] = a;
-            }
-            float x[48];
-            vload48(s_pose + lane * kWorldRow4, x);
-            VBones B;
-            vbones(x, B);
-            vkcs_vjp(B, gk, g);
-        }
+        float x[48];
+        vload48(s_pose + lane * kWorldRow4, x);
+        VBones B;
+        vbones(x, B);
+        vkcs_vjp(B, gk, g);
         vstore48(s_pose + lane * kWorldRow4, g);
     }
     __syncwarp();
-    if (rows == kTile) store_padded_tile<kWorldChunks>(s_pose, p.out_pos, row0);
-    else stage_padded_out<kWorldChunks>(s_pose, p.out_pos, row0, rows);
+    // store loop: KCS part from shared memory + the positional part from global memory, 16 bytes per lane, coalesced
+    const float4* gdp4 = reinterpret_cast<const float4*>(p.g_dpos);
+    const float4* gp4 = reinterpret_cast<const float4*>(p.g_pos);
+    float4* out4 = reinterpret_cast<float4*>(p.out_pos) + row0 * kWorldChunks;
+#pragma unroll 2
+    for (int i = lane; i < rows * kWorldChunks; i += kTile) {
+        const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
+        float4 v = KCS ? s_pose[slot * kWorldRow4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (GP) {
+            const float4 a = __ldg(gp4 + (size_t)s_map_f[slot] * kWorldChunks + c);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
+        if (GDP) {
+            const int rp = s_map_d[slot], rn = s_map_d[slot + 1];
+            if (rp >= 0) {
+                const float4 a = __ldg(gdp4 + (size_t)rp * kWorldChunks + c);
+                v.x = fmaf(sgn, a.x, v.x); v.y = fmaf(sgn, a.y, v.y); v.z = fmaf(sgn, a.z, v.z); v.w = fmaf(sgn, a.w, v.w);
+            }
+            if (rn >= 0) {
+                const float4 a = __ldg(gdp4 + (size_t)rn * kWorldChunks + c);
+                v.x = fmaf(-sgn, a.x, v.x); v.y = fmaf(-sgn, a.y, v.y); v.z = fmaf(-sgn, a.z, v.z); v.w = fmaf(-sgn, a.w, v.w);
+            }
+        }
+        __stcs(out4 + i, v);
+    }
 }
 
 // ---- 2-D motion critic: root-joint differences (Fk_discriminator.py:566-579) ------------------------------------
@@ -393,8 +392,8 @@ __global__ void __launch_bounds__(256) dhfk_video_root_diff_bwd_kernel(const __g
 }
 
 static size_t video_fwd_smem(bool jvp, bool dpos) {
-    return sizeof(float4) * kTile * kWorldRow4 * (1 + (jvp ? 1 : 0) + (dpos ? 1 : 0)) + sizeof(float) * kTile * 30 +
-           sizeof(int) * kTile * 2;
+    (void)dpos;
+    return sizeof(float4) * kTile * kWorldRow4 * (1 + (jvp ? 1 : 0)) + sizeof(float) * kTile * 30 + sizeof(int) * kTile * 2;
 }
 
 // launch_tiles sizes the grid as ceil(p.n / 32); forward / jvp tiles advance 31 rows, so they get their own launcher
@@ -444,8 +443,7 @@ int launch_video_critic_bwd(const float* pose, int frames, unsigned flags, const
     p.pose = pose; p.g_kcs = g_kcs; p.g_dkcs = g_dkcs; p.g_dpos = g_dpos; p.g_pos = g_pos; p.out_pos = g_pose;
     p.n = n; p.frames = frames; p.flags = flags;
     const bool gk = g_kcs != nullptr, gdk = g_dkcs != nullptr, gdp = g_dpos != nullptr, gp = g_pos != nullptr;
-    const size_t smem = sizeof(float4) * (kTile * kWorldRow4 * (1 + (gp ? 1 : 0)) + (gdp ? (kTile + 1) * kWorldRow4 : 0)) +
-                        sizeof(float) * ((gk ? kTile * 15 : 0) + (gdk ? (kTile + 1) * 15 : 0)) +
+    const size_t smem = sizeof(float4) * kTile * kWorldRow4 + sizeof(float) * ((gk ? kTile * 15 : 0) + (gdk ? (kTile + 1) * 15 : 0)) +
                         sizeof(int) * (2 * kTile + 2);
     const long long blocks = (n + kTile - 1) / kTile;
     // the combinations the critics produce: everything (3-D motion critic with both extra branches), features only,

@@ -278,7 +278,9 @@ def test_kernels_match_oracle_at_ragged_sizes(frames, clips, rev):
     assert np.array_equal(pb.cpu().numpy(), o2["pos"].astype(np.float32))
     g_rd, g_pb = rng.randn(clips, frames - 1, 2).astype(np.float32), rng.randn(clips, frames, 32).astype(np.float32)
     gu = torch.full((n, 16, 2), float("nan"), device=dev)
-    _cabi.check(lib.dhfk_video_root_diff_backward(P(T(g_rd)), P(T(g_pb)), frames, flags, P(gu), n, st), "root diff T")
+    g_rd_d, g_pb_d = T(g_rd), T(g_pb)         # keep them alive: a temporary's block is handed to the next allocation
+    _cabi.check(lib.dhfk_video_root_diff_backward(P(g_rd_d), P(g_pb_d), frames, flags, P(gu), n, st), "root diff T")
+    torch.cuda.synchronize()
     assert_parity(gu.cpu().numpy(), c_oracle.video_root_diff_backward(frames, g_rd, g_pb, reverse=rev), "root diff T F=%d" % frames)
 
 

@@ -114,7 +114,7 @@ def measure(dev, big=1 << 20, small=(1024, 4608), peak_gbs=6528.7, profile=False
         torch.cuda.synchronize(dev)
         rec = {"us_per_step_wall": wall * 1e6, "us_per_step_gpu_events": e0.elapsed_time(e1) / 100 * 1e3,
                "note": "wall = host-bound: three torch.autograd.Function nodes each way + the caller's own slicing"}
-        for attempt in range(2):    # the same step captured once and replayed: what the GPU itself needs (the C-ABI calls
+        for attempt in range(4):    # the same step captured once and replayed: what the GPU itself needs (the C-ABI calls
           try:                      # are plain stream work); a first capture in a process can trip over lazy initialisation
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
