@@ -795,9 +795,9 @@ def run_native(args):
 
         def sustained():
             # the same step for >= 1.5 s: the board's power cap (sw_power_cap) pulls the SM clock down after ~0.1 s of
-            # continuous work, so a long run sits below the burst the K-step region above measures (tools sweep:
-            # profiles/r2e_sweep.txt).  Reported so that both regimes are on the line; the headline keeps the contract
-            # (K steps after W warm-ups).
+            # continuous work of THESE kernels (a plain copy holds its rate), so a long run sits below the burst the K-step
+            # region above measures (profiles/r2e_sweep.txt).  Reported so that both regimes are on the line; the headline
+            # keeps the contract (K steps after W warm-ups).
             k = max(steps, int(1.5 / max(ms_per_step * 1e-3, 1e-6)))
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for i in range(k // 4):
@@ -808,10 +808,38 @@ def run_native(args):
             s1.record(stream)
             torch.cuda.synchronize(dev)
             sms = s0.elapsed_time(s1) / k
-            return {"poses_per_s": n / (sms * 1e-3), "ms_per_step": sms, "steps": k,
-                    "frac_of_copy_peak": (FWD_BYTES + BWD_BYTES) * n / (sms * 1e-3) / 1e9 / peak,
+            # the same question for the roofline's own denominator: a plain device copy (how MEASURED_PEAKS.json's
+            # hbm_gbs was taken: b.copy_(a), read + write bytes), best of 10 and held for >= 1.5 s, on this box, now
+            copy = None
+            try:
+                a = torch.empty(1 << 29, dtype=torch.bfloat16, device=dev)      # 1 GiB each
+                b = torch.empty_like(a)
+                nbytes = 2 * a.numel() * a.element_size()
+                best = float("inf")
+                for _ in range(10):
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record(stream); b.copy_(a); c1.record(stream)
+                    torch.cuda.synchronize(dev)
+                    best = min(best, c0.elapsed_time(c1))
+                reps = max(10, int(1.5e3 / best))
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream)
+                for _ in range(reps):
+                    b.copy_(a)
+                c1.record(stream)
+                torch.cuda.synchronize(dev)
+                copy = {"burst_gbs": nbytes / (best * 1e-3) / 1e9, "sustained_gbs": nbytes * reps / (c0.elapsed_time(c1) * 1e-3) / 1e9,
+                        "what": "torch b.copy_(a) over 1 GiB bf16 tensors (read + write bytes): best of 10, then %d back to back" % reps}
+                del a, b
+            except Exception as e:
+                copy = {"error": repr(e)[:200]}
+            gbs = (FWD_BYTES + BWD_BYTES) * n / (sms * 1e-3) / 1e9
+            return {"poses_per_s": n / (sms * 1e-3), "ms_per_step": sms, "steps": k, "hbm_gbs": gbs,
+                    "frac_of_copy_peak": gbs / peak, "device_copy_now": copy,
+                    "frac_of_sustained_copy": (gbs / copy["sustained_gbs"]) if copy and "sustained_gbs" in copy else None,
                     "what": "same step, %d back-to-back steps (>= 1.5 s) after %d more as warm-up: the power-capped steady "
-                            "state (the copy peak it is divided by is a burst figure)" % (k, k // 4)}
+                            "state.  A plain device copy does NOT drop when held (device_copy_now): the gap is SM power -- "
+                            "instructions per pose -- not memory" % (k, k // 4)}
 
         guarded("generator_mode", generator_mode)
         guarded("sustained", sustained)

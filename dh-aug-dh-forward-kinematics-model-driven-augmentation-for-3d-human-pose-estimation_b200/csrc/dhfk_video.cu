@@ -231,14 +231,15 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_kernel(const __grid_c
 // backward: g_pose[r] = J_kcs(x_r)^T ( g_kcs[pf(r)] + s g_dkcs[d(r-1)] - s g_dkcs[d(r)] )
 //                       + g_pos[pf(r)] + s g_dpos[d(r-1)] - s g_dpos[d(r)]
 // with pf / d the output rows of video_rows(), s = -1 in reverse mode, terms outside the clip dropped.
-// The KCS part is per-lane work on the staged pose rows; the positional part is linear and independent of the pose, so
-// it is added in the cooperative store loop straight from global memory (coalesced 16-byte loads of the mapped rows):
-// no 48-float gradient rows in shared memory, 20 CTAs per SM instead of 9 - 12.
-// Shared slots of the 15-float gradients: per-frame slot = lane; differences slot j <-> storage row row0 - 1 + j (33).
+// The positional part is linear and independent of the pose: every lane sums its three 48-float rows straight from
+// global memory into the registers that later take the KCS part (the loads are issued before the staged rows are
+// waited for, so they overlap that round trip).  Only the pose rows and the 15-float gradients are staged in shared
+// memory: 10.8 kB per CTA, 20 CTAs per SM (staging the 48-float gradient rows as well: 12 CTAs, 0.75 of the copy peak;
+// adding them in the store loop from global memory: dependent loads, 0.67).
 template <bool GK, bool GDK, bool GDP, bool GP>
 __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __grid_constant__ VideoParams p) {
     extern __shared__ __align__(16) float smem[];
-    float4* s_pose = reinterpret_cast<float4*>(smem);                        // 32 padded rows; the KCS part of g_pose
+    float4* s_pose = reinterpret_cast<float4*>(smem);                        // 32 padded rows; g_pose leaves from here
     float* s_gk = reinterpret_cast<float*>(s_pose + kTile * kWorldRow4);     // g_kcs, 32 x 15 (odd stride: conflict-free)
     float* s_gdk = s_gk + (GK ? kTile * 15 : 0);                             // g_dkcs, 33 x 15
     int* s_map_f = reinterpret_cast<int*>(s_gdk + (GDK ? (kTile + 1) * 15 : 0));
@@ -250,14 +251,14 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
     const int rows = left < kTile ? (int)left : kTile;
     const bool rev = (p.flags & kVideoReverse) != 0;
     constexpr bool KCS = GK || GDK;
-    {
-        VideoRows o;
-        o.per_frame = o.diff = -1;
-        if (lane < rows) o = video_rows((unsigned)(row0 + lane), (unsigned)p.frames, rev);
-        s_map_f[lane] = o.per_frame;
-        s_map_d[lane + 1] = o.diff;
-        if (lane == 0) s_map_d[0] = row0 > 0 ? video_rows((unsigned)(row0 - 1), (unsigned)p.frames, rev).diff : -1;
-    }
+    VideoRows o;
+    o.per_frame = o.diff = -1;
+    if (lane < rows) o = video_rows((unsigned)(row0 + lane), (unsigned)p.frames, rev);
+    int prev_diff = __shfl_up_sync(0xffffffffu, o.diff, 1);
+    if (lane == 0) prev_diff = row0 > 0 ? video_rows((unsigned)(row0 - 1), (unsigned)p.frames, rev).diff : -1;
+    s_map_f[lane] = o.per_frame;
+    s_map_d[lane + 1] = o.diff;
+    if (lane == 0) s_map_d[0] = prev_diff;
     if (KCS) {
         if (rows == kTile) ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
         else stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
@@ -276,56 +277,67 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
             if (c < 15 && row >= 0) ldgsts4(s_gdk + slot * 15 + c, p.g_dkcs + (size_t)row * 15 + c);
         }
     }
+    const float sgn = rev ? -1.f : 1.f;
+    const bool has_prev = prev_diff >= 0, has_next = o.diff >= 0;
+    float g[48];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) g[i] = 0.f;
+    if (lane < rows) {      // positional part: this lane's rows, 128-bit loads (neighbouring lanes read neighbouring rows)
+        if (GP) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.g_pos) + (size_t)o.per_frame * kWorldChunks;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                const float4 v = __ldg(r4 + c);
+                g[4 * c] = v.x; g[4 * c + 1] = v.y; g[4 * c + 2] = v.z; g[4 * c + 3] = v.w;
+            }
+        }
+        if (GDP) {
+            const float4* g4 = reinterpret_cast<const float4*>(p.g_dpos);
+            if (has_prev) {
+                const float4* r4 = g4 + (size_t)prev_diff * kWorldChunks;
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    const float4 v = __ldg(r4 + c);
+                    g[4 * c] = fmaf(sgn, v.x, g[4 * c]); g[4 * c + 1] = fmaf(sgn, v.y, g[4 * c + 1]);
+                    g[4 * c + 2] = fmaf(sgn, v.z, g[4 * c + 2]); g[4 * c + 3] = fmaf(sgn, v.w, g[4 * c + 3]);
+                }
+            }
+            if (has_next) {
+                const float4* r4 = g4 + (size_t)o.diff * kWorldChunks;
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    const float4 v = __ldg(r4 + c);
+                    g[4 * c] = fmaf(-sgn, v.x, g[4 * c]); g[4 * c + 1] = fmaf(-sgn, v.y, g[4 * c + 1]);
+                    g[4 * c + 2] = fmaf(-sgn, v.z, g[4 * c + 2]); g[4 * c + 3] = fmaf(-sgn, v.w, g[4 * c + 3]);
+                }
+            }
+        }
+    }
     ldgsts_wait_all();
     __syncwarp();
-    const float sgn = rev ? -1.f : 1.f;
-    if (KCS && lane < rows) {
-        const bool has_prev = s_map_d[lane] >= 0, has_next = s_map_d[lane + 1] >= 0;
-        float g[48], gk[15];
+    if (lane < rows) {
+        if (KCS) {
+            float gk[15];
 #pragma unroll
-        for (int i = 0; i < 48; ++i) g[i] = 0.f;
-#pragma unroll
-        for (int q = 0; q < 15; ++q) {
-            float a = GK ? s_gk[lane * 15 + q] : 0.f;
-            if (GDK) {
-                if (has_prev) a = fmaf(sgn, s_gdk[lane * 15 + q], a);
-                if (has_next) a = fmaf(-sgn, s_gdk[(lane + 1) * 15 + q], a);
+            for (int q = 0; q < 15; ++q) {
+                float a = GK ? s_gk[lane * 15 + q] : 0.f;
+                if (GDK) {
+                    if (has_prev) a = fmaf(sgn, s_gdk[lane * 15 + q], a);
+                    if (has_next) a = fmaf(-sgn, s_gdk[(lane + 1) * 15 + q], a);
+                }
+                gk[q] = a;
             }
-            gk[q] = a;
+            float x[48];
+            vload48(s_pose + lane * kWorldRow4, x);
+            VBones B;
+            vbones(x, B);
+            vkcs_vjp(B, gk, g);
         }
-        float x[48];
-        vload48(s_pose + lane * kWorldRow4, x);
-        VBones B;
-        vbones(x, B);
-        vkcs_vjp(B, gk, g);
         vstore48(s_pose + lane * kWorldRow4, g);
     }
     __syncwarp();
-    // store loop: KCS part from shared memory + the positional part from global memory, 16 bytes per lane, coalesced
-    const float4* gdp4 = reinterpret_cast<const float4*>(p.g_dpos);
-    const float4* gp4 = reinterpret_cast<const float4*>(p.g_pos);
-    float4* out4 = reinterpret_cast<float4*>(p.out_pos) + row0 * kWorldChunks;
-#pragma unroll 2
-    for (int i = lane; i < rows * kWorldChunks; i += kTile) {
-        const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
-        float4 v = KCS ? s_pose[slot * kWorldRow4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (GP) {
-            const float4 a = __ldg(gp4 + (size_t)s_map_f[slot] * kWorldChunks + c);
-            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-        }
-        if (GDP) {
-            const int rp = s_map_d[slot], rn = s_map_d[slot + 1];
-            if (rp >= 0) {
-                const float4 a = __ldg(gdp4 + (size_t)rp * kWorldChunks + c);
-                v.x = fmaf(sgn, a.x, v.x); v.y = fmaf(sgn, a.y, v.y); v.z = fmaf(sgn, a.z, v.z); v.w = fmaf(sgn, a.w, v.w);
-            }
-            if (rn >= 0) {
-                const float4 a = __ldg(gdp4 + (size_t)rn * kWorldChunks + c);
-                v.x = fmaf(-sgn, a.x, v.x); v.y = fmaf(-sgn, a.y, v.y); v.z = fmaf(-sgn, a.z, v.z); v.w = fmaf(-sgn, a.w, v.w);
-            }
-        }
-        __stcs(out4 + i, v);
-    }
+    if (rows == kTile) store_padded_tile<kWorldChunks>(s_pose, p.out_pos, row0);
+    else stage_padded_out<kWorldChunks>(s_pose, p.out_pos, row0, rows);
 }
 
 // ---- 2-D motion critic: root-joint differences (Fk_discriminator.py:566-579) ------------------------------------

@@ -216,3 +216,20 @@ def test_scatter_16_to_32_reproduces_the_reference_tensor(golden):
     gv = golden("video36")
     out = scatter_16_to_32(T(gv["world16"]), T(gv["root"]).view(4, 9, 3))
     assert np.array_equal(out.cpu().numpy(), gv["world32"])
+
+
+def test_cpu_float64_callers_get_their_own_device_and_dtype_back(golden):
+    """common/camera.py::wrap feeds CPU float64 tensors and calls .numpy() on the result (the
+    `--data_enhancement_method normal` path, model_fk_gan_train.py:74): the kernels run on the GPU in fp32, the result
+    comes back where and as what the caller's tensors were."""
+    from dhfk import camera
+    g = golden("camera_ops")
+    x = torch.tensor(g["x"], dtype=torch.float64)
+    uv = camera.project_to_2d(x, torch.tensor(g["cam_rows9"], dtype=torch.float64))
+    assert uv.device.type == "cpu" and uv.dtype == torch.float64
+    assert_parity(uv.numpy(), g["uv"], "uv")
+    cam = camera.GAN_torch_world_to_camera(torch.tensor(g["w_x"], dtype=torch.float64),
+                                           torch.tensor(g["w_q"], dtype=torch.float64).view(1, 4),
+                                           torch.tensor(g["w_t"], dtype=torch.float64).view(1, 3))
+    assert cam.device.type == "cpu" and cam.dtype == torch.float64
+    assert_parity(cam.numpy(), g["w_cam"], "w_cam")

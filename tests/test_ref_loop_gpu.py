@@ -71,3 +71,26 @@ def test_reference_loop_with_dropin_matches_unpatched_cpu_run(golden, mode, inst
     if install.get("critics"):
         assert mods["dis"].Video_motion_Fk_3D_Discriminator.forward is dhfk.Fk_discriminator.video_motion_3d_forward
     assert torch.cuda.is_available()
+
+
+def test_reference_wrap_helper_works_with_the_dropin_installed():
+    """traditional_solutions_FK_generator (model_fk_gan_train.py:36-94, `--data_enhancement_method normal`) calls
+    wrap(project_to_2d, True, numpy, numpy): CPU float64 in, `.numpy()` on the result.  With the drop-in installed that
+    call must still work (it used to get a CUDA tensor back)."""
+    _need_archive()
+    import ref_loop
+    import dhfk
+    mods = ref_loop.load(force_cpu=False)
+    dhfk.dropin.install()
+    from utils.utils import wrap                      # the reference's own helper (utils/utils.py:137-165)
+    from dhfk import tables
+    rng = np.random.RandomState(0)
+    pose = rng.randn(50, 16, 3) * 0.3 + np.array([0.0, 0.0, 4.5])
+    cam9 = tables.camera_block("S1", 0)[7:16].astype(np.float64)
+    out = wrap(mods["train"].project_to_2d, True, pose, cam9)
+    assert isinstance(out, np.ndarray) and out.shape == (50, 16, 2)
+    import torch_port
+    import torch
+    want = torch_port.project_to_2d(torch.tensor(pose, dtype=torch.float32),
+                                    torch.tensor(cam9, dtype=torch.float32).view(1, 9).repeat(50, 1)).numpy()
+    assert np.abs(out - want).max() <= 1e-5

@@ -33,9 +33,10 @@ for row in csv.reader(io.StringIO(raw)):
     mix[kernel][op] += n
     total[kernel] += n
     warps.setdefault(kernel, n)
-    ex = int(row[hdr["L1 Wavefronts Shared Excessive"]] or 0)
-    if ex:
-        conf[kernel].append((ex, int(row[hdr["L1 Wavefronts Shared"]] or 0), src))
+    if "L1 Wavefronts Shared Excessive" in hdr:       # absent for kernels that never touch shared memory
+        ex = int(row[hdr["L1 Wavefronts Shared Excessive"]] or 0)
+        if ex:
+            conf[kernel].append((ex, int(row[hdr["L1 Wavefronts Shared"]] or 0), src))
 for k in mix:
     w = max(warps.get(k, 1), 1)
     print("=== %s\n    executed warp-instructions %d  (%.0f per warp, %d warps)" % (k, total[k], total[k] / w, w))
