@@ -105,6 +105,8 @@ def parse():
                     help="auto: configs[1] at --gpus 1, configs[4] (16M poses sharded + in-step gradient all-reduce) otherwise")
     ap.add_argument("--total-poses", type=int, default=1 << 24, help="configs[4]: poses per step over all ranks")
     ap.add_argument("--no-extras", action="store_true", help="skip side-kernel / drop-in path / GAN-step extras")
+    ap.add_argument("--nccl-max-ctas", type=int, default=int(os.environ.get("DHFK_NCCL_MAX_CTAS", "4")),
+                    help="CTAs of the gradient all-reduce's own NCCL communicator (0 = NCCL's default communicator)")
     return ap.parse_args()
 
 
@@ -586,6 +588,9 @@ def run_native(args):
         gbuf = parallel.FlatGradBuffer([*G.parameters(), *D3.parameters(), *D2.parameters()])
         gbuf.flat.fill_(1.0)
         side = torch.cuda.Stream(dev)
+        ggroup = parallel.grad_allreduce_group(args.nccl_max_ctas)
+        gbuf_allreduce = gbuf.allreduce
+        gbuf.allreduce = lambda: gbuf_allreduce(group=ggroup)        # every call below goes through the dedicated communicator
         for _ in range(5):
             gbuf.allreduce()
         torch.cuda.synchronize(dev)
@@ -598,6 +603,7 @@ def run_native(args):
         torch.cuda.synchronize(dev)
         (alone_ms,) = max_over_ranks([a0.elapsed_time(a1) / 50], dev, True)
         allreduce_extra = {"bytes": int(nel) * 4, "ms_alone": alone_ms, "backend": "nccl", "collectives_per_step": 1,
+                           "communicator": ("dedicated, max_ctas=%d" % args.nccl_max_ctas) if ggroup is not None else "default",
                            "what": "dhfk.parallel.FlatGradBuffer.allreduce: generator + 3-D critic + 2-D critic gradients "
                                    "(dense 256) live in one persistent buffer (the slices are the .grad tensors), one "
                                    "ncclAllReduce(AVG), no pack / unpack kernels; ms_alone = back to back on an idle GPU"}

@@ -187,6 +187,8 @@ CamConst make_cam(const float* cam) {
     if (cam) {
         camera_matrix(cam, cc.M);
         for (int i = 0; i < 3; ++i) cc.t[i] = cam[4 + i];
+        for (int i = 0; i < 3; ++i) cc.Mc[i] = make_float2(cc.M[i], cc.M[3 + i]);
+        cc.txy = make_float2(cc.t[0], cc.t[1]);
         cc.f = make_float2(cam[7], cam[8]); cc.c = make_float2(cam[9], cam[10]);
         cc.k[0] = cam[11]; cc.k[1] = cam[12]; cc.k[2] = cam[13]; cc.p = make_float2(cam[14], cam[15]);
         cc.k1x2 = 2.f * cc.k[1];

@@ -16,11 +16,29 @@ struct Wrench { V3 F, M; };        // sum of forces / moments about the chain or
 #define DHFK_DI __device__ __forceinline__
 
 DHFK_DI V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+// Packed fp32x2 arithmetic for the (x, y) lanes of a 3-vector (sm_100 FFMA2 / FMUL2 / FADD2: one instruction for both
+// lanes, IEEE per lane -- bit-identical to the scalar forms below, operation for operation).  The tree walk is
+// element-wise 3-vector arithmetic, and these kernels are issue / power-bound: 3 scalar instructions become 2.
+#ifndef DHFK_PACKED_V3
+#define DHFK_PACKED_V3 1
+#endif
+#if DHFK_PACKED_V3
+DHFK_DI float2 xy_of(V3 a) { return make_float2(a.x, a.y); }
+DHFK_DI V3 v3p(float2 p, float z) { return v3(p.x, p.y, z); }
+DHFK_DI V3 operator+(V3 a, V3 b) { return v3p(__fadd2_rn(xy_of(a), xy_of(b)), a.z + b.z); }
+DHFK_DI V3 operator-(V3 a, V3 b) {      // fma(b, -1, a) = a - b exactly
+    return v3p(__ffma2_rn(xy_of(b), make_float2(-1.f, -1.f), xy_of(a)), a.z - b.z);
+}
+DHFK_DI V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+DHFK_DI V3 axpy(float s, V3 a, V3 b) { return v3p(__ffma2_rn(make_float2(s, s), xy_of(a), xy_of(b)), fmaf(s, a.z, b.z)); }
+DHFK_DI V3 scale(float s, V3 a) { return v3p(__fmul2_rn(make_float2(s, s), xy_of(a)), s * a.z); }
+#else
 DHFK_DI V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 DHFK_DI V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 DHFK_DI V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 DHFK_DI V3 axpy(float s, V3 a, V3 b) { return v3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
 DHFK_DI V3 scale(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+#endif
 DHFK_DI float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 DHFK_DI V3 cross(V3 a, V3 b) {
     return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
@@ -242,10 +260,37 @@ DHFK_DI Frame identity_frame() {
 struct alignas(8) CamConst {
     float M[9];
     float t[3];
+    float2 Mc[3];      // columns of the top two rows of M: (M00,M10), (M01,M11), (M02,M12) -- packed operands of cam_mat_vec
+    float2 txy;        // (t[0], t[1])
     float2 f, c, p;    // focal, principal point, tangential distortion as (x, y) pairs: FFMA2 operands
     float k[3];
     float k1x2, k2x3;  // 2*k[1], 3*k[2]
 };
+
+// X_cam = M (W - t) and M g + b with the camera constants, (x, y) lanes packed; same operation order as mat_vec /
+// mat_vec_add, so the results are bit-identical to the scalar forms
+DHFK_DI V3 cam_space(const CamConst& cc, V3 W) {
+#if DHFK_PACKED_V3
+    const float2 dxy = __fadd2_rn(xy_of(W), make_float2(-cc.txy.x, -cc.txy.y));
+    const float dz = W.z - cc.t[2];
+    float2 r = __fmul2_rn(cc.Mc[2], make_float2(dz, dz));
+    r = __ffma2_rn(cc.Mc[1], make_float2(dxy.y, dxy.y), r);
+    r = __ffma2_rn(cc.Mc[0], make_float2(dxy.x, dxy.x), r);
+    return v3p(r, fmaf(cc.M[6], dxy.x, fmaf(cc.M[7], dxy.y, cc.M[8] * dz)));
+#else
+    return mat_vec(cc.M, v3(W.x - cc.t[0], W.y - cc.t[1], W.z - cc.t[2]));
+#endif
+}
+DHFK_DI V3 cam_mat_vec_add(const CamConst& cc, V3 v, V3 b) {
+#if DHFK_PACKED_V3
+    float2 r = __ffma2_rn(cc.Mc[2], make_float2(v.z, v.z), xy_of(b));
+    r = __ffma2_rn(cc.Mc[1], make_float2(v.y, v.y), r);
+    r = __ffma2_rn(cc.Mc[0], make_float2(v.x, v.x), r);
+    return v3p(r, fmaf(cc.M[6], v.x, fmaf(cc.M[7], v.y, fmaf(cc.M[8], v.z, b.z))));
+#else
+    return mat_vec_add(cc.M, v, b);
+#endif
+}
 
 // Packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): the projection works on (x, y) lanes, so every
 // per-lane product/FMA is one instruction for both lanes; scalar operands broadcast for free (".F32").

@@ -339,7 +339,7 @@ struct FwdCtx {
         else W = o + root;
         w[3 * K] = W.x; w[3 * K + 1] = W.y; w[3 * K + 2] = W.z;
         if (CAM || UV) {
-            V3 X = mat_vec(cc->M, v3(W.x - cc->t[0], W.y - cc->t[1], W.z - cc->t[2]));
+            V3 X = cam_space(*cc, W);
             if (CAM) { cm[3 * K] = X.x; cm[3 * K + 1] = X.y; cm[3 * K + 2] = X.z; }
             if (UV) {
                 ProjAux a;
@@ -554,7 +554,7 @@ struct BwdCtx {
                 for (int j = 0; j < 3; ++j)
                     MR[3 * i + j] = fmaf(cc->M[3 * i], R[j], fmaf(cc->M[3 * i + 1], R[3 + j], cc->M[3 * i + 2] * R[6 + j]));
             base.X = v3(MR[0], MR[3], MR[6]); base.Y = v3(MR[1], MR[4], MR[7]); base.Z = v3(MR[2], MR[5], MR[8]);
-            v0 = mat_vec(cc->M, v3(root.x - cc->t[0], root.y - cc->t[1], root.z - cc->t[2]));
+            v0 = cam_space(*cc, root);
         } else {
             base.X = v3(R[0], R[3], R[6]); base.Y = v3(R[1], R[4], R[7]); base.Z = v3(R[2], R[5], R[8]);
             v0 = v3(0.f, 0.f, 0.f);
@@ -567,7 +567,7 @@ struct BwdCtx {
         if constexpr (!cam_frame) return g;
         else if constexpr (GW) {
             sum_gw = sum_gw + g;
-            return mat_vec_add(cc->M, g, gc);      // M g_w + g_c
+            return cam_mat_vec_add(*cc, g, gc);    // M g_w + g_c
         } else return gc;
     }
     // d/d root (world axes) from the total force over the 16 outputs (working frame)
