@@ -105,6 +105,8 @@ def parse():
                     help="auto: configs[1] at --gpus 1, configs[4] (16M poses sharded + in-step gradient all-reduce) otherwise")
     ap.add_argument("--total-poses", type=int, default=1 << 24, help="configs[4]: poses per step over all ranks")
     ap.add_argument("--no-extras", action="store_true", help="skip side-kernel / drop-in path / GAN-step extras")
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 17, help="rows per chunk of the host-buffer pipeline")
+    ap.add_argument("--e2e-slots", type=int, default=3, help="device slots of the host-buffer pipeline")
     ap.add_argument("--nccl-max-ctas", type=int, default=int(os.environ.get("DHFK_NCCL_MAX_CTAS", "4")),
                     help="CTAs of the gradient all-reduce's own NCCL communicator (0 = NCCL's default communicator)")
     return ap.parse_args()
@@ -688,7 +690,7 @@ def run_native(args):
         h_gw, h_gu = pin(up["g_world"]), pin(up["g_uv"])
         out = {}
         e2e_steps = max(3, min(steps, 10))
-        chunk, slots = 1 << 17, 3
+        chunk, slots = args.e2e_chunk, args.e2e_slots
         call = lambda o, gw_, gu_: dhfk.fk_project_host(h_ang, h_grot, h_bone, h_root, blk, gw_, gu_, chunk_rows=chunk,
                                                         num_streams=slots, workspace=o.get("_workspace"), out=o,
                                                         fast_trig=args.fast_trig, accurate_grad=args.accurate_trig)

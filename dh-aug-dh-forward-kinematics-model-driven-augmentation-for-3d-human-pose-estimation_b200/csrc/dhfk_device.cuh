@@ -134,6 +134,13 @@ DHFK_DI void sincos_deg(float deg, float& s, float& c) {
         constexpr float C2 = (float)(4.166664568298827e-2 * D * D * D * D);
         constexpr float C3 = (float)(-1.388731625493765e-3 * D * D * D * D * D * D);
         constexpr float C4 = (float)(2.443315711809948e-5 * D * D * D * D * D * D * D * D);
+#if DHFK_PACKED_V3    // the two Horner chains side by side in the lanes of FFMA2: 3 instructions instead of 6
+        float2 pp = __ffma2_rn(make_float2(r2, r2), make_float2(S3, C4), make_float2(S2, C3));
+        pp = __ffma2_rn(make_float2(r2, r2), pp, make_float2(S1, C2));
+        pp = __ffma2_rn(make_float2(r2, r2), pp, make_float2(S0, C1));
+        float sv = r * pp.x;
+        float cv = fmaf(r2, pp.y, 1.0f);
+#else
         float ps = fmaf(r2, S3, S2);
         ps = fmaf(r2, ps, S1);
         ps = fmaf(r2, ps, S0);
@@ -142,6 +149,7 @@ DHFK_DI void sincos_deg(float deg, float& s, float& c) {
         pc = fmaf(r2, pc, C2);
         pc = fmaf(r2, pc, C1);
         float cv = fmaf(r2, pc, 1.0f);
+#endif
         bool odd = (n & 1) != 0;
         float so = odd ? cv : sv;
         float co = odd ? sv : cv;
@@ -182,6 +190,13 @@ DHFK_DI void sincos_deg_rt(float deg, int q0, float& s, float& c) {
         constexpr float C2 = (float)(4.166664568298827e-2 * D * D * D * D);
         constexpr float C3 = (float)(-1.388731625493765e-3 * D * D * D * D * D * D);
         constexpr float C4 = (float)(2.443315711809948e-5 * D * D * D * D * D * D * D * D);
+#if DHFK_PACKED_V3    // the two Horner chains side by side in the lanes of FFMA2: 3 instructions instead of 6
+        float2 pp = __ffma2_rn(make_float2(r2, r2), make_float2(S3, C4), make_float2(S2, C3));
+        pp = __ffma2_rn(make_float2(r2, r2), pp, make_float2(S1, C2));
+        pp = __ffma2_rn(make_float2(r2, r2), pp, make_float2(S0, C1));
+        float sv = r * pp.x;
+        float cv = fmaf(r2, pp.y, 1.0f);
+#else
         float ps = fmaf(r2, S3, S2);
         ps = fmaf(r2, ps, S1);
         ps = fmaf(r2, ps, S0);
@@ -190,6 +205,7 @@ DHFK_DI void sincos_deg_rt(float deg, int q0, float& s, float& c) {
         pc = fmaf(r2, pc, C2);
         pc = fmaf(r2, pc, C1);
         float cv = fmaf(r2, pc, 1.0f);
+#endif
         bool odd = (n & 1) != 0;
         float so = odd ? cv : sv;
         float co = odd ? sv : cv;
