@@ -107,8 +107,10 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip side-kernel / drop-in path / GAN-step extras")
     ap.add_argument("--e2e-chunk", type=int, default=1 << 17, help="rows per chunk of the host-buffer pipeline")
     ap.add_argument("--e2e-slots", type=int, default=3, help="device slots of the host-buffer pipeline")
-    ap.add_argument("--nccl-max-ctas", type=int, default=int(os.environ.get("DHFK_NCCL_MAX_CTAS", "4")),
-                    help="CTAs of the gradient all-reduce's own NCCL communicator (0 = NCCL's default communicator)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=int(os.environ.get("DHFK_NCCL_MAX_CTAS", "0")),
+                    help="CTAs of a dedicated NCCL communicator for the gradient all-reduce; 0 (default) = NCCL's default "
+                         "communicator, which measured best (profiles/r2k_nccl_sweep.txt: fewer CTAs make the 6 MB "
+                         "all-reduce 2-6x slower, too slow to hide behind a 0.2 ms step)")
     return ap.parse_args()
 
 
@@ -472,7 +474,7 @@ def max_over_ranks(vals, dev, distributed):
     return [float(x) if x >= 0 else None for x in t.tolist()]
 
 
-def copy_ceiling(n, dev, chunk, reps=5):
+def copy_ceiling(n, dev, chunk, reps=10):
     """A bare pinned-memory H2D + D2H of the bytes the e2e step moves (536 B/row up, 476 B/row down), in the same chunk
     sizes, on two streams with no kernel and no dependency between them: the PCIe / host-memory floor of `e2e`."""
     import torch

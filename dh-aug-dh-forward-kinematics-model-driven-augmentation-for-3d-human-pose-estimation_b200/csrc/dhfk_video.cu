@@ -231,16 +231,17 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_kernel(const __grid_c
 // backward: g_pose[r] = J_kcs(x_r)^T ( g_kcs[pf(r)] + s g_dkcs[d(r-1)] - s g_dkcs[d(r)] )
 //                       + g_pos[pf(r)] + s g_dpos[d(r-1)] - s g_dpos[d(r)]
 // with pf / d the output rows of video_rows(), s = -1 in reverse mode, terms outside the clip dropped.
-// The positional part is linear and independent of the pose: every lane sums its three 48-float rows straight from
-// global memory into the registers that later take the KCS part (the loads are issued before the staged rows are
-// waited for, so they overlap that round trip).  Only the pose rows and the 15-float gradients are staged in shared
-// memory: 10.8 kB per CTA, 20 CTAs per SM (staging the 48-float gradient rows as well: 12 CTAs, 0.75 of the copy peak;
-// adding them in the store loop from global memory: dependent loads, 0.67).
+// ONE 33-row tile of shared memory is used twice: first for the pose rows (each lane copies its row into registers),
+// then -- while the lanes do the KCS part on those registers -- cp.async refills it with the 33 g_dpos rows the tile
+// needs (difference rows r-1 .. r+31, gathered through the slot -> row table), and once more with the g_pos rows when
+// that gradient exists.  10.9 kB per CTA; the loads stay coalesced 16-byte cp.async and overlap the arithmetic.
+// (Staging everything at once: 17.7 kB, 12 CTAs per SM, 0.75 of the copy peak; adding the positional part from global
+// memory in the store loop: dependent loads, 0.67; per-lane 128-bit global loads: 32 sectors per instruction, 0.67.)
 template <bool GK, bool GDK, bool GDP, bool GP>
 __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __grid_constant__ VideoParams p) {
     extern __shared__ __align__(16) float smem[];
-    float4* s_pose = reinterpret_cast<float4*>(smem);                        // 32 padded rows; g_pose leaves from here
-    float* s_gk = reinterpret_cast<float*>(s_pose + kTile * kWorldRow4);     // g_kcs, 32 x 15 (odd stride: conflict-free)
+    float4* s_tile = reinterpret_cast<float4*>(smem);                        // 33 padded rows, reused (see above)
+    float* s_gk = reinterpret_cast<float*>(s_tile + (kTile + 1) * kWorldRow4);   // g_kcs, 32 x 15 (odd stride)
     float* s_gdk = s_gk + (GK ? kTile * 15 : 0);                             // g_dkcs, 33 x 15
     int* s_map_f = reinterpret_cast<int*>(s_gdk + (GDK ? (kTile + 1) * 15 : 0));
     int* s_map_d = s_map_f + kTile;                                          // 33 entries
@@ -260,8 +261,8 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
     s_map_d[lane + 1] = o.diff;
     if (lane == 0) s_map_d[0] = prev_diff;
     if (KCS) {
-        if (rows == kTile) ldgsts_padded_tile<kWorldChunks>(s_pose, p.pose, row0);
-        else stage_padded_in<kWorldChunks>(s_pose, p.pose, row0, rows);
+        if (rows == kTile) ldgsts_padded_tile<kWorldChunks>(s_tile, p.pose, row0);
+        else stage_padded_in<kWorldChunks>(s_tile, p.pose, row0, rows);
     }
     __syncwarp();
     // mapped gathers of the 15-float upstream gradients (cp.async, one row per half-warp and pass)
@@ -277,67 +278,78 @@ __global__ void __launch_bounds__(kTile) dhfk_video_critic_bwd_kernel(const __gr
             if (c < 15 && row >= 0) ldgsts4(s_gdk + slot * 15 + c, p.g_dkcs + (size_t)row * 15 + c);
         }
     }
+    ldgsts_wait_all();
+    __syncwarp();
     const float sgn = rev ? -1.f : 1.f;
     const bool has_prev = prev_diff >= 0, has_next = o.diff >= 0;
+    float x[48], gk[15];
+    if (KCS && lane < rows) {
+        vload48(s_tile + lane * kWorldRow4, x);
+#pragma unroll
+        for (int q = 0; q < 15; ++q) {
+            float a = GK ? s_gk[lane * 15 + q] : 0.f;
+            if (GDK) {
+                if (has_prev) a = fmaf(sgn, s_gdk[lane * 15 + q], a);
+                if (has_next) a = fmaf(-sgn, s_gdk[(lane + 1) * 15 + q], a);
+            }
+            gk[q] = a;
+        }
+    }
+    __syncwarp();        // every lane holds its pose row: the tile can be refilled
+    if (GDP) {           // difference rows r-1 .. r+31 of g_dpos -> slots 0 .. 32
+        const float4* g4 = reinterpret_cast<const float4*>(p.g_dpos);
+        for (int i = lane; i < (rows + 1) * kWorldChunks; i += kTile) {
+            const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
+            const int row = s_map_d[slot];
+            if (row >= 0) ldgsts16(s_tile + slot * kWorldRow4 + c, g4 + (size_t)row * kWorldChunks + c);
+        }
+    }
     float g[48];
 #pragma unroll
     for (int i = 0; i < 48; ++i) g[i] = 0.f;
-    if (lane < rows) {      // positional part: this lane's rows, 128-bit loads (neighbouring lanes read neighbouring rows)
-        if (GP) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.g_pos) + (size_t)o.per_frame * kWorldChunks;
-#pragma unroll
-            for (int c = 0; c < 12; ++c) {
-                const float4 v = __ldg(r4 + c);
-                g[4 * c] = v.x; g[4 * c + 1] = v.y; g[4 * c + 2] = v.z; g[4 * c + 3] = v.w;
-            }
-        }
-        if (GDP) {
-            const float4* g4 = reinterpret_cast<const float4*>(p.g_dpos);
+    if (KCS && lane < rows) {        // the KCS part, on registers, while the refill is in flight
+        VBones B;
+        vbones(x, B);
+        vkcs_vjp(B, gk, g);
+    }
+    if (GDP) {
+        ldgsts_wait_all();
+        __syncwarp();
+        if (lane < rows) {
+            float t[48];
             if (has_prev) {
-                const float4* r4 = g4 + (size_t)prev_diff * kWorldChunks;
+                vload48(s_tile + lane * kWorldRow4, t);
 #pragma unroll
-                for (int c = 0; c < 12; ++c) {
-                    const float4 v = __ldg(r4 + c);
-                    g[4 * c] = fmaf(sgn, v.x, g[4 * c]); g[4 * c + 1] = fmaf(sgn, v.y, g[4 * c + 1]);
-                    g[4 * c + 2] = fmaf(sgn, v.z, g[4 * c + 2]); g[4 * c + 3] = fmaf(sgn, v.w, g[4 * c + 3]);
-                }
+                for (int i = 0; i < 48; ++i) g[i] = fmaf(sgn, t[i], g[i]);
             }
             if (has_next) {
-                const float4* r4 = g4 + (size_t)o.diff * kWorldChunks;
+                vload48(s_tile + (lane + 1) * kWorldRow4, t);
 #pragma unroll
-                for (int c = 0; c < 12; ++c) {
-                    const float4 v = __ldg(r4 + c);
-                    g[4 * c] = fmaf(-sgn, v.x, g[4 * c]); g[4 * c + 1] = fmaf(-sgn, v.y, g[4 * c + 1]);
-                    g[4 * c + 2] = fmaf(-sgn, v.z, g[4 * c + 2]); g[4 * c + 3] = fmaf(-sgn, v.w, g[4 * c + 3]);
-                }
+                for (int i = 0; i < 48; ++i) g[i] = fmaf(-sgn, t[i], g[i]);
             }
         }
+        __syncwarp();
     }
-    ldgsts_wait_all();
-    __syncwarp();
-    if (lane < rows) {
-        if (KCS) {
-            float gk[15];
-#pragma unroll
-            for (int q = 0; q < 15; ++q) {
-                float a = GK ? s_gk[lane * 15 + q] : 0.f;
-                if (GDK) {
-                    if (has_prev) a = fmaf(sgn, s_gdk[lane * 15 + q], a);
-                    if (has_next) a = fmaf(-sgn, s_gdk[(lane + 1) * 15 + q], a);
-                }
-                gk[q] = a;
-            }
-            float x[48];
-            vload48(s_pose + lane * kWorldRow4, x);
-            VBones B;
-            vbones(x, B);
-            vkcs_vjp(B, gk, g);
+    if (GP) {            // g_pos rows (per-frame output rows of this tile) -> slots 0 .. 31
+        const float4* g4 = reinterpret_cast<const float4*>(p.g_pos);
+        for (int i = lane; i < rows * kWorldChunks; i += kTile) {
+            const int slot = i / kWorldChunks, c = i - slot * kWorldChunks;
+            ldgsts16(s_tile + slot * kWorldRow4 + c, g4 + (size_t)s_map_f[slot] * kWorldChunks + c);
         }
-        vstore48(s_pose + lane * kWorldRow4, g);
+        ldgsts_wait_all();
+        __syncwarp();
+        if (lane < rows) {
+            float t[48];
+            vload48(s_tile + lane * kWorldRow4, t);
+#pragma unroll
+            for (int i = 0; i < 48; ++i) g[i] += t[i];
+        }
+        __syncwarp();
     }
+    if (lane < rows) vstore48(s_tile + lane * kWorldRow4, g);
     __syncwarp();
-    if (rows == kTile) store_padded_tile<kWorldChunks>(s_pose, p.out_pos, row0);
-    else stage_padded_out<kWorldChunks>(s_pose, p.out_pos, row0, rows);
+    if (rows == kTile) store_padded_tile<kWorldChunks>(s_tile, p.out_pos, row0);
+    else stage_padded_out<kWorldChunks>(s_tile, p.out_pos, row0, rows);
 }
 
 // ---- 2-D motion critic: root-joint differences (Fk_discriminator.py:566-579) ------------------------------------
@@ -455,8 +467,8 @@ int launch_video_critic_bwd(const float* pose, int frames, unsigned flags, const
     p.pose = pose; p.g_kcs = g_kcs; p.g_dkcs = g_dkcs; p.g_dpos = g_dpos; p.g_pos = g_pos; p.out_pos = g_pose;
     p.n = n; p.frames = frames; p.flags = flags;
     const bool gk = g_kcs != nullptr, gdk = g_dkcs != nullptr, gdp = g_dpos != nullptr, gp = g_pos != nullptr;
-    const size_t smem = sizeof(float4) * kTile * kWorldRow4 + sizeof(float) * ((gk ? kTile * 15 : 0) + (gdk ? (kTile + 1) * 15 : 0)) +
-                        sizeof(int) * (2 * kTile + 2);
+    const size_t smem = sizeof(float4) * (kTile + 1) * kWorldRow4 +
+                        sizeof(float) * ((gk ? kTile * 15 : 0) + (gdk ? (kTile + 1) * 15 : 0)) + sizeof(int) * (2 * kTile + 2);
     const long long blocks = (n + kTile - 1) / kTile;
     // the combinations the critics produce: everything (3-D motion critic with both extra branches), features only,
     // and the two single-branch configurations (motion_Dis_whether_use_3dPos_branch / _3dDiff_branch)

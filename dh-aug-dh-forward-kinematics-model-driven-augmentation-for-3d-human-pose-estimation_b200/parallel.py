@@ -118,9 +118,11 @@ def grad_allreduce_group(max_ctas=4):
 
     The gradients of the GAN's three MLPs are a few MB: latency-bound, a handful of CTAs move them at NVLink speed.
     NCCL's default launch takes 16-32 CTAs -- a fifth of the SMs -- and holds them while it waits for its peers, which is
-    what the FK kernels running beside it on the main stream pay for (measured at N = 4, 16 M poses per step: the
-    all-reduce takes 46 us alone but cost the overlapped step 54 us with the default communicator).  Returns None
-    (= the default group) off NCCL or when the installed torch cannot configure it."""
+    what kernels running beside it on another stream pay for.  Measured on 4 B200s (profiles/r2k_nccl_sweep.txt), 6.4 MB:
+    default communicator 45 us alone; max_ctas 8 / 4 / 2: 94 / 153 / 283 us.  Behind a 0.85 ms FK step all of them hide
+    completely and the FK kernels run 3 % faster beside the small ones; behind a 0.2 ms step only the default one fits.
+    So this is an option for long overlapped steps, not the default (bench.py --nccl-max-ctas).  Returns None (= the
+    default group) off NCCL or when the installed torch cannot configure it."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_backend() != "nccl" or not max_ctas:
         return None
     try:

@@ -96,6 +96,8 @@ def _flatbuf_worker(rank, world, port, q):
         before_G = [p.grad.clone() for p in G.parameters()]
         buf.allreduce(average=False, span=buf.span_of(D))
         g_untouched = all(torch.equal(a, p.grad) for a, p in zip(before_G, G.parameters()))
+        # off NCCL there is no CTA limit to configure: the helper falls back to the default group
+        assert parallel.grad_allreduce_group(4) is None
         q.put((rank, aliased, checks, g_untouched, buf.flat.numel(), buf.span_of(G), buf.span_of(D)))
     finally:
         dist.destroy_process_group()
