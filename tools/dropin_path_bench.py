@@ -123,7 +123,7 @@ def measure(dev, big=1 << 20, small=(1024, 4608), peak_gbs=6528.7, profile=False
                     step()
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):   # the autograd worker thread runs the backward
                 step()
             for _ in range(10):
                 graph.replay()
