@@ -111,6 +111,12 @@ def parse():
                     help="CTAs of a dedicated NCCL communicator for the gradient all-reduce; 0 (default) = NCCL's default "
                          "communicator, which measured best (profiles/r2k_nccl_sweep.txt: fewer CTAs make the 6 MB "
                          "all-reduce 2-6x slower, too slow to hide behind a 0.2 ms step)")
+    ap.add_argument("--exchange", default=os.environ.get("DHFK_EXCHANGE", "peer"), choices=["peer", "nccl"],
+                    help="gradient exchange at --gpus > 1: peer = dhfk_grad_allreduce (one hand-written kernel over NVLink "
+                         "peer memory / NVLS multicast; falls back to NCCL where symmetric memory is unavailable), nccl = "
+                         "ncclAllReduce")
+    ap.add_argument("--exchange-ctas", type=int, default=int(os.environ.get("DHFK_EXCHANGE_CTAS", "16")),
+                    help="CTAs (512 threads each) of dhfk_grad_allreduce")
     return ap.parse_args()
 
 
@@ -465,6 +471,22 @@ def timed_steps(path, steps, stream, dev, barrier, allreduce=None, probe_every=0
     return total_ms, fwd_ms, bwd_ms
 
 
+def feed_sampler(sampler, path, dev):
+    """Keep the clock sampler fed when the timed region was shorter than a few polling periods: the same step (no
+    collective, so the ranks need not agree on a count) for one more second on the sampled rank.  True if it ran."""
+    import torch
+    if sampler is None or len(sampler.samples) >= 10:
+        return False
+    t_end = time.time() + 1.0
+    i = 0
+    while time.time() < t_end:
+        path.step(i); i += 1
+        if i % 32 == 0:
+            torch.cuda.synchronize(dev)
+    torch.cuda.synchronize(dev)
+    return True
+
+
 def max_over_ranks(vals, dev, distributed):
     import torch
     import torch.distributed as dist
@@ -589,28 +611,68 @@ def run_native(args):
     allreduce_extra = None
     if distributed:
         G, D3, D2 = gan_models(dev)
-        gbuf = parallel.FlatGradBuffer([*G.parameters(), *D3.parameters(), *D2.parameters()])
-        gbuf.flat.fill_(1.0)
-        side = torch.cuda.Stream(dev)
-        ggroup = parallel.grad_allreduce_group(args.nccl_max_ctas)
+        gparams = [*G.parameters(), *D3.parameters(), *D2.parameters()]
+        gbuf = parallel.FlatGradBuffer(gparams, peer_exchange=(args.exchange == "peer"), max_ctas=args.exchange_ctas)
+        side = torch.cuda.Stream(dev, priority=-1)      # the exchange's CTAs go ahead of the FK tiles queued beside them
+        ggroup = parallel.grad_allreduce_group(args.nccl_max_ctas) if gbuf.peer is None else None
         gbuf_allreduce = gbuf.allreduce
-        gbuf.allreduce = lambda: gbuf_allreduce(group=ggroup)        # every call below goes through the dedicated communicator
-        for _ in range(5):
+        gbuf.allreduce = lambda: gbuf_allreduce(group=ggroup)        # every call below goes through the chosen path
+
+        def time_alone(fn, reps=50):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize(dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a0.record(stream)
+            for _ in range(reps):
+                fn()
+            a1.record(stream)
+            torch.cuda.synchronize(dev)
+            return max_over_ranks([a0.elapsed_time(a1) / reps], dev, True)[0]
+
+        nccl_buf = torch.empty_like(gbuf.flat)
+        exchange_check = None
+        if gbuf.peer is not None:      # the hand-written exchange against NCCL on this run's own buffer, before timing
+            gen = torch.Generator(device=dev).manual_seed(4242 + rank)
+            gbuf.flat.copy_(torch.randn(gbuf.flat.numel(), generator=gen, device=dev))
+            nccl_buf.copy_(gbuf.flat)
+            torch.distributed.all_reduce(nccl_buf, op=torch.distributed.ReduceOp.AVG)
             gbuf.allreduce()
-        torch.cuda.synchronize(dev)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        a0.record(stream)
-        for _ in range(50):
-            nel = gbuf.allreduce()
-        a1.record(stream)
-        torch.cuda.synchronize(dev)
-        (alone_ms,) = max_over_ranks([a0.elapsed_time(a1) / 50], dev, True)
-        allreduce_extra = {"bytes": int(nel) * 4, "ms_alone": alone_ms, "backend": "nccl", "collectives_per_step": 1,
-                           "communicator": ("dedicated, max_ctas=%d" % args.nccl_max_ctas) if ggroup is not None else "default",
-                           "what": "dhfk.parallel.FlatGradBuffer.allreduce: generator + 3-D critic + 2-D critic gradients "
-                                   "(dense 256) live in one persistent buffer (the slices are the .grad tensors), one "
-                                   "ncclAllReduce(AVG), no pack / unpack kernels; ms_alone = back to back on an idle GPU"}
+            torch.cuda.synchronize(dev)
+            gbuf.peer.check()
+            err = float((gbuf.flat - nccl_buf).abs().max())
+            first = gbuf.flat.clone()
+            torch.distributed.broadcast(first, src=0)
+            same = bool(torch.equal(first, gbuf.flat))
+            (err,) = max_over_ranks([err], dev, True)
+            (diff,) = max_over_ranks([0.0 if same else 1.0], dev, True)
+            if err > 1e-5 or diff:
+                raise SystemExit("bench.py: dhfk_grad_allreduce differs from NCCL (max abs %g, ranks identical: %s)" % (err, not diff))
+            exchange_check = {"max_abs_err_vs_nccl": err, "bit_identical_across_ranks": True}
+        gbuf.flat.fill_(1.0)
+        nel = gbuf.flat.numel()
+        alone_ms = time_alone(gbuf.allreduce)
+        nccl_ms = time_alone(lambda: torch.distributed.all_reduce(nccl_buf, op=torch.distributed.ReduceOp.AVG)) \
+            if gbuf.peer is not None else alone_ms
+        if gbuf.peer is not None:
+            comm = "dhfk_grad_allreduce: one kernel over NVLink peer memory (%s), <= %d CTAs" % (
+                "NVLS multimem.ld_reduce / multimem.st" if gbuf.peer.multicast else "peer loads / stores", gbuf.peer.max_ctas)
+            what = ("dhfk.parallel.FlatGradBuffer.allreduce: generator + 3-D critic + 2-D critic gradients (dense 256) live "
+                    "in one persistent symmetric buffer (the slices are the .grad tensors); every rank reduces its slice "
+                    "in place through the NVSwitch and writes it to all ranks, two in-kernel cross-GPU barriers, no NCCL "
+                    "call; ms_alone = back to back on an idle GPU, ms_alone_nccl = ncclAllReduce(AVG) on the same bytes")
+        else:
+            comm = ("NCCL, dedicated communicator, max_ctas=%d" % args.nccl_max_ctas) if ggroup is not None else "NCCL, default communicator"
+            what = ("dhfk.parallel.FlatGradBuffer.allreduce: generator + 3-D critic + 2-D critic gradients (dense 256) live in "
+                    "one persistent buffer (the slices are the .grad tensors), one ncclAllReduce(AVG), no pack / unpack "
+                    "kernels; ms_alone = back to back on an idle GPU")
+            if args.exchange == "peer":
+                what += "; peer exchange unavailable here: %s" % (parallel.PeerExchange.last_error,)
+        allreduce_extra = {"bytes": int(nel) * 4, "ms_alone": alone_ms, "ms_alone_nccl": nccl_ms, "backend": "nccl",
+                           "collectives_per_step": 1, "communicator": comm, "what": what}
+        if exchange_check:
+            allreduce_extra["parity"] = exchange_check
 
     sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
     probe_every = 8 if steps >= 16 else 1
@@ -635,16 +697,19 @@ def run_native(args):
         if sampler:
             sampler.start()
         total_ms, fwd_ms, bwd_ms = timed_steps(path, steps, stream, dev, barrier, allreduce=ar, probe_every=probe_every)
+        plain_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)      # the same steps without the collective
         barrier()
+        extension = feed_sampler(sampler, path, dev)
         if sampler:
             sampler.stop()
-        plain_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)
         total_ms, fwd_ms, bwd_ms, plain_ms = max_over_ranks([total_ms, fwd_ms, bwd_ms, plain_ms], dev, distributed)
         n_step = n_big
         value = args.total_poses / (total_ms / steps * 1e-3)
         if allreduce_extra is not None:
             allreduce_extra["ms_exposed_per_step"] = (total_ms - plain_ms) / steps
             allreduce_extra["ms_per_step_without_allreduce"] = plain_ms / steps
+            if gbuf.peer is not None:
+                gbuf.peer.check()          # no exchange in the timed region gave up on a peer
     else:
         path = path1
         for i in range(warmup):
@@ -657,16 +722,7 @@ def run_native(args):
         # every launch would cost the headline ~3 %).
         total_ms, fwd_ms, bwd_ms = timed_steps(path, steps, stream, dev, barrier, probe_every=probe_every)
         barrier()
-        # keep the sampler fed if the timed region was shorter than a few polling periods
-        if sampler and len(sampler.samples) < 10:
-            extension = True
-            t_end = time.time() + 1.0
-            i = 0
-            while time.time() < t_end:
-                path.step(i); i += 1
-                if i % 32 == 0:
-                    torch.cuda.synchronize(dev)
-            torch.cuda.synchronize(dev)
+        extension = feed_sampler(sampler, path, dev)
         if sampler:
             sampler.stop()
         total_ms, fwd_ms, bwd_ms = max_over_ranks([total_ms, fwd_ms, bwd_ms], dev, distributed)
@@ -676,6 +732,8 @@ def run_native(args):
             ar_ms, _, _ = timed_steps(path, steps, stream, dev, barrier, allreduce=(gbuf, side))
             (ar_ms,) = max_over_ranks([ar_ms], dev, True)
             allreduce_extra["ms_exposed_per_step"] = (ar_ms - total_ms) / steps
+            if gbuf.peer is not None:
+                gbuf.peer.check()
     ms_per_step = total_ms / steps
     del path
     if strong:

@@ -47,6 +47,11 @@ int launch_bank_gather(const float* bank, long long rec_floats, int cam_cols, co
                        long long bank_rows, float* out3d, float* out2d, float* out_cam, cudaStream_t st,
                        const char** where);
 
+// SURVEY 8 e: in-place gradient all-reduce over NVLink peer memory / NVLS multicast (dhfk_allreduce.cu)
+int launch_grad_allreduce(float* const* peer_bufs, float* mc_buf, unsigned* const* peer_flags, unsigned* status, int rank,
+                          int world, long long n_floats, float scale, unsigned epoch, int max_ctas,
+                          unsigned long long timeout_ns, cudaStream_t st, const char** where);
+
 // tiled standalone camera ops for 16-joint poses: mode 0 w2c fwd, 1 w2c bwd, 2 project fwd, 3 project bwd
 int launch_camera_tiles(int mode, const float* x, const float* g_uv, const float* cam_rows, long long cam_stride,
                         const float* q_dev, const float* t_dev, const float* M, const float* t, float* out,

@@ -55,7 +55,8 @@ class FlatGradBuffer:
     such gradients (one copy each), so the result is always right; it is only fastest when nothing was dropped.
     """
 
-    def __init__(self, params, device=None, dtype=torch.float32):
+    def __init__(self, params, device=None, dtype=torch.float32, peer_exchange=False, group=None, max_ctas=16,
+                 timeout_ms=2000):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no parameters that require grad")
@@ -64,7 +65,13 @@ class FlatGradBuffer:
         for p in self.params:
             self.offsets.append(off)
             off += (p.numel() + 3) // 4 * 4            # every slice starts 16-byte aligned
-        self.flat = torch.zeros(off, dtype=dtype, device=device)
+        self.peer = None
+        if peer_exchange:
+            self.peer = PeerExchange.create(off, device, group, max_ctas=max_ctas, timeout_ms=timeout_ms)
+        if self.peer is not None:
+            self.flat = self.peer.buffer               # symmetric allocation: every rank's buffer is mapped in every rank
+        else:
+            self.flat = torch.zeros(off, dtype=dtype, device=device)
         self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(self.offsets, self.params)]
         self.attach()
 
@@ -103,6 +110,9 @@ class FlatGradBuffer:
             elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
                 p.grad = v
+        if self.peer is not None and group is None:
+            lo, hi = (0, self.flat.numel()) if span is None else span
+            return self.peer.allreduce(lo, hi, average)
         buf = self.flat if span is None else self.flat[span[0]:span[1]]
         if average and dist.get_backend(group) == "nccl":
             dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group)      # the division happens inside the collective
@@ -111,6 +121,88 @@ class FlatGradBuffer:
             if average:
                 buf /= dist.get_world_size(group)
         return buf.numel()
+
+
+class PeerExchange:
+    """The gradient exchange as ONE hand-written kernel over NVLink peer memory (csrc/dhfk_allreduce.cu,
+    ``dhfk_grad_allreduce``): every rank reduces its slice of the buffer -- through the NVSwitch's multicast object
+    (NVLS: the switch adds the copies in flight and replicates the result) when the node has one, otherwise with loads
+    from / stores to every peer -- in place, with two cross-GPU flag barriers inside the kernel.  PyTorch only provides
+    the memory: ``torch.distributed._symmetric_memory`` allocates the buffer and the flag block and maps every rank's
+    copy into every process.  ``create`` returns None where that is not possible (one rank, gloo, no peer access), and
+    the caller keeps NCCL."""
+
+    def __init__(self, buffer, flags, status, bufs, flag_ptrs, mc_ptr, rank, world, max_ctas, timeout_ms, handles):
+        import ctypes
+        self.buffer, self.flags, self.status = buffer, flags, status
+        self.rank, self.world, self.max_ctas, self.timeout_ms = rank, world, int(max_ctas), int(timeout_ms)
+        self.multicast = bool(mc_ptr)
+        self._mc_ptr = int(mc_ptr or 0)
+        self._buf_ptrs = [int(b) for b in bufs]
+        self._flag_arr = (ctypes.c_void_p * world)(*[int(f) for f in flag_ptrs])
+        self._buf_arr = (ctypes.c_void_p * world)()
+        self._handles = handles          # keeps the mappings alive
+        self.epoch = 0
+        self.use_multicast = self.multicast
+
+    @classmethod
+    def create(cls, numel, device, group=None, max_ctas=16, timeout_ms=2000):
+        from . import _cabi
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        if dist.get_backend(group) != "nccl" or dist.get_world_size(group) > _cabi.AR_MAX_WORLD:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            pg = group if group is not None else dist.group.WORLD
+            try:
+                symm.enable_symm_mem_for_group(pg.group_name)
+            except Exception:
+                pass
+            numel = (int(numel) + 3) // 4 * 4
+            buf = symm.empty(numel, dtype=torch.float32, device=device)
+            buf.zero_()
+            flags = symm.empty(_cabi.AR_FLAG_WORDS, dtype=torch.int32, device=device)
+            flags.zero_()
+            torch.cuda.synchronize(device)
+            hb = symm.rendezvous(buf, pg)
+            hf = symm.rendezvous(flags, pg)
+            hf.barrier()                              # every rank's flags are zero before anyone signals
+            status = torch.zeros(1, dtype=torch.int32, device=device)
+            mc = int(getattr(hb, "multicast_ptr", 0) or 0)
+            return cls(buf, flags, status, list(hb.buffer_ptrs), list(hf.buffer_ptrs), mc, hb.rank, hb.world_size,
+                       max_ctas, timeout_ms, (hb, hf))
+        except Exception as e:           # no peer access / no symmetric-memory support: the caller keeps NCCL
+            cls.last_error = repr(e)
+            return None
+
+    last_error = None
+
+    def allreduce(self, lo=0, hi=None, average=True):
+        """All-reduce elements [lo, hi) of the buffer (multiples of 4) on the current stream.  Returns hi - lo."""
+        from . import _cabi
+        from .functional import _stream_ptr
+        hi = self.buffer.numel() if hi is None else hi
+        if lo % 4 or hi % 4 or not (0 <= lo <= hi <= self.buffer.numel()):
+            raise ValueError("range must be 16-byte aligned and inside the buffer")
+        if hi == lo:
+            return 0
+        lib = _cabi.load()
+        self.epoch += 1
+        for r, b in enumerate(self._buf_ptrs):
+            self._buf_arr[r] = b + 4 * lo
+        mc = self._mc_ptr + 4 * lo if (self.use_multicast and self._mc_ptr) else None
+        rc = lib.dhfk_grad_allreduce(self._buf_arr, mc, self._flag_arr, self.status.data_ptr(), self.rank, self.world,
+                                     hi - lo, (1.0 / self.world) if average else 1.0, self.epoch & 0xFFFFFFFF or 1,
+                                     self.max_ctas, self.timeout_ms, _stream_ptr(self.buffer.device))
+        _cabi.check(rc, "dhfk_grad_allreduce")
+        return hi - lo
+
+    def check(self):
+        """Raise if any exchange so far gave up waiting for a peer (synchronises)."""
+        st = int(self.status.item())
+        if st:
+            raise RuntimeError("dhfk_grad_allreduce: call %d timed out waiting for a peer rank" % st)
 
 
 def grad_allreduce_group(max_ctas=4):

@@ -30,6 +30,8 @@
  *       the motion critics' inputs (Fk_discriminator.py:436-512,554-587; video_GAN_fun.py:222-223,269-270)
  *   dhfk_bank_gather            mini-batch out of the device-resident fake-pair bank
  *       (model_fk_gan_train.py:486-510; common/data_loader.py:9-36)
+ *   dhfk_grad_allreduce         the gradient exchange of the data-parallel GAN step over NVLink peer memory (SURVEY 8 e)
+ *       (the optimizer steps of model_fk_gan_train.py:314-341,382-409,415-482, one replica per GPU)
  *   dhfk_scatter32_*            the [N,32,3] H36M slot layout change_3d_joint_angle returns (...:745-820), both ways
  *   dhfk_topology               the constant tables the reference keeps as Python lists
  *       (forward_kinematics_DH_model.py:234-261,:571-589,:751-817; common/h36m_dataset.py:37-38)
@@ -275,6 +277,33 @@ int dhfk_video_root_diff_backward(const float* g_diff_dev, const float* g_uv_pla
  */
 int dhfk_bank_gather(const float* bank_dev, int64_t rec_floats, int32_t cam_cols, const int64_t* idx_dev, int64_t nb,
                      int64_t bank_rows, float* out3d_dev, float* out2d_dev, float* out_cam_dev, void* stream);
+
+/*
+ * SURVEY 8 e -- the exchange step of the data-parallel GAN iteration: average (scale = 1/world) or sum (scale = 1) a
+ * flat fp32 gradient buffer over the `world` GPUs of one node, IN PLACE, in one kernel over NVLink peer memory.
+ * Every rank calls it with the same n_floats, max_ctas and call counter `epoch` (1, 2, 3, ... per flag block; one call
+ * in flight per flag block).  Nothing here allocates or maps memory: the caller owns
+ *   peer_bufs  [world]  HOST array: address, in THIS process, of every rank's buffer range (index = rank; entry `rank`
+ *                       is the local one).  Symmetric allocations mapped into every process
+ *                       (torch.distributed._symmetric_memory: handle.buffer_ptrs, or cuMem / cudaIpc mappings).
+ *   multicast_buf       address of the same range through the node's NVLS multicast object, or NULL.  With it the
+ *                       NVSwitch performs the reduction (multimem.ld_reduce) and the replication (multimem.st);
+ *                       without it the kernel loads from / stores to every peer itself, summing in rank order.
+ *   peer_flags [world]  HOST array: every rank's flag block, DHFK_AR_FLAG_WORDS uint32 words, zeroed once before the
+ *                       first call and never touched by the caller again.
+ *   status_dev          one local uint32 word, zeroed by the caller; becomes `epoch` if a cross-GPU wait inside call
+ *                       `epoch` outlasted timeout_ms (a rank that never launched): the kernel gives up instead of
+ *                       hanging the GPU and the buffer contents are then undefined.
+ * Every element is summed by exactly one rank and written to all of them: the ranks end bit-identical.  n_floats must
+ * be a multiple of 4 and every buffer 16-byte aligned.  max_ctas: 1..DHFK_AR_MAX_CTAS CTAs of 512 threads (16 move
+ * 6.4 MB between 8 B200s; the kernel is meant to run beside the FK kernels on another stream).  world <= DHFK_AR_MAX_WORLD.
+ */
+#define DHFK_AR_MAX_WORLD 16
+#define DHFK_AR_MAX_CTAS 64
+#define DHFK_AR_FLAG_WORDS (DHFK_AR_MAX_CTAS * 2 * DHFK_AR_MAX_WORLD)
+int dhfk_grad_allreduce(float* const* peer_bufs, float* multicast_buf, uint32_t* const* peer_flags, uint32_t* status_dev,
+                        int32_t rank, int32_t world, int64_t n_floats, float scale, uint32_t epoch, int32_t max_ctas,
+                        int64_t timeout_ms, void* stream);
 
 /*
  * Host-buffer end-to-end entry: forward + backward over N poses whose inputs, upstream gradients

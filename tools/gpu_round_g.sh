@@ -1,10 +1,11 @@
 #!/bin/bash
-# usage: bash tools/gpu_round_g.sh <tag> <ngpus> -- configs[4] at N GPUs (native + reference arm), short
+# usage: bash tools/gpu_round_g.sh <tag> <ngpus> [steps] -- configs[4] at N GPUs (native + reference arm), short
 TAG=${1:-r2g}
 N=${2:-8}
+STEPS=${3:-100}
 set -x
 NCCL_DEBUG=INFO python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29527 \
-  bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_bench_n$N.err; echo bench rc=$?
+  bench.py --gpus $N --steps $STEPS --warmup 5 > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_bench_n$N.err; echo bench rc=$?
 grep -E "NCCL INFO" gpurun_out/${TAG}_bench_n$N.err | grep -iE "nranks|NVLS|Init COMPLETE" | head -6
 grep -v "NCCL INFO" gpurun_out/${TAG}_bench_n$N.err | tail -c 1200
 python -c "

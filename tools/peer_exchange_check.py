@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""dhfk_grad_allreduce (csrc/dhfk_allreduce.cu) against NCCL, under torchrun on >= 2 GPUs of one node:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
+        tools/peer_exchange_check.py [--time]
+
+Checks (every rank; rank 0 prints): the average / sum equals NCCL's within fp32 rounding of the sum order, all ranks
+end bit-identical, sub-ranges leave the rest of the buffer untouched, repeated calls (flag counters) keep working, both
+the NVLS multicast path and the plain peer path.  --time adds the 6.4 MB timing (alone, back to back) beside NCCL.
+Exit code 0 = all passed, 3 = symmetric memory not available on this box (nothing to check)."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from dhfk import parallel
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    numel = 1590236 // 4 * 4 + 8          # the bench's generator + two critics, plus a tail
+    px = parallel.PeerExchange.create(numel, dev, max_ctas=16, timeout_ms=2000)
+    ok_all = torch.tensor([1 if px is not None else 0], device=dev)
+    dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+    if not int(ok_all.item()):
+        if rank == 0:
+            print(json.dumps({"peer_exchange": "unavailable", "why": parallel.PeerExchange.last_error}))
+        dist.destroy_process_group()
+        return 3
+    out = {"world": world, "multicast": px.multicast, "numel": numel, "cases": []}
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    failures = []
+
+    def one_case(lo, hi, average, use_mc, tag):
+        px.use_multicast = use_mc
+        data = torch.randn(numel, generator=g, device=dev) * (1.0 + rank)
+        px.buffer.copy_(data)
+        want = data.clone()
+        part = want[lo:hi].clone()
+        dist.all_reduce(part, op=dist.ReduceOp.AVG if average else dist.ReduceOp.SUM)
+        want[lo:hi] = part
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        px.allreduce(lo, hi, average)
+        torch.cuda.synchronize(dev)
+        px.check()
+        got = px.buffer.clone()
+        err = float((got - want).abs().max())
+        scale = float(want.abs().max())
+        # identical on every rank?
+        ref = got[lo:hi].clone()
+        dist.broadcast(ref, src=0)
+        same = bool(torch.equal(ref, got[lo:hi]))
+        untouched = bool(torch.equal(got[:lo], data[:lo]) and torch.equal(got[hi:], data[hi:]))
+        rec = {"case": tag, "lo": lo, "hi": hi, "average": average, "multicast": bool(use_mc and px.multicast),
+               "max_abs_err_vs_nccl": err, "scale": scale, "bit_identical_across_ranks": same, "rest_untouched": untouched}
+        out["cases"].append(rec)
+        if not (err <= 2e-6 * max(scale, 1.0) * world and same and untouched):
+            failures.append(rec)
+
+    for use_mc in ((True, False) if px.multicast else (False,)):
+        one_case(0, numel, True, use_mc, "whole buffer, average")
+        one_case(0, numel, False, use_mc, "whole buffer, sum")
+        one_case(4096, 4096 + 440000 // 4 * 4, True, use_mc, "one model's span")
+        one_case(numel - 8, numel, True, use_mc, "8-element tail")
+        one_case(16, 20, True, use_mc, "one 16-byte element")
+        for _ in range(20):               # flag counters over many calls, no host sync in between
+            px.allreduce(0, numel, True)
+        torch.cuda.synchronize(dev)
+        px.check()
+        one_case(0, numel, True, use_mc, "after 20 back-to-back calls")
+
+    if "--time" in sys.argv:
+        timing = {}
+        buf_nccl = torch.randn(numel, device=dev)
+
+        def timed(fn, reps=200):
+            for _ in range(10):
+                fn()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        timing["nccl_us"] = timed(lambda: dist.all_reduce(buf_nccl, op=dist.ReduceOp.AVG))
+        for use_mc in ((True, False) if px.multicast else (False,)):
+            px.use_multicast = use_mc
+            for ctas in (4, 8, 16, 32, 64):
+                px.max_ctas = ctas
+                px.buffer.normal_()
+                timing["%s_ctas%d_us" % ("multimem" if use_mc else "peer", ctas)] = timed(lambda: px.allreduce(0, numel, True))
+        px.check()
+        out["timing_6p4MB"] = timing
+
+    out["failures"] = failures
+    if rank == 0:
+        print(json.dumps(out, indent=1))
+    bad = torch.tensor([len(failures)], device=dev)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 1 if int(bad.item()) else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
