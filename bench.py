@@ -116,7 +116,11 @@ def parse():
                          "peer memory / NVLS multicast; falls back to NCCL where symmetric memory is unavailable), nccl = "
                          "ncclAllReduce")
     ap.add_argument("--exchange-ctas", type=int, default=int(os.environ.get("DHFK_EXCHANGE_CTAS", "16")),
-                    help="CTAs (512 threads each) of dhfk_grad_allreduce")
+                    help="CTAs of dhfk_grad_allreduce")
+    ap.add_argument("--exchange-threads", type=int, default=int(os.environ.get("DHFK_EXCHANGE_THREADS", "512")),
+                    help="threads per CTA of dhfk_grad_allreduce")
+    ap.add_argument("--exchange-priority", type=int, default=int(os.environ.get("DHFK_EXCHANGE_PRIORITY", "-1")),
+                    help="priority of the side stream the exchange runs on (-1 = high)")
     return ap.parse_args()
 
 
@@ -612,8 +616,9 @@ def run_native(args):
     if distributed:
         G, D3, D2 = gan_models(dev)
         gparams = [*G.parameters(), *D3.parameters(), *D2.parameters()]
-        gbuf = parallel.FlatGradBuffer(gparams, peer_exchange=(args.exchange == "peer"), max_ctas=args.exchange_ctas)
-        side = torch.cuda.Stream(dev, priority=-1)      # the exchange's CTAs go ahead of the FK tiles queued beside them
+        gbuf = parallel.FlatGradBuffer(gparams, peer_exchange=(args.exchange == "peer"), max_ctas=args.exchange_ctas,
+                                       cta_threads=args.exchange_threads)
+        side = torch.cuda.Stream(dev, priority=args.exchange_priority)   # -1: the exchange's CTAs go ahead of the FK tiles queued beside them
         ggroup = parallel.grad_allreduce_group(args.nccl_max_ctas) if gbuf.peer is None else None
         gbuf_allreduce = gbuf.allreduce
         gbuf.allreduce = lambda: gbuf_allreduce(group=ggroup)        # every call below goes through the chosen path
@@ -657,7 +662,8 @@ def run_native(args):
             if gbuf.peer is not None else alone_ms
         if gbuf.peer is not None:
             comm = "dhfk_grad_allreduce: one kernel over NVLink peer memory (%s), <= %d CTAs" % (
-                "NVLS multimem.ld_reduce / multimem.st" if gbuf.peer.multicast else "peer loads / stores", gbuf.peer.max_ctas)
+                "NVLS multimem.ld_reduce / multimem.st" if gbuf.peer.multicast else "peer loads / stores", gbuf.peer.max_ctas) + \
+                " of %d threads, side stream priority %d" % (gbuf.peer.cta_threads, args.exchange_priority)
             what = ("dhfk.parallel.FlatGradBuffer.allreduce: generator + 3-D critic + 2-D critic gradients (dense 256) live "
                     "in one persistent symmetric buffer (the slices are the .grad tensors); every rank reduces its slice "
                     "in place through the NVSwitch and writes it to all ranks, two in-kernel cross-GPU barriers, no NCCL "
@@ -686,28 +692,38 @@ def run_native(args):
         # weak companion first (1M poses per rank, same in-step all-reduce), then the headline
         for i in range(warmup):
             path1.step(i)
+        # with / without / without / with the exchange: the board's power state drifts while it is loaded, and the
+        # mirrored order cancels a linear drift out of the difference
         w_ms, _, _ = timed_steps(path1, steps, stream, dev, barrier, allreduce=ar)
         w_plain, _, _ = timed_steps(path1, steps, stream, dev, barrier)
-        w_ms, w_plain = max_over_ranks([w_ms, w_plain], dev, distributed)
+        w_plain2, _, _ = timed_steps(path1, steps, stream, dev, barrier)
+        w_ms2, _, _ = timed_steps(path1, steps, stream, dev, barrier, allreduce=ar)
+        w_ms, w_plain, w_plain2, w_ms2 = max_over_ranks([w_ms, w_plain, w_plain2, w_ms2], dev, distributed)
         weak_extra = {"poses_per_gpu": n, "value": n * world_size / (w_ms / steps * 1e-3), "unit": UNIT,
-                      "ms_per_step": w_ms / steps, "ms_per_step_without_allreduce": w_plain / steps,
-                      "what": "weak scaling: 1,048,576 poses per rank + the same in-step gradient all-reduce"}
+                      "ms_per_step": w_ms / steps, "ms_per_step_without_allreduce": (w_plain + w_plain2) / 2 / steps,
+                      "ms_exposed_per_step": ((w_ms + w_ms2) - (w_plain + w_plain2)) / 2 / steps,
+                      "what": "weak scaling: 1,048,576 poses per rank + the same in-step gradient all-reduce; exposed = "
+                              "mean of two runs with it - mean of two without, order with / without / without / with"}
         for i in range(warmup):
             path.step(i)
         if sampler:
             sampler.start()
         total_ms, fwd_ms, bwd_ms = timed_steps(path, steps, stream, dev, barrier, allreduce=ar, probe_every=probe_every)
-        plain_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)      # the same steps without the collective
+        plain_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)      # the same steps without the collective,
+        plain2_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)     # twice, then with it again (drift cancels)
+        total2_ms, _, _ = timed_steps(path, steps, stream, dev, barrier, allreduce=ar)
         barrier()
         extension = feed_sampler(sampler, path, dev)
         if sampler:
             sampler.stop()
-        total_ms, fwd_ms, bwd_ms, plain_ms = max_over_ranks([total_ms, fwd_ms, bwd_ms, plain_ms], dev, distributed)
+        total_ms, fwd_ms, bwd_ms, plain_ms, plain2_ms, total2_ms = max_over_ranks(
+            [total_ms, fwd_ms, bwd_ms, plain_ms, plain2_ms, total2_ms], dev, distributed)
         n_step = n_big
         value = args.total_poses / (total_ms / steps * 1e-3)
         if allreduce_extra is not None:
-            allreduce_extra["ms_exposed_per_step"] = (total_ms - plain_ms) / steps
-            allreduce_extra["ms_per_step_without_allreduce"] = plain_ms / steps
+            allreduce_extra["ms_exposed_per_step"] = ((total_ms + total2_ms) - (plain_ms + plain2_ms)) / 2 / steps
+            allreduce_extra["ms_per_step_without_allreduce"] = (plain_ms + plain2_ms) / 2 / steps
+            allreduce_extra["ms_per_step_second_run_with_it"] = total2_ms / steps
             if gbuf.peer is not None:
                 gbuf.peer.check()          # no exchange in the timed region gave up on a peer
     else:

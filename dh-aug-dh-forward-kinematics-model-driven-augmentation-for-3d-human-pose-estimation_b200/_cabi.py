@@ -60,7 +60,7 @@ SIGNATURES = {
     "dhfk_video_root_diff_backward": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _u32, _vp, _i64, _vp]),
     "dhfk_bank_gather": (ctypes.c_int, [_vp, _i64, ctypes.c_int32, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "dhfk_grad_allreduce": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _i64, ctypes.c_float, _u32,
-                                           ctypes.c_int32, _i64, _vp]),
+                                           ctypes.c_int32, ctypes.c_int32, _i64, _vp]),
     "dhfk_host_workspace_bytes": (_i64, [_i64, ctypes.c_int32]),
     "dhfk_forward_backward_host": (ctypes.c_int, [_vp] * 12 + [_i64, _i64, ctypes.c_int32, _vp, _i64, _u32]),
 }

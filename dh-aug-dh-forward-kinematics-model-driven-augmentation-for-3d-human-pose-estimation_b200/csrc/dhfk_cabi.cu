@@ -709,7 +709,7 @@ int dhfk_bank_gather(const float* bank, int64_t rec_floats, int32_t cam_cols, co
 // ---- SURVEY 8 e: gradient exchange over peer memory ---------------------------------------------------
 int dhfk_grad_allreduce(float* const* peer_bufs, float* multicast_buf, uint32_t* const* peer_flags, uint32_t* status_dev,
                         int32_t rank, int32_t world, int64_t n_floats, float scale, uint32_t epoch, int32_t max_ctas,
-                        int64_t timeout_ms, void* stream) {
+                        int32_t cta_threads, int64_t timeout_ms, void* stream) {
     if (world < 1 || world > DHFK_AR_MAX_WORLD || rank < 0 || rank >= world)
         return fail(DHFK_E_INVAL, "need 0 <= rank < world <= DHFK_AR_MAX_WORLD");
     if (n_floats < 0 || n_floats % 4 != 0) return fail(DHFK_E_INVAL, "n_floats must be a non-negative multiple of 4");
@@ -717,6 +717,8 @@ int dhfk_grad_allreduce(float* const* peer_bufs, float* multicast_buf, uint32_t*
     if (!peer_bufs || !peer_flags || !status_dev) return fail(DHFK_E_INVAL, "peer_bufs / peer_flags / status_dev must be non-null");
     if (epoch == 0) return fail(DHFK_E_INVAL, "epoch counts calls from 1");
     if (max_ctas < 1 || max_ctas > DHFK_AR_MAX_CTAS) return fail(DHFK_E_INVAL, "max_ctas must be in 1..DHFK_AR_MAX_CTAS");
+    if (cta_threads < 32 || cta_threads > 512 || cta_threads % 32 != 0)
+        return fail(DHFK_E_INVAL, "cta_threads must be a multiple of 32 in 32..512");
     if (timeout_ms <= 0) return fail(DHFK_E_INVAL, "timeout_ms must be positive");
     for (int r = 0; r < world; ++r) {
         if (!peer_bufs[r] || !peer_flags[r]) return fail(DHFK_E_INVAL, "null peer buffer / flag block");
@@ -726,7 +728,7 @@ int dhfk_grad_allreduce(float* const* peer_bufs, float* multicast_buf, uint32_t*
     const char* where = "";
     int e = dhfk::launch_grad_allreduce(peer_bufs, multicast_buf, reinterpret_cast<unsigned* const*>(peer_flags),
                                         reinterpret_cast<unsigned*>(status_dev), rank, world, n_floats, scale, epoch,
-                                        max_ctas, (unsigned long long)timeout_ms * 1000000ull, (cudaStream_t)stream, &where);
+                                        max_ctas, cta_threads, (unsigned long long)timeout_ms * 1000000ull, (cudaStream_t)stream, &where);
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }
 

@@ -56,7 +56,7 @@ class FlatGradBuffer:
     """
 
     def __init__(self, params, device=None, dtype=torch.float32, peer_exchange=False, group=None, max_ctas=16,
-                 timeout_ms=2000):
+                 cta_threads=512, timeout_ms=2000):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no parameters that require grad")
@@ -67,7 +67,8 @@ class FlatGradBuffer:
             off += (p.numel() + 3) // 4 * 4            # every slice starts 16-byte aligned
         self.peer = None
         if peer_exchange:
-            self.peer = PeerExchange.create(off, device, group, max_ctas=max_ctas, timeout_ms=timeout_ms)
+            self.peer = PeerExchange.create(off, device, group, max_ctas=max_ctas, cta_threads=cta_threads,
+                                            timeout_ms=timeout_ms)
         if self.peer is not None:
             self.flat = self.peer.buffer               # symmetric allocation: every rank's buffer is mapped in every rank
         else:
@@ -132,21 +133,25 @@ class PeerExchange:
     copy into every process.  ``create`` returns None where that is not possible (one rank, gloo, no peer access), and
     the caller keeps NCCL."""
 
-    def __init__(self, buffer, flags, status, bufs, flag_ptrs, mc_ptr, rank, world, max_ctas, timeout_ms, handles):
+    def __init__(self, buffer, flags, status, bufs, flag_ptrs, mc_ptr, rank, world, max_ctas, cta_threads, timeout_ms,
+                 handles):
         import ctypes
         self.buffer, self.flags, self.status = buffer, flags, status
-        self.rank, self.world, self.max_ctas, self.timeout_ms = rank, world, int(max_ctas), int(timeout_ms)
+        self.rank, self.world, self.timeout_ms = rank, world, int(timeout_ms)
+        self.max_ctas, self.cta_threads = int(max_ctas), int(cta_threads)
         self.multicast = bool(mc_ptr)
         self._mc_ptr = int(mc_ptr or 0)
         self._buf_ptrs = [int(b) for b in bufs]
         self._flag_arr = (ctypes.c_void_p * world)(*[int(f) for f in flag_ptrs])
-        self._buf_arr = (ctypes.c_void_p * world)()
+        self._ranges = {}                # lo -> ctypes array of every rank's address of element lo
         self._handles = handles          # keeps the mappings alive
+        self._status_ptr = status.data_ptr()
+        self._dev_index = buffer.device.index
         self.epoch = 0
         self.use_multicast = self.multicast
 
     @classmethod
-    def create(cls, numel, device, group=None, max_ctas=16, timeout_ms=2000):
+    def create(cls, numel, device, group=None, max_ctas=16, cta_threads=512, timeout_ms=2000):
         from . import _cabi
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
@@ -155,10 +160,6 @@ class PeerExchange:
         try:
             import torch.distributed._symmetric_memory as symm
             pg = group if group is not None else dist.group.WORLD
-            try:
-                symm.enable_symm_mem_for_group(pg.group_name)
-            except Exception:
-                pass
             numel = (int(numel) + 3) // 4 * 4
             buf = symm.empty(numel, dtype=torch.float32, device=device)
             buf.zero_()
@@ -171,7 +172,7 @@ class PeerExchange:
             status = torch.zeros(1, dtype=torch.int32, device=device)
             mc = int(getattr(hb, "multicast_ptr", 0) or 0)
             return cls(buf, flags, status, list(hb.buffer_ptrs), list(hf.buffer_ptrs), mc, hb.rank, hb.world_size,
-                       max_ctas, timeout_ms, (hb, hf))
+                       max_ctas, cta_threads, timeout_ms, (hb, hf))
         except Exception as e:           # no peer access / no symmetric-memory support: the caller keeps NCCL
             cls.last_error = repr(e)
             return None
@@ -181,21 +182,23 @@ class PeerExchange:
     def allreduce(self, lo=0, hi=None, average=True):
         """All-reduce elements [lo, hi) of the buffer (multiples of 4) on the current stream.  Returns hi - lo."""
         from . import _cabi
-        from .functional import _stream_ptr
         hi = self.buffer.numel() if hi is None else hi
         if lo % 4 or hi % 4 or not (0 <= lo <= hi <= self.buffer.numel()):
             raise ValueError("range must be 16-byte aligned and inside the buffer")
         if hi == lo:
             return 0
-        lib = _cabi.load()
-        self.epoch += 1
-        for r, b in enumerate(self._buf_ptrs):
-            self._buf_arr[r] = b + 4 * lo
+        arr = self._ranges.get(lo)
+        if arr is None:
+            import ctypes
+            arr = self._ranges[lo] = (ctypes.c_void_p * self.world)(*[b + 4 * lo for b in self._buf_ptrs])
+        self.epoch = self.epoch % 0xFFFFFFFF + 1          # 1, 2, ... (never 0)
         mc = self._mc_ptr + 4 * lo if (self.use_multicast and self._mc_ptr) else None
-        rc = lib.dhfk_grad_allreduce(self._buf_arr, mc, self._flag_arr, self.status.data_ptr(), self.rank, self.world,
-                                     hi - lo, (1.0 / self.world) if average else 1.0, self.epoch & 0xFFFFFFFF or 1,
-                                     self.max_ctas, self.timeout_ms, _stream_ptr(self.buffer.device))
-        _cabi.check(rc, "dhfk_grad_allreduce")
+        rc = _cabi.load().dhfk_grad_allreduce(arr, mc, self._flag_arr, self._status_ptr, self.rank, self.world, hi - lo,
+                                              (1.0 / self.world) if average else 1.0, self.epoch, self.max_ctas,
+                                              self.cta_threads, self.timeout_ms,
+                                              torch._C._cuda_getCurrentRawStream(self._dev_index))
+        if rc:
+            _cabi.check(rc, "dhfk_grad_allreduce")
         return hi - lo
 
     def check(self):

@@ -295,15 +295,16 @@ int dhfk_bank_gather(const float* bank_dev, int64_t rec_floats, int32_t cam_cols
  *                       `epoch` outlasted timeout_ms (a rank that never launched): the kernel gives up instead of
  *                       hanging the GPU and the buffer contents are then undefined.
  * Every element is summed by exactly one rank and written to all of them: the ranks end bit-identical.  n_floats must
- * be a multiple of 4 and every buffer 16-byte aligned.  max_ctas: 1..DHFK_AR_MAX_CTAS CTAs of 512 threads (16 move
- * 6.4 MB between 8 B200s; the kernel is meant to run beside the FK kernels on another stream).  world <= DHFK_AR_MAX_WORLD.
+ * be a multiple of 4 and every buffer 16-byte aligned.  max_ctas: 1..DHFK_AR_MAX_CTAS CTAs of cta_threads (a multiple
+ * of 32 in 32..512) threads; the kernel is meant to run beside the FK kernels on another stream, and small CTAs fit
+ * into the register / thread slots those leave free on an SM.  world <= DHFK_AR_MAX_WORLD.
  */
 #define DHFK_AR_MAX_WORLD 16
 #define DHFK_AR_MAX_CTAS 64
 #define DHFK_AR_FLAG_WORDS (DHFK_AR_MAX_CTAS * 2 * DHFK_AR_MAX_WORLD)
 int dhfk_grad_allreduce(float* const* peer_bufs, float* multicast_buf, uint32_t* const* peer_flags, uint32_t* status_dev,
                         int32_t rank, int32_t world, int64_t n_floats, float scale, uint32_t epoch, int32_t max_ctas,
-                        int64_t timeout_ms, void* stream);
+                        int32_t cta_threads, int64_t timeout_ms, void* stream);
 
 /*
  * Host-buffer end-to-end entry: forward + backward over N poses whose inputs, upstream gradients

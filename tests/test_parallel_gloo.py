@@ -70,7 +70,9 @@ def _flatbuf_worker(rank, world, port, q):
         G = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 5))
         D = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 1))
         x = torch.randn(n, 8)
-        buf = parallel.FlatGradBuffer(list(G.parameters()) + list(D.parameters()))
+        # peer_exchange asks for the NVLink kernel; off NCCL / GPUs there is none and the buffer keeps the collective
+        buf = parallel.FlatGradBuffer(list(G.parameters()) + list(D.parameters()), peer_exchange=True)
+        assert buf.peer is None and parallel.PeerExchange.create(64, torch.device("cpu")) is None
         aliased = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(buf.params, buf.views))
         checks = []
         for it in range(3):

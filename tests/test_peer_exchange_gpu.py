@@ -1,0 +1,64 @@
+"""SURVEY 8 e: dhfk_grad_allreduce, the gradient exchange as one kernel over NVLink peer memory.
+One GPU: the kernel with a world of one (its own buffer is the only peer: barriers, slicing, scaling, sub-ranges).
+Two or more GPUs: tools/peer_exchange_check.py under torchrun -- against NCCL, bit-identical ranks, NVLS and peer paths."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from dhfk import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,ctas,threads", [(4, 1, 32), (1000, 4, 128), (1590236, 16, 512), (1590236, 64, 256)])
+def test_world_of_one(n, ctas, threads):
+    lib = _cabi.load()
+    dev = torch.device("cuda", 0)
+    n4 = n // 4 * 4
+    x = torch.randn(n4 + 64, device=dev)
+    want = x.clone()
+    want[32:32 + n4] *= 0.25
+    flags = torch.zeros(_cabi.AR_FLAG_WORDS, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    bufs = (ctypes.c_void_p * 1)(x.data_ptr() + 4 * 32)
+    fl = (ctypes.c_void_p * 1)(flags.data_ptr())
+    st = torch.cuda.current_stream(dev).cuda_stream
+    # scale 0.5 twice: the second call runs on the flag words the first one left behind (call counter 2)
+    for epoch in (1, 2):
+        rc = lib.dhfk_grad_allreduce(bufs, None, fl, status.data_ptr(), 0, 1, n4, 0.5, epoch, ctas, threads, 1000, st)
+        _cabi.check(rc, "dhfk_grad_allreduce")
+    torch.cuda.synchronize(dev)
+    assert int(status.item()) == 0
+    assert torch.equal(x, want)            # halving is exact; nothing outside the range moved
+
+
+def test_missing_peer_times_out_instead_of_hanging():
+    """A world of two whose second rank never launches: the kernel gives up after timeout_ms and raises the status word."""
+    lib = _cabi.load()
+    dev = torch.device("cuda", 0)
+    x = torch.ones(1024, device=dev)
+    ghost = torch.ones(1024, device=dev)
+    flags = torch.zeros(2 * _cabi.AR_FLAG_WORDS, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    bufs = (ctypes.c_void_p * 2)(x.data_ptr(), ghost.data_ptr())
+    fl = (ctypes.c_void_p * 2)(flags.data_ptr(), flags.data_ptr() + 4 * _cabi.AR_FLAG_WORDS)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    rc = lib.dhfk_grad_allreduce(bufs, None, fl, status.data_ptr(), 0, 2, 1024, 0.5, 7, 4, 128, 50, st)
+    _cabi.check(rc, "dhfk_grad_allreduce")
+    torch.cuda.synchronize(dev)
+    assert int(status.item()) == 7
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one node")
+def test_against_nccl_two_ranks():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29543", os.path.join(ROOT, "tools", "peer_exchange_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if r.returncode == 3:
+        pytest.skip("symmetric memory unavailable on this box: " + r.stdout[-300:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -82,30 +82,50 @@ def main():
         timing = {}
         buf_nccl = torch.randn(numel, device=dev)
 
+        import time
+
         def timed(fn, reps=200):
             for _ in range(10):
                 fn()
             torch.cuda.synchronize(dev)
             dist.barrier()
+            torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
             e0.record()
             for _ in range(reps):
                 fn()
             e1.record()
+            host = (time.perf_counter() - t0) / reps * 1e6      # time to ENQUEUE one call: GPU-bound only if well below gpu
             torch.cuda.synchronize(dev)
-            t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=dev)
+            t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3, host], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
+            return {"gpu_us": round(float(t[0]), 2), "host_enqueue_us": round(float(t[1]), 2)}
 
-        timing["nccl_us"] = timed(lambda: dist.all_reduce(buf_nccl, op=dist.ReduceOp.AVG))
+        timing["nccl"] = timed(lambda: dist.all_reduce(buf_nccl, op=dist.ReduceOp.AVG))
         for use_mc in ((True, False) if px.multicast else (False,)):
             px.use_multicast = use_mc
-            for ctas in (4, 8, 16, 32, 64):
-                px.max_ctas = ctas
+            for threads, ctas in ((512, 8), (512, 16), (512, 32), (256, 32), (256, 64), (128, 32), (128, 64)):
+                px.max_ctas, px.cta_threads = ctas, threads
                 px.buffer.normal_()
-                timing["%s_ctas%d_us" % ("multimem" if use_mc else "peer", ctas)] = timed(lambda: px.allreduce(0, numel, True))
+                timing["%s_%dx%d" % ("multimem" if use_mc else "peer", ctas, threads)] = timed(lambda: px.allreduce(0, numel, True))
+        px.use_multicast, px.max_ctas, px.cta_threads = px.multicast, 16, 512
         px.check()
         out["timing_6p4MB"] = timing
+        # latency vs bandwidth: the same call over growing ranges (16 B = the two barriers and the launch, nothing else)
+        sizes = {}
+        for use_mc in ((True, False) if px.multicast else (False,)):
+            px.use_multicast = use_mc
+            px.max_ctas, px.cta_threads = (16, 512) if use_mc else (32, 512)
+            for nfl in (4, 16384, 262144, 1048576, numel):
+                nfl = min(nfl, numel) // 4 * 4
+                sizes["%s_%d_bytes" % ("multimem" if use_mc else "peer", nfl * 4)] = timed(lambda: px.allreduce(0, nfl, True))
+        for nfl in (4, 16384, 262144, 1048576, numel):
+            nfl = min(nfl, numel) // 4 * 4
+            sizes["nccl_%d_bytes" % (nfl * 4)] = timed(lambda: dist.all_reduce(buf_nccl[:nfl], op=dist.ReduceOp.AVG))
+        px.use_multicast, px.max_ctas, px.cta_threads = px.multicast, 16, 512
+        px.check()
+        out["timing_by_size"] = sizes
 
     out["failures"] = failures
     if rank == 0:
