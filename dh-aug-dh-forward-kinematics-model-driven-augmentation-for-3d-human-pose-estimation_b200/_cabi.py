@@ -19,7 +19,7 @@ FLAG_ACCURATE_TRIG = 0x2
 CRITIC_CENTRE, CRITIC_FLIP = 0x1, 0x2
 VIDEO_REVERSE = 0x1
 AR_MAX_WORLD, AR_MAX_CTAS = 16, 64
-AR_FLAG_WORDS = AR_MAX_CTAS * 2 * AR_MAX_WORLD
+AR_FLAG_WORDS = AR_MAX_CTAS * 2 * AR_MAX_WORLD + AR_MAX_CTAS
 E_INVAL, E_ALIGN, E_UNSUPPORTED = -1, -2, -3
 
 _c_f32p = ctypes.c_void_p  # raw device/host addresses are passed as integers
@@ -59,7 +59,7 @@ SIGNATURES = {
     "dhfk_video_root_diff_forward": (ctypes.c_int, [_vp, ctypes.c_int32, _u32, _vp, _vp, _i64, _vp]),
     "dhfk_video_root_diff_backward": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _u32, _vp, _i64, _vp]),
     "dhfk_bank_gather": (ctypes.c_int, [_vp, _i64, ctypes.c_int32, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
-    "dhfk_grad_allreduce": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _i64, ctypes.c_float, _u32,
+    "dhfk_grad_allreduce": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _i64, ctypes.c_float,
                                            ctypes.c_int32, ctypes.c_int32, _i64, _vp]),
     "dhfk_host_workspace_bytes": (_i64, [_i64, ctypes.c_int32]),
     "dhfk_forward_backward_host": (ctypes.c_int, [_vp] * 12 + [_i64, _i64, ctypes.c_int32, _vp, _i64, _u32]),

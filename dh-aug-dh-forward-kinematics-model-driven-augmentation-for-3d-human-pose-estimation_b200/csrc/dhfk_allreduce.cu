@@ -14,10 +14,11 @@
 //   Each element is read and written by exactly one thread of one rank, so the exchange is in place without a
 //   staging buffer, and every rank ends up with bit-identical values (replicas cannot drift apart).
 //
-// Two cross-GPU barriers bracket the pass (CTA b of every rank with CTA b of every other rank; flag words in peer
-// memory carry a call counter, so they are never reset): "every rank's gradients are complete" before the first load,
-// "every rank's stores are visible" before the kernel ends.  A spin that outlasts `timeout_ns` gives up and raises
-// *status instead of hanging the GPU.
+// Two cross-GPU barriers bracket the pass (CTA b of every rank with CTA b of every other rank): "every rank's gradients
+// are complete" before the first load, "every rank's stores are visible" before the kernel ends.  The flag words in
+// peer memory carry a call counter and are never reset; the counter itself lives in device memory next to the flags
+// (one word per CTA slot, advanced by the kernel), so the launch has no per-call argument and a captured CUDA graph
+// can replay it.  A spin that outlasts `timeout_ns` gives up and raises *status instead of hanging the GPU.
 #include "../../include/dhfk.h"
 #include "dhfk_launch.h"
 
@@ -31,12 +32,12 @@ constexpr int kArUnroll = 4;           // register / thread slots the FK kernels
 struct ArParams {
     float4* buf[kArMaxWorld];       // every rank's buffer range (peer-mapped addresses), index = rank
     float4* mc;                     // multicast address of the same range, or null
-    unsigned* flags[kArMaxWorld];   // every rank's flag block: [kArMaxCtas][2][kArMaxWorld] words
+    unsigned* flags[kArMaxWorld];   // every rank's flag block: [kArMaxCtas][2][kArMaxWorld] flag words, then
+                                    // [kArMaxCtas] call counters (only the local rank's counters are used)
     unsigned* status;               // local word: set to the call counter when a barrier timed out
     long long nvec;                 // 16-byte elements in the range
     unsigned long long timeout_ns;
     float scale;
-    unsigned epoch;                 // call counter (same on every rank), starts at 1
     int rank, world;
 };
 
@@ -77,29 +78,32 @@ DHFK_DI void multimem_st_v4(float4* p, float4 v) {
 }
 
 // CTA `b` of this rank meets CTA `b` of every other rank.  Thread t < world signals rank t and waits for rank t.
-DHFK_DI bool ar_barrier(const ArParams& p, int b, int phase) {
+DHFK_DI bool ar_barrier(const ArParams& p, int b, int phase, unsigned epoch) {
     __syncthreads();                      // every thread's stores of this CTA are ordered before the signal
     bool ok = true;
     if ((int)threadIdx.x < p.world) {
         const int peer = threadIdx.x;
         const int slot = (b * 2 + phase) * kArMaxWorld;
         if (phase) __threadfence_system();     // phase 0 follows no store of this kernel
-        st_release_sys(p.flags[peer] + slot + p.rank, p.epoch);
+        st_release_sys(p.flags[peer] + slot + p.rank, epoch);
         const unsigned* mine = p.flags[p.rank] + slot + peer;
         const unsigned long long t0 = global_ns();
-        while ((int)(ld_acquire_sys(mine) - p.epoch) < 0) {
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
             if (global_ns() - t0 > p.timeout_ns) { ok = false; break; }
         }
     }
     ok = __syncthreads_and(ok) != 0;
-    if (!ok && threadIdx.x == 0) atomicExch(p.status, p.epoch);
+    if (!ok && threadIdx.x == 0) atomicExch(p.status, epoch ? epoch : 1u);
     return ok;
 }
 
 template <bool MC>
 __global__ void __launch_bounds__(kArMaxThreads) dhfk_allreduce_kernel(const __grid_constant__ ArParams p) {
     const int b = blockIdx.x;
-    if (!ar_barrier(p, b, 0)) return;
+    // this CTA slot's call counter: every rank has made the same calls, so the slots agree across ranks
+    unsigned* counter = p.flags[p.rank] + kArMaxCtas * 2 * kArMaxWorld + b;
+    const unsigned epoch = *counter + 1;
+    if (!ar_barrier(p, b, 0, epoch)) return;
     const long long per_rank = (p.nvec + p.world - 1) / p.world;
     const long long lo = per_rank * p.rank < p.nvec ? per_rank * p.rank : p.nvec;
     const long long hi = lo + per_rank < p.nvec ? lo + per_rank : p.nvec;
@@ -136,11 +140,11 @@ __global__ void __launch_bounds__(kArMaxThreads) dhfk_allreduce_kernel(const __g
             }
         }
     }
-    ar_barrier(p, b, 1);
+    if (ar_barrier(p, b, 1, epoch) && threadIdx.x == 0) *counter = epoch;
 }
 
 int launch_grad_allreduce(float* const* peer_bufs, float* mc_buf, unsigned* const* peer_flags, unsigned* status, int rank,
-                          int world, long long n_floats, float scale, unsigned epoch, int max_ctas, int threads,
+                          int world, long long n_floats, float scale, int max_ctas, int threads,
                           unsigned long long timeout_ns, cudaStream_t st, const char** where) {
     ArParams p = {};
     for (int r = 0; r < world; ++r) {
@@ -152,7 +156,6 @@ int launch_grad_allreduce(float* const* peer_bufs, float* mc_buf, unsigned* cons
     p.nvec = n_floats / 4;
     p.timeout_ns = timeout_ns;
     p.scale = scale;
-    p.epoch = epoch;
     p.rank = rank;
     p.world = world;
     // the same grid on every rank (CTA b pairs with CTA b): a function of the range and the world size only

@@ -708,14 +708,13 @@ int dhfk_bank_gather(const float* bank, int64_t rec_floats, int32_t cam_cols, co
 
 // ---- SURVEY 8 e: gradient exchange over peer memory ---------------------------------------------------
 int dhfk_grad_allreduce(float* const* peer_bufs, float* multicast_buf, uint32_t* const* peer_flags, uint32_t* status_dev,
-                        int32_t rank, int32_t world, int64_t n_floats, float scale, uint32_t epoch, int32_t max_ctas,
-                        int32_t cta_threads, int64_t timeout_ms, void* stream) {
+                        int32_t rank, int32_t world, int64_t n_floats, float scale, int32_t max_ctas, int32_t cta_threads,
+                        int64_t timeout_ms, void* stream) {
     if (world < 1 || world > DHFK_AR_MAX_WORLD || rank < 0 || rank >= world)
         return fail(DHFK_E_INVAL, "need 0 <= rank < world <= DHFK_AR_MAX_WORLD");
     if (n_floats < 0 || n_floats % 4 != 0) return fail(DHFK_E_INVAL, "n_floats must be a non-negative multiple of 4");
     if (n_floats == 0) return DHFK_OK;
     if (!peer_bufs || !peer_flags || !status_dev) return fail(DHFK_E_INVAL, "peer_bufs / peer_flags / status_dev must be non-null");
-    if (epoch == 0) return fail(DHFK_E_INVAL, "epoch counts calls from 1");
     if (max_ctas < 1 || max_ctas > DHFK_AR_MAX_CTAS) return fail(DHFK_E_INVAL, "max_ctas must be in 1..DHFK_AR_MAX_CTAS");
     if (cta_threads < 32 || cta_threads > 512 || cta_threads % 32 != 0)
         return fail(DHFK_E_INVAL, "cta_threads must be a multiple of 32 in 32..512");
@@ -727,7 +726,7 @@ int dhfk_grad_allreduce(float* const* peer_bufs, float* multicast_buf, uint32_t*
     if (multicast_buf && !aligned16(multicast_buf)) return fail(DHFK_E_ALIGN, "multicast_buf must be 16-byte aligned");
     const char* where = "";
     int e = dhfk::launch_grad_allreduce(peer_bufs, multicast_buf, reinterpret_cast<unsigned* const*>(peer_flags),
-                                        reinterpret_cast<unsigned*>(status_dev), rank, world, n_floats, scale, epoch,
+                                        reinterpret_cast<unsigned*>(status_dev), rank, world, n_floats, scale,
                                         max_ctas, cta_threads, (unsigned long long)timeout_ms * 1000000ull, (cudaStream_t)stream, &where);
     return e == 0 ? DHFK_OK : cuda_fail((cudaError_t)e, where);
 }

@@ -49,7 +49,7 @@ int launch_bank_gather(const float* bank, long long rec_floats, int cam_cols, co
 
 // SURVEY 8 e: in-place gradient all-reduce over NVLink peer memory / NVLS multicast (dhfk_allreduce.cu)
 int launch_grad_allreduce(float* const* peer_bufs, float* mc_buf, unsigned* const* peer_flags, unsigned* status, int rank,
-                          int world, long long n_floats, float scale, unsigned epoch, int max_ctas, int threads,
+                          int world, long long n_floats, float scale, int max_ctas, int threads,
                           unsigned long long timeout_ns, cudaStream_t st, const char** where);
 
 // tiled standalone camera ops for 16-joint poses: mode 0 w2c fwd, 1 w2c bwd, 2 project fwd, 3 project bwd

@@ -147,7 +147,6 @@ class PeerExchange:
         self._handles = handles          # keeps the mappings alive
         self._status_ptr = status.data_ptr()
         self._dev_index = buffer.device.index
-        self.epoch = 0
         self.use_multicast = self.multicast
 
     @classmethod
@@ -191,10 +190,9 @@ class PeerExchange:
         if arr is None:
             import ctypes
             arr = self._ranges[lo] = (ctypes.c_void_p * self.world)(*[b + 4 * lo for b in self._buf_ptrs])
-        self.epoch = self.epoch % 0xFFFFFFFF + 1          # 1, 2, ... (never 0)
         mc = self._mc_ptr + 4 * lo if (self.use_multicast and self._mc_ptr) else None
         rc = _cabi.load().dhfk_grad_allreduce(arr, mc, self._flag_arr, self._status_ptr, self.rank, self.world, hi - lo,
-                                              (1.0 / self.world) if average else 1.0, self.epoch, self.max_ctas,
+                                              (1.0 / self.world) if average else 1.0, self.max_ctas,
                                               self.cta_threads, self.timeout_ms,
                                               torch._C._cuda_getCurrentRawStream(self._dev_index))
         if rc:
@@ -205,7 +203,7 @@ class PeerExchange:
         """Raise if any exchange so far gave up waiting for a peer (synchronises)."""
         st = int(self.status.item())
         if st:
-            raise RuntimeError("dhfk_grad_allreduce: call %d timed out waiting for a peer rank" % st)
+            raise RuntimeError("dhfk_grad_allreduce: exchange %d timed out waiting for a peer rank" % st)
 
 
 def grad_allreduce_group(max_ctas=4):

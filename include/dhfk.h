@@ -281,8 +281,10 @@ int dhfk_bank_gather(const float* bank_dev, int64_t rec_floats, int32_t cam_cols
 /*
  * SURVEY 8 e -- the exchange step of the data-parallel GAN iteration: average (scale = 1/world) or sum (scale = 1) a
  * flat fp32 gradient buffer over the `world` GPUs of one node, IN PLACE, in one kernel over NVLink peer memory.
- * Every rank calls it with the same n_floats, max_ctas and call counter `epoch` (1, 2, 3, ... per flag block; one call
- * in flight per flag block).  Nothing here allocates or maps memory: the caller owns
+ * Every rank makes the same sequence of calls (same n_floats, max_ctas, cta_threads), one call in flight per flag
+ * block.  The call has no per-call state on the host -- the call counter the cross-GPU barriers use lives in the flag
+ * block and is advanced by the kernel -- so it can be captured in a CUDA graph and replayed.  Nothing here allocates
+ * or maps memory: the caller owns
  *   peer_bufs  [world]  HOST array: address, in THIS process, of every rank's buffer range (index = rank; entry `rank`
  *                       is the local one).  Symmetric allocations mapped into every process
  *                       (torch.distributed._symmetric_memory: handle.buffer_ptrs, or cuMem / cudaIpc mappings).
@@ -290,10 +292,11 @@ int dhfk_bank_gather(const float* bank_dev, int64_t rec_floats, int32_t cam_cols
  *                       NVSwitch performs the reduction (multimem.ld_reduce) and the replication (multimem.st);
  *                       without it the kernel loads from / stores to every peer itself, summing in rank order.
  *   peer_flags [world]  HOST array: every rank's flag block, DHFK_AR_FLAG_WORDS uint32 words, zeroed once before the
- *                       first call and never touched by the caller again.
- *   status_dev          one local uint32 word, zeroed by the caller; becomes `epoch` if a cross-GPU wait inside call
- *                       `epoch` outlasted timeout_ms (a rank that never launched): the kernel gives up instead of
- *                       hanging the GPU and the buffer contents are then undefined.
+ *                       first call (on every rank, before any rank's first call) and never touched by the caller again.
+ *   status_dev          one local uint32 word, zeroed by the caller; becomes non-zero (the number of the call) if a
+ *                       cross-GPU wait outlasted timeout_ms (a rank that never launched): the kernel gives up instead
+ *                       of hanging the GPU; the buffer contents are then undefined and the flag blocks must be zeroed
+ *                       again on every rank before further use.
  * Every element is summed by exactly one rank and written to all of them: the ranks end bit-identical.  n_floats must
  * be a multiple of 4 and every buffer 16-byte aligned.  max_ctas: 1..DHFK_AR_MAX_CTAS CTAs of cta_threads (a multiple
  * of 32 in 32..512) threads; the kernel is meant to run beside the FK kernels on another stream, and small CTAs fit
@@ -301,10 +304,10 @@ int dhfk_bank_gather(const float* bank_dev, int64_t rec_floats, int32_t cam_cols
  */
 #define DHFK_AR_MAX_WORLD 16
 #define DHFK_AR_MAX_CTAS 64
-#define DHFK_AR_FLAG_WORDS (DHFK_AR_MAX_CTAS * 2 * DHFK_AR_MAX_WORLD)
+#define DHFK_AR_FLAG_WORDS (DHFK_AR_MAX_CTAS * 2 * DHFK_AR_MAX_WORLD + DHFK_AR_MAX_CTAS)
 int dhfk_grad_allreduce(float* const* peer_bufs, float* multicast_buf, uint32_t* const* peer_flags, uint32_t* status_dev,
-                        int32_t rank, int32_t world, int64_t n_floats, float scale, uint32_t epoch, int32_t max_ctas,
-                        int32_t cta_threads, int64_t timeout_ms, void* stream);
+                        int32_t rank, int32_t world, int64_t n_floats, float scale, int32_t max_ctas, int32_t cta_threads,
+                        int64_t timeout_ms, void* stream);
 
 /*
  * Host-buffer end-to-end entry: forward + backward over N poses whose inputs, upstream gradients

@@ -124,21 +124,19 @@ def test_argument_validation_of_the_gradient_exchange_without_gpu():
     flags = (ctypes.c_void_p * 2)(p + 2048, p + 4096)
     st = p + 8192
     call = lambda *a: lib.dhfk_grad_allreduce(*a)
-    assert call(two, None, flags, st, 0, 2, 0, 0.5, 1, 16, 512, 100, None) == 0                 # empty range: no-op
-    assert call(two, None, flags, st, 2, 2, 64, 0.5, 1, 16, 512, 100, None) == _cabi.E_INVAL    # rank outside the world
-    assert call(two, None, flags, st, 0, 17, 64, 0.5, 1, 16, 512, 100, None) == _cabi.E_INVAL   # world > DHFK_AR_MAX_WORLD
-    assert call(two, None, flags, st, 0, 2, 62, 0.5, 1, 16, 512, 100, None) == _cabi.E_INVAL    # not a multiple of 4
-    assert call(two, None, flags, st, 0, 2, 64, 0.5, 0, 16, 512, 100, None) == _cabi.E_INVAL    # call counter starts at 1
-    assert "epoch" in _cabi.last_error()
-    assert call(two, None, flags, st, 0, 2, 64, 0.5, 1, 0, 512, 100, None) == _cabi.E_INVAL     # max_ctas
-    assert call(two, None, flags, st, 0, 2, 64, 0.5, 1, 65, 512, 100, None) == _cabi.E_INVAL
-    assert call(two, None, flags, st, 0, 2, 64, 0.5, 1, 16, 500, 100, None) == _cabi.E_INVAL    # cta_threads % 32
-    assert call(two, None, flags, st, 0, 2, 64, 0.5, 1, 16, 512, 0, None) == _cabi.E_INVAL      # timeout
-    assert call(None, None, flags, st, 0, 2, 64, 0.5, 1, 16, 512, 100, None) == _cabi.E_INVAL
-    assert call(two, None, flags, None, 0, 2, 64, 0.5, 1, 16, 512, 100, None) == _cabi.E_INVAL  # no status word
+    assert call(two, None, flags, st, 0, 2, 0, 0.5, 16, 512, 100, None) == 0                 # empty range: no-op
+    assert call(two, None, flags, st, 2, 2, 64, 0.5, 16, 512, 100, None) == _cabi.E_INVAL    # rank outside the world
+    assert call(two, None, flags, st, 0, 17, 64, 0.5, 16, 512, 100, None) == _cabi.E_INVAL   # world > DHFK_AR_MAX_WORLD
+    assert call(two, None, flags, st, 0, 2, 62, 0.5, 16, 512, 100, None) == _cabi.E_INVAL    # not a multiple of 4
+    assert call(two, None, flags, st, 0, 2, 64, 0.5, 0, 512, 100, None) == _cabi.E_INVAL     # max_ctas
+    assert call(two, None, flags, st, 0, 2, 64, 0.5, 65, 512, 100, None) == _cabi.E_INVAL
+    assert call(two, None, flags, st, 0, 2, 64, 0.5, 16, 500, 100, None) == _cabi.E_INVAL    # cta_threads % 32
+    assert call(two, None, flags, st, 0, 2, 64, 0.5, 16, 512, 0, None) == _cabi.E_INVAL      # timeout
+    assert call(None, None, flags, st, 0, 2, 64, 0.5, 16, 512, 100, None) == _cabi.E_INVAL
+    assert call(two, None, flags, None, 0, 2, 64, 0.5, 16, 512, 100, None) == _cabi.E_INVAL  # no status word
     hole = (ctypes.c_void_p * 2)(p, None)
-    assert call(hole, None, flags, st, 0, 2, 64, 0.5, 1, 16, 512, 100, None) == _cabi.E_INVAL
+    assert call(hole, None, flags, st, 0, 2, 64, 0.5, 16, 512, 100, None) == _cabi.E_INVAL
     odd = (ctypes.c_void_p * 2)(p, p + 4)
-    assert call(odd, None, flags, st, 0, 2, 64, 0.5, 1, 16, 512, 100, None) == _cabi.E_ALIGN
-    assert call(two, p + 4, flags, st, 0, 2, 64, 0.5, 1, 16, 512, 100, None) == _cabi.E_ALIGN   # multicast address
-    assert _cabi.AR_FLAG_WORDS == 64 * 2 * 16
+    assert call(odd, None, flags, st, 0, 2, 64, 0.5, 16, 512, 100, None) == _cabi.E_ALIGN
+    assert call(two, p + 4, flags, st, 0, 2, 64, 0.5, 16, 512, 100, None) == _cabi.E_ALIGN   # multicast address
+    assert _cabi.AR_FLAG_WORDS == 64 * 2 * 16 + 64

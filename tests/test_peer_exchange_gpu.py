@@ -28,9 +28,9 @@ def test_world_of_one(n, ctas, threads):
     bufs = (ctypes.c_void_p * 1)(x.data_ptr() + 4 * 32)
     fl = (ctypes.c_void_p * 1)(flags.data_ptr())
     st = torch.cuda.current_stream(dev).cuda_stream
-    # scale 0.5 twice: the second call runs on the flag words the first one left behind (call counter 2)
-    for epoch in (1, 2):
-        rc = lib.dhfk_grad_allreduce(bufs, None, fl, status.data_ptr(), 0, 1, n4, 0.5, epoch, ctas, threads, 1000, st)
+    # scale 0.5 twice: the second call runs on the flag words and call counters the first one left behind
+    for _ in range(2):
+        rc = lib.dhfk_grad_allreduce(bufs, None, fl, status.data_ptr(), 0, 1, n4, 0.5, ctas, threads, 1000, st)
         _cabi.check(rc, "dhfk_grad_allreduce")
     torch.cuda.synchronize(dev)
     assert int(status.item()) == 0
@@ -48,10 +48,39 @@ def test_missing_peer_times_out_instead_of_hanging():
     bufs = (ctypes.c_void_p * 2)(x.data_ptr(), ghost.data_ptr())
     fl = (ctypes.c_void_p * 2)(flags.data_ptr(), flags.data_ptr() + 4 * _cabi.AR_FLAG_WORDS)
     st = torch.cuda.current_stream(dev).cuda_stream
-    rc = lib.dhfk_grad_allreduce(bufs, None, fl, status.data_ptr(), 0, 2, 1024, 0.5, 7, 4, 128, 50, st)
+    rc = lib.dhfk_grad_allreduce(bufs, None, fl, status.data_ptr(), 0, 2, 1024, 0.5, 4, 128, 50, st)
     _cabi.check(rc, "dhfk_grad_allreduce")
     torch.cuda.synchronize(dev)
-    assert int(status.item()) == 7
+    assert int(status.item()) == 1           # the first exchange on these flags
+
+
+def test_replays_from_a_cuda_graph():
+    """No per-call host state: the call counter lives beside the flags, so a captured launch can be replayed."""
+    lib = _cabi.load()
+    dev = torch.device("cuda", 0)
+    x = torch.randn(8192, device=dev)
+    want = x * 0.5 ** 5
+    flags = torch.zeros(_cabi.AR_FLAG_WORDS, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    bufs = (ctypes.c_void_p * 1)(x.data_ptr())
+    fl = (ctypes.c_void_p * 1)(flags.data_ptr())
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        rc = lib.dhfk_grad_allreduce(bufs, None, fl, status.data_ptr(), 0, 1, 8192, 0.5, 4, 128, 1000, side.cuda_stream)
+        _cabi.check(rc, "dhfk_grad_allreduce")                                   # eager: call 1
+    torch.cuda.current_stream(dev).wait_stream(side)
+    with torch.cuda.graph(graph):
+        rc = lib.dhfk_grad_allreduce(bufs, None, fl, status.data_ptr(), 0, 1, 8192, 0.5, 4, 128, 1000,
+                                     torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(rc, "dhfk_grad_allreduce")
+    for _ in range(4):                                                           # calls 2..5
+        graph.replay()
+    torch.cuda.synchronize(dev)
+    assert int(status.item()) == 0
+    assert torch.equal(x, want)
+    assert int(flags[64 * 2 * 16].item()) == 5                                   # CTA slot 0's call counter
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one node")

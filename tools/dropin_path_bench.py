@@ -57,7 +57,7 @@ def _setup(n, dev, seed=0):
     idx = list(tables.H36M_32_To_16_Table)
     from dhfk import camera
 
-    def step():
+    def step(accumulate=True):
         slots.grad = None          # what zero_grad() does: the gradients are assigned, not accumulated
         root.grad = None
         s = slots * 1.0            # the generator's tensor is a non-leaf
@@ -70,7 +70,10 @@ def _setup(n, dev, seed=0):
         w16 = w32[:, idx]
         cam = camera.GAN_torch_world_to_camera(w16, R=R, t=t)
         uv = camera.project_to_2d(cam, rows)
-        torch.autograd.backward((w16, uv), (gw, gu))
+        if accumulate:
+            torch.autograd.backward((w16, uv), (gw, gu))
+        else:                      # same graph, no AccumulateGrad nodes (they carry the stream the leaves were made on)
+            return torch.autograd.grad((w16, uv), (slots, root), (gw, gu))
         return w16, uv
 
     return step
@@ -114,20 +117,23 @@ def measure(dev, big=1 << 20, small=(1024, 4608), peak_gbs=6528.7, profile=False
         torch.cuda.synchronize(dev)
         rec = {"us_per_step_wall": wall * 1e6, "us_per_step_gpu_events": e0.elapsed_time(e1) / 100 * 1e3,
                "note": "wall = host-bound: three torch.autograd.Function nodes each way + the caller's own slicing"}
-        for attempt in range(4):    # the same step captured once and replayed: what the GPU itself needs (the C-ABI calls
-          try:                      # are plain stream work); a first capture in a process can trip over lazy initialisation
+        # The same step captured once and replayed: what the GPU itself needs (the C-ABI calls are plain stream work).
+        # First as it is; if the capture trips over the leaves' AccumulateGrad nodes ("legacy stream depends on a
+        # capturing stream": they are bound to the stream the leaf tensors were created on), with the gradients taken
+        # by torch.autograd.grad instead -- same kernels, same launches.
+        for attempt, (mode, acc) in enumerate((("relaxed", True), ("relaxed", False), ("thread_local", False))):
+          try:
+            fn = (lambda: step(True)) if acc else (lambda: step(False))
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(3):
-                    step()
+                    keep = fn()
             torch.cuda.current_stream(dev).wait_stream(side)
+            del keep
             graph = torch.cuda.CUDAGraph()
-            # the autograd worker thread runs the backward, and the first capture of a process trips over one-time
-            # initialisation in the stricter modes (tools/graph_capture_probe.py: "legacy stream depends on a capturing
-            # stream" once, then never again): start relaxed
-            with torch.cuda.graph(graph, capture_error_mode=("relaxed", "thread_local", "global", "relaxed")[attempt]):
-                step()
+            with torch.cuda.graph(graph, capture_error_mode=mode):
+                keep = fn()
             for _ in range(10):
                 graph.replay()
             torch.cuda.synchronize(dev)
@@ -137,10 +143,15 @@ def measure(dev, big=1 << 20, small=(1024, 4608), peak_gbs=6528.7, profile=False
             e1.record()
             torch.cuda.synchronize(dev)
             rec["us_per_step_cuda_graph"] = e0.elapsed_time(e1) / 200 * 1e3
+            rec["cuda_graph_backward"] = ".backward() into .grad" if acc else "torch.autograd.grad (no AccumulateGrad nodes)"
+            del graph, keep
             break
           except Exception as e:
             rec["us_per_step_cuda_graph"] = {"error": repr(e)[:200]}
-            torch.cuda.synchronize(dev)
+            try:
+                torch.cuda.synchronize(dev)
+            except Exception:
+                pass
         out["at_%d" % n] = rec
         if profile and n == small[0]:
             import cProfile

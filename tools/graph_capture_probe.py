@@ -40,6 +40,11 @@ def capture(step, dev, mode):
 
 def main():
     dev = torch.device("cuda", 0)
+    if "--measure" in sys.argv:        # the bench extra's own code path, in its own order (1 M, then 1 024, then 4 608)
+        import json
+        out = dp.measure(dev, big=1 << 20)
+        print(json.dumps({k: out[k] for k in ("at_1024", "at_4608")}, indent=1))
+        return
     for n in (1024, 1056, 2048, 4608, 992, 1024):
         for mode in ("thread_local", "relaxed", "global"):
             step = dp._setup(n, dev)

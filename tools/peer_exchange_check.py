@@ -78,6 +78,29 @@ def main():
         px.check()
         one_case(0, numel, True, use_mc, "after 20 back-to-back calls")
 
+    # the exchange captured in a CUDA graph and replayed: after the first replay the ranks are identical, and averaging
+    # identical values is exact, so five replays still equal NCCL's average of the initial data
+    px.use_multicast = px.multicast
+    data = torch.randn(numel, generator=g, device=dev) * (1.0 + rank)
+    want = data.clone()
+    dist.all_reduce(want, op=dist.ReduceOp.AVG)
+    px.buffer.copy_(data)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        px.allreduce(0, numel, True)
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize(dev)
+    px.check()
+    err = float((px.buffer - want).abs().max())
+    rec = {"case": "captured in a CUDA graph, replayed 5x", "max_abs_err_vs_nccl": err, "multicast": px.multicast}
+    out["cases"].append(rec)
+    if not err <= 2e-6 * float(want.abs().max()) * world:
+        failures.append(rec)
+    del graph
+
     if "--time" in sys.argv:
         timing = {}
         buf_nccl = torch.randn(numel, device=dev)
