@@ -27,7 +27,10 @@ namespace dhfk {
 constexpr int kArMaxWorld = DHFK_AR_MAX_WORLD;
 constexpr int kArMaxCtas = DHFK_AR_MAX_CTAS;
 constexpr int kArMaxThreads = 512;     // threads per CTA are a launch parameter (128..512): small CTAs fit into the
-constexpr int kArUnroll = 4;           // register / thread slots the FK kernels leave free on an SM, see launch below
+#ifndef DHFK_AR_UNROLL
+#define DHFK_AR_UNROLL 4
+#endif
+constexpr int kArUnroll = DHFK_AR_UNROLL;   // register / thread slots the FK kernels leave free on an SM, see launch below
 
 struct ArParams {
     float4* buf[kArMaxWorld];       // every rank's buffer range (peer-mapped addresses), index = rank
