@@ -28,7 +28,7 @@ constexpr int kArMaxWorld = DHFK_AR_MAX_WORLD;
 constexpr int kArMaxCtas = DHFK_AR_MAX_CTAS;
 constexpr int kArMaxThreads = 512;     // threads per CTA are a launch parameter (128..512): small CTAs fit into the
 #ifndef DHFK_AR_UNROLL
-#define DHFK_AR_UNROLL 4
+#define DHFK_AR_UNROLL 8      // 16-byte loads in flight per thread (4 needs 16 CTAs to reach the floor, 8 needs 8; profiles/r2u_*)
 #endif
 constexpr int kArUnroll = DHFK_AR_UNROLL;   // register / thread slots the FK kernels leave free on an SM, see launch below
 

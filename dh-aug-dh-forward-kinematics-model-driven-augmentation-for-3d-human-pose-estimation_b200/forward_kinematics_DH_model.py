@@ -319,14 +319,20 @@ class Forward_Kinematics_DH_Model:
                 cols.append(to(v).reshape(-1))
             bone = torch.stack(cols, dim=1)
         root = to(root_3d_pos).reshape(-1, 3)
-        self.global_rot_angle = generator_global_rot_3d_pos_angle
+        # forward_kinematics_DH_model.py:564 keeps this attribute; a detached view, so that the model does not keep the
+        # previous iteration's autograd graph (and the leaves' AccumulateGrad nodes, bound to the stream of their first
+        # use) alive -- that is what breaks a later CUDA-graph capture of the caller's step
+        self.global_rot_angle = (generator_global_rot_3d_pos_angle.detach()
+                                 if torch.is_tensor(generator_global_rot_3d_pos_angle) else generator_global_rot_3d_pos_angle)
         wide = _wide_layout(ang, grot) if ang._base is not None else None
         if wide is not None:      # the generator's own [N,37] tensor goes to the kernels as one slab per tile
             world16 = fk_world16_wide(wide[0], wide[1], bone, root)
         else:
             world16 = fk_world16(ang, grot, bone, root)
-        self.single_generator_3d_world_32keyPoint = LazyWorld32(world16, root)
-        return self.single_generator_3d_world_32keyPoint
+        # the reference keeps its result as an attribute (forward_kinematics_DH_model.py:745-820); here the attribute is a
+        # detached twin of what is returned, for the same reason as global_rot_angle above
+        self.single_generator_3d_world_32keyPoint = LazyWorld32(world16.detach(), root.detach())
+        return LazyWorld32(world16, root)
 
     def _single_pose_numpy(self, ll, rl, body, lh, rh, grot, lens, root):
         if not torch.cuda.is_available():
