@@ -500,24 +500,28 @@ def max_over_ranks(vals, dev, distributed):
     return [float(x) if x >= 0 else None for x in t.tolist()]
 
 
-def copy_ceiling(n, dev, chunk, reps=10):
+def copy_ceiling(n, dev, chunk, reps=10, split=False):
     """A bare pinned-memory H2D + D2H of the bytes the e2e step moves (536 B/row up, 476 B/row down), in the same chunk
-    sizes, on two streams with no kernel and no dependency between them: the PCIe / host-memory floor of `e2e`."""
+    sizes, on two streams with no kernel and no dependency between them: the PCIe / host-memory floor of `e2e`.
+    split=True moves them as the e2e entry does -- six arrays up (33, 3, 15, 3, 48, 32 floats per row), five down
+    (48, 32, 33, 3, 3) -- instead of one buffer each way."""
     import torch
-    up_b, down_b = 536, 476
-    h_up = torch.empty(n * up_b // 4, dtype=torch.float32).pin_memory()
-    h_dn = torch.empty(n * down_b // 4, dtype=torch.float32).pin_memory()
-    d_up = torch.empty(chunk * up_b // 4, dtype=torch.float32, device=dev)
-    d_dn = torch.empty(chunk * down_b // 4, dtype=torch.float32, device=dev)
+    ups, downs = ((33, 3, 15, 3, 48, 32), (48, 32, 33, 3, 3)) if split else ((134,), (119,))
+    h_up = [torch.empty(n * w, dtype=torch.float32).pin_memory() for w in ups]
+    h_dn = [torch.empty(n * w, dtype=torch.float32).pin_memory() for w in downs]
+    d_up = [torch.empty(chunk * w, dtype=torch.float32, device=dev) for w in ups]
+    d_dn = [torch.empty(chunk * w, dtype=torch.float32, device=dev) for w in downs]
     s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
     def once():
         for r0 in range(0, n, chunk):
             rows = min(chunk, n - r0)
             with torch.cuda.stream(s_up):
-                d_up[:rows * up_b // 4].copy_(h_up[r0 * up_b // 4:(r0 + rows) * up_b // 4], non_blocking=True)
+                for w, h, d in zip(ups, h_up, d_up):
+                    d[:rows * w].copy_(h[r0 * w:(r0 + rows) * w], non_blocking=True)
             with torch.cuda.stream(s_dn):
-                h_dn[r0 * down_b // 4:(r0 + rows) * down_b // 4].copy_(d_dn[:rows * down_b // 4], non_blocking=True)
+                for w, h, d in zip(downs, h_dn, d_dn):
+                    h[r0 * w:(r0 + rows) * w].copy_(d[:rows * w], non_blocking=True)
         s_up.synchronize(); s_dn.synchronize()
 
     once()
@@ -790,11 +794,14 @@ def run_native(args):
         fo_s = (time.perf_counter() - t0) / e2e_steps
         barrier()
         ceil_s = copy_ceiling(n, dev, chunk)
-        e2e_s, fo_s, ceil_s = max_over_ranks([e2e_s, fo_s, ceil_s], dev, distributed)
+        barrier()
+        ceil_split_s = copy_ceiling(n, dev, chunk, split=True)
+        e2e_s, fo_s, ceil_s, ceil_split_s = max_over_ranks([e2e_s, fo_s, ceil_s, ceil_split_s], dev, distributed)
         h2d, d2h = n * 536, n * 476
         e2e = {"value": n * world_size / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "poses_per_rank": n,
                "copy_ceiling_ms": ceil_s * 1e3, "frac_of_ceiling": ceil_s / e2e_s,
+               "copy_ceiling_same_arrays_ms": ceil_split_s * 1e3,     # the same bytes as the entry's 6 + 5 separate arrays
                "per_rank_gbs": {"h2d": h2d / e2e_s / 1e9, "d2h": d2h / e2e_s / 1e9,
                                 "ceiling_h2d": h2d / ceil_s / 1e9, "ceiling_d2h": d2h / ceil_s / 1e9},
                "copy_ceiling": "bare pinned H2D (536 B/row) + D2H (476 B/row) of the same bytes in the same %d-row chunks on "

@@ -115,7 +115,7 @@ class FlatGradBuffer:
             lo, hi = (0, self.flat.numel()) if span is None else span
             return self.peer.allreduce(lo, hi, average)
         buf = self.flat if span is None else self.flat[span[0]:span[1]]
-        if average and dist.get_backend(group) == "nccl":
+        if average and "nccl" in str(dist.get_backend(group)):
             dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group)      # the division happens inside the collective
         else:
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
@@ -154,7 +154,7 @@ class PeerExchange:
         from . import _cabi
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
-        if dist.get_backend(group) != "nccl" or dist.get_world_size(group) > _cabi.AR_MAX_WORLD:
+        if "nccl" not in str(dist.get_backend(group)) or dist.get_world_size(group) > _cabi.AR_MAX_WORLD:
             return None
         try:
             import torch.distributed._symmetric_memory as symm

@@ -106,6 +106,27 @@ def test_ragged_sizes_vs_c_oracle(c_oracle, n):
     assert_parity(g_root, b["g_root"], "g_root")
 
 
+def test_every_training_camera_vs_c_oracle(c_oracle):
+    """the 20 (train subject, camera) pairs the GAN loop draws from (model_fk_gan_train.py:344-372)."""
+    from dhfk import synthetic, tables
+    n = 224
+    for si, subj in enumerate(tables.TRAIN_SUBJECTS):
+        for cam_id in range(4):
+            inp = synthetic.gan_like(n, seed=900 + 4 * si + cam_id)
+            up = synthetic.upstream_grads(n, seed=950 + 4 * si + cam_id)
+            blk = tables.camera_block(subj, cam_id)
+            g = dict(inp, cam_block=blk, **up)
+            world, cam, uv, g_ang, g_grot, g_root = run_fused(g, "default", "wcu")
+            o = c_oracle.forward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk)
+            b = c_oracle.backward(inp["ang"], inp["grot"], inp["bone"], inp["root"], blk, g_world=up["g_world"],
+                                  g_cam=up["g_cam"], g_uv=up["g_uv"])
+            tag = " %s cam %d" % (subj, cam_id)
+            assert_parity(world, o["world16"], "world16" + tag); assert_parity(cam, o["cam"], "cam" + tag)
+            assert_parity(uv, o["uv"], "uv" + tag)
+            assert_parity(g_ang, b["g_ang"], "g_ang" + tag); assert_parity(g_grot, b["g_grot"], "g_grot" + tag)
+            assert_parity(g_root, b["g_root"], "g_root" + tag)
+
+
 def test_empty_batch():
     import dhfk
     w, c, u = dhfk.fk_project(T(np.zeros((0, 33))), T(np.zeros((0, 3))), T(np.zeros((0, 15))), T(np.zeros((0, 3))),
