@@ -696,26 +696,27 @@ def run_native(args):
         # weak companion first (1M poses per rank, same in-step all-reduce), then the headline
         for i in range(warmup):
             path1.step(i)
-        # with / without / without / with the exchange: the board's power state drifts while it is loaded, and the
-        # mirrored order cancels a linear drift out of the difference
+        # with (the reported run) / without / with / without the exchange: the exposed time is the second run with it
+        # minus the mean of the two runs without it around it -- the first run of a series sits in the board's burst
+        # regime, the later ones do not, and a linear drift cancels out of the bracketed difference
         w_ms, _, _ = timed_steps(path1, steps, stream, dev, barrier, allreduce=ar)
         w_plain, _, _ = timed_steps(path1, steps, stream, dev, barrier)
-        w_plain2, _, _ = timed_steps(path1, steps, stream, dev, barrier)
         w_ms2, _, _ = timed_steps(path1, steps, stream, dev, barrier, allreduce=ar)
+        w_plain2, _, _ = timed_steps(path1, steps, stream, dev, barrier)
         w_ms, w_plain, w_plain2, w_ms2 = max_over_ranks([w_ms, w_plain, w_plain2, w_ms2], dev, distributed)
         weak_extra = {"poses_per_gpu": n, "value": n * world_size / (w_ms / steps * 1e-3), "unit": UNIT,
                       "ms_per_step": w_ms / steps, "ms_per_step_without_allreduce": (w_plain + w_plain2) / 2 / steps,
-                      "ms_exposed_per_step": ((w_ms + w_ms2) - (w_plain + w_plain2)) / 2 / steps,
+                      "ms_exposed_per_step": (w_ms2 - (w_plain + w_plain2) / 2) / steps,
                       "what": "weak scaling: 1,048,576 poses per rank + the same in-step gradient all-reduce; exposed = "
-                              "mean of two runs with it - mean of two without, order with / without / without / with"}
+                              "second run with it - mean of the runs without it before and after"}
         for i in range(warmup):
             path.step(i)
         if sampler:
             sampler.start()
         total_ms, fwd_ms, bwd_ms = timed_steps(path, steps, stream, dev, barrier, allreduce=ar, probe_every=probe_every)
         plain_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)      # the same steps without the collective,
-        plain2_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)     # twice, then with it again (drift cancels)
-        total2_ms, _, _ = timed_steps(path, steps, stream, dev, barrier, allreduce=ar)
+        total2_ms, _, _ = timed_steps(path, steps, stream, dev, barrier, allreduce=ar)   # with it again,
+        plain2_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)     # and without it again (see above)
         barrier()
         extension = feed_sampler(sampler, path, dev)
         if sampler:
@@ -725,7 +726,7 @@ def run_native(args):
         n_step = n_big
         value = args.total_poses / (total_ms / steps * 1e-3)
         if allreduce_extra is not None:
-            allreduce_extra["ms_exposed_per_step"] = ((total_ms + total2_ms) - (plain_ms + plain2_ms)) / 2 / steps
+            allreduce_extra["ms_exposed_per_step"] = (total2_ms - (plain_ms + plain2_ms) / 2) / steps
             allreduce_extra["ms_per_step_without_allreduce"] = (plain_ms + plain2_ms) / 2 / steps
             allreduce_extra["ms_per_step_second_run_with_it"] = total2_ms / steps
             if gbuf.peer is not None:

@@ -156,6 +156,7 @@ class PeerExchange:
             return None
         if "nccl" not in str(dist.get_backend(group)) or dist.get_world_size(group) > _cabi.AR_MAX_WORLD:
             return None
+        px = None
         try:
             import torch.distributed._symmetric_memory as symm
             pg = group if group is not None else dist.group.WORLD
@@ -170,11 +171,27 @@ class PeerExchange:
             hf.barrier()                              # every rank's flags are zero before anyone signals
             status = torch.zeros(1, dtype=torch.int32, device=device)
             mc = int(getattr(hb, "multicast_ptr", 0) or 0)
-            return cls(buf, flags, status, list(hb.buffer_ptrs), list(hf.buffer_ptrs), mc, hb.rank, hb.world_size,
-                       max_ctas, cta_threads, timeout_ms, (hb, hf))
+            px = cls(buf, flags, status, list(hb.buffer_ptrs), list(hf.buffer_ptrs), mc, hb.rank, hb.world_size,
+                     max_ctas, cta_threads, timeout_ms, (hb, hf))
         except Exception as e:           # no peer access / no symmetric-memory support: the caller keeps NCCL
             cls.last_error = repr(e)
+        # all ranks or none: a rank on the kernel and a rank on NCCL would wait for each other forever.  The multicast
+        # mapping must agree too (a rank without it would take the peer path while the others use the switch).
+        try:
+            state = torch.tensor([1 if px is not None else 0, 1 if (px is not None and px.multicast) else 0],
+                                 dtype=torch.int32, device=device)
+            dist.all_reduce(state, op=dist.ReduceOp.MIN, group=group)
+            everyone, everyone_mc = (int(v) for v in state.tolist())
+        except Exception as e:
+            cls.last_error = repr(e)
             return None
+        if not everyone:
+            if px is not None:
+                cls.last_error = "symmetric memory unavailable on another rank"
+            return None
+        if not everyone_mc:
+            px.multicast = px.use_multicast = False
+        return px
 
     last_error = None
 
