@@ -1008,7 +1008,8 @@ def run_native(args):
         "roofline_step": {"achieved": (FWD_BYTES + BWD_BYTES) * n_step / (ms_per_step * 1e-3) / 1e9, "peak": peak,
                           "frac": (FWD_BYTES + BWD_BYTES) * n_step / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"},
         "clocks": dict(sampler.summary(), window="timed region" + (" + 1 s extension of the same loop" if extension else "")),
-        "gpu_launches": 2 * steps,
+        # per rank, inside the timed region: forward + backward per step, + the exchange kernel per step when it is ours
+        "gpu_launches": (3 if (strong and gbuf is not None and gbuf.peer is not None) else 2) * steps,
     }
     if parity:
         line["parity"] = parity
