@@ -337,7 +337,7 @@ int dhfk_backward(const float* ang, int64_t ang_stride, const float* grot, int64
 // ---- generator-epilogue mode -----------------------------------------------------
 static int fill_gen_scale(dhfk::GenScale& gs, const float* half37, const float* mid37, float root_scale) {
     if (!half37 || !mid37) return fail(DHFK_E_INVAL, "gen_half37 / gen_mid37 (host, 37 floats each) are required");
-    for (int i = 0; i < dhfk::GEN_NSLOT; ++i) { gs.half[i] = half37[i]; gs.mid[i] = mid37[i]; }
+    for (int i = 0; i < dhfk::GEN_NSLOT; ++i) gs.hm[i] = make_float2(half37[i], mid37[i]);
     gs.root_scale = root_scale;
     return DHFK_OK;
 }

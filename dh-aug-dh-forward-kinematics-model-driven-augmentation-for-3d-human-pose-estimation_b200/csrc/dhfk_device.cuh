@@ -407,18 +407,9 @@ DHFK_DI float sech2_from_tanh(float t) { return fmaf(-t, t, 1.0f); }
 // per-slot affine map of the generator epilogue (host-filled: half = (hi-lo)/2, mid = (hi+lo)/2, or
 // 180 / 0 when GAN_whether_use_preAngle is off) and the root scale (10)
 struct GenScale {
-    float half[GEN_NSLOT];
-    float mid[GEN_NSLOT];
+    float2 hm[GEN_NSLOT];     // (half, mid) per slot: one 64-bit constant load where the slot index is a run-time value
     float root_scale;
 };
-static __constant__ int c_gen_src[GEN_NSLOT] = {
-    gen_src_col(0),  gen_src_col(1),  gen_src_col(2),  gen_src_col(3),  gen_src_col(4),  gen_src_col(5),
-    gen_src_col(6),  gen_src_col(7),  gen_src_col(8),  gen_src_col(9),  gen_src_col(10), gen_src_col(11),
-    gen_src_col(12), gen_src_col(13), gen_src_col(14), gen_src_col(15), gen_src_col(16), gen_src_col(17),
-    gen_src_col(18), gen_src_col(19), gen_src_col(20), gen_src_col(21), gen_src_col(22), gen_src_col(23),
-    gen_src_col(24), gen_src_col(25), gen_src_col(26), gen_src_col(27), gen_src_col(28), gen_src_col(29),
-    gen_src_col(30), gen_src_col(31), gen_src_col(32), gen_src_col(33), gen_src_col(34), gen_src_col(35),
-    gen_src_col(36)};
 
 // ---------------------------------------------------------------------------------------
 // Forward walker: depth-first over the compile-time tree.  Ctx provides
@@ -456,9 +447,10 @@ DHFK_DI void fwd_walk(Frame F, Ctx& ctx) {
 // where (F_j, M_j) sums the outputs strictly below j (the joint's own origin does not
 // depend on its own theta), z_j is the joint axis after the alpha twist, o_j its origin.
 // Ctx provides ang, bone and
-//   template<int J> float angle() / float angle_rt(int j)
+//   template<int J> float angle()            -- body joints (compile-time index)
+//   template<int K> float limb_angle(L)      -- joint K of limb L (run-time limb, compile-time position)
 //   template<int K> V3 upstream(V3 origin)   -- total dL/d(origin) in the chain frame
-//   template<int J> void grad_angle(float g) / void grad_angle_rt(int j, float g), zero_grad_angle*()
+//   template<int J> void grad_angle(float g), zero_grad_angle<J>();  limb_grad<K>(L, g), limb_zero_leaf(L)
 //   void grad_bone(int b, float g)           -- only called when Ctx::kBoneGrad
 // ---------------------------------------------------------------------------------------
 template <int TRIG, int J, class Ctx> DHFK_DI Wrench bwd_walk(Frame F, Ctx& ctx);
@@ -471,30 +463,29 @@ static __constant__ LimbDesc c_limbs[NLIMB] = {make_limb(0), make_limb(1), make_
 // Extra Ctx members used:  void load_limb(const LimbDesc&),  template<int I> V3 upstream_limb(V3 origin)
 template <int TRIG, class Ctx>
 DHFK_DI Wrench bwd_limb(const Frame& B, const LimbDesc& L, Ctx& ctx) {
-    const int j0 = L.ang0;
     const float sg = L.sigma;
     float s, c;
     ctx.load_limb(L);     // the limb's 3 upstream-gradient rows: 128-bit shared loads, no bank conflicts
     // joint 0: hip / shoulder offset along parent x, rotation about B.Z
     const V3 o0 = axpy(L.sgn0 * ctx.bone[L.b0], B.X, B.O);
     const V3 g0 = ctx.template upstream_limb<0>(o0);
-    sincos_deg_rt<TRIG>(ctx.angle_rt(j0), L.q0, s, c);
+    sincos_deg_rt<TRIG>(ctx.template limb_angle<0>(L), L.q0, s, c);
     const V3 X1 = axpy(s, B.Y, scale(c, B.X));
     const V3 Y1 = axpy(c, B.Y, scale(-s, B.X));
     // joint 1: alpha = sigma*90  =>  y' = sigma z_p, z' = -sigma y_p
     const V3 zj1 = scale(-sg, Y1);
-    sincos_deg_rt<TRIG>(ctx.angle_rt(j0 + 1), -1, s, c);
+    sincos_deg_rt<TRIG>(ctx.template limb_angle<1>(L), -1, s, c);
     const V3 X2 = axpy(s * sg, B.Z, scale(c, X1));
     const V3 Y2 = axpy(c * sg, B.Z, scale(-s, X1));
     // joint 2: same twist
     const V3 zj2 = scale(-sg, Y2);
-    sincos_deg_rt<TRIG>(ctx.angle_rt(j0 + 2), L.q2, s, c);
+    sincos_deg_rt<TRIG>(ctx.template limb_angle<2>(L), L.q2, s, c);
     const V3 X3 = axpy(s * sg, zj1, scale(c, X2));
     const V3 Y3 = axpy(c * sg, zj1, scale(-s, X2));
     // joint 3: knee / elbow, alpha 0, axis zj2
     const V3 o3 = axpy(ctx.bone[L.b3], X3, o0);
     const V3 g3 = ctx.template upstream_limb<1>(o3);
-    sincos_deg_rt<TRIG>(ctx.angle_rt(j0 + 3), 0, s, c);
+    sincos_deg_rt<TRIG>(ctx.template limb_angle<3>(L), 0, s, c);
     const V3 X4 = axpy(s, Y3, scale(c, X3));
     // joint 4: foot / wrist, leaf
     const V3 o4 = axpy(ctx.bone[L.b4], X4, o3);
@@ -503,16 +494,16 @@ DHFK_DI Wrench bwd_limb(const Frame& B, const LimbDesc& L, Ctx& ctx) {
     Wrench w;
     w.F = g4;
     w.M = cross(o4, g4);
-    ctx.zero_grad_angle_rt(j0 + 4);
-    ctx.grad_angle_rt(j0 + 3, kDegToRad * dot(zj2, sub_cross(w.M, o3, w.F)));
+    ctx.limb_zero_leaf(L);
+    ctx.template limb_grad<3>(L, kDegToRad * dot(zj2, sub_cross(w.M, o3, w.F)));
     if (Ctx::kBoneGrad) ctx.grad_bone(L.b4, dot(X4, w.F));
     w.F = w.F + g3;
     w.M = add_cross(w.M, o3, g3);
     if (Ctx::kBoneGrad) ctx.grad_bone(L.b3, dot(X3, w.F));
     const V3 tau = sub_cross(w.M, o0, w.F);
-    ctx.grad_angle_rt(j0 + 2, kDegToRad * dot(zj2, tau));
-    ctx.grad_angle_rt(j0 + 1, kDegToRad * dot(zj1, tau));
-    ctx.grad_angle_rt(j0, kDegToRad * dot(B.Z, tau));
+    ctx.template limb_grad<2>(L, kDegToRad * dot(zj2, tau));
+    ctx.template limb_grad<1>(L, kDegToRad * dot(zj1, tau));
+    ctx.template limb_grad<0>(L, kDegToRad * dot(B.Z, tau));
     w.F = w.F + g0;
     w.M = add_cross(w.M, o0, g0);
     if (Ctx::kBoneGrad) ctx.grad_bone(L.b0, L.sgn0 * dot(B.X, w.F));

@@ -321,8 +321,8 @@ struct FwdCtx {
         if constexpr (!GEN) return ang[J];
         else {
             constexpr int SRC = gen_src_col(J);
-            if constexpr (SRC < 0) return gs->mid[J];
-            else return fmaf(ang[SRC], gs->half[J], gs->mid[J]);
+            if constexpr (SRC < 0) return gs->hm[J].y;
+            else return fmaf(ang[SRC], gs->hm[J].x, gs->hm[J].y);
         }
     }
     float R[9];
@@ -427,8 +427,8 @@ __global__ void __launch_bounds__(kTile) dhfk_fwd_kernel(const __grid_constant__
             float g[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                g[i] = fmaf(ctx.ang[gen_src_col(GEN_GROT_SLOT) + i], p.gs.half[GEN_GROT_SLOT + i],
-                            p.gs.mid[GEN_GROT_SLOT + i]);
+                g[i] = fmaf(ctx.ang[gen_src_col(GEN_GROT_SLOT) + i], p.gs.hm[GEN_GROT_SLOT + i].x,
+                            p.gs.hm[GEN_GROT_SLOT + i].y);
             global_rotation<TRIG>(g, ctx.R, sx, cx, sy, cy);
             ctx.root = v3(ctx.ang[GEN_ROOT_COL] * p.gs.root_scale, ctx.ang[GEN_ROOT_COL + 1] * p.gs.root_scale,
                           ctx.ang[GEN_ROOT_COL + 2] * p.gs.root_scale);
@@ -491,28 +491,37 @@ struct BwdCtx {
         if constexpr (!GEN) return ang[J];
         else {
             constexpr int SRC = gen_src_col(J);
-            if constexpr (SRC < 0) return gs->mid[J];
-            else return fmaf(ang[SRC], gs->half[J], gs->mid[J]);
+            if constexpr (SRC < 0) return gs->hm[J].y;
+            else return fmaf(ang[SRC], gs->hm[J].x, gs->hm[J].y);
         }
     }
-    DHFK_DI float angle_rt(int j) {
-        if (!GEN) return ang[j];
-        const int src = c_gen_src[j];       // warp-uniform
-        if (src < 0) return gs->mid[j];
-        return fmaf(ang[src], gs->half[j], gs->mid[j]);
+    // joint K (0..3) of limb L: the limb is a run-time value (warp-uniform), the position inside it is not.  GEN: the
+    // column comes from the limb descriptor (uniform datapath) and (half, mid) from one 64-bit constant load.
+    template <int K>
+    DHFK_DI float limb_angle(const LimbDesc& L) {
+        if (!GEN) return ang[L.ang0 + K];
+        const float2 hm = gs->hm[L.ang0 + K];
+        if (K == 0) return L.gcol0 < 0 ? hm.y : fmaf(ang[L.gcol0], hm.x, hm.y);
+        return fmaf(ang[L.gcol1 + (K - 1)], hm.x, hm.y);
+    }
+    template <int K>
+    DHFK_DI void limb_grad(const LimbDesc& L, float g) {
+        if (!GEN) { g_ang[L.ang0 + K] = g; return; }
+        const int col = K == 0 ? L.gcol0 : L.gcol1 + (K - 1);
+        if (K == 0 && col < 0) return;
+        g_ang[col] = g * gs->hm[L.ang0 + K].x * sech2_from_tanh(g_ang[col]);
+    }
+    DHFK_DI void limb_zero_leaf(const LimbDesc& L) {
+        if (!GEN) { g_ang[L.ang0 + 4] = 0.f; return; }
+        if (L.gcol4 >= 0) g_ang[L.gcol4] = 0.f;
     }
     template <int J>
     DHFK_DI void grad_angle(float g) {
         if constexpr (!GEN) g_ang[J] = g;
         else {
             constexpr int SRC = gen_src_col(J);
-            if constexpr (SRC >= 0) g_ang[SRC] = g * gs->half[J] * sech2_from_tanh(g_ang[SRC]);
+            if constexpr (SRC >= 0) g_ang[SRC] = g * gs->hm[J].x * sech2_from_tanh(g_ang[SRC]);
         }
-    }
-    DHFK_DI void grad_angle_rt(int j, float g) {
-        if (!GEN) { g_ang[j] = g; return; }
-        const int src = c_gen_src[j];
-        if (src >= 0) g_ang[src] = g * gs->half[j] * sech2_from_tanh(g_ang[src]);
     }
     template <int J>
     DHFK_DI void zero_grad_angle() {
@@ -521,11 +530,6 @@ struct BwdCtx {
             constexpr int SRC = gen_src_col(J);
             if constexpr (SRC >= 0) g_ang[SRC] = 0.f;
         }
-    }
-    DHFK_DI void zero_grad_angle_rt(int j) {
-        if (!GEN) { g_ang[j] = 0.f; return; }
-        const int src = c_gen_src[j];
-        if (src >= 0) g_ang[src] = 0.f;
     }
     const float4* gw4;   // padded shared rows of the upstream gradients (may be null)
     const float4* gc4;
@@ -752,8 +756,8 @@ __global__ void __launch_bounds__(kTile) dhfk_bwd_kernel(const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const float tg = ctx.ang[gen_src_col(GEN_GROT_SLOT) + i], tr = ctx.ang[GEN_ROOT_COL + i];
-                g[i] = fmaf(tg, p.gs.half[GEN_GROT_SLOT + i], p.gs.mid[GEN_GROT_SLOT + i]);
-                chain_g[i] = sech2_from_tanh(tg) * p.gs.half[GEN_GROT_SLOT + i];
+                g[i] = fmaf(tg, p.gs.hm[GEN_GROT_SLOT + i].x, p.gs.hm[GEN_GROT_SLOT + i].y);
+                chain_g[i] = sech2_from_tanh(tg) * p.gs.hm[GEN_GROT_SLOT + i].x;
                 r[i] = tr * p.gs.root_scale;
                 chain_r[i] = sech2_from_tanh(tr) * p.gs.root_scale;
             }

@@ -127,14 +127,26 @@ struct LimbDesc {
     // and float offset inside it (the 9 / 6 floats are then read with 3 / 2 conflict-free 128-bit loads)
     int wc0, woff;     // [16,3] rows: floats 3*k0 .. 3*k0+8
     int uc0, uoff;     // [16,2] rows: floats 2*k0 .. 2*k0+5
+    // generator mode: network column feeding joint 0 (-1: a fixed slot), joint 1 (joints 2 and 3 follow it) and the
+    // leaf joint 4 (-1: a fixed slot)
+    int gcol0, gcol1, gcol4;
 };
 constexpr LimbDesc make_limb(int l) {
     const int j = LIMB_ROOT[l];
     return LimbDesc{j, out_index_of_joint(j), LEN_BONE[j], LEN_BONE[j + 3], LEN_BONE[j + 4],
                     THETA0_Q[j], THETA0_Q[j + 2], (float)LEN_SIGN[j], (float)ALPHA_Q[j + 1],
                     (3 * out_index_of_joint(j)) / 4, (3 * out_index_of_joint(j)) % 4,
-                    (2 * out_index_of_joint(j)) / 4, (2 * out_index_of_joint(j)) % 4};
+                    (2 * out_index_of_joint(j)) / 4, (2 * out_index_of_joint(j)) % 4,
+                    gen_src_col(j), gen_src_col(j + 1), gen_src_col(j + 4)};
 }
+// the three inner joints of a limb are fed by consecutive network columns
+constexpr bool limb_gen_cols_ok(int l) {
+    const int j = LIMB_ROOT[l];
+    return gen_src_col(j + 1) >= 0 && gen_src_col(j + 2) == gen_src_col(j + 1) + 1 &&
+           gen_src_col(j + 3) == gen_src_col(j + 1) + 2;
+}
+static_assert(limb_gen_cols_ok(0) && limb_gen_cols_ok(1) && limb_gen_cols_ok(2) && limb_gen_cols_ok(3),
+              "generator columns of a limb's inner joints are not consecutive");
 // the 128-bit limb loads stay inside the 12- / 8-chunk rows and only the offsets handled below occur
 constexpr bool limb_chunks_ok(int l) {
     const LimbDesc d = make_limb(l);
