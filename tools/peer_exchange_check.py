@@ -101,6 +101,44 @@ def main():
         failures.append(rec)
     del graph
 
+    # end to end: a data-parallel gradient through FlatGradBuffer(peer_exchange=True) equals the full-batch gradient
+    # (the same check tests/test_parallel_gloo.py makes on CPU), including re-adoption after zero_grad() and a span
+    torch.manual_seed(0)
+    G = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 5)).to(dev)
+    D = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 1)).to(dev)
+    nrow = 64 * world
+    x = torch.randn(nrow, 8, generator=torch.Generator().manual_seed(3)).to(dev)
+    lo, hi = parallel.shard_rows(nrow, rank, world)
+    fb = parallel.FlatGradBuffer(list(G.parameters()) + list(D.parameters()), peer_exchange=True)
+    dp_ok = fb.peer is not None
+    worst = 0.0
+    for it in range(3):
+        if it == 1:
+            G.zero_grad(); D.zero_grad()              # drops the .grad tensors: the buffer must re-adopt them
+        else:
+            fb.zero()
+        (D(G(x[lo:hi])).sum() / nrow * world).backward()
+        fb.allreduce(average=True)
+        refG = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 5)).to(dev)
+        refD = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 1)).to(dev)
+        refG.load_state_dict(G.state_dict()); refD.load_state_dict(D.state_dict())
+        (refD(refG(x)).sum() / nrow).backward()
+        for a, b in zip(list(G.parameters()) + list(D.parameters()), list(refG.parameters()) + list(refD.parameters())):
+            worst = max(worst, float((a.grad - b.grad).abs().max()))
+            dp_ok = dp_ok and a.grad.data_ptr() == fb.views[[id(q) for q in fb.params].index(id(a))].data_ptr()
+    fb.zero()
+    (D(G(x[lo:hi])).sum() * (rank + 1)).backward()
+    before_G = [q.grad.clone() for q in G.parameters()]
+    fb.allreduce(average=False, span=fb.span_of(D))    # one model's span: the other model's gradients stay local
+    torch.cuda.synchronize(dev)
+    fb.peer.check()
+    dp_ok = dp_ok and all(torch.equal(a, q.grad) for a, q in zip(before_G, G.parameters()))
+    rec = {"case": "FlatGradBuffer(peer_exchange=True): data-parallel gradient vs full batch", "max_abs_err": worst,
+           "aliased_and_span_ok": bool(dp_ok)}
+    out["cases"].append(rec)
+    if not (worst < 1e-6 and dp_ok):
+        failures.append(rec)
+
     if "--time" in sys.argv:
         timing = {}
         buf_nccl = torch.randn(numel, device=dev)
