@@ -26,11 +26,12 @@ namespace dhfk {
 
 constexpr int kArMaxWorld = DHFK_AR_MAX_WORLD;
 constexpr int kArMaxCtas = DHFK_AR_MAX_CTAS;
-constexpr int kArMaxThreads = 512;     // threads per CTA are a launch parameter (128..512): small CTAs fit into the
-#ifndef DHFK_AR_UNROLL
-#define DHFK_AR_UNROLL 8      // 16-byte loads in flight per thread (4 needs 16 CTAs to reach the floor, 8 needs 8; profiles/r2u_*)
-#endif
-constexpr int kArUnroll = DHFK_AR_UNROLL;   // register / thread slots the FK kernels leave free on an SM, see launch below
+constexpr int kArMaxThreads = 512;     // threads per CTA are a launch parameter (32..512)
+// 16-byte elements in flight per thread.  NVLS path: 8 lets 8 CTAs reach the floor that 4 needs 16 CTAs for
+// (profiles/r2u_unroll_n2.txt).  Peer path: every element is `world` loads, and 8 x 8 in flight measured 88 us for 6.4 MB
+// on 8 GPUs where 4 x 8 takes 49 us (profiles/r2t2_peer_exchange_n8.json vs r2t_peer_exchange_n8.json).
+constexpr int kArUnrollMc = 8;
+constexpr int kArUnrollPeer = 4;
 
 struct ArParams {
     float4* buf[kArMaxWorld];       // every rank's buffer range (peer-mapped addresses), index = rank
@@ -102,6 +103,7 @@ DHFK_DI bool ar_barrier(const ArParams& p, int b, int phase, unsigned epoch) {
 
 template <bool MC>
 __global__ void __launch_bounds__(kArMaxThreads) dhfk_allreduce_kernel(const __grid_constant__ ArParams p) {
+    constexpr int kArUnroll = MC ? kArUnrollMc : kArUnrollPeer;
     const int b = blockIdx.x;
     // this CTA slot's call counter: every rank has made the same calls, so the slots agree across ranks
     unsigned* counter = p.flags[p.rank] + kArMaxCtas * 2 * kArMaxWorld + b;
@@ -163,7 +165,8 @@ int launch_grad_allreduce(float* const* peer_bufs, float* mc_buf, unsigned* cons
     p.world = world;
     // the same grid on every rank (CTA b pairs with CTA b): a function of the range and the world size only
     const long long per_rank = (p.nvec + world - 1) / world;
-    long long want = (per_rank + (long long)threads * kArUnroll - 1) / ((long long)threads * kArUnroll);
+    const int unroll = mc_buf ? kArUnrollMc : kArUnrollPeer;
+    long long want = (per_rank + (long long)threads * unroll - 1) / ((long long)threads * unroll);
     if (want < 1) want = 1;
     if (max_ctas < 1) max_ctas = 1;
     if (max_ctas > kArMaxCtas) max_ctas = kArMaxCtas;
