@@ -148,6 +148,7 @@ class PeerExchange:
         self._status_ptr = status.data_ptr()
         self._dev_index = buffer.device.index
         self.use_multicast = self.multicast
+        self.peer_min_ctas = 32
 
     @classmethod
     def create(cls, numel, device, group=None, max_ctas=16, cta_threads=512, timeout_ms=2000):
@@ -210,7 +211,7 @@ class PeerExchange:
         mc = self._mc_ptr + 4 * lo if (self.use_multicast and self._mc_ptr) else None
         # without the switch every element is `world` round trips: the peer path wants twice the CTAs (6.4 MB on 2 / 8
         # GPUs: 66 us with 16 CTAs, 41 / 49 us with 32; the NVLS path is flat from 8 CTAs on)
-        ctas = self.max_ctas if mc is not None else min(max(self.max_ctas, 32), _cabi.AR_MAX_CTAS)
+        ctas = self.max_ctas if mc is not None else min(max(self.max_ctas, self.peer_min_ctas), _cabi.AR_MAX_CTAS)
         rc = _cabi.load().dhfk_grad_allreduce(arr, mc, self._flag_arr, self._status_ptr, self.rank, self.world, hi - lo,
                                               (1.0 / self.world) if average else 1.0, ctas,
                                               self.cta_threads, self.timeout_ms,

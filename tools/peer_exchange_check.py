@@ -163,6 +163,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return {"gpu_us": round(float(t[0]), 2), "host_enqueue_us": round(float(t[1]), 2)}
 
+        px.peer_min_ctas = 1          # the sweep below sets the CTA count itself
         timing["nccl"] = timed(lambda: dist.all_reduce(buf_nccl, op=dist.ReduceOp.AVG))
         for use_mc in ((True, False) if px.multicast else (False,)):
             px.use_multicast = use_mc
