@@ -50,6 +50,11 @@ class FlatGradBuffer:
     share one buffer (``FlatGradBuffer([*G.parameters(), *D3.parameters(), *D2.parameters()])``) and be reduced in one
     call, or separately through ``allreduce(span=buf.span_of(model))``.
 
+    ``peer_exchange=True`` (NCCL process group, one node): the buffer is a symmetric allocation and ``allreduce`` over
+    the group it was created for is ``dhfk_grad_allreduce`` -- one hand-written kernel over NVLink peer memory / the
+    NVSwitch multicast object, in place (see ``PeerExchange``); where that is not available the buffer is an ordinary
+    tensor and the same call is NCCL's.
+
     Zero the gradients with ``buf.zero()`` (or ``zero_grad(set_to_none=False)``): ``zero_grad()``'s default drops the
     ``.grad`` tensors, after which autograd allocates fresh ones outside the buffer.  ``allreduce`` notices and re-adopts
     such gradients (one copy each), so the result is always right; it is only fastest when nothing was dropped.
@@ -65,8 +70,8 @@ class FlatGradBuffer:
         for p in self.params:
             self.offsets.append(off)
             off += (p.numel() + 3) // 4 * 4            # every slice starts 16-byte aligned
-        self.peer = None
-        if peer_exchange:
+        self.peer, self._peer_group = None, group
+        if peer_exchange and dtype == torch.float32:
             self.peer = PeerExchange.create(off, device, group, max_ctas=max_ctas, cta_threads=cta_threads,
                                             timeout_ms=timeout_ms)
         if self.peer is not None:
@@ -111,7 +116,7 @@ class FlatGradBuffer:
             elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
                 p.grad = v
-        if self.peer is not None and group is None:
+        if self.peer is not None and group is self._peer_group:      # the ranks the symmetric buffer was set up over
             lo, hi = (0, self.flat.numel()) if span is None else span
             return self.peer.allreduce(lo, hi, average)
         buf = self.flat if span is None else self.flat[span[0]:span[1]]
