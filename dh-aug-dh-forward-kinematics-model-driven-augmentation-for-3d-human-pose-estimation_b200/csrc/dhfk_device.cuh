@@ -96,6 +96,10 @@ enum { TRIG_ACCURATE = 0, TRIG_MUFU = 1 };
 #ifndef DHFK_ACCURATE_TABLE
 #define DHFK_ACCURATE_TABLE 1
 #endif
+// TRIG_ACCURATE polynomial path: 1 = reduce by half turns (sign only), 0 = by quarter turns (swap + sign)
+#ifndef DHFK_SINCOS_HALFTURN
+#define DHFK_SINCOS_HALFTURN 1
+#endif
 static __device__ const float2 c_sincos_table[DHFK_SINCOS_TABLE_SIZE] = {DHFK_SINCOS_TABLE_VALUES};
 static_assert(DHFK_SINCOS_TABLE_SIZE == 128, "index arithmetic below assumes 128 entries");
 
@@ -119,6 +123,53 @@ DHFK_DI void sincos_deg(float deg, float& s, float& c) {
     const float kMagic = 12582912.0f;  // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x) for |x| < 2^22
     if (TRIG == TRIG_ACCURATE && DHFK_ACCURATE_TABLE) {
         sincos_table_core(deg, Q0, s, c);
+    } else if (TRIG == TRIG_ACCURATE && DHFK_SINCOS_HALFTURN) {
+        // Reduce by half turns: r = deg - 180*rint(deg/180) is exact, |r| <= 90, and sin / cos of the angle are those of
+        // r up to ONE common sign (the parity of the half-turn count) -- no swap, no per-quadrant selects.  The price is
+        // one more term per polynomial (least-squares fit on Chebyshev nodes over |r| <= 90 deg, absolute-error weighted,
+        // tools/sincos_reduction_study.py): max abs error 1.23e-7 / 1.11e-7 (sin / cos, fp32 emulation over [-720, 720]
+        // deg) against 8.0e-8 for the quarter-turn scheme below -- the reference's own fl(fl(deg/180)*pi) argument
+        // rounding costs it 1.1e-6 -- for 13 instead of 18 instructions per sincos.  The compile-time theta0 quadrant
+        // folds into which of the two values is the sine and into the constant part of the sign mask.
+        float t = fmaf(deg, 1.0f / 180.0f, kMagic);
+        const unsigned sign = (unsigned)__float_as_int(t) << 31;
+        float q = t - kMagic;
+        float r = fmaf(q, -180.0f, deg);
+        float r2 = r * r;
+        constexpr double D = 3.14159265358979323846 / 180.0;
+        constexpr float S0 = (float)(9.99999976513755717e-01 * D);
+        constexpr float S1 = (float)(-1.66666475934896696e-01 * D * D * D);
+        constexpr float S2 = (float)(8.33289922283364168e-03 * D * D * D * D * D);
+        constexpr float S3 = (float)(-1.98008653071941475e-04 * D * D * D * D * D * D * D);
+        constexpr float S4 = (float)(2.59043003061907403e-06 * D * D * D * D * D * D * D * D * D);
+        constexpr float C0 = (float)(-4.99999995353595350e-01 * D * D);
+        constexpr float C1 = (float)(4.16666402579548498e-02 * D * D * D * D);
+        constexpr float C2 = (float)(-1.38883983513082084e-03 * D * D * D * D * D * D);
+        constexpr float C3 = (float)(2.47616556899794226e-05 * D * D * D * D * D * D * D * D);
+        constexpr float C4 = (float)(-2.60734800845432612e-07 * D * D * D * D * D * D * D * D * D * D);
+#if DHFK_PACKED_V3
+        float2 pp = __ffma2_rn(make_float2(r2, r2), make_float2(S4, C4), make_float2(S3, C3));
+        pp = __ffma2_rn(make_float2(r2, r2), pp, make_float2(S2, C2));
+        pp = __ffma2_rn(make_float2(r2, r2), pp, make_float2(S1, C1));
+        pp = __ffma2_rn(make_float2(r2, r2), pp, make_float2(S0, C0));
+        const float ps = pp.x, pc = pp.y;
+#else
+        float ps = fmaf(r2, S4, S3);
+        ps = fmaf(r2, ps, S2);
+        ps = fmaf(r2, ps, S1);
+        ps = fmaf(r2, ps, S0);
+        float pc = fmaf(r2, C4, C3);
+        pc = fmaf(r2, pc, C2);
+        pc = fmaf(r2, pc, C1);
+        pc = fmaf(r2, pc, C0);
+#endif
+        const float sv = r * ps;
+        const float cv = fmaf(r2, pc, 1.0f);
+        constexpr int Q = ((Q0 % 4) + 4) % 4;     // sin / cos (x + 90 Q): (s, c), (c, -s), (-s, -c), (-c, s)
+        constexpr unsigned fs = (Q == 2 || Q == 3) ? 0x80000000u : 0u;
+        constexpr unsigned fc = (Q == 1 || Q == 2) ? 0x80000000u : 0u;
+        s = __int_as_float(__float_as_int((Q & 1) ? cv : sv) ^ (sign ^ fs));
+        c = __int_as_float(__float_as_int((Q & 1) ? sv : cv) ^ (sign ^ fc));
     } else if (TRIG == TRIG_ACCURATE) {
         float t = fmaf(deg, 1.0f / 90.0f, kMagic);
         int n = __float_as_int(t) + Q0;           // low 2 bits: quadrant
