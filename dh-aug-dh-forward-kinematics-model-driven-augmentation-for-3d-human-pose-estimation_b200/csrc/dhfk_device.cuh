@@ -96,6 +96,15 @@ enum { TRIG_ACCURATE = 0, TRIG_MUFU = 1 };
 #ifndef DHFK_ACCURATE_TABLE
 #define DHFK_ACCURATE_TABLE 1
 #endif
+// TRIG_MUFU: 1 (default) = reduce the angle exactly to |r| <= 180 deg before the two multiplies in front of MUFU.SIN /
+// MUFU.COS (deg -> rad, rad -> turns), 0 = hand deg * pi/180 to them as it is.  The unit works on the fractional turn
+// either way; what the reduction buys is that the two multiply roundings (1.8e-7 relative, together) act on |r| <= 180
+// instead of on |deg|.  Measured and rejected (profiles/r2i1_ab_mufu_direct.txt): without it a sincos is 4 instead of 7
+// instructions and the backward runs 0.5 % faster (generator mode 0.2120 -> 0.2096 ms), but the stress parity test
+// (angles up to +-360 deg after theta0, clamp active) fails its 1e-5 bound.
+#ifndef DHFK_MUFU_EXACT_REDUCTION
+#define DHFK_MUFU_EXACT_REDUCTION 1
+#endif
 // TRIG_ACCURATE polynomial path: 1 = reduce by half turns (sign only), 0 = by quarter turns (swap + sign)
 #ifndef DHFK_SINCOS_HALFTURN
 #define DHFK_SINCOS_HALFTURN 1
@@ -207,10 +216,14 @@ DHFK_DI void sincos_deg(float deg, float& s, float& c) {
         s = __int_as_float(__float_as_int(so) ^ ((n << 30) & 0x80000000));
         c = __int_as_float(__float_as_int(co) ^ (((n + 1) << 30) & 0x80000000));
     } else {
+#if DHFK_MUFU_EXACT_REDUCTION
         float t = fmaf(deg, 1.0f / 360.0f, kMagic);
         float q = t - kMagic;
         float r = fmaf(q, -360.0f, deg);          // exact, |r| <= 180
         float x = r * kDegToRad;
+#else
+        float x = deg * kDegToRad;                // MUFU takes the fractional turn itself, see DHFK_MUFU_EXACT_REDUCTION
+#endif
         float sv = __sinf(x), cv = __cosf(x);
         constexpr int Q = ((Q0 % 4) + 4) % 4;
         if (Q == 0) { s = sv; c = cv; }
@@ -265,10 +278,14 @@ DHFK_DI void sincos_deg_rt(float deg, int q0, float& s, float& c) {
     } else {
         // the reference itself forms fl(theta0 + angle) in fp32 before sin/cos (:601 etc.)
         float d2 = fmaf(90.0f, (float)q0, deg);
+#if DHFK_MUFU_EXACT_REDUCTION
         float t = fmaf(d2, 1.0f / 360.0f, kMagic);
         float q = t - kMagic;
         float r = fmaf(q, -360.0f, d2);
         float x = r * kDegToRad;
+#else
+        float x = d2 * kDegToRad;
+#endif
         s = __sinf(x);
         c = __cosf(x);
     }
