@@ -52,14 +52,18 @@ def fit(kind, nterms, half_range_deg=90.0):
 
 
 def scheme_b(deg, ns, nc):
+    return emulate_halfturn(deg, fit("sin", ns), fit("cos", nc))
+
+
+def emulate_halfturn(deg, cs, cc):
+    """The kernels' half-turn scheme in fp32 emulation with explicit coefficients (radian units, lowest order first)."""
+    ns, nc = len(cs), len(cc)
     magic = f32(12582912.0)
     t = fma(deg, np.full_like(deg, f32(1.0 / 180.0)), np.full_like(deg, magic))
     n = t.view(np.int32).astype(np.int64)
     q = (t - magic).astype(f32)
     r = fma(q, np.full_like(deg, f32(-180.0)), deg)          # exact, |r| <= 90
     r2 = (r * r).astype(f32)
-    cs = fit("sin", ns)
-    cc = fit("cos", nc)
     S = [cs[i] * D ** (2 * i + 1) for i in range(ns)]        # degree units
     C = [cc[i] * D ** (2 * i + 2) for i in range(nc)]
     ps = np.full_like(deg, f32(S[-1]))
