@@ -61,7 +61,7 @@ class FlatGradBuffer:
     """
 
     def __init__(self, params, device=None, dtype=torch.float32, peer_exchange=False, group=None, max_ctas=16,
-                 cta_threads=512, timeout_ms=2000):
+                 cta_threads=512, timeout_ms=20000):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no parameters that require grad")
@@ -136,7 +136,9 @@ class PeerExchange:
     from / stores to every peer -- in place, with two cross-GPU flag barriers inside the kernel.  PyTorch only provides
     the memory: ``torch.distributed._symmetric_memory`` allocates the buffer and the flag block and maps every rank's
     copy into every process.  ``create`` returns None where that is not possible (one rank, gloo, no peer access), and
-    the caller keeps NCCL."""
+    the caller keeps NCCL.  ``timeout_ms`` bounds how long a rank's kernel waits for the slowest rank to reach the same
+    call (20 s by default: ranks of a training loop drift apart by far less; a rank that never arrives must not hang
+    the GPU) -- ``check()`` tells whether that ever happened."""
 
     def __init__(self, buffer, flags, status, bufs, flag_ptrs, mc_ptr, rank, world, max_ctas, cta_threads, timeout_ms,
                  handles):
@@ -156,7 +158,7 @@ class PeerExchange:
         self.peer_min_ctas = 32
 
     @classmethod
-    def create(cls, numel, device, group=None, max_ctas=16, cta_threads=512, timeout_ms=2000):
+    def create(cls, numel, device, group=None, max_ctas=16, cta_threads=512, timeout_ms=20000):
         from . import _cabi
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
