@@ -988,6 +988,13 @@ def run_native(args):
 
     bwd_gbs = BWD_BYTES * n_step / (bwd_ms * 1e-3) / 1e9
     fwd_gbs = FWD_BYTES * n_step / (fwd_ms * 1e-3) / 1e9
+    # The bracketed durations above include the event records around the launches (a ~2 us bubble each: fwd + bwd
+    # bracketed add up to more than ms_per_step, which is dominated by the un-probed steps).  The same live shares applied
+    # to the step time give durations that add up to the step: reported beside the bracketed ones, not instead of them.
+    share_b = bwd_ms / (fwd_ms + bwd_ms)
+    bwd_ms_share, fwd_ms_share = ms_per_step * share_b, ms_per_step * (1.0 - share_b)
+    share_note = ("ms_per_launch = CUDA events around the launch in every 8th step of the timed region (includes the event "
+                  "bubbles); *_step_share = ms_per_step x this kernel's share of the bracketed pair (adds up to the step)")
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")     # written from an `ncu --set full` capture (per launch)
     if os.path.exists(tp):
@@ -1011,10 +1018,13 @@ def run_native(args):
                                                 % (nbuf, n * (216 + 320) / 1e9))}),
         "roofline": {"bound": "hbm", "kernel": "dhfk_bwd_kernel<GUV=1,GBONE=0>", "achieved": bwd_gbs, "peak": peak,
                      "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "peak_source": peak_src, "ms_per_launch": bwd_ms, "algorithmic_bytes_per_launch": BWD_BYTES * n_step},
+                     "peak_source": peak_src, "ms_per_launch": bwd_ms, "algorithmic_bytes_per_launch": BWD_BYTES * n_step,
+                     "ms_per_launch_step_share": bwd_ms_share,
+                     "frac_step_share": BWD_BYTES * n_step / (bwd_ms_share * 1e-3) / 1e9 / peak, "timing": share_note},
         "roofline_fwd": {"bound": "hbm", "kernel": "dhfk_fwd_kernel<CAM=0,UV=1>", "achieved": fwd_gbs, "peak": peak,
                          "unit": "GB/s", "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
-                         "algorithmic_bytes_per_launch": FWD_BYTES * n_step},
+                         "algorithmic_bytes_per_launch": FWD_BYTES * n_step, "ms_per_launch_step_share": fwd_ms_share,
+                         "frac_step_share": FWD_BYTES * n_step / (fwd_ms_share * 1e-3) / 1e9 / peak},
         "roofline_step": {"achieved": (FWD_BYTES + BWD_BYTES) * n_step / (ms_per_step * 1e-3) / 1e9, "peak": peak,
                           "frac": (FWD_BYTES + BWD_BYTES) * n_step / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"},
         "clocks": dict(sampler.summary(), window="timed region" + (" + 1 s extension of the same loop" if extension else "")),
