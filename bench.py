@@ -491,6 +491,32 @@ def feed_sampler(sampler, path, dev):
     return True
 
 
+EXPOSED_HOW = ("after 0.3 s of the same steps (the board's burst regime is over by then), five K-step runs without / with / "
+               "without / with / without the exchange: mean of the two with it - mean of the three without it, per step")
+
+
+def exchange_exposure(path, steps, stream, dev, barrier, ar, distributed):
+    """(exposed ms per step, ms per step without the exchange) in the board's steady state.  Measured apart from the
+    headline run: a run out of idle sits in the burst regime and the clocks step down ~0.1 s into a series, which a
+    with / without pair straddling that moment reads as +-5 % (profiles/r2t3_bench_n2.json).  Symmetric order: a linear
+    drift cancels."""
+    import torch
+    t_end = time.time() + 0.3
+    i = 0
+    while time.time() < t_end:
+        path.step(i); i += 1
+        if i % 16 == 0:
+            torch.cuda.synchronize(dev)
+    torch.cuda.synchronize(dev)
+    runs = []
+    for k in range(5):
+        ms, _, _ = timed_steps(path, steps, stream, dev, barrier, allreduce=(ar if k % 2 else None))
+        runs.append(ms)
+    runs = max_over_ranks(runs, dev, distributed)
+    plain = (runs[0] + runs[2] + runs[4]) / 3 / steps
+    return (runs[1] + runs[3]) / 2 / steps - plain, plain
+
+
 def max_over_ranks(vals, dev, distributed):
     import torch
     import torch.distributed as dist
@@ -693,44 +719,41 @@ def run_native(args):
         n_big = hi - lo
         path = HotPath(lib, n_big, dev, 1 if n_big >= (1 << 21) else 2, 777 + 97 * rank, flags, cam_ptr, sp)
         ar = (gbuf, side) if distributed else None
-        # weak companion first (1M poses per rank, same in-step all-reduce), then the headline
-        for i in range(warmup):
-            path1.step(i)
-        # with (the reported run) / without / with / without the exchange: the exposed time is the second run with it
-        # minus the mean of the two runs without it around it -- the first run of a series sits in the board's burst
-        # regime, the later ones do not, and a linear drift cancels out of the bracketed difference
-        w_ms, _, _ = timed_steps(path1, steps, stream, dev, barrier, allreduce=ar)
-        w_plain, _, _ = timed_steps(path1, steps, stream, dev, barrier)
-        w_ms2, _, _ = timed_steps(path1, steps, stream, dev, barrier, allreduce=ar)
-        w_plain2, _, _ = timed_steps(path1, steps, stream, dev, barrier)
-        w_ms, w_plain, w_plain2, w_ms2 = max_over_ranks([w_ms, w_plain, w_plain2, w_ms2], dev, distributed)
-        weak_extra = {"poses_per_gpu": n, "value": n * world_size / (w_ms / steps * 1e-3), "unit": UNIT,
-                      "ms_per_step": w_ms / steps, "ms_per_step_without_allreduce": (w_plain + w_plain2) / 2 / steps,
-                      "ms_exposed_per_step": (w_ms2 - (w_plain + w_plain2) / 2) / steps,
-                      "what": "weak scaling: 1,048,576 poses per rank + the same in-step gradient all-reduce; exposed = "
-                              "second run with it - mean of the runs without it before and after"}
+        # the headline first, out of idle like the N = 1 line: K steps with the exchange inside them
         for i in range(warmup):
             path.step(i)
         if sampler:
             sampler.start()
         total_ms, fwd_ms, bwd_ms = timed_steps(path, steps, stream, dev, barrier, allreduce=ar, probe_every=probe_every)
-        plain_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)      # the same steps without the collective,
-        total2_ms, _, _ = timed_steps(path, steps, stream, dev, barrier, allreduce=ar)   # with it again,
-        plain2_ms, _, _ = timed_steps(path, steps, stream, dev, barrier)     # and without it again (see above)
         barrier()
         extension = feed_sampler(sampler, path, dev)
         if sampler:
             sampler.stop()
-        total_ms, fwd_ms, bwd_ms, plain_ms, plain2_ms, total2_ms = max_over_ranks(
-            [total_ms, fwd_ms, bwd_ms, plain_ms, plain2_ms, total2_ms], dev, distributed)
+        total_ms, fwd_ms, bwd_ms = max_over_ranks([total_ms, fwd_ms, bwd_ms], dev, distributed)
         n_step = n_big
         value = args.total_poses / (total_ms / steps * 1e-3)
         if allreduce_extra is not None:
-            allreduce_extra["ms_exposed_per_step"] = (total2_ms - (plain_ms + plain2_ms) / 2) / steps
-            allreduce_extra["ms_per_step_without_allreduce"] = (plain_ms + plain2_ms) / 2 / steps
-            allreduce_extra["ms_per_step_second_run_with_it"] = total2_ms / steps
+            exposed, plain = exchange_exposure(path, steps, stream, dev, barrier, ar, distributed)
+            allreduce_extra["ms_exposed_per_step"] = exposed
+            allreduce_extra["ms_per_step_without_allreduce"] = plain
+            allreduce_extra["exposed_how"] = EXPOSED_HOW
+        # weak companion (1 M poses per rank, the same in-step exchange): its value out of idle as well, then its exposure
+        torch.cuda.synchronize(dev)
+        time.sleep(0.5)
+        for i in range(warmup):
+            path1.step(i)
+        w_ms, _, _ = timed_steps(path1, steps, stream, dev, barrier, allreduce=ar)
+        (w_ms,) = max_over_ranks([w_ms], dev, distributed)
+        weak_extra = {"poses_per_gpu": n, "value": n * world_size / (w_ms / steps * 1e-3), "unit": UNIT,
+                      "ms_per_step": w_ms / steps,
+                      "what": "weak scaling: 1,048,576 poses per rank + the same in-step gradient exchange, %d steps after "
+                              "0.5 s of idle and the warm-ups" % steps}
+        if ar is not None:
+            exposed, plain = exchange_exposure(path1, steps, stream, dev, barrier, ar, distributed)
+            weak_extra["ms_exposed_per_step"] = exposed
+            weak_extra["ms_per_step_without_allreduce"] = plain
             if gbuf.peer is not None:
-                gbuf.peer.check()          # no exchange in the timed region gave up on a peer
+                gbuf.peer.check()          # no exchange in the timed regions gave up on a peer
     else:
         path = path1
         for i in range(warmup):
