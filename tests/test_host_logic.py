@@ -240,3 +240,23 @@ def test_lazy_world32_answers_the_joint_gather_without_materialising(monkeypatch
     assert np.array_equal(np.asarray(x), x.tensor().detach().numpy())
     assert len(calls) == 1
     assert torch.equal(x[:, 4], root) and torch.equal(x[:, 31], root)          # free slots hold the root
+
+
+def test_peer_exchange_range_checks_without_gpu():
+    """dhfk.parallel.PeerExchange.allreduce validates the element range before anything reaches the library."""
+    import pytest
+    import torch
+    from dhfk import parallel
+    buf = torch.zeros(64)
+    px = parallel.PeerExchange(buf, torch.zeros(8, dtype=torch.int32), torch.zeros(1, dtype=torch.int32),
+                               [buf.data_ptr(), buf.data_ptr()], [0x1000, 0x2000], 0, 0, 2, 16, 512, 100, None)
+    assert px.multicast is False and px.peer_min_ctas == 32
+    assert px.allreduce(8, 8) == 0                      # empty range: nothing launched
+    for lo, hi in ((2, 8), (0, 6), (-4, 8), (0, 68), (16, 8)):
+        with pytest.raises(ValueError):
+            px.allreduce(lo, hi)
+    # off NCCL there is nothing to set up, and FlatGradBuffer keeps an ordinary tensor
+    assert parallel.PeerExchange.create(64, torch.device("cpu")) is None
+    lin = torch.nn.Linear(3, 2)
+    fb = parallel.FlatGradBuffer(lin.parameters(), peer_exchange=True)
+    assert fb.peer is None and fb.flat.numel() == 8 + 4 and lin.weight.grad.data_ptr() == fb.flat.data_ptr()
